@@ -44,40 +44,55 @@ enum {
 int psfem_version(void);
 const char *psfem_last_error(void);
 int psfem_nodes_per_element(int etype);
+/* bind the calling host thread to a CUDA device (the library links its own static CUDA runtime;
+ * the Python side calls this with torch's current device before any other entry point) */
+int psfem_set_device(int device);
+
+/* CSR operand of the sparse kernels.  row_ptr values are absolute offsets into col_idx / vals, so a
+ * contiguous row slice of a larger matrix (the owned rows of a strip) is a valid operand:
+ * row_ptr + first_row, n_rows = rows in the slice.  col_idx address the (extended) input vector.
+ * rowblk / n_blocks / max_row_nnz come from psfem_spmv_plan. */
+typedef struct psfem_csr {
+    int64_t n_rows;
+    int64_t nnz;            /* row_ptr[n_rows] - row_ptr[0] */
+    const int32_t *row_ptr; /* n_rows + 1 */
+    const int32_t *col_idx;
+    const double *vals;
+    const int32_t *rowblk;  /* n_blocks + 2 ints (plan + one scratch slot) */
+    int64_t n_blocks;
+    int64_t max_row_nnz;
+} psfem_csr;
 
 /* ---- mesh: Polygones.mesh, Polygones.py:62-108 ------------------------------------------
  * Nodes of the node columns [col0, col0+ncols) and elements of the cell columns
  * [cell0, cell0+ncells) of the structured mesh mesh(L,l,N,M,offX,offY,etype).  Node ids written
  * to d_conn are LOCAL: global id - col0*m (m = nodes per column), so a strip is a self-contained
- * mesh; col0=0, ncols=n, cell0=0, ncells=N gives the reference's whole mesh.
- * L_is_int / l_is_int: Python forms i*L exactly when L is an int (Polygones.py:77); pass 1 so the
- * product is formed in integer arithmetic before the division.
- * d_nodes: ncols*m*2 doubles, d_conn: ncells*M*(1 or 2)*npe int32. */
+ * mesh; col0=0, ncols=n, cell0=0, ncells=N gives the reference's whole mesh.  Coordinates are
+ * bit-identical to Polygones.py:77 (product, IEEE division, subtraction; no FMA contraction).
+ * d_nodes: ncols*m*2 doubles, d_conn: ncells*M*(2 for triangles)*npe int32.  Either may be NULL. */
 int psfem_mesh_rect(double L, double l, int64_t N, int64_t M, double offX, double offY, int etype,
                     int64_t col0, int64_t ncols, int64_t cell0, int64_t ncells,
                     double *d_nodes, int32_t *d_conn, void *stream);
 
 /* ---- symbolic CSR pattern: replaces the dense np.zeros((2n,2n)) of Polygones.py:715,1349 ----
  * Structural pattern of K and M: row 2a+p has the sorted columns {2b+q : node b shares an
- * element with node a}.  Built by a radix sort + run-length unique of the npe^2 (a,b) node-pair
- * keys of every element.  The stable sort also yields the ASSEMBLY PLAN: for every unique pair
+ * element with node a}.  Built by a stable radix sort + run-length unique of the npe^2 (a,b)
+ * node-pair keys of every element.  The sort also yields the ASSEMBLY PLAN: for every unique pair
  * the contributing (element,i,j) codes in ascending element id -- the order of the reference's
  * scatter loop Polygones.py:717-726 -- which makes the numeric phase a deterministic, atomic-free
  * segmented reduction.
- *   step 1  psfem_pattern_count : sort/unique; returns n_pairs (nnz = 4*n_pairs); state in ws
- *   step 2  psfem_pattern_fill  : writes row_ptr, col_idx and the plan into caller arrays
- */
+ *   step 1  psfem_pattern_count : sort/unique; d_perm (nel*npe^2 codes e*npe^2+i*npe+j, sorted by
+ *                                 pair) is final; returns n_pairs (nnz = 4*n_pairs); state in d_ws
+ *   step 2  psfem_pattern_fill  : writes row_ptr, col_idx and the rest of the plan (same d_ws) */
 int psfem_pattern_workspace(int64_t nel, int npe, int64_t n_nodes, size_t *bytes);
-int psfem_pattern_count(const int32_t *d_conn, int64_t nel, int npe, int64_t n_nodes,
+int psfem_pattern_count(const int32_t *d_conn, int64_t nel, int npe, int64_t n_nodes, int32_t *d_perm,
                         void *d_ws, size_t ws_bytes, int64_t *h_n_pairs, void *stream);
-int psfem_pattern_fill(int64_t nel, int npe, int64_t n_nodes, int64_t n_pairs,
-                       const void *d_ws, size_t ws_bytes,
-                       int32_t *d_row_ptr,   /* 2*n_nodes+1 */
-                       int32_t *d_col_idx,   /* 4*n_pairs   */
-                       int32_t *d_node_ptr,  /* n_nodes+1 : first pair of each node row        */
-                       int32_t *d_pair_row,  /* n_pairs   : row node of each pair               */
-                       int32_t *d_pair_ptr,  /* n_pairs+1 : segment bounds into d_perm          */
-                       int32_t *d_perm,      /* nel*npe^2 : contribution codes e*npe^2+i*npe+j  */
+int psfem_pattern_fill(int64_t nel, int npe, int64_t n_nodes, int64_t n_pairs, void *d_ws, size_t ws_bytes,
+                       int32_t *d_row_ptr,  /* 2*n_nodes+1 */
+                       int32_t *d_col_idx,  /* 4*n_pairs   */
+                       int32_t *d_node_ptr, /* n_nodes+1 : first pair of each node row */
+                       int32_t *d_pair_row, /* n_pairs   : row node of each pair        */
+                       int32_t *d_pair_ptr, /* n_pairs+1 : segment bounds into d_perm   */
                        void *stream);
 
 /* ---- numeric assembly: Polygones.global_stiffness_matrix :710-728 / global_mass_matrix :1344-1364
@@ -87,24 +102,26 @@ int psfem_pattern_fill(int64_t nel, int npe, int64_t n_nodes, int64_t n_pairs,
  * else -1; the call then returns PSFEM_EJACOBIAN.  Synchronises the stream. */
 int psfem_assemble_workspace(int64_t nel, int etype, int what, size_t *bytes);
 int psfem_assemble(const double *d_nodes, const int32_t *d_conn, int64_t nel, int etype, int64_t n_nodes,
-                   double E, double nu, double rho, double t, int what,
-                   int64_t n_pairs, const int32_t *d_node_ptr, const int32_t *d_pair_row,
-                   const int32_t *d_pair_ptr, const int32_t *d_perm,
-                   double *d_K_vals, double *d_M_vals,
+                   double E, double nu, double rho, double t, int what, int64_t n_pairs,
+                   const int32_t *d_node_ptr, const int32_t *d_pair_row, const int32_t *d_pair_ptr,
+                   const int32_t *d_perm, double *d_K_vals, double *d_M_vals,
                    void *d_ws, size_t ws_bytes, int64_t *h_bad_element, void *stream);
 
-/* element matrices only (block layout e-major): Polygones.element_stiffness_matrix :566,
- * element_mass_matrix :1250.  d_Ke: nel*(2npe)^2 row-major per element; d_Me likewise. */
+/* element matrices only: Polygones.element_stiffness_matrix :566, element_mass_matrix :1250.
+ * d_Ke / d_Me: nel*(2npe)^2 doubles, one row-major (2npe x 2npe) matrix per element.
+ * Work space: psfem_assemble_workspace(nel, etype, what). */
 int psfem_element_matrices(const double *d_nodes, const int32_t *d_conn, int64_t nel, int etype,
-                           double E, double nu, double rho, double t, int what,
-                           double *d_Ke, double *d_Me, int64_t *h_bad_element, void *stream);
+                           double E, double nu, double rho, double t, int what, double *d_Ke, double *d_Me,
+                           void *d_ws, size_t ws_bytes, int64_t *h_bad_element, void *stream);
 
 /* ---- boundary conditions: Polygones.apply_boundary_conditions :989-1006, reduce :898-911 ----
- * psfem_free_map: d_constrained (nc DOF ids, duplicates allowed) -> d_new_id[n] (reduced index or
- * -1) and d_free_dofs (ascending complement, Polygones.py:1000); returns n_free.
+ * psfem_free_map: d_constrained (nc DOF ids, duplicates and out-of-range ids allowed, as the list
+ * membership test of :1000 allows them) -> d_new_id[n] (reduced index or -1) and d_free_dofs
+ * (ascending complement); returns n_free.
  * psfem_reduce_count/fill: K[np.ix_(free,free)] on CSR; d_keep[k] = position in the full value
- * array of reduced entry k, so M and K_eff reduce with psfem_gather. */
-int psfem_free_map_workspace(int64_t n, size_t *bytes);
+ * array of reduced entry k, so K, M and K_eff values reduce with psfem_gather.
+ * Work space for all three: psfem_scan_workspace(n). */
+int psfem_scan_workspace(int64_t n, size_t *bytes);
 int psfem_free_map(int64_t n, const int32_t *d_constrained, int64_t nc, int32_t *d_new_id,
                    int32_t *d_free_dofs, int64_t *h_n_free, void *d_ws, size_t ws_bytes, void *stream);
 int psfem_reduce_count(int64_t n, const int32_t *d_row_ptr, const int32_t *d_col_idx, const int32_t *d_new_id,
@@ -113,72 +130,70 @@ int psfem_reduce_count(int64_t n, const int32_t *d_row_ptr, const int32_t *d_col
 int psfem_reduce_fill(int64_t n, const int32_t *d_row_ptr, const int32_t *d_col_idx, const int32_t *d_new_id,
                       const int32_t *d_row_ptr_red, int32_t *d_col_idx_red, int32_t *d_keep, void *stream);
 int psfem_gather(const double *d_src, const int32_t *d_index, int64_t n, double *d_dst, void *stream);
-/* reconstruct_full_vector(s) Polygones.py:913-936: d_full[free[i]] = d_red[i], zeros elsewhere (nvec rows) */
+/* reconstruct_full_vector(s) Polygones.py:913-936: d_full[v, free[i]] = d_red[v, i], zeros elsewhere */
 int psfem_scatter_free(const double *d_red, const int32_t *d_free_dofs, int64_t n_free, int64_t n_full,
                        int64_t nvec, double *d_full, void *stream);
 
 /* ---- sparse kernels used by the static / Newmark / modal drivers -------------------------
  * SpMV stages row blocks of the CSR stream through shared memory (coalesced vals/col_idx reads,
- * per-row reduction from shared memory); d_rowblk from psfem_spmv_plan. */
+ * per-row reduction from shared memory in column order). */
 int psfem_spmv_plan_size(int64_t n, int64_t nnz, int64_t *n_blocks);
-int psfem_spmv_plan(int64_t n, const int32_t *d_row_ptr, int64_t nnz, int32_t *d_rowblk, int64_t n_blocks, void *stream);
-/* y = alpha*A*x + beta*z   (z may be NULL -> beta ignored; y may alias z) */
-int psfem_spmv(int64_t n, const int32_t *d_row_ptr, const int32_t *d_col_idx, const double *d_vals,
-               const int32_t *d_rowblk, int64_t n_blocks,
-               const double *d_x, double alpha, double beta, const double *d_z, double *d_y, void *stream);
-/* y = alpha*A1*x1 + beta*A2*x2 + gamma*z on a shared pattern (Newmark RHS main.py:310) */
-int psfem_spmv2(int64_t n, const int32_t *d_row_ptr, const int32_t *d_col_idx,
-                const double *d_vals1, const double *d_vals2, const int32_t *d_rowblk, int64_t n_blocks,
-                const double *d_x1, const double *d_x2, double alpha, double beta, double gamma,
-                const double *d_z, double *d_y, void *stream);
-int psfem_extract_diag(int64_t n, const int32_t *d_row_ptr, const int32_t *d_col_idx, const double *d_vals,
-                       int64_t col_offset, double *d_diag, void *stream);
+int psfem_spmv_plan(int64_t n, const int32_t *d_row_ptr, int64_t nnz, int32_t *d_rowblk /* n_blocks+2 */,
+                    int64_t n_blocks, int64_t *h_max_row_nnz, void *stream);
+/* y = alpha*A*x + gamma*z   (z may be NULL; y may alias z) */
+int psfem_spmv(const psfem_csr *A, const double *d_x, double alpha, double gamma, const double *d_z,
+               double *d_y, void *stream);
+/* y = alpha*A1*x1 + beta*A2*x2 + gamma*z, A2 = (pattern of A, d_vals2): Newmark RHS main.py:310 */
+int psfem_spmv2(const psfem_csr *A, const double *d_vals2, const double *d_x1, const double *d_x2,
+                double alpha, double beta, double gamma, const double *d_z, double *d_y, void *stream);
+/* diag[r] = A[r, r+col_offset] (invert != 0: its reciprocal = the Jacobi preconditioner) */
+int psfem_extract_diag(const psfem_csr *A, int64_t col_offset, int invert, double *d_diag, void *stream);
 
 /* Jacobi-preconditioned CG: replaces np.linalg.solve / scipy.linalg.solve / lu_solve of
  * Statictest.py:69, StaticTest2.py:71, Beamexemple.py:63, main.py:286,314.
- * x0 = d_x on entry, stop when ||r||_2 <= rtol*||b||_2, residual checked every check_every
- * iterations (device-side scalars; one host sync per check).  h_info: [0]=iterations,
- * [1]=relative residual, [2]=b norm. */
+ * x0 = d_x on entry; stops when ||r||_2 <= rtol*||b||_2 (decided on the device, so the iteration
+ * count is exact); the host polls every check_every iterations.  Systems of <= 16384 rows run in a
+ * single-CTA kernel (one launch per solve).  h_info: [0]=iterations, [1]=relative residual, [2]=||b||. */
 int psfem_pcg_workspace(int64_t n, int64_t n_blocks, size_t *bytes);
-int psfem_pcg_jacobi(int64_t n, const int32_t *d_row_ptr, const int32_t *d_col_idx, const double *d_vals,
-                     const int32_t *d_rowblk, int64_t n_blocks,
-                     const double *d_b, double *d_x, double rtol, int64_t maxit, int64_t check_every,
-                     double *h_info, void *d_ws, size_t ws_bytes, void *stream);
+int psfem_pcg_jacobi(const psfem_csr *A, const double *d_b, double *d_x, double rtol, int64_t maxit,
+                     int64_t check_every, double *h_info, void *d_ws, size_t ws_bytes, void *stream);
 
-/* The three kernels of one PCG iteration, exposed so that the strip-partitioned multi-GPU
- * driver can put its halo exchange and all-reduces between them.  Scalars live in d_scal:
- * [0]=rz [1]=pq [2]=rz_new [3]=rr [4]=alpha [5]=beta.  col indices address the EXTENDED local
- * vector (owned rows start at x_offset). */
-int psfem_pcg_spmv_dot(int64_t n_rows, const int32_t *d_row_ptr, const int32_t *d_col_idx, const double *d_vals,
-                       const int32_t *d_rowblk, int64_t n_blocks, const double *d_p_ext, int64_t x_offset,
-                       double *d_q, double *d_scal, double *d_partials, void *stream);
+/* The kernels of one PCG iteration, exposed so the strip-partitioned multi-GPU driver can put its
+ * halo exchange and all-reduces between them (scalars stay on the device):
+ *   init    : p = dinv*r ; out3 = {r.dinv r, r.r, b.b}  (local sums)
+ *   spmv_dot: q = A p_ext ; *d_pq = p_own . q  (p_own = p_ext + x_offset)
+ *   update  : alpha = *d_rz / *d_pq ; x += alpha p ; r -= alpha q ; out2 = {r.dinv r, r.r}
+ *   pupdate : beta = *d_rz_new / *d_rz_old ; p = dinv*r + beta p
+ * d_partials: max(n_blocks, 1184)*3 doubles, d_counter: zero-initialised uint32. */
+int psfem_pcg_init(int64_t n, const double *d_r, const double *d_dinv, const double *d_b, double *d_p,
+                   double *d_out3, double *d_partials, uint32_t *d_counter, void *stream);
+int psfem_pcg_spmv_dot(const psfem_csr *A, const double *d_p_ext, int64_t x_offset, double *d_q, double *d_pq,
+                       double *d_partials, uint32_t *d_counter, void *stream);
 int psfem_pcg_update(int64_t n, double *d_x, double *d_r, const double *d_p, const double *d_q,
-                     const double *d_dinv, double *d_scal, double *d_partials, void *stream);
+                     const double *d_dinv, const double *d_rz, const double *d_pq, double *d_out2,
+                     double *d_partials, uint32_t *d_counter, void *stream);
 int psfem_pcg_pupdate(int64_t n, double *d_p, const double *d_r, const double *d_dinv,
-                      const double *d_scal, void *stream);
-int psfem_pcg_init(int64_t n, const double *d_r, const double *d_dinv, double *d_p, double *d_scal,
-                   double *d_partials, void *stream);
+                      const double *d_rz_old, const double *d_rz_new, void *stream);
 
-/* ---- BLAS-1 helpers for the drivers (Lanczos, energies) ---------------------------------- */
-int psfem_axpby(int64_t n, double a, const double *d_x, double b, const double *d_y, double *d_out, void *stream);
-int psfem_dot(int64_t n, const double *d_x, const double *d_y, double *h_out, void *d_ws, size_t ws_bytes, void *stream);
+/* ---- BLAS-1 helpers for the drivers (Lanczos, K_eff = K + c M, energies) ------------------ */
+int psfem_axpby(int64_t n, double a, const double *d_x, double b, const double *d_y /* may be NULL */,
+                double *d_out, void *stream);
 int psfem_dot_workspace(int64_t n, size_t *bytes);
+int psfem_dot(int64_t n, const double *d_x, const double *d_y, double *h_out, void *d_ws, size_t ws_bytes, void *stream);
 /* out[j] = V[j,:] . w  for j<m  (V row-major m x n): Gram-Schmidt coefficients */
 int psfem_multi_dot(int64_t m, int64_t n, const double *d_V, const double *d_w, double *d_out, void *stream);
 /* w -= sum_j c[j] V[j,:] */
 int psfem_multi_axpy(int64_t m, int64_t n, const double *d_V, const double *d_c, double *d_w, void *stream);
 
 /* ---- Newmark-beta as implemented by main.py:264-332 (NOT the textbook scheme) -------------
- * Runs steps 1..n_steps-1 on the reduced system.  Load of step i: d_fshape * h_fscale[i]
- * (main.py:226-251 is a fixed nodal pattern times a time ramp).  K, M, K_eff share the pattern.
- * d_U, d_V, d_A: n_store columns each (column-major, n rows), column c holds step c*store_every.
+ * Runs steps 1..n_steps-1 on the reduced system K (vals = K), d_M_vals, d_Keff_vals on one pattern.
+ * Load of step i: d_fshape * h_fscale[i] (main.py:226-251 is a fixed nodal pattern times a ramp).
+ * d_U, d_V, d_A: column c (n doubles each) holds step c*store_every; any may be NULL.
  * d_energy: n_steps x 3 (kinetic, potential, total; main.py:377-385) or NULL.
- * Solves use Jacobi-PCG with rtol, warm-started from the previous acceleration.
- * h_info: [0]=total PCG iterations, [1]=max relres, [2]=number of stabiliser triggers (main.py:324-332). */
+ * Solves: Jacobi-PCG to rtol, warm-started from the previous acceleration.
+ * h_info: [0]=total PCG iterations, [1]=max relres, [2]=stabiliser triggers (main.py:324-332). */
 int psfem_newmark_workspace(int64_t n, int64_t n_blocks, size_t *bytes);
-int psfem_newmark_run(int64_t n, const int32_t *d_row_ptr, const int32_t *d_col_idx,
-                      const double *d_K, const double *d_M, const double *d_Keff,
-                      const int32_t *d_rowblk, int64_t n_blocks,
+int psfem_newmark_run(const psfem_csr *K, const double *d_M_vals, const double *d_Keff_vals,
                       const double *d_fshape, const double *h_fscale, int64_t n_steps,
                       double dt, double gamma, double beta, double alpha_R, double beta_R,
                       const double *d_a0, int64_t store_every,

@@ -1,0 +1,150 @@
+"""ctypes binding of libpsfem.so (include/psfem.h) -- the only bridge to the CUDA kernels.
+
+There is no CPU fallback: if the shared library is missing the import fails loudly, and every
+compute call needs a CUDA device.  Torch is used for device memory and the current stream only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpsfem.so")
+
+OK, EINVAL, ECUDA, EJACOBIAN, ENOCONV = 0, 1, 2, 3, 4
+T3, Q4, T6, Q9 = 0, 1, 2, 3
+
+ETYPE = {("tri", "coarse"): T3, ("quad", "coarse"): Q4, ("tri", "fine"): T6, ("quad", "fine"): Q9}
+NPE = {T3: 3, Q4: 4, T6: 6, Q9: 9}
+
+
+class ConvergenceError(RuntimeError):
+    """Jacobi-PCG reached maxit before the requested relative residual."""
+
+
+class psfem_csr(C.Structure):
+    _fields_ = [("n_rows", C.c_int64), ("nnz", C.c_int64), ("row_ptr", C.c_void_p), ("col_idx", C.c_void_p),
+                ("vals", C.c_void_p), ("rowblk", C.c_void_p), ("n_blocks", C.c_int64), ("max_row_nnz", C.c_int64)]
+
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} is missing: build the CUDA library first (python -c 'import __graft_entry__ as g; g.build()' "
+        "or make -C plane-stress-fem-with-python_b200/csrc). There is no CPU fallback.")
+
+lib = C.CDLL(LIB_PATH)
+
+_i64, _i32, _dbl, _ptr, _sz = C.c_int64, C.c_int, C.c_double, C.c_void_p, C.c_size_t
+_pi64 = C.POINTER(C.c_int64)
+_pdbl = C.POINTER(C.c_double)
+_psz = C.POINTER(C.c_size_t)
+_pcsr = C.POINTER(psfem_csr)
+
+# name -> argtypes; must list every symbol include/psfem.h declares (tests/test_capi_symbols.py checks)
+SIGNATURES = {
+    "psfem_version": [],
+    "psfem_nodes_per_element": [_i32],
+    "psfem_set_device": [_i32],
+    "psfem_mesh_rect": [_dbl, _dbl, _i64, _i64, _dbl, _dbl, _i32, _i64, _i64, _i64, _i64, _ptr, _ptr, _ptr],
+    "psfem_pattern_workspace": [_i64, _i32, _i64, _psz],
+    "psfem_pattern_count": [_ptr, _i64, _i32, _i64, _ptr, _ptr, _sz, _pi64, _ptr],
+    "psfem_pattern_fill": [_i64, _i32, _i64, _i64, _ptr, _sz, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr],
+    "psfem_assemble_workspace": [_i64, _i32, _i32, _psz],
+    "psfem_assemble": [_ptr, _ptr, _i64, _i32, _i64, _dbl, _dbl, _dbl, _dbl, _i32, _i64, _ptr, _ptr, _ptr, _ptr,
+                       _ptr, _ptr, _ptr, _sz, _pi64, _ptr],
+    "psfem_element_matrices": [_ptr, _ptr, _i64, _i32, _dbl, _dbl, _dbl, _dbl, _i32, _ptr, _ptr, _ptr, _sz, _pi64, _ptr],
+    "psfem_scan_workspace": [_i64, _psz],
+    "psfem_free_map": [_i64, _ptr, _i64, _ptr, _ptr, _pi64, _ptr, _sz, _ptr],
+    "psfem_reduce_count": [_i64, _ptr, _ptr, _ptr, _i64, _ptr, _pi64, _ptr, _sz, _ptr],
+    "psfem_reduce_fill": [_i64, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr],
+    "psfem_gather": [_ptr, _ptr, _i64, _ptr, _ptr],
+    "psfem_scatter_free": [_ptr, _ptr, _i64, _i64, _i64, _ptr, _ptr],
+    "psfem_spmv_plan_size": [_i64, _i64, _pi64],
+    "psfem_spmv_plan": [_i64, _ptr, _i64, _ptr, _i64, _pi64, _ptr],
+    "psfem_spmv": [_pcsr, _ptr, _dbl, _dbl, _ptr, _ptr, _ptr],
+    "psfem_spmv2": [_pcsr, _ptr, _ptr, _ptr, _dbl, _dbl, _dbl, _ptr, _ptr, _ptr],
+    "psfem_extract_diag": [_pcsr, _i64, _i32, _ptr, _ptr],
+    "psfem_pcg_workspace": [_i64, _i64, _psz],
+    "psfem_pcg_jacobi": [_pcsr, _ptr, _ptr, _dbl, _i64, _i64, _pdbl, _ptr, _sz, _ptr],
+    "psfem_pcg_init": [_i64, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr],
+    "psfem_pcg_spmv_dot": [_pcsr, _ptr, _i64, _ptr, _ptr, _ptr, _ptr, _ptr],
+    "psfem_pcg_update": [_i64, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr],
+    "psfem_pcg_pupdate": [_i64, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr],
+    "psfem_axpby": [_i64, _dbl, _ptr, _dbl, _ptr, _ptr, _ptr],
+    "psfem_dot_workspace": [_i64, _psz],
+    "psfem_dot": [_i64, _ptr, _ptr, _pdbl, _ptr, _sz, _ptr],
+    "psfem_multi_dot": [_i64, _i64, _ptr, _ptr, _ptr, _ptr],
+    "psfem_multi_axpy": [_i64, _i64, _ptr, _ptr, _ptr, _ptr],
+    "psfem_newmark_workspace": [_i64, _i64, _psz],
+    "psfem_newmark_run": [_pcsr, _ptr, _ptr, _ptr, _pdbl, _i64, _dbl, _dbl, _dbl, _dbl, _dbl, _ptr, _i64,
+                          _ptr, _ptr, _ptr, _ptr, _dbl, _i64, _pdbl, _ptr, _sz, _ptr],
+}
+
+for _name, _args in SIGNATURES.items():
+    _f = getattr(lib, _name)      # AttributeError here = library / header mismatch: fail loudly
+    _f.argtypes = _args
+    _f.restype = C.c_int
+lib.psfem_last_error.argtypes = []
+lib.psfem_last_error.restype = C.c_char_p
+
+
+def last_error() -> str:
+    return (lib.psfem_last_error() or b"").decode()
+
+
+def check(rc: int, bad_element: int | None = None):
+    """Map a C return code to the exception the reference would raise."""
+    if rc == OK:
+        return
+    msg = last_error()
+    if rc == EJACOBIAN:
+        # Polygones.py:686-687
+        raise ValueError(f"Jacobian determinant near zero for element {bad_element}" if bad_element is not None else msg)
+    if rc == EINVAL:
+        raise ValueError(msg)
+    if rc == ENOCONV:
+        raise ConvergenceError(msg)
+    raise RuntimeError(f"libpsfem CUDA error: {msg}")
+
+
+def call(name: str, *args):
+    check(getattr(lib, name)(*args))
+
+
+# ---- torch plumbing: device memory + current stream ------------------------------------------
+def torch_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("psfem_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch
+
+
+_bound_device = None
+
+
+def bind_device():
+    """Make the library's CUDA runtime follow torch's current device."""
+    global _bound_device
+    torch = torch_cuda()
+    dev = torch.cuda.current_device()
+    if dev != _bound_device:
+        call("psfem_set_device", dev)
+        _bound_device = dev
+    return dev
+
+
+def stream_ptr():
+    torch = torch_cuda()
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    """device pointer of a torch tensor (None -> NULL)"""
+    if t is None:
+        return C.c_void_p(0)
+    return C.c_void_p(t.data_ptr())
+
+
+def workspace(nbytes: int):
+    torch = torch_cuda()
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device="cuda")

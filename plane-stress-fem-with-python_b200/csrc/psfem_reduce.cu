@@ -1,0 +1,170 @@
+// psfem_reduce.cu -- boundary-condition reduction on CSR.
+// Polygones.apply_boundary_conditions (Polygones.py:989-1006) and reduce (:898-911) build
+// free_dofs with an O(n*c) list scan and slice the dense matrix with np.ix_; here the free map is a
+// flag + exclusive scan and the reduced CSR is a two-pass row/column compaction.  Outputs are
+// bit-identical to K_csr[free][:,free] (ascending free DOFs, column order preserved).
+#include <cub/cub.cuh>
+#include "psfem_common.cuh"
+
+using namespace psfem;
+
+namespace {
+
+__global__ void fill_i32_kernel(int32_t *p, int64_t n, int32_t v) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// DOFs outside [0,n) never match `i in constrained_dofs` in the reference (:1000) -> ignored
+__global__ void mark_constrained_kernel(const int32_t *__restrict__ constrained, int64_t nc, int64_t n, int32_t *__restrict__ flag) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= nc) return;
+    int32_t d = constrained[i];
+    if (d >= 0 && d < n) flag[d] = 0;
+}
+
+__global__ void free_map_kernel(const int32_t *__restrict__ flag, const int32_t *__restrict__ scan, int64_t n,
+                                int32_t *__restrict__ new_id, int32_t *__restrict__ free_dofs) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (flag[i]) {
+        new_id[i] = scan[i];
+        free_dofs[scan[i]] = (int32_t)i;
+    } else {
+        new_id[i] = -1;
+    }
+}
+
+__global__ void reduce_count_kernel(int64_t n, const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col_idx,
+                                    const int32_t *__restrict__ new_id, int32_t *__restrict__ cnt) {
+    int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    int32_t nr = new_id[r];
+    if (nr < 0) return;
+    int32_t c = 0;
+    for (int32_t k = row_ptr[r]; k < row_ptr[r + 1]; ++k) c += (new_id[col_idx[k]] >= 0);
+    cnt[nr] = c;
+}
+
+__global__ void reduce_fill_kernel(int64_t n, const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col_idx,
+                                   const int32_t *__restrict__ new_id, const int32_t *__restrict__ row_ptr_red,
+                                   int32_t *__restrict__ col_idx_red, int32_t *__restrict__ keep) {
+    int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    int32_t nr = new_id[r];
+    if (nr < 0) return;
+    int32_t o = row_ptr_red[nr];
+    for (int32_t k = row_ptr[r]; k < row_ptr[r + 1]; ++k) {
+        int32_t nc = new_id[col_idx[k]];
+        if (nc >= 0) {
+            col_idx_red[o] = nc;
+            keep[o] = k;
+            ++o;
+        }
+    }
+}
+
+__global__ void gather_kernel(const double *__restrict__ src, const int32_t *__restrict__ index, int64_t n, double *__restrict__ dst) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[index[i]];
+}
+
+__global__ void scatter_free_kernel(const double *__restrict__ red, const int32_t *__restrict__ free_dofs, int64_t n_free,
+                                    int64_t n_full, int64_t nvec, double *__restrict__ full) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n_free * nvec) return;
+    int64_t v = i / n_free, k = i - v * n_free;
+    full[v * n_full + free_dofs[k]] = red[v * n_free + k];
+}
+
+size_t scan_temp_bytes(int64_t n) {
+    size_t b = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, b, (int32_t *)nullptr, (int32_t *)nullptr, (int)n + 1);
+    return align_up(b) + 256;
+}
+
+}  // namespace
+
+extern "C" int psfem_scan_workspace(int64_t n, size_t *bytes) {
+    PSFEM_REQUIRE(bytes && n >= 0 && n < (int64_t)INT32_MAX - 1, "scan_workspace: bad size");
+    *bytes = 2 * align_up((n + 1) * sizeof(int32_t)) + scan_temp_bytes(n);
+    return PSFEM_OK;
+}
+
+extern "C" int psfem_free_map(int64_t n, const int32_t *d_constrained, int64_t nc, int32_t *d_new_id,
+                              int32_t *d_free_dofs, int64_t *h_n_free, void *d_ws, size_t ws_bytes, void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    PSFEM_REQUIRE(n > 0 && n < (int64_t)INT32_MAX - 1 && h_n_free, "free_map: bad arguments");
+    Carver c(d_ws);
+    int32_t *flag = c.take<int32_t>(n + 1);
+    int32_t *scan = c.take<int32_t>(n + 1);
+    size_t tb = scan_temp_bytes(n);
+    void *tmp = c.take<char>(tb);
+    PSFEM_REQUIRE(ws_bytes >= c.used(), "free_map: workspace too small");
+    const int T = 256;
+    fill_i32_kernel<<<(unsigned)ceil_div(n, T), T, 0, stream>>>(flag, n, 1);
+    PSFEM_LAUNCH_CHECK();
+    PSFEM_CUDA_CHECK(cudaMemsetAsync(flag + n, 0, sizeof(int32_t), stream));
+    if (nc > 0) {
+        mark_constrained_kernel<<<(unsigned)ceil_div(nc, T), T, 0, stream>>>(d_constrained, nc, n, flag);
+        PSFEM_LAUNCH_CHECK();
+    }
+    PSFEM_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(tmp, tb, flag, scan, (int)n + 1, stream));
+    free_map_kernel<<<(unsigned)ceil_div(n, T), T, 0, stream>>>(flag, scan, n, d_new_id, d_free_dofs);
+    PSFEM_LAUNCH_CHECK();
+    int32_t total = 0;
+    PSFEM_CUDA_CHECK(cudaMemcpyAsync(&total, scan + n, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+    PSFEM_CUDA_CHECK(cudaStreamSynchronize(stream));
+    *h_n_free = total;
+    return PSFEM_OK;
+}
+
+extern "C" int psfem_reduce_count(int64_t n, const int32_t *d_row_ptr, const int32_t *d_col_idx, const int32_t *d_new_id,
+                                  int64_t n_free, int32_t *d_row_ptr_red, int64_t *h_nnz_red, void *d_ws, size_t ws_bytes,
+                                  void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    PSFEM_REQUIRE(n > 0 && n_free >= 0 && n_free <= n && h_nnz_red, "reduce_count: bad arguments");
+    Carver c(d_ws);
+    int32_t *cnt = c.take<int32_t>(n + 1);
+    (void)c.take<int32_t>(n + 1);
+    size_t tb = scan_temp_bytes(n);
+    void *tmp = c.take<char>(tb);
+    PSFEM_REQUIRE(ws_bytes >= c.used(), "reduce_count: workspace too small");
+    const int T = 256;
+    PSFEM_CUDA_CHECK(cudaMemsetAsync(cnt, 0, (n_free + 1) * sizeof(int32_t), stream));
+    reduce_count_kernel<<<(unsigned)ceil_div(n, T), T, 0, stream>>>(n, d_row_ptr, d_col_idx, d_new_id, cnt);
+    PSFEM_LAUNCH_CHECK();
+    PSFEM_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(tmp, tb, cnt, d_row_ptr_red, (int)n_free + 1, stream));
+    int32_t total = 0;
+    PSFEM_CUDA_CHECK(cudaMemcpyAsync(&total, d_row_ptr_red + n_free, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+    PSFEM_CUDA_CHECK(cudaStreamSynchronize(stream));
+    *h_nnz_red = total;
+    return PSFEM_OK;
+}
+
+extern "C" int psfem_reduce_fill(int64_t n, const int32_t *d_row_ptr, const int32_t *d_col_idx, const int32_t *d_new_id,
+                                 const int32_t *d_row_ptr_red, int32_t *d_col_idx_red, int32_t *d_keep, void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const int T = 256;
+    reduce_fill_kernel<<<(unsigned)ceil_div(n, T), T, 0, stream>>>(n, d_row_ptr, d_col_idx, d_new_id, d_row_ptr_red, d_col_idx_red, d_keep);
+    PSFEM_LAUNCH_CHECK();
+    return PSFEM_OK;
+}
+
+extern "C" int psfem_gather(const double *d_src, const int32_t *d_index, int64_t n, double *d_dst, void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (n == 0) return PSFEM_OK;
+    gather_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, stream>>>(d_src, d_index, n, d_dst);
+    PSFEM_LAUNCH_CHECK();
+    return PSFEM_OK;
+}
+
+extern "C" int psfem_scatter_free(const double *d_red, const int32_t *d_free_dofs, int64_t n_free, int64_t n_full,
+                                  int64_t nvec, double *d_full, void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    PSFEM_CUDA_CHECK(cudaMemsetAsync(d_full, 0, n_full * nvec * sizeof(double), stream));
+    if (n_free * nvec == 0) return PSFEM_OK;
+    scatter_free_kernel<<<(unsigned)ceil_div(n_free * nvec, 256), 256, 0, stream>>>(d_red, d_free_dofs, n_free, n_full, nvec, d_full);
+    PSFEM_LAUNCH_CHECK();
+    return PSFEM_OK;
+}

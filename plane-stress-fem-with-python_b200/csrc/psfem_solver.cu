@@ -1,0 +1,651 @@
+// psfem_solver.cu -- HBM-bound sparse kernels: shared-memory-staged CSR SpMV, the three fused
+// kernels of a Jacobi-PCG iteration, a single-CTA PCG for small systems, BLAS-1 helpers.
+//
+// SpMV ("CSR stream"): a CTA owns a block of consecutive rows holding ~SPMV_T non-zeros.  All
+// threads stream vals/col_idx of the block with perfectly coalesced loads, multiply by the
+// gathered x entries (L1/L2 hits: FEM rows touch a narrow window of x) and park the products in
+// shared memory; then one thread per row reduces its products in column order (deterministic,
+// same order as scipy's CSR mat-vec).  12 B/nnz of HBM traffic is read exactly once.
+//
+// Replaces: np.linalg.solve / scipy.linalg.solve / lu_factor+lu_solve (Statictest.py:69,
+// StaticTest2.py:71, Beamexemple.py:63, main.py:286,295,314) and the dense mat-vecs of
+// main.py:310,383-384.
+#include "psfem_common.cuh"
+
+using namespace psfem;
+
+namespace {
+
+constexpr int SPMV_THREADS = 256;
+constexpr int SPMV_T = 4096;  // target non-zeros per row block (32 KB of fp64 products)
+constexpr int EW_THREADS = 256;
+
+int ew_grid(int64_t n) {
+    int64_t g = ceil_div(n, EW_THREADS * 4);
+    int64_t cap = 148 * 8;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+// ---------------------------------------------------------------------------------------------
+// row-block plan
+// ---------------------------------------------------------------------------------------------
+__global__ void spmv_plan_kernel(const int32_t *__restrict__ row_ptr, int64_t n, int64_t n_blocks, int32_t *__restrict__ rowblk) {
+    int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (b > n_blocks) return;
+    if (b == n_blocks) { rowblk[b] = (int32_t)n; return; }
+    if (b == 0) { rowblk[0] = 0; return; }
+    const int64_t target = (int64_t)row_ptr[0] + b * SPMV_T;
+    int64_t lo = 0, hi = n;
+    while (lo < hi) {  // first row whose start is >= target
+        int64_t mid = lo + ((hi - lo) >> 1);
+        if (row_ptr[mid] < target) lo = mid + 1; else hi = mid;
+    }
+    rowblk[b] = (int32_t)lo;
+}
+
+__global__ void max_row_kernel(const int32_t *__restrict__ row_ptr, int64_t n, int *__restrict__ out) {
+    int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    int len = 0;
+    if (r < n) len = row_ptr[r + 1] - row_ptr[r];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, o));
+    if ((threadIdx.x & 31) == 0 && len > 0) atomicMax(out, len);
+}
+
+// ---------------------------------------------------------------------------------------------
+// deterministic grid-wide sums: per-block partials, the last block to finish adds them in a fixed
+// order (no floating-point atomics).
+// ---------------------------------------------------------------------------------------------
+template <int THREADS, int NV>
+__device__ __forceinline__ bool grid_sum(double (&v)[NV], double *__restrict__ partials, unsigned int *counter,
+                                         double *smem, double (&total)[NV]) {
+    __shared__ bool is_last;
+    const int nb = gridDim.x;
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+        double s = block_sum<THREADS>(v[q], smem);
+        if (threadIdx.x == 0) partials[(int64_t)q * nb + blockIdx.x] = s;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int ticket = atomicAdd(counter, 1u);
+        is_last = (ticket == (unsigned)nb - 1);
+    }
+    __syncthreads();
+    if (!is_last) return false;
+    __threadfence();
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+        double s = 0;
+        for (int i = threadIdx.x; i < nb; i += THREADS) s += __ldcg(partials + (int64_t)q * nb + i);
+        total[q] = block_sum<THREADS>(s, smem);
+    }
+    if (threadIdx.x == 0) *counter = 0;
+    return threadIdx.x == 0;  // totals valid in thread 0 of the last block
+}
+
+// device-side control block of one PCG solve
+struct PcgCtl {
+    double rz[2];
+    double pq;
+    double rr;
+    double bb;
+    double tol2;
+    long long iters;
+    int done;
+    int parity;
+};
+
+// ---------------------------------------------------------------------------------------------
+// SpMV
+// ---------------------------------------------------------------------------------------------
+// y[r] = sum_k (alpha*v1[k]*x1[c[k]] (+ beta*v2[k]*x2[c[k]])) + gamma*z[r];   DOT: dot_out = sum_r xdot[r]*y[r]
+template <bool DUAL, bool DOT>
+__global__ void __launch_bounds__(SPMV_THREADS)
+spmv_kernel(const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col_idx, const double *__restrict__ v1,
+            const double *__restrict__ v2, const int32_t *__restrict__ rowblk, const double *__restrict__ x1,
+            const double *__restrict__ x2, double alpha, double beta, double gamma, const double *__restrict__ z,
+            double *__restrict__ y, const double *__restrict__ xdot, double *__restrict__ dot_out,
+            double *__restrict__ partials, unsigned int *counter, const int *__restrict__ done) {
+    extern __shared__ double prod[];
+    __shared__ double red[SPMV_THREADS / 32];
+    if (done && *done) return;
+    const int t = threadIdx.x;
+    const int r0 = rowblk[blockIdx.x], r1 = rowblk[blockIdx.x + 1];
+    const int k0 = row_ptr[r0], k1 = row_ptr[r1];
+    // phase 1: coalesced stream of the block's non-zeros, 4 independent loads in flight per thread
+    int k = k0 + t;
+    for (; k + 3 * SPMV_THREADS < k1; k += 4 * SPMV_THREADS) {
+        int c[4];
+        double a[4], b[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            c[u] = __ldg(col_idx + k + u * SPMV_THREADS);
+            a[u] = __ldg(v1 + k + u * SPMV_THREADS);
+            if (DUAL) b[u] = __ldg(v2 + k + u * SPMV_THREADS);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            double p = alpha * a[u] * x1[c[u]];
+            if (DUAL) p += beta * b[u] * x2[c[u]];
+            prod[k - k0 + u * SPMV_THREADS] = p;
+        }
+    }
+    for (; k < k1; k += SPMV_THREADS) {
+        const int c = __ldg(col_idx + k);
+        double p = alpha * __ldg(v1 + k) * x1[c];
+        if (DUAL) p += beta * __ldg(v2 + k) * x2[c];
+        prod[k - k0] = p;
+    }
+    __syncthreads();
+    // phase 2: one thread per row, products summed in column order
+    double dot[1] = {0.0};
+    for (int r = r0 + t; r < r1; r += SPMV_THREADS) {
+        const int a = row_ptr[r] - k0, b = row_ptr[r + 1] - k0;
+        double s = 0.0;
+        for (int q = a; q < b; ++q) s += prod[q];
+        if (z) s += gamma * z[r];
+        y[r] = s;
+        if (DOT) dot[0] += xdot[r] * s;
+    }
+    if (DOT) {
+        double total[1];
+        if (grid_sum<SPMV_THREADS, 1>(dot, partials, counter, red, total)) *dot_out = total[0];
+    }
+}
+
+int launch_spmv(const psfem_csr *A, const double *v2, const double *x1, const double *x2, double alpha, double beta,
+                double gamma, const double *z, double *y, const double *xdot, double *dot_out, double *partials,
+                unsigned int *counter, const int *done, cudaStream_t stream) {
+    PSFEM_REQUIRE(A && A->rowblk && A->n_blocks > 0, "spmv: matrix has no row-block plan (psfem_spmv_plan)");
+    const size_t smem = (size_t)(SPMV_T + A->max_row_nnz + 8) * sizeof(double);
+    PSFEM_REQUIRE(smem <= 200 * 1024, "spmv: a row with %lld non-zeros does not fit the shared-memory stage", (long long)A->max_row_nnz);
+    const bool dual = v2 != nullptr, dot = dot_out != nullptr;
+#define PSFEM_SPMV_LAUNCH(D, O)                                                                                      \
+    do {                                                                                                             \
+        if (smem > 48 * 1024)                                                                                        \
+            PSFEM_CUDA_CHECK(cudaFuncSetAttribute(spmv_kernel<D, O>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        spmv_kernel<D, O><<<(unsigned)A->n_blocks, SPMV_THREADS, smem, stream>>>(                                    \
+            A->row_ptr, A->col_idx, A->vals, v2, A->rowblk, x1, x2, alpha, beta, gamma, z, y, xdot, dot_out, partials, counter, done); \
+    } while (0)
+    if (dual && dot) PSFEM_SPMV_LAUNCH(true, true);
+    else if (dual) PSFEM_SPMV_LAUNCH(true, false);
+    else if (dot) PSFEM_SPMV_LAUNCH(false, true);
+    else PSFEM_SPMV_LAUNCH(false, false);
+#undef PSFEM_SPMV_LAUNCH
+    PSFEM_LAUNCH_CHECK();
+    return PSFEM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// diagonal, element-wise PCG kernels
+// ---------------------------------------------------------------------------------------------
+__global__ void extract_diag_kernel(int64_t n, const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col_idx,
+                                    const double *__restrict__ vals, int64_t col_offset, double *__restrict__ diag, int invert) {
+    int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const int32_t want = (int32_t)(r + col_offset);
+    double d = 0.0;
+    for (int32_t k = row_ptr[r]; k < row_ptr[r + 1]; ++k)
+        if (col_idx[k] == want) { d = vals[k]; break; }
+    diag[r] = invert ? 1.0 / d : d;
+}
+
+// z = dinv*r, p = z, rz = r.z, rr = r.r, bb = b.b   (PCG start)
+__global__ void __launch_bounds__(EW_THREADS)
+pcg_init_kernel(int64_t n, const double *__restrict__ r, const double *__restrict__ dinv, const double *__restrict__ b,
+                double *__restrict__ p, double *__restrict__ out3, double *__restrict__ partials, unsigned int *counter,
+                PcgCtl *ctl, double rtol) {
+    __shared__ double red[EW_THREADS / 32];
+    double v[3] = {0, 0, 0};
+    for (int64_t i = blockIdx.x * (int64_t)EW_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * EW_THREADS) {
+        const double ri = r[i], zi = dinv[i] * ri;
+        p[i] = zi;
+        v[0] += ri * zi;
+        v[1] += ri * ri;
+        if (b) { const double bi = b[i]; v[2] += bi * bi; }
+    }
+    double tot[3];
+    if (grid_sum<EW_THREADS, 3>(v, partials, counter, red, tot)) {
+        if (out3) { out3[0] = tot[0]; out3[1] = tot[1]; out3[2] = tot[2]; }
+        if (ctl) {
+            ctl->rz[0] = tot[0]; ctl->rz[1] = 0; ctl->pq = 0; ctl->rr = tot[1]; ctl->bb = tot[2];
+            ctl->tol2 = rtol * rtol * tot[2];
+            ctl->iters = 0; ctl->parity = 0;
+            ctl->done = (tot[2] == 0.0 || tot[1] <= ctl->tol2) ? 1 : 0;
+        }
+    }
+}
+
+// x += alpha p; r -= alpha q; rz_new = r.(dinv r); rr = r.r      alpha = rz/pq
+__global__ void __launch_bounds__(EW_THREADS)
+pcg_update_kernel(int64_t n, double *__restrict__ x, double *__restrict__ r, const double *__restrict__ p,
+                  const double *__restrict__ q, const double *__restrict__ dinv, const double *__restrict__ rz_in,
+                  const double *__restrict__ pq_in, double *__restrict__ out2, double *__restrict__ partials,
+                  unsigned int *counter, PcgCtl *ctl) {
+    __shared__ double red[EW_THREADS / 32];
+    double rz, pq;
+    if (ctl) {
+        if (ctl->done) return;
+        rz = ctl->rz[ctl->parity]; pq = ctl->pq;
+    } else {
+        rz = *rz_in; pq = *pq_in;
+    }
+    const double alpha = rz / pq;
+    double v[2] = {0, 0};
+    for (int64_t i = blockIdx.x * (int64_t)EW_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * EW_THREADS) {
+        const double pi = p[i], qi = q[i];
+        x[i] += alpha * pi;
+        const double ri = r[i] - alpha * qi;
+        r[i] = ri;
+        v[0] += ri * (dinv[i] * ri);
+        v[1] += ri * ri;
+    }
+    double tot[2];
+    if (grid_sum<EW_THREADS, 2>(v, partials, counter, red, tot)) {
+        if (ctl) {
+            ctl->rz[ctl->parity ^ 1] = tot[0];
+            ctl->rr = tot[1];
+            ctl->iters += 1;
+            // `done` and `parity` are published by pcg_pupdate_kernel so that every kernel of this
+            // iteration sees one consistent state
+        } else {
+            out2[0] = tot[0]; out2[1] = tot[1];
+        }
+    }
+}
+
+// p = dinv*r + beta p     beta = rz_new/rz_old
+__global__ void __launch_bounds__(EW_THREADS)
+pcg_pupdate_kernel(int64_t n, double *__restrict__ p, const double *__restrict__ r, const double *__restrict__ dinv,
+                   const double *__restrict__ rz_old_in, const double *__restrict__ rz_new_in, PcgCtl *ctl,
+                   unsigned int *counter) {
+    double rz_old, rz_new;
+    if (ctl) {
+        if (ctl->done) return;
+        rz_old = ctl->rz[ctl->parity]; rz_new = ctl->rz[ctl->parity ^ 1];
+    } else {
+        rz_old = *rz_old_in; rz_new = *rz_new_in;
+    }
+    const double beta = rz_new / rz_old;
+    for (int64_t i = blockIdx.x * (int64_t)EW_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * EW_THREADS)
+        p[i] = dinv[i] * r[i] + beta * p[i];
+    if (ctl) {
+        // last block flips parity / sets done after every block has read the old state
+        __shared__ bool is_last;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            unsigned int ticket = atomicAdd(counter, 1u);
+            is_last = (ticket == gridDim.x - 1);
+        }
+        __syncthreads();
+        if (is_last && threadIdx.x == 0) {
+            *counter = 0;
+            ctl->parity ^= 1;
+            if (ctl->rr <= ctl->tol2 || !(ctl->pq > 0.0)) ctl->done = 1;  // converged or breakdown
+            __threadfence();
+        }
+    }
+}
+
+__global__ void pq_store_kernel(PcgCtl *ctl, const double *pq) { ctl->pq = *pq; }
+
+// ---------------------------------------------------------------------------------------------
+// single-CTA PCG for small systems (whole solve in one launch; Newmark / modal on small meshes)
+// ---------------------------------------------------------------------------------------------
+constexpr int SMALL_THREADS = 1024;
+constexpr int SMALL_MAX_N = 16384;
+
+__global__ void __launch_bounds__(SMALL_THREADS)
+pcg_small_kernel(int n, const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col_idx,
+                 const double *__restrict__ vals, const double *__restrict__ b, double *__restrict__ x,
+                 double *__restrict__ r, double *__restrict__ p, double *__restrict__ q, const double *__restrict__ dinv,
+                 double rtol, long long maxit, double *__restrict__ info /* iters, relres, bnorm, status */) {
+    __shared__ double red[SMALL_THREADS / 32];
+    __shared__ double bc[2];
+    const int t = threadIdx.x;
+    auto bsum = [&](double v) -> double {
+        double s = block_sum<SMALL_THREADS>(v, red);
+        if (t == 0) bc[0] = s;
+        __syncthreads();
+        double o = bc[0];
+        __syncthreads();
+        return o;
+    };
+    // r = b - A x ; z = dinv r ; p = z
+    double lrz = 0, lrr = 0, lbb = 0;
+    for (int i = t; i < n; i += SMALL_THREADS) {
+        double s = 0;
+        for (int k = row_ptr[i]; k < row_ptr[i + 1]; ++k) s += vals[k] * x[col_idx[k]];
+        const double bi = b[i], ri = bi - s, zi = dinv[i] * ri;
+        r[i] = ri; p[i] = zi;
+        lrz += ri * zi; lrr += ri * ri; lbb += bi * bi;
+    }
+    double rz = bsum(lrz), rr = bsum(lrr);
+    const double bb = bsum(lbb);
+    const double tol2 = rtol * rtol * bb;
+    long long it = 0;
+    int status = 0;
+    while (bb > 0.0 && rr > tol2 && it < maxit) {
+        double lpq = 0;
+        for (int i = t; i < n; i += SMALL_THREADS) {
+            double s = 0;
+            for (int k = row_ptr[i]; k < row_ptr[i + 1]; ++k) s += vals[k] * p[col_idx[k]];
+            q[i] = s;
+            lpq += p[i] * s;
+        }
+        const double pq = bsum(lpq);
+        if (!(pq > 0.0)) { status = 2; break; }
+        const double alpha = rz / pq;
+        lrz = 0; lrr = 0;
+        for (int i = t; i < n; i += SMALL_THREADS) {
+            x[i] += alpha * p[i];
+            const double ri = r[i] - alpha * q[i];
+            r[i] = ri;
+            lrz += ri * (dinv[i] * ri); lrr += ri * ri;
+        }
+        const double rz_new = bsum(lrz);
+        rr = bsum(lrr);
+        const double beta = rz_new / rz;
+        rz = rz_new;
+        for (int i = t; i < n; i += SMALL_THREADS) p[i] = dinv[i] * r[i] + beta * p[i];
+        __syncthreads();
+        ++it;
+    }
+    if (t == 0) {
+        if (status == 0 && bb > 0.0 && rr > tol2) status = 1;
+        info[0] += (double)it;
+        const double rel = bb > 0.0 ? sqrt(rr / bb) : 0.0;
+        info[1] = fmax(info[1], rel);
+        info[2] = sqrt(bb);
+        info[3] = fmax(info[3], (double)status);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// BLAS-1
+// ---------------------------------------------------------------------------------------------
+__global__ void axpby_kernel(int64_t n, double a, const double *__restrict__ x, double b, const double *__restrict__ y, double *__restrict__ out) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double v = a * x[i];
+        if (y) v += b * y[i];
+        out[i] = v;
+    }
+}
+
+__global__ void __launch_bounds__(EW_THREADS)
+dot_kernel(int64_t n, const double *__restrict__ x, const double *__restrict__ y, double *__restrict__ out,
+           double *__restrict__ partials, unsigned int *counter) {
+    __shared__ double red[EW_THREADS / 32];
+    double v[1] = {0};
+    for (int64_t i = blockIdx.x * (int64_t)EW_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * EW_THREADS) v[0] += x[i] * y[i];
+    double tot[1];
+    if (grid_sum<EW_THREADS, 1>(v, partials, counter, red, tot)) *out = tot[0];
+}
+
+// out[j] = V[j,:] . w : one CTA per row j, deterministic block tree
+__global__ void __launch_bounds__(EW_THREADS)
+multi_dot_kernel(int64_t n, const double *__restrict__ V, const double *__restrict__ w, double *__restrict__ out) {
+    __shared__ double red[EW_THREADS / 32];
+    const double *v = V + (int64_t)blockIdx.x * n;
+    double s = 0;
+    for (int64_t i = threadIdx.x; i < n; i += EW_THREADS) s += v[i] * w[i];
+    s = block_sum<EW_THREADS>(s, red);
+    if (threadIdx.x == 0) out[blockIdx.x] = s;
+}
+
+// w -= sum_j c[j] V[j,:]
+__global__ void multi_axpy_kernel(int64_t m, int64_t n, const double *__restrict__ V, const double *__restrict__ c, double *__restrict__ w) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double s = w[i];
+        for (int64_t j = 0; j < m; ++j) s -= c[j] * V[j * n + i];
+        w[i] = s;
+    }
+}
+
+struct PcgWs {
+    double *r, *p, *q, *dinv, *partials, *scal;
+    PcgCtl *ctl;
+    unsigned int *counter;
+    size_t total;
+};
+
+PcgWs carve_pcg(void *ws, int64_t n, int64_t n_blocks) {
+    PcgWs w;
+    Carver c(ws);
+    w.r = c.take<double>(n);
+    w.p = c.take<double>(n);
+    w.q = c.take<double>(n);
+    w.dinv = c.take<double>(n);
+    int64_t np = n_blocks > 148 * 8 ? n_blocks : 148 * 8;
+    w.partials = c.take<double>(3 * np);
+    w.scal = c.take<double>(16);
+    w.ctl = c.take<PcgCtl>(1);
+    w.counter = c.take<unsigned int>(4);
+    w.total = c.used();
+    return w;
+}
+
+}  // namespace
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" int psfem_spmv_plan_size(int64_t n, int64_t nnz, int64_t *n_blocks) {
+    PSFEM_REQUIRE(n_blocks && n >= 0 && nnz >= 0, "spmv_plan_size: bad arguments");
+    int64_t b = ceil_div(nnz, SPMV_T);
+    *n_blocks = b < 1 ? 1 : b;
+    return PSFEM_OK;
+}
+
+extern "C" int psfem_spmv_plan(int64_t n, const int32_t *d_row_ptr, int64_t nnz, int32_t *d_rowblk, int64_t n_blocks,
+                               int64_t *h_max_row_nnz, void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    int64_t want = 0;
+    psfem_spmv_plan_size(n, nnz, &want);
+    PSFEM_REQUIRE(n_blocks == want && h_max_row_nnz, "spmv_plan: n_blocks must come from psfem_spmv_plan_size");
+    spmv_plan_kernel<<<(unsigned)ceil_div(n_blocks + 1, 256), 256, 0, stream>>>(d_row_ptr, n, n_blocks, d_rowblk);
+    PSFEM_LAUNCH_CHECK();
+    // the max row length is parked in the slot after the plan (d_rowblk has n_blocks+2 entries)
+    int *d_max = reinterpret_cast<int *>(d_rowblk + n_blocks + 1);
+    PSFEM_CUDA_CHECK(cudaMemsetAsync(d_max, 0, sizeof(int), stream));
+    if (n > 0) {
+        max_row_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, stream>>>(d_row_ptr, n, d_max);
+        PSFEM_LAUNCH_CHECK();
+    }
+    int h = 0;
+    PSFEM_CUDA_CHECK(cudaMemcpyAsync(&h, d_max, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    PSFEM_CUDA_CHECK(cudaStreamSynchronize(stream));
+    *h_max_row_nnz = h;
+    return PSFEM_OK;
+}
+
+extern "C" int psfem_spmv(const psfem_csr *A, const double *d_x, double alpha, double gamma, const double *d_z,
+                          double *d_y, void *stream_) {
+    return launch_spmv(A, nullptr, d_x, nullptr, alpha, 0.0, gamma, d_z, d_y, nullptr, nullptr, nullptr, nullptr, nullptr,
+                       static_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int psfem_spmv2(const psfem_csr *A, const double *d_vals2, const double *d_x1, const double *d_x2, double alpha,
+                           double beta, double gamma, const double *d_z, double *d_y, void *stream_) {
+    PSFEM_REQUIRE(d_vals2 && d_x2, "spmv2: second operand missing");
+    return launch_spmv(A, d_vals2, d_x1, d_x2, alpha, beta, gamma, d_z, d_y, nullptr, nullptr, nullptr, nullptr, nullptr,
+                       static_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int psfem_extract_diag(const psfem_csr *A, int64_t col_offset, int invert, double *d_diag, void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    PSFEM_REQUIRE(A && d_diag, "extract_diag: null argument");
+    if (A->n_rows == 0) return PSFEM_OK;
+    extract_diag_kernel<<<(unsigned)ceil_div(A->n_rows, 256), 256, 0, stream>>>(A->n_rows, A->row_ptr, A->col_idx, A->vals, col_offset, d_diag, invert);
+    PSFEM_LAUNCH_CHECK();
+    return PSFEM_OK;
+}
+
+extern "C" int psfem_pcg_workspace(int64_t n, int64_t n_blocks, size_t *bytes) {
+    PSFEM_REQUIRE(bytes && n >= 0, "pcg_workspace: bad arguments");
+    *bytes = carve_pcg(nullptr, n, n_blocks).total;
+    return PSFEM_OK;
+}
+
+// q = A p_ext ; *d_pq = p_own . q
+extern "C" int psfem_pcg_spmv_dot(const psfem_csr *A, const double *d_p_ext, int64_t x_offset, double *d_q, double *d_pq,
+                                  double *d_partials, uint32_t *d_counter, void *stream_) {
+    return launch_spmv(A, nullptr, d_p_ext, nullptr, 1.0, 0.0, 0.0, nullptr, d_q, d_p_ext + x_offset, d_pq, d_partials,
+                       d_counter, nullptr, static_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int psfem_pcg_init(int64_t n, const double *d_r, const double *d_dinv, const double *d_b, double *d_p,
+                              double *d_out3, double *d_partials, uint32_t *d_counter, void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    pcg_init_kernel<<<ew_grid(n), EW_THREADS, 0, stream>>>(n, d_r, d_dinv, d_b, d_p, d_out3, d_partials, d_counter, nullptr, 0.0);
+    PSFEM_LAUNCH_CHECK();
+    return PSFEM_OK;
+}
+
+extern "C" int psfem_pcg_update(int64_t n, double *d_x, double *d_r, const double *d_p, const double *d_q,
+                                const double *d_dinv, const double *d_rz, const double *d_pq, double *d_out2,
+                                double *d_partials, uint32_t *d_counter, void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    pcg_update_kernel<<<ew_grid(n), EW_THREADS, 0, stream>>>(n, d_x, d_r, d_p, d_q, d_dinv, d_rz, d_pq, d_out2, d_partials, d_counter, nullptr);
+    PSFEM_LAUNCH_CHECK();
+    return PSFEM_OK;
+}
+
+extern "C" int psfem_pcg_pupdate(int64_t n, double *d_p, const double *d_r, const double *d_dinv, const double *d_rz_old,
+                                 const double *d_rz_new, void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    pcg_pupdate_kernel<<<ew_grid(n), EW_THREADS, 0, stream>>>(n, d_p, d_r, d_dinv, d_rz_old, d_rz_new, nullptr, nullptr);
+    PSFEM_LAUNCH_CHECK();
+    return PSFEM_OK;
+}
+
+namespace psfem {
+// shared with psfem_newmark.cu: enqueue one complete PCG solve (no host sync unless large).
+// Small systems: single-CTA kernel.  Large: batches of `check_every` iterations with a device-side
+// done flag; the host only polls the flag between batches.
+double *pcg_dinv_ptr(void *d_ws, int64_t n, int64_t n_blocks) { return carve_pcg(d_ws, n, n_blocks).dinv; }
+
+// h_info (optional): iterations, relres, ||b|| of THIS solve (forces a sync on the small path).
+// d_info: device accumulators of the single-CTA path (sum of iterations, max relres, ||b||, status).
+// h_acc (optional): host accumulators of the multi-kernel path (sum of iterations, max relres, status).
+int pcg_solve(const psfem_csr *A, const double *d_b, double *d_x, double rtol, int64_t maxit, int64_t check_every,
+              double *h_info, double *d_info, double *h_acc, void *d_ws, size_t ws_bytes, bool have_dinv,
+              cudaStream_t stream) {
+    const int64_t n = A->n_rows;
+    PcgWs w = carve_pcg(d_ws, n, A->n_blocks);
+    PSFEM_REQUIRE(ws_bytes >= w.total, "pcg: workspace too small (%zu < %zu)", ws_bytes, w.total);
+    if (!have_dinv) {
+        int rc = psfem_extract_diag(A, 0, 1, w.dinv, stream);
+        if (rc) return rc;
+    }
+    if (n <= SMALL_MAX_N) {
+        pcg_small_kernel<<<1, SMALL_THREADS, 0, stream>>>((int)n, A->row_ptr, A->col_idx, A->vals, d_b, d_x, w.r, w.p, w.q,
+                                                          w.dinv, rtol, (long long)maxit, d_info);
+        PSFEM_LAUNCH_CHECK();
+        if (h_info) {
+            double h[4];
+            PSFEM_CUDA_CHECK(cudaMemcpyAsync(h, d_info, sizeof(h), cudaMemcpyDeviceToHost, stream));
+            PSFEM_CUDA_CHECK(cudaStreamSynchronize(stream));
+            h_info[0] = h[0]; h_info[1] = h[1]; h_info[2] = h[2];
+            if (h[3] != 0.0) { set_error("pcg: not converged (relres %.3e after %.0f iterations, status %.0f)", h[1], h[0], h[3]); return PSFEM_ENOCONV; }
+        }
+        return PSFEM_OK;
+    }
+    PSFEM_CUDA_CHECK(cudaMemsetAsync(w.counter, 0, 4 * sizeof(unsigned int), stream));
+    // r = b - A x
+    int rc = launch_spmv(A, nullptr, d_x, nullptr, -1.0, 0.0, 1.0, d_b, w.r, nullptr, nullptr, nullptr, nullptr, nullptr, stream);
+    if (rc) return rc;
+    const int g = ew_grid(n);
+    pcg_init_kernel<<<g, EW_THREADS, 0, stream>>>(n, w.r, w.dinv, d_b, w.p, nullptr, w.partials, w.counter, w.ctl, rtol);
+    PSFEM_LAUNCH_CHECK();
+    if (check_every < 1) check_every = 50;
+    PcgCtl h{};
+    int64_t launched = 0;
+    while (true) {
+        PSFEM_CUDA_CHECK(cudaMemcpyAsync(&h, w.ctl, sizeof(h), cudaMemcpyDeviceToHost, stream));
+        PSFEM_CUDA_CHECK(cudaStreamSynchronize(stream));
+        if (h.done || launched >= maxit) break;
+        int64_t batch = check_every;
+        if (launched + batch > maxit) batch = maxit - launched;
+        for (int64_t it = 0; it < batch; ++it) {
+            rc = launch_spmv(A, nullptr, w.p, nullptr, 1.0, 0.0, 0.0, nullptr, w.q, w.p, &w.ctl->pq, w.partials, w.counter, &w.ctl->done, stream);
+            if (rc) return rc;
+            pcg_update_kernel<<<g, EW_THREADS, 0, stream>>>(n, d_x, w.r, w.p, w.q, w.dinv, nullptr, nullptr, nullptr, w.partials, w.counter + 1, w.ctl);
+            pcg_pupdate_kernel<<<g, EW_THREADS, 0, stream>>>(n, w.p, w.r, w.dinv, nullptr, nullptr, w.ctl, w.counter + 2);
+        }
+        PSFEM_LAUNCH_CHECK();
+        launched += batch;
+    }
+    const double rel = h.bb > 0 ? sqrt(h.rr / h.bb) : 0.0;
+    if (h_info) { h_info[0] = (double)h.iters; h_info[1] = rel; h_info[2] = sqrt(h.bb); }
+    if (h_acc) { h_acc[0] += (double)h.iters; if (rel > h_acc[1]) h_acc[1] = rel; }
+    if (!(h.rr <= h.tol2) && h.bb > 0) {
+        if (h_acc) h_acc[2] = 1.0;
+        set_error("pcg: not converged (relres %.3e after %lld iterations)", rel, h.iters);
+        return PSFEM_ENOCONV;
+    }
+    return PSFEM_OK;
+}
+}  // namespace psfem
+
+extern "C" int psfem_pcg_jacobi(const psfem_csr *A, const double *d_b, double *d_x, double rtol, int64_t maxit,
+                                int64_t check_every, double *h_info, void *d_ws, size_t ws_bytes, void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    PSFEM_REQUIRE(A && d_b && d_x && h_info, "pcg_jacobi: null argument");
+    PSFEM_REQUIRE(A->n_rows > 0, "pcg_jacobi: empty system");
+    PcgWs w = carve_pcg(d_ws, A->n_rows, A->n_blocks);
+    PSFEM_REQUIRE(ws_bytes >= w.total, "pcg_jacobi: workspace too small (%zu < %zu)", ws_bytes, w.total);
+    PSFEM_CUDA_CHECK(cudaMemsetAsync(w.scal, 0, 16 * sizeof(double), stream));
+    return psfem::pcg_solve(A, d_b, d_x, rtol, maxit, check_every, h_info, w.scal, nullptr, d_ws, ws_bytes, false, stream);
+}
+
+extern "C" int psfem_axpby(int64_t n, double a, const double *d_x, double b, const double *d_y, double *d_out, void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (n == 0) return PSFEM_OK;
+    axpby_kernel<<<ew_grid(n), EW_THREADS, 0, stream>>>(n, a, d_x, b, d_y, d_out);
+    PSFEM_LAUNCH_CHECK();
+    return PSFEM_OK;
+}
+
+extern "C" int psfem_dot_workspace(int64_t n, size_t *bytes) {
+    PSFEM_REQUIRE(bytes, "dot_workspace: null output");
+    *bytes = align_up(148 * 8 * sizeof(double)) + 512;
+    return PSFEM_OK;
+}
+
+extern "C" int psfem_dot(int64_t n, const double *d_x, const double *d_y, double *h_out, void *d_ws, size_t ws_bytes, void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    PSFEM_REQUIRE(h_out && d_ws, "dot: null argument");
+    Carver c(d_ws);
+    double *partials = c.take<double>(148 * 8);
+    double *out = c.take<double>(1);
+    unsigned int *counter = c.take<unsigned int>(1);
+    PSFEM_REQUIRE(ws_bytes >= c.used(), "dot: workspace too small");
+    PSFEM_CUDA_CHECK(cudaMemsetAsync(counter, 0, sizeof(unsigned int), stream));
+    dot_kernel<<<ew_grid(n), EW_THREADS, 0, stream>>>(n, d_x, d_y, out, partials, counter);
+    PSFEM_LAUNCH_CHECK();
+    PSFEM_CUDA_CHECK(cudaMemcpyAsync(h_out, out, sizeof(double), cudaMemcpyDeviceToHost, stream));
+    PSFEM_CUDA_CHECK(cudaStreamSynchronize(stream));
+    return PSFEM_OK;
+}
+
+extern "C" int psfem_multi_dot(int64_t m, int64_t n, const double *d_V, const double *d_w, double *d_out, void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (m == 0) return PSFEM_OK;
+    multi_dot_kernel<<<(unsigned)m, EW_THREADS, 0, stream>>>(n, d_V, d_w, d_out);
+    PSFEM_LAUNCH_CHECK();
+    return PSFEM_OK;
+}
+
+extern "C" int psfem_multi_axpy(int64_t m, int64_t n, const double *d_V, const double *d_c, double *d_w, void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (m == 0 || n == 0) return PSFEM_OK;
+    multi_axpy_kernel<<<ew_grid(n), EW_THREADS, 0, stream>>>(m, n, d_V, d_c, d_w);
+    PSFEM_LAUNCH_CHECK();
+    return PSFEM_OK;
+}

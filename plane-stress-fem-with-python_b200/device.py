@@ -1,0 +1,393 @@
+"""Device-resident objects of the hot path: element tables, the symbolic pattern / assembly plan,
+CSR matrices with their SpMV plan, boundary-condition reduction, PCG.
+
+Everything here calls the C ABI of libpsfem.so through `_capi`; torch only owns the buffers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from collections.abc import Mapping
+
+import numpy as np
+import scipy.sparse as sparse
+
+from . import _capi
+from ._capi import ETYPE, NPE, call, check, lib, ptr, stream_ptr, workspace
+
+
+# --------------------------------------------------------------------------------------------
+# elements: array-backed stand-in for the reference's dict[int, list[int]] (Polygones.py:74-107)
+# --------------------------------------------------------------------------------------------
+class ElementTable(Mapping):
+    """Behaves like the reference's `elements` dict (`for e in elements`, `elements[e][k]`,
+    `len(elements[e])`, Polygones.py:717-721) but is backed by one (nel, npe) int32 array, so a
+    16.7 M-element mesh does not become 16.7 M Python lists."""
+
+    def __init__(self, conn: np.ndarray):
+        conn = np.ascontiguousarray(conn, dtype=np.int32)
+        assert conn.ndim == 2
+        self.conn = conn
+        self._dev = None          # cached device copy
+        self._plan = None         # cached Assembler (symbolic phase), built on first assembly
+
+    def __len__(self):
+        return self.conn.shape[0]
+
+    def __iter__(self):
+        return iter(range(self.conn.shape[0]))
+
+    def __getitem__(self, e):
+        if isinstance(e, (int, np.integer)):
+            if e < 0 or e >= self.conn.shape[0]:
+                raise KeyError(e)
+            return self.conn[e].tolist()
+        raise KeyError(e)
+
+    def __repr__(self):
+        return f"ElementTable(nel={self.conn.shape[0]}, npe={self.conn.shape[1]})"
+
+    def device(self):
+        torch = _capi.torch_cuda()
+        if self._dev is None:
+            self._dev = torch.from_numpy(self.conn).cuda()
+        return self._dev
+
+
+def as_element_table(elements, npe_expected=None) -> ElementTable:
+    """Accept an ElementTable, a plain dict (2Dexemple.py:12-17 passes a literal) or an array.
+    A dict is read in ITERATION order, which is the order of the reference's scatter loop
+    (Polygones.py:717)."""
+    if isinstance(elements, ElementTable):
+        tab = elements
+    elif isinstance(elements, np.ndarray):
+        tab = ElementTable(elements)
+    else:
+        rows = [elements[k] for k in elements]
+        tab = ElementTable(np.array(rows, dtype=np.int32).reshape(len(rows), -1))
+    if npe_expected is not None and len(tab) and tab.conn.shape[1] != npe_expected:
+        raise ValueError(f"elements have {tab.conn.shape[1]} nodes, element type expects {npe_expected}")
+    return tab
+
+
+# --------------------------------------------------------------------------------------------
+# CSR on the device
+# --------------------------------------------------------------------------------------------
+class DeviceCSR:
+    """CSR matrix in HBM: int32 row_ptr/col_idx, fp64 vals, plus the SpMV row-block plan."""
+
+    def __init__(self, n_rows, n_cols, row_ptr, col_idx, vals, nnz=None):
+        self.n_rows, self.n_cols = int(n_rows), int(n_cols)
+        self.row_ptr, self.col_idx, self.vals = row_ptr, col_idx, vals
+        self.nnz = int(col_idx.numel()) if nnz is None else int(nnz)
+        self._plan = None
+
+    @property
+    def shape(self):
+        return (self.n_rows, self.n_cols)
+
+    def with_vals(self, vals):
+        """Same pattern (and SpMV plan), other values: M, K_eff share K's pattern."""
+        o = DeviceCSR(self.n_rows, self.n_cols, self.row_ptr, self.col_idx, vals, self.nnz)
+        o._plan = self._plan
+        return o
+
+    def plan(self):
+        if self._plan is None:
+            torch = _capi.torch_cuda()
+            _capi.bind_device()
+            nb = C.c_int64(0)
+            call("psfem_spmv_plan_size", self.n_rows, self.nnz, C.byref(nb))
+            rowblk = torch.empty(nb.value + 2, dtype=torch.int32, device="cuda")
+            mx = C.c_int64(0)
+            call("psfem_spmv_plan", self.n_rows, ptr(self.row_ptr), self.nnz, ptr(rowblk), nb.value, C.byref(mx), stream_ptr())
+            self._plan = (rowblk, nb.value, mx.value)
+        return self._plan
+
+    def struct(self, vals=None):
+        rowblk, nb, mx = self.plan()
+        s = _capi.psfem_csr()
+        s.n_rows, s.nnz = self.n_rows, self.nnz
+        s.row_ptr, s.col_idx = self.row_ptr.data_ptr(), self.col_idx.data_ptr()
+        s.vals = (self.vals if vals is None else vals).data_ptr()
+        s.rowblk, s.n_blocks, s.max_row_nnz = rowblk.data_ptr(), nb, mx
+        return s
+
+    def to_scipy(self):
+        torch = _capi.torch_cuda()
+        torch.cuda.current_stream().synchronize()
+        return sparse.csr_matrix((self.vals.cpu().numpy(), self.col_idx.cpu().numpy(), self.row_ptr.cpu().numpy()),
+                                 shape=self.shape)
+
+    @classmethod
+    def from_scipy(cls, A):
+        torch = _capi.torch_cuda()
+        A = sparse.csr_matrix(A)
+        if not A.has_sorted_indices:
+            A = A.sorted_indices()
+        if A.nnz >= 2 ** 31 - 8192:
+            raise ValueError("matrix has too many non-zeros for one GPU (int32 indices): partition it")
+        return cls(A.shape[0], A.shape[1],
+                   torch.from_numpy(np.ascontiguousarray(A.indptr, dtype=np.int32)).cuda(),
+                   torch.from_numpy(np.ascontiguousarray(A.indices, dtype=np.int32)).cuda(),
+                   torch.from_numpy(np.ascontiguousarray(A.data, dtype=np.float64)).cuda())
+
+    # y = alpha*A@x + gamma*z
+    def matvec(self, x, alpha=1.0, gamma=0.0, z=None, out=None):
+        torch = _capi.torch_cuda()
+        _capi.bind_device()
+        if out is None:
+            out = torch.empty(self.n_rows, dtype=torch.float64, device="cuda")
+        s = self.struct()
+        call("psfem_spmv", C.byref(s), ptr(x), float(alpha), float(gamma), ptr(z), ptr(out), stream_ptr())
+        return out
+
+    def diagonal(self, invert=False):
+        torch = _capi.torch_cuda()
+        _capi.bind_device()
+        d = torch.empty(self.n_rows, dtype=torch.float64, device="cuda")
+        s = self.struct()
+        call("psfem_extract_diag", C.byref(s), 0, 1 if invert else 0, ptr(d), stream_ptr())
+        return d
+
+
+# --------------------------------------------------------------------------------------------
+# symbolic phase + numeric assembly
+# --------------------------------------------------------------------------------------------
+class Assembler:
+    """Symbolic phase (structural CSR pattern + deterministic assembly plan) of one mesh; reused by
+    K, M and every re-assembly.  Replaces the dense target of Polygones.py:715 / :1349."""
+
+    def __init__(self, conn_dev, n_nodes: int, etype: int):
+        torch = _capi.torch_cuda()
+        _capi.bind_device()
+        self.etype, self.npe = etype, NPE[etype]
+        self.conn = conn_dev
+        self.nel = int(conn_dev.shape[0])
+        self.n_nodes = int(n_nodes)
+        nk = self.nel * self.npe * self.npe
+        sz = C.c_size_t(0)
+        call("psfem_pattern_workspace", self.nel, self.npe, self.n_nodes, C.byref(sz))
+        ws = workspace(sz.value)
+        self.perm = torch.empty(max(nk, 1), dtype=torch.int32, device="cuda")
+        npairs = C.c_int64(0)
+        call("psfem_pattern_count", ptr(conn_dev), self.nel, self.npe, self.n_nodes, ptr(self.perm), ptr(ws), sz.value,
+             C.byref(npairs), stream_ptr())
+        self.n_pairs = npairs.value
+        self.nnz = 4 * self.n_pairs
+        i32 = dict(dtype=torch.int32, device="cuda")
+        self.row_ptr = torch.empty(2 * self.n_nodes + 1, **i32)
+        self.col_idx = torch.empty(max(self.nnz, 1), **i32)[: self.nnz]
+        self.node_ptr = torch.empty(self.n_nodes + 1, **i32)
+        self.pair_row = torch.empty(max(self.n_pairs, 1), **i32)
+        self.pair_ptr = torch.empty(self.n_pairs + 1, **i32)
+        call("psfem_pattern_fill", self.nel, self.npe, self.n_nodes, self.n_pairs, ptr(ws), sz.value, ptr(self.row_ptr),
+             ptr(self.col_idx), ptr(self.node_ptr), ptr(self.pair_row), ptr(self.pair_ptr), stream_ptr())
+        torch.cuda.current_stream().synchronize()
+        del ws
+        self._asm_ws = {}
+        self._csr = None
+
+    def pattern_csr(self, vals):
+        """DeviceCSR over this pattern (K and M share row_ptr/col_idx and the SpMV plan)."""
+        if self._csr is None:
+            self._csr = DeviceCSR(2 * self.n_nodes, 2 * self.n_nodes, self.row_ptr, self.col_idx, vals, self.nnz)
+            return self._csr
+        return self._csr.with_vals(vals)
+
+    def _ws(self, what):
+        if what not in self._asm_ws:
+            sz = C.c_size_t(0)
+            call("psfem_assemble_workspace", self.nel, self.etype, what, C.byref(sz))
+            self._asm_ws[what] = (workspace(sz.value), sz.value)
+        return self._asm_ws[what]
+
+    def release_workspace(self):
+        self._asm_ws = {}
+
+    def assemble(self, nodes_dev, E=0.0, nu=0.0, rho=0.0, t=1.0, what=1, K_out=None, M_out=None):
+        """Numeric phase.  what: 1 = K, 2 = M, 3 = both.  Returns (K_vals, M_vals) device tensors."""
+        torch = _capi.torch_cuda()
+        _capi.bind_device()
+        f64 = dict(dtype=torch.float64, device="cuda")
+        K_vals = (K_out if K_out is not None else torch.empty(max(self.nnz, 1), **f64)[: self.nnz]) if what & 1 else None
+        M_vals = (M_out if M_out is not None else torch.empty(max(self.nnz, 1), **f64)[: self.nnz]) if what & 2 else None
+        ws, nbytes = self._ws(what)
+        bad = C.c_int64(-1)
+        rc = lib.psfem_assemble(ptr(nodes_dev), ptr(self.conn), self.nel, self.etype, self.n_nodes, float(E), float(nu),
+                                float(rho), float(t), what, self.n_pairs, ptr(self.node_ptr), ptr(self.pair_row),
+                                ptr(self.pair_ptr), ptr(self.perm), ptr(K_vals), ptr(M_vals), ptr(ws), nbytes,
+                                C.byref(bad), stream_ptr())
+        check(rc, bad.value)
+        return K_vals, M_vals
+
+    def element_matrices(self, nodes_dev, E=0.0, nu=0.0, rho=0.0, t=1.0, what=1):
+        torch = _capi.torch_cuda()
+        _capi.bind_device()
+        nd = 2 * self.npe
+        f64 = dict(dtype=torch.float64, device="cuda")
+        Ke = torch.empty((self.nel, nd, nd), **f64) if what & 1 else None
+        Me = torch.empty((self.nel, nd, nd), **f64) if what & 2 else None
+        ws, nbytes = self._ws(what)
+        bad = C.c_int64(-1)
+        rc = lib.psfem_element_matrices(ptr(nodes_dev), ptr(self.conn), self.nel, self.etype, float(E), float(nu), float(rho),
+                                        float(t), what, ptr(Ke), ptr(Me), ptr(ws), nbytes, C.byref(bad), stream_ptr())
+        check(rc, bad.value)
+        return Ke, Me
+
+
+def device_mesh(L, l, N, M=0, offsetX=0, offsetY=0, element_type="tri", mesh_type="coarse",
+                col0=None, ncols=None, cell0=None, ncells=None):
+    """Polygones.mesh on the device: (nodes (ncols*m,2) f64, conn (nel,npe) int32) torch tensors.
+    col/cell ranges select a strip (ids local to the strip) for the multi-GPU partition."""
+    torch = _capi.torch_cuda()
+    _capi.bind_device()
+    et = ETYPE[(element_type, mesh_type)]
+    N, M = int(N), int(M)
+    if M == 0:
+        M = N
+    fine = mesh_type == "fine"
+    n, m = (2 * N + 1, 2 * M + 1) if fine else (N + 1, M + 1)
+    col0 = 0 if col0 is None else col0
+    ncols = n - col0 if ncols is None else ncols
+    cell0 = 0 if cell0 is None else cell0
+    ncells = N - cell0 if ncells is None else ncells
+    per_cell = 2 if element_type == "tri" else 1
+    nodes = torch.empty((ncols * m, 2), dtype=torch.float64, device="cuda")
+    conn = torch.empty((ncells * M * per_cell, NPE[et]), dtype=torch.int32, device="cuda")
+    call("psfem_mesh_rect", float(L), float(l), N, M, float(offsetX), float(offsetY), et, col0, ncols, cell0, ncells,
+         ptr(nodes), ptr(conn), stream_ptr())
+    return nodes, conn
+
+
+# --------------------------------------------------------------------------------------------
+# boundary conditions
+# --------------------------------------------------------------------------------------------
+def constrained_dofs_of(bc):
+    """Polygones.py:992-997: bc order, duplicates kept, values ignored (any non-None = fixed to 0)."""
+    out = []
+    for node, disp in bc:
+        if disp[0] is not None:
+            out.append(2 * node)
+        if disp[1] is not None:
+            out.append(2 * node + 1)
+    return out
+
+
+class FreeMap:
+    """free/constrained DOF bookkeeping of Polygones.py:1000 / :901 / :916 in O(n) on the device."""
+
+    def __init__(self, n_total: int, constrained):
+        torch = _capi.torch_cuda()
+        _capi.bind_device()
+        self.n_total = int(n_total)
+        cd = np.asarray(list(constrained), dtype=np.int64)
+        # DOFs beyond int32 can never match a row index; drop them before the int32 cast
+        cd = cd[(cd >= 0) & (cd < self.n_total)].astype(np.int32)
+        self.constrained_dev = torch.from_numpy(cd).cuda() if cd.size else None
+        self.new_id = torch.empty(self.n_total, dtype=torch.int32, device="cuda")
+        self.free_dofs = torch.empty(self.n_total, dtype=torch.int32, device="cuda")
+        sz = C.c_size_t(0)
+        call("psfem_scan_workspace", self.n_total, C.byref(sz))
+        self._ws = workspace(sz.value)
+        self._ws_bytes = sz.value
+        nf = C.c_int64(0)
+        call("psfem_free_map", self.n_total, ptr(self.constrained_dev), int(cd.size), ptr(self.new_id), ptr(self.free_dofs),
+             C.byref(nf), ptr(self._ws), sz.value, stream_ptr())
+        self.n_free = nf.value
+        self.free_dofs = self.free_dofs[: self.n_free]
+        self._keep = {}
+
+    def reduce_csr(self, A: DeviceCSR) -> DeviceCSR:
+        """K[np.ix_(free, free)] (Polygones.py:1003 / :907) on CSR."""
+        torch = _capi.torch_cuda()
+        assert A.n_rows == self.n_total and A.n_cols == self.n_total
+        key = (A.row_ptr.data_ptr(), A.col_idx.data_ptr())
+        if key not in self._keep:
+            row_ptr_red = torch.empty(self.n_free + 1, dtype=torch.int32, device="cuda")
+            nnz = C.c_int64(0)
+            call("psfem_reduce_count", self.n_total, ptr(A.row_ptr), ptr(A.col_idx), ptr(self.new_id), self.n_free,
+                 ptr(row_ptr_red), C.byref(nnz), ptr(self._ws), self._ws_bytes, stream_ptr())
+            col_red = torch.empty(max(nnz.value, 1), dtype=torch.int32, device="cuda")[: nnz.value]
+            keep = torch.empty(max(nnz.value, 1), dtype=torch.int32, device="cuda")[: nnz.value]
+            call("psfem_reduce_fill", self.n_total, ptr(A.row_ptr), ptr(A.col_idx), ptr(self.new_id), ptr(row_ptr_red),
+                 ptr(col_red), ptr(keep), stream_ptr())
+            proto = DeviceCSR(self.n_free, self.n_free, row_ptr_red, col_red, None, nnz.value)
+            self._keep[key] = (proto, keep, A.row_ptr, A.col_idx)    # keep refs alive: key is a pointer pair
+        proto, keep, _, _ = self._keep[key]
+        vals = torch.empty(max(proto.nnz, 1), dtype=torch.float64, device="cuda")[: proto.nnz]
+        call("psfem_gather", ptr(A.vals), ptr(keep), proto.nnz, ptr(vals), stream_ptr())
+        out = DeviceCSR(self.n_free, self.n_free, proto.row_ptr, proto.col_idx, vals, proto.nnz)
+        if proto._plan is None:
+            proto.vals = vals
+            proto.plan()
+        out._plan = proto._plan
+        return out
+
+    def reduce_vec(self, v_dev):
+        """F[free_dofs] (Polygones.py:1004 / :905)."""
+        torch = _capi.torch_cuda()
+        out = torch.empty(self.n_free, dtype=torch.float64, device="cuda")
+        call("psfem_gather", ptr(v_dev), ptr(self.free_dofs), self.n_free, ptr(out), stream_ptr())
+        return out
+
+    def expand(self, red_dev, nvec=1):
+        """reconstruct_full_vector(s), Polygones.py:913-936: zeros at constrained DOFs."""
+        torch = _capi.torch_cuda()
+        full = torch.empty((nvec, self.n_total) if nvec > 1 else self.n_total, dtype=torch.float64, device="cuda")
+        call("psfem_scatter_free", ptr(red_dev), ptr(self.free_dofs), self.n_free, self.n_total, nvec, ptr(full), stream_ptr())
+        return full
+
+
+# --------------------------------------------------------------------------------------------
+# solvers
+# --------------------------------------------------------------------------------------------
+def pcg_jacobi(A: DeviceCSR, b, x0=None, rtol=1e-8, maxit=None, check_every=50, raise_on_fail=True):
+    """Jacobi-PCG on the device.  Returns (x, info) with info = dict(iterations, relres, bnorm)."""
+    torch = _capi.torch_cuda()
+    _capi.bind_device()
+    n = A.n_rows
+    x = torch.zeros(n, dtype=torch.float64, device="cuda") if x0 is None else x0.clone()
+    if maxit is None:
+        maxit = 10 * n + 100
+    s = A.struct()
+    sz = C.c_size_t(0)
+    call("psfem_pcg_workspace", n, s.n_blocks, C.byref(sz))
+    ws = workspace(sz.value)
+    info = (C.c_double * 4)()
+    rc = lib.psfem_pcg_jacobi(C.byref(s), ptr(b), ptr(x), float(rtol), int(maxit), int(check_every), info, ptr(ws), sz.value,
+                              stream_ptr())
+    out = dict(iterations=int(info[0]), relres=float(info[1]), bnorm=float(info[2]), converged=(rc == _capi.OK))
+    if rc == _capi.ENOCONV and not raise_on_fail:
+        return x, out
+    check(rc)
+    return x, out
+
+
+class Blas:
+    """Small device BLAS-1 set for the Lanczos driver."""
+
+    def __init__(self):
+        sz = C.c_size_t(0)
+        call("psfem_dot_workspace", 0, C.byref(sz))
+        self._ws = workspace(sz.value)
+        self._bytes = sz.value
+
+    def dot(self, x, y):
+        out = C.c_double(0)
+        call("psfem_dot", x.numel(), ptr(x), ptr(y), C.byref(out), ptr(self._ws), self._bytes, stream_ptr())
+        return out.value
+
+    @staticmethod
+    def axpby(a, x, b, y, out):
+        call("psfem_axpby", x.numel(), float(a), ptr(x), float(b), ptr(y), ptr(out), stream_ptr())
+        return out
+
+    @staticmethod
+    def multi_dot(V, m, w, out):
+        call("psfem_multi_dot", m, w.numel(), ptr(V), ptr(w), ptr(out), stream_ptr())
+        return out
+
+    @staticmethod
+    def multi_axpy(V, m, c, w):
+        call("psfem_multi_axpy", m, w.numel(), ptr(V), ptr(c), ptr(w), stream_ptr())
+        return w

@@ -1,0 +1,226 @@
+"""Static, Newmark-beta and modal drivers.
+
+The reference has no driver functions: these are the module-level arithmetic of its scripts turned
+into functions, with the dense LAPACK calls replaced by device kernels:
+  static_solve : TestBeam/Statictest.py:66-78, StaticTest2.py:66-81, Beamexemple.py:59-65
+  newmark      : main.py:226-332 + 377-385 (reproduced literally, quirks included -- SURVEY A.9)
+  modal        : freeModes.py:53-77 (Beamexemple.py:86-160)
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+from ._capi import call, check, lib, ptr, stream_ptr, workspace
+from .device import Blas, DeviceCSR, FreeMap, constrained_dofs_of, pcg_jacobi
+from .Polygones import device_copy
+
+
+def _scaled(x, a, out=None):
+    """out = a*x on the device (psfem_axpby)."""
+    torch = _capi.torch_cuda()
+    if out is None:
+        out = torch.empty_like(x)
+    call("psfem_axpby", x.numel(), float(a), ptr(x), 0.0, ptr(None), ptr(out), stream_ptr())
+    return out
+
+
+def _to_dev(v):
+    torch = _capi.torch_cuda()
+    if isinstance(v, np.ndarray) or not hasattr(v, "data_ptr"):
+        return torch.from_numpy(np.ascontiguousarray(v, dtype=np.float64)).cuda()
+    return v
+
+
+# ---------------------------------------------------------------------------------------------
+# static
+# ---------------------------------------------------------------------------------------------
+def static_solve(K, F, bc, rtol=1e-8, maxit=None, check_every=50, return_device=False):
+    """Solve K U = F with the DOFs of `bc` fixed to zero.
+
+    Same steps as Statictest.py:66-75: apply_boundary_conditions -> solve -> scatter back with zeros
+    at constrained DOFs; the dense LU (`np.linalg.solve`, :69) is replaced by Jacobi-PCG on the
+    device (x0 = 0, stop at ||r|| <= rtol ||b||).
+    Returns (U, U_reduced, constrained_dofs, info)."""
+    torch = _capi.torch_cuda()
+    constrained = constrained_dofs_of(bc)
+    Kd = device_copy(K)
+    fm = FreeMap(Kd.n_rows, constrained)
+    K_red = fm.reduce_csr(Kd)
+    F_red = fm.reduce_vec(_to_dev(F))
+    U_red, info = pcg_jacobi(K_red, F_red, rtol=rtol, maxit=maxit, check_every=check_every)
+    U = fm.expand(U_red)
+    if return_device:
+        return U, U_red, constrained, info
+    torch.cuda.current_stream().synchronize()
+    return U.cpu().numpy(), U_red.cpu().numpy(), constrained, info
+
+
+# ---------------------------------------------------------------------------------------------
+# Newmark-beta (main.py)
+# ---------------------------------------------------------------------------------------------
+def ramp_load(n_nodes, L, P=1e6, T=10.0, dt=1e-3, accel_ratio=3):
+    """Load history of main.py:201,208-209,226-236: every node gets F_y(t) = -(accel_ratio*P*t/T)*L/n
+    up to step T0 = nbPoints//accel_ratio, then -P*L/n; F_x = 0.
+    Returns (shape (2n,) with ones at y DOFs, scale (nbPoints,), times)."""
+    nb = int(T / dt) + 1
+    times = np.linspace(0, T, nb)
+    T0 = nb // accel_ratio
+    scale = np.empty(nb)
+    scale[:T0 + 1] = -(accel_ratio * P * times[:T0 + 1] / T) * L / n_nodes
+    scale[T0 + 1:] = -P * L / n_nodes
+    shape = np.zeros(2 * n_nodes)
+    shape[1::2] = 1.0
+    return shape, scale, times
+
+
+def newmark(K, M, bc, f_shape, f_scale, dt=1e-3, gamma=0.5, beta=0.25, alpha_R=0.1, beta_R=0.01,
+            store_every=1, energies=True, rtol=1e-13, maxit=None):
+    """Newmark-beta exactly as main.py:264-332 implements it, on the device.
+
+    K, M: full matrices (CSR); bc: boundary conditions (reduced with apply_boundary_conditions /
+    reduce, main.py:56-57); load of step i = f_shape * f_scale[i] (full-size shape vector).
+    Returns a dict: U, V, A (n_free, n_stored) like main.py's U_reduced / V_reduced / A_reduced,
+    kinetic/potential/total energy series (main.py:377-385), constrained_dofs, info."""
+    torch = _capi.torch_cuda()
+    _capi.bind_device()
+    constrained = constrained_dofs_of(bc)
+    Kd, Md = device_copy(K), device_copy(M)
+    fm = FreeMap(Kd.n_rows, constrained)
+    K_red = fm.reduce_csr(Kd)
+    M_red = fm.reduce_csr(Md)
+    if M_red.nnz != K_red.nnz:
+        raise ValueError("K and M must share one sparsity pattern (assemble both with this package)")
+    n = K_red.n_rows
+    f_scale = np.ascontiguousarray(f_scale, dtype=np.float64)
+    n_steps = int(f_scale.size)
+    fshape_red = fm.reduce_vec(_to_dev(f_shape))
+    f64 = dict(dtype=torch.float64, device="cuda")
+    # K_eff = K + M/(beta dt^2)   (main.py:290; no damping term)
+    Keff_vals = torch.empty(K_red.nnz, **f64)
+    call("psfem_axpby", K_red.nnz, 1.0, ptr(K_red.vals), 1.0 / (beta * dt ** 2), ptr(M_red.vals), ptr(Keff_vals), stream_ptr())
+    # a0 = M^-1 (F0 - K u0), u0 = 0   (main.py:286)
+    f0 = torch.empty(n, **f64)
+    call("psfem_axpby", n, float(f_scale[0]), ptr(fshape_red), 0.0, ptr(None), ptr(f0), stream_ptr())
+    a0, _ = pcg_jacobi(M_red, f0, rtol=rtol, maxit=maxit)
+    n_store = (n_steps - 1) // store_every + 1
+    U = torch.empty((n_store, n), **f64)
+    V = torch.empty((n_store, n), **f64)
+    A = torch.empty((n_store, n), **f64)
+    E = torch.empty((n_steps, 3), **f64) if energies else None
+    s = K_red.struct()
+    sz = C.c_size_t(0)
+    call("psfem_newmark_workspace", n, s.n_blocks, C.byref(sz))
+    ws = workspace(sz.value)
+    info = (C.c_double * 4)()
+    scale_c = f_scale.ctypes.data_as(C.POINTER(C.c_double))
+    rc = lib.psfem_newmark_run(C.byref(s), ptr(M_red.vals), ptr(Keff_vals), ptr(fshape_red), scale_c, n_steps,
+                               float(dt), float(gamma), float(beta), float(alpha_R), float(beta_R), ptr(a0),
+                               int(store_every), ptr(U), ptr(V), ptr(A), ptr(E), float(rtol),
+                               int(maxit if maxit is not None else 10 * n + 100), info, ptr(ws), sz.value, stream_ptr())
+    check(rc)
+    torch.cuda.current_stream().synchronize()
+    out = dict(U=U.cpu().numpy().T, V=V.cpu().numpy().T, A=A.cpu().numpy().T, constrained_dofs=constrained,
+               info=dict(pcg_iterations=int(info[0]), max_relres=float(info[1]), stabiliser_triggers=int(info[2])))
+    if energies:
+        e = E.cpu().numpy()
+        out.update(kinetic_energy=e[:, 0].copy(), potential_energy=e[:, 1].copy(), total_energy=e[:, 2].copy())
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# modal (freeModes.py)
+# ---------------------------------------------------------------------------------------------
+def modal(K, M, bc, k=20, tol=1e-10, max_lanczos=None, pcg_rtol=1e-14):
+    """First k natural frequencies and mode shapes.
+
+    freeModes.py:53-77: reduce, scale K and M by their largest |diagonal| entry, generalized
+    symmetric eigenproblem, clip at 0, f = sqrt(lambda * k_max/m_max)/(2 pi), modes rebuilt to
+    full length as rows.  The dense LAPACK `eigh` (:74, all modes, O(n^3)) is replaced by a
+    shift-invert Lanczos iteration (sigma = 0) in the M-inner product with full
+    reorthogonalisation; every operator application is a device SpMV and a Jacobi-PCG solve.
+    Eigenvectors are M_hat-orthonormal like LAPACK's (sign arbitrary).
+    Returns (frequencies (k,), modes (k, total_dofs), constrained_dofs, info)."""
+    torch = _capi.torch_cuda()
+    _capi.bind_device()
+    constrained = constrained_dofs_of(bc)
+    Kd, Md = device_copy(K), device_copy(M)
+    fm = FreeMap(Kd.n_rows, constrained)
+    K_red = fm.reduce_csr(Kd)
+    M_red = fm.reduce_csr(Md)
+    n = K_red.n_rows
+    k = min(k, n)
+    f64 = dict(dtype=torch.float64, device="cuda")
+    blas = Blas()
+    torch.cuda.current_stream().synchronize()
+    k_max = float(np.max(np.abs(K_red.diagonal().cpu().numpy())))  # freeModes.py:58-59
+    m_max = float(np.max(np.abs(M_red.diagonal().cpu().numpy())))
+    scaling = k_max / m_max                                        # :60
+    Kh = K_red.with_vals(_scaled(K_red.vals, 1.0 / k_max))         # :62-63
+    Mh = M_red.with_vals(_scaled(M_red.vals, 1.0 / m_max))
+    m_lanczos = min(n, max_lanczos or max(4 * k + 40, 100))
+    Vb = torch.zeros((m_lanczos + 1, n), **f64)                    # Lanczos basis (rows), M-orthonormal
+    MV = torch.zeros((m_lanczos + 1, n), **f64)                    # M_hat @ basis
+    coef = torch.empty(m_lanczos + 1, **f64)
+    alphas, betas = [], []
+    rng = np.random.default_rng(12345)
+    v = torch.from_numpy(rng.standard_normal(n)).cuda()
+    # start in range(K^-1 M): removes components in the null space of M
+    mv = Mh.matvec(v)
+    v, _ = pcg_jacobi(Kh, mv, rtol=pcg_rtol)
+    mv = Mh.matvec(v)
+    nrm = np.sqrt(blas.dot(v, mv))
+    _scaled(v, 1.0 / nrm, Vb[0])
+    _scaled(mv, 1.0 / nrm, MV[0])
+    total_pcg = 0
+    theta = None
+    converged = False
+    j_used = 0
+    for j in range(m_lanczos):
+        # w = K^-1 M v_j
+        w, inf = pcg_jacobi(Kh, MV[j], rtol=pcg_rtol)
+        total_pcg += inf["iterations"]
+        # full reorthogonalisation against v_0..v_j in the M inner product (twice is enough)
+        for _ in range(2):
+            blas.multi_dot(MV, j + 1, w, coef)
+            if _ == 0:
+                alphas.append(float(coef[j].item()))
+            blas.multi_axpy(Vb, j + 1, coef, w)
+        mw = Mh.matvec(w)
+        b2 = blas.dot(w, mw)
+        b = np.sqrt(max(b2, 0.0))
+        j_used = j + 1
+        # Ritz values of T (eigenvalues of K^-1 M = 1/lambda): check every few steps
+        if j_used >= k and (j_used % 5 == 0 or j_used == m_lanczos or b < 1e-300):
+            T = np.diag(alphas) + np.diag(betas, 1) + np.diag(betas, -1)
+            th, S = np.linalg.eigh(T)
+            order = np.argsort(-th)[:k]
+            resid = np.abs(b * S[-1, order]) / np.abs(th[order])
+            theta, Ssel = th[order], S[:, order]
+            if np.all(resid < tol) or b < 1e-300:
+                converged = True
+                break
+        if j + 1 < m_lanczos + 1 and b > 0:
+            betas.append(b)
+            _scaled(w, 1.0 / b, Vb[j + 1])
+            _scaled(mw, 1.0 / b, MV[j + 1])
+    if theta is None:
+        T = np.diag(alphas) + np.diag(betas[: len(alphas) - 1], 1) + np.diag(betas[: len(alphas) - 1], -1)
+        th, S = np.linalg.eigh(T)
+        order = np.argsort(-th)[:k]
+        theta, Ssel = th[order], S[:, order]
+    lam = 1.0 / theta                                              # eigenvalues of (K_hat, M_hat), ascending
+    lam = np.maximum(lam, 0)                                       # freeModes.py:75
+    freqs = np.sqrt(lam * scaling) / (2 * np.pi)                   # :76
+    # Ritz vectors: modes = S^T V  (rows), M_hat-orthonormal
+    S_dev = torch.from_numpy(np.ascontiguousarray(-Ssel.T)).cuda()  # (k, j_used), negated: multi_axpy subtracts
+    modes_red = torch.zeros((k, n), **f64)
+    for i in range(k):
+        # modes_red[i] = sum_j S[j,i] V[j]
+        call("psfem_multi_axpy", S_dev.shape[1], n, ptr(Vb), ptr(S_dev[i]), ptr(modes_red[i]), stream_ptr())
+    modes_full = fm.expand(modes_red.contiguous(), nvec=k) if k > 1 else fm.expand(modes_red[0]).reshape(1, -1)
+    torch.cuda.current_stream().synchronize()
+    info = dict(lanczos_steps=j_used, pcg_iterations=total_pcg, converged=bool(converged), k_max=k_max, m_max=m_max)
+    return freqs, modes_full.cpu().numpy().reshape(k, -1), constrained, info

@@ -1,0 +1,68 @@
+"""Host-side (index / load) logic of the facade against the reference fixtures -- runs on CPU."""
+import numpy as np
+
+BC = [(1, [0, 0]), (13, [None, 0]), (7, [5.0, None]), (1, [0, None]), (4, [None, None])]
+
+
+def test_boundary_edge_forces_merge(psfem, golden):
+    P = psfem.Polygones
+    d = golden("ref_bc_loads.npz")
+    for dr in ("top", "bottom", "left", "right"):
+        for mt in ("coarse", "fine"):
+            b = P.boundary(dr, [0, None], 4, 2, mesh_type=mt)
+            assert [k for k, _ in b] == list(d[f"boundary_{dr}_{mt}"])
+            assert all(disp == [0, None] for _, disp in b)
+            n_ = 15 if mt == "coarse" else 45
+            Fz = np.zeros(2 * n_)
+            Fz[3] = 1.0
+            out = P.edgeForces(Fz, [3.0, -1e6], dr, 2.0, 4, 2, mesh_type=mt)
+            assert out is Fz                                    # mutated in place and returned (Polygones.py:1125-1149)
+            assert np.array_equal(out, d[f"edge_{dr}_{mt}"])
+    merged = P.merge_boudary_conditions(P.boundary("left", [0, 0], 3), P.boundary("bottom", [0, 0], 3))
+    assert [k for k, _ in merged] == list(d["merge"])
+
+
+def test_dense_bc_paths_bit_exact(psfem, golden):
+    """Dense inputs (what the reference's own scripts pass) go through the same index logic."""
+    P = psfem.Polygones
+    d = golden("ref_bc_loads.npz")
+    K = d["bc_K"]
+    F = np.arange(K.shape[0], dtype=float)
+    K_red, F_red, cd = P.apply_boundary_conditions(K, F, BC)
+    assert cd == list(d["bc_constrained"])                      # bc order, duplicates kept
+    assert np.array_equal(K_red, d["bc_K_red"]) and np.array_equal(F_red, d["bc_F_red"])
+    assert np.array_equal(P.reduce(F, cd), d["bc_reduce_vec"])
+    assert np.array_equal(P.reduce(K, cd), d["bc_reduce_mat"])
+    assert np.array_equal(P.reconstruct_full_vector(F_red, cd, K.shape[0]), d["bc_full_vec"])
+    assert np.array_equal(P.reconstruct_full_vectors(np.stack([F_red, 2 * F_red], axis=1), cd, K.shape[0]), d["bc_full_vecs"])
+    assert np.array_equal(P.reconstruct_full_matrix(K_red, cd, K.shape[0]), d["bc_full_mat"])
+    import pytest
+    with pytest.raises(ValueError, match="either a vector"):
+        P.reduce(np.zeros((2, 2, 2)), cd)
+
+
+def test_displacement_and_element_table(psfem, golden):
+    P = psfem.Polygones
+    d = golden("ref_bc_loads.npz")
+    import psfem_oracle as O
+    nodes, conn = O.mesh(4, 2, 4, 2)
+    U = np.linspace(-1, 1, 2 * len(nodes))
+    assert np.array_equal(P.displacement(nodes, U, scale=2.5), d["displacement"])
+    tab = psfem.ElementTable(conn)
+    assert len(tab) == len(conn) and list(tab)[:3] == [0, 1, 2]
+    assert tab[1] == [int(v) for v in conn[1]] and len(tab[0]) == 3
+    assert dict(tab.items())[5] == tab[5]
+    import pytest
+    with pytest.raises(KeyError):
+        tab[len(conn)]
+    with pytest.raises(ValueError, match="Integration method"):
+        P.global_stiffness_matrix(nodes, tab, 1.0, 0.3, 1.0, integration="bogus")
+
+
+def test_ramp_load_matches_main_py(psfem, golden):
+    d = golden("ref_newmark.npz")
+    shape, scale, times = psfem.ramp_load(63, 20)
+    assert scale.size == int(d["nm_t3_nbPoints"]) == 10001
+    assert scale[0] == 0.0 and scale[-1] == -1e6 * 20 / 63
+    T0 = 10001 // 3
+    assert scale[T0] == -(3 * 1e6 * times[T0] / 10.0) * 20 / 63
