@@ -179,7 +179,7 @@ def element_stiffness(nodes, conn, E, nu, t, element_type="tri", mesh_type="coar
             B[:, 2, 2 * i] = c
             B[:, 2, 2 * i + 1] = b
         vol = 0.5 * delta * t
-        return np.einsum("eki,kl,elj->eij", B, D, B) * vol[:, None, None]
+        return np.matmul(B.transpose(0, 2, 1), np.matmul(D, B)) * vol[:, None, None]
     pts, ws = gauss_points(element_type)
     Ke = np.zeros((nel, 2 * npe, 2 * npe))
     for (xi, eta), w in zip(pts, ws):
@@ -200,7 +200,7 @@ def element_stiffness(nodes, conn, E, nu, t, element_type="tri", mesh_type="coar
         B[:, 1, 1::2] = dy
         B[:, 2, 0::2] = dy
         B[:, 2, 1::2] = dx
-        Ke += np.einsum("eki,kl,elj->eij", B, D, B) * (w * np.abs(detJ) * t)[:, None, None]
+        Ke += np.matmul(B.transpose(0, 2, 1), np.matmul(D, B)) * (w * np.abs(detJ) * t)[:, None, None]
     return Ke
 
 
@@ -420,6 +420,65 @@ def jacobi_pcg(A, b, rtol=1e-8, maxit=100000, x0=None):
         rz = rz_new
         it += 1
     return x, it, float(np.sqrt(r @ r) / bnorm)
+
+
+def jacobi_pcg_threads(A, b, iters, nthreads):
+    """The recurrence of jacobi_pcg for a FIXED number of iterations with the SpMV and the vector
+    updates split over `nthreads` row blocks (SciPy's CSR mat-vec and NumPy's element-wise loops
+    release the GIL).  Only used to time the CPU side of bench.py with every host core busy.
+    Returns (x, relres, seconds spent in the iteration loop -- the row-block split is set-up)."""
+    from concurrent.futures import ThreadPoolExecutor
+    A = A.tocsr()
+    n = A.shape[0]
+    bounds = np.linspace(0, n, nthreads + 1).astype(np.int64)
+    blocks = [A[bounds[i]:bounds[i + 1]] for i in range(nthreads)]
+    sl = [slice(bounds[i], bounds[i + 1]) for i in range(nthreads)]
+    dinv = 1.0 / A.diagonal()
+    x = np.zeros_like(b)
+    r = b.copy()
+    z = dinv * r
+    p = z.copy()
+    q = np.empty_like(b)
+    rz = r @ z
+    with ThreadPoolExecutor(nthreads) as pool:
+        def spmv(i):
+            q[sl[i]] = blocks[i] @ p
+            return p[sl[i]] @ q[sl[i]]
+
+        def update(i, alpha):
+            s = sl[i]
+            x[s] += alpha * p[s]
+            r[s] -= alpha * q[s]
+            z[s] = dinv[s] * r[s]
+            return r[s] @ z[s], r[s] @ r[s]
+
+        def pupd(i, beta):
+            s = sl[i]
+            p[s] = z[s] + beta * p[s]
+
+        import time as _time
+        t0 = _time.perf_counter()
+        for _ in range(iters):
+            pq = sum(pool.map(spmv, range(nthreads)))
+            alpha = rz / pq
+            parts = list(pool.map(lambda i: update(i, alpha), range(nthreads)))
+            rz_new = sum(a for a, _ in parts)
+            beta = rz_new / rz
+            list(pool.map(lambda i: pupd(i, beta), range(nthreads)))
+            rz = rz_new
+        seconds = _time.perf_counter() - t0
+    return x, float(np.sqrt(sum(c for _, c in parts)) / np.sqrt(b @ b)), seconds
+
+
+def element_stiffness_threads(nodes, conn, E, nu, t, element_type, mesh_type, nthreads):
+    """element_stiffness over `nthreads` element chunks (NumPy's batched matmul releases the GIL)."""
+    from concurrent.futures import ThreadPoolExecutor
+    conn = np.asarray(conn)
+    bounds = np.linspace(0, len(conn), nthreads + 1).astype(np.int64)
+    with ThreadPoolExecutor(nthreads) as pool:
+        parts = list(pool.map(lambda i: element_stiffness(nodes, conn[bounds[i]:bounds[i + 1]], E, nu, t, element_type, mesh_type),
+                              range(nthreads)))
+    return np.concatenate(parts, axis=0)
 
 
 def newmark_forces(n_nodes, L, P=1e6, T=10.0, dt=1e-3, accel_ratio=3):

@@ -1,0 +1,349 @@
+"""Strip partition of a structured plate across GPUs (one process per GPU, torch.distributed).
+
+Node id = i*m + j with i the x index (Polygones.py:77), so contiguous node / DOF ranges are
+x-strips.  Rank r owns the node columns [c0, c1); it meshes every cell column touching an owned node
+(its own cells plus its left neighbour's last cell column) and all their node columns (a halo of one
+cell column on the left, one node column on the right), assembles that extended strip with
+no communication (the interface cell columns are computed on both sides, 1/4096 of the work) and
+keeps the rows of its owned DOFs, which are complete and bit-identical to the same rows of the
+single-GPU matrix.  Per PCG iteration the only exchanges are
+  * the halo: the free DOFs of my first / last owned column go to my left / right neighbour
+    (2*(M+1) doubles each, grouped NCCL send/recv straight out of / into the extended p vector),
+  * two all-reduces of scalars (p.q, then r.z and r.r together).
+All scalars stay on the device; the host never waits inside the iteration.
+
+`StripPartition` is pure index arithmetic (tested on CPU); `pcg_iterations` is the rank-local
+iteration loop written against a small `ops` interface so that the CPU/gloo tests drive exactly the
+same control flow with NumPy ops; `StripProblem` binds it to the CUDA kernels.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import time
+
+import numpy as np
+
+from . import _capi
+from ._capi import call, ptr, stream_ptr
+
+
+class StripPartition:
+    """Which node columns / cell columns / DOFs a rank owns and meshes (coarse or fine meshes).
+
+    Cell columns are split evenly; rank r owns the node columns from the left edge of its first cell
+    column up to (not including) the left edge of the next rank's first cell column, the last rank
+    also owns the right edge.  It meshes every cell column touching an owned node column, i.e. its
+    own cells plus the last cell column of its left neighbour, and all node columns of those cells:
+    a left halo of `step` node columns (1 coarse, 2 fine) and a right halo of one node column."""
+
+    def __init__(self, N: int, M: int, world: int, rank: int, fine: bool = False):
+        assert 0 <= rank < world
+        self.N, self.M, self.world, self.rank, self.fine = N, M, world, rank, fine
+        self.n = (2 * N + 1) if fine else (N + 1)           # node columns (Polygones.py:66-71)
+        self.m = (2 * M + 1) if fine else (M + 1)           # nodes per column
+        self.step = step = 2 if fine else 1                 # node columns per cell column
+        base, rem = divmod(N, world)
+        assert base >= 1, "more ranks than cell columns"
+        cs = [r * base + min(r, rem) for r in range(world + 1)]
+        self.cell_start = cs
+        self.c0 = step * cs[rank]                           # owned node columns [c0, c1)
+        self.c1 = step * cs[rank + 1] if rank < world - 1 else self.n
+        self.cell0, self.cell1 = max(cs[rank] - 1, 0), cs[rank + 1]      # meshed cell columns
+        self.e0, self.e1 = step * self.cell0, step * self.cell1 + 1       # meshed node columns
+        self.left_halo_cols = self.c0 - self.e0             # 0 or step
+        self.right_halo_cols = self.e1 - self.c1            # 0 or 1
+        self.n_ext_nodes = (self.e1 - self.e0) * self.m
+        self.n_owned_nodes = (self.c1 - self.c0) * self.m
+        self.dof_shift = 2 * self.m * self.e0               # global dof = extended-local dof + shift
+        self.own_lo = 2 * self.m * (self.c0 - self.e0)      # owned DOF range in extended-local numbering
+        self.own_hi = 2 * self.m * (self.c1 - self.e0)
+        self.n_ext_dof = 2 * self.n_ext_nodes
+
+    @property
+    def left(self):
+        return self.rank - 1 if self.rank > 0 else None
+
+    @property
+    def right(self):
+        return self.rank + 1 if self.rank < self.world - 1 else None
+
+    def local_constrained(self, constrained_global):
+        """global constrained DOF list -> extended-local ids (those outside the strip dropped)."""
+        cd = np.asarray(list(constrained_global), dtype=np.int64) - self.dof_shift
+        return cd[(cd >= 0) & (cd < self.n_ext_dof)]
+
+    def halo_plan(self, free_mask_ext=None, count_free=None):
+        """Index ranges, in the REDUCED (free-DOF) extended vector, of the halo exchange.
+        `count_free(a, b)` = number of free extended-local DOFs in [a, b) (or pass the boolean mask).
+        own = (lo, hi): owned entries; recv_left = [0, lo), recv_right = [hi, n_ext_free);
+        send_left = my first node column (my left neighbour's right halo), send_right = my last `step`
+        node columns (my right neighbour's left halo).  Both sides count the same global DOFs, so the
+        message sizes agree without negotiation."""
+        if count_free is None:
+            csum = np.concatenate([[0], np.cumsum(np.asarray(free_mask_ext).astype(np.int64))])
+            count_free = lambda a, b: int(csum[b] - csum[a])
+        col = 2 * self.m
+        lo = count_free(0, self.own_lo)
+        hi = lo + count_free(self.own_lo, self.own_hi)
+        n_ext_free = hi + count_free(self.own_hi, self.n_ext_dof)
+        plan = dict(own=(lo, hi), n_ext_free=n_ext_free, send_left=None, send_right=None, recv_left=None, recv_right=None)
+        if self.left is not None:
+            plan["recv_left"] = (0, lo)
+            plan["send_left"] = (lo, lo + count_free(self.own_lo, self.own_lo + col))
+        if self.right is not None:
+            plan["recv_right"] = (hi, n_ext_free)
+            plan["send_right"] = (hi - count_free(self.own_hi - self.step * col, self.own_hi), hi)
+        return plan
+
+
+# ------------------------------------------------------------------------------------------------
+# rank-local PCG iteration loop (backend-agnostic)
+# ------------------------------------------------------------------------------------------------
+class Comm:
+    """torch.distributed plumbing of the strip solver: halo send/recv + scalar all-reduce."""
+
+    def __init__(self, part: StripPartition, plan: dict, dist_module=None):
+        self.part, self.plan, self.dist = part, plan, dist_module
+        self.active = part.world > 1
+
+    def halo(self, p_ext):
+        if not self.active:
+            return
+        d = self.dist
+        ops = []
+        pl = self.plan
+        if self.part.left is not None:
+            a, b = pl["send_left"]
+            ops.append(d.P2POp(d.isend, p_ext[a:b], self.part.left))
+            a, b = pl["recv_left"]
+            ops.append(d.P2POp(d.irecv, p_ext[a:b], self.part.left))
+        if self.part.right is not None:
+            a, b = pl["send_right"]
+            ops.append(d.P2POp(d.isend, p_ext[a:b], self.part.right))
+            a, b = pl["recv_right"]
+            ops.append(d.P2POp(d.irecv, p_ext[a:b], self.part.right))
+        for w in d.batch_isend_irecv(ops):
+            w.wait()
+
+    def allreduce(self, t):
+        if self.active:
+            self.dist.all_reduce(t)
+
+
+def pcg_iterations(ops, comm: Comm, st: dict, k: int):
+    """k Jacobi-PCG iterations on the strip-partitioned system.  `st` holds x, r, q, dinv (owned rows),
+    p_ext (extended, halo up to date on entry), scalar tensors rz (2 slots), pq, out2, and `parity`.
+    Identical recurrence to the single-GPU solver; only the two reductions and the halo are global."""
+    lo, hi = comm.plan["own"]
+    for _ in range(k):
+        cur, nxt = st["parity"], st["parity"] ^ 1
+        ops.spmv_dot(st["p_ext"], lo, st["q"], st["pq"])                 # q = A p ; pq = p_own . q (local)
+        comm.allreduce(st["pq"])
+        ops.update(st["x"], st["r"], st["p_ext"][lo:hi], st["q"], st["dinv"], st["rz"][cur:cur + 1], st["pq"], st["out2"])
+        comm.allreduce(st["out2"])                                        # {r.z, r.r}
+        ops.copy_scalar(st["out2"][0:1], st["rz"][nxt:nxt + 1])
+        ops.pupdate(st["p_ext"][lo:hi], st["r"], st["dinv"], st["rz"][cur:cur + 1], st["rz"][nxt:nxt + 1])
+        comm.halo(st["p_ext"])
+        st["parity"] = nxt
+        st["iters"] += 1
+
+
+def pcg_start(ops, comm: Comm, st: dict, b_own):
+    """x = 0, r = b, p = dinv r (+ halo), rz = r.z, rr, bb."""
+    lo, hi = comm.plan["own"]
+    ops.init(st["r"], st["dinv"], b_own, st["p_ext"][lo:hi], st["out3"])   # r already holds b
+    comm.allreduce(st["out3"])
+    ops.copy_scalar(st["out3"][0:1], st["rz"][0:1])
+    comm.halo(st["p_ext"])
+    st["parity"] = 0
+    st["iters"] = 0
+
+
+# ------------------------------------------------------------------------------------------------
+# CUDA backend
+# ------------------------------------------------------------------------------------------------
+class CudaOps:
+    def __init__(self, A_struct, n_own, n_blocks):
+        torch = _capi.torch_cuda()
+        self.A = A_struct
+        self.n = n_own
+        npart = max(n_blocks, 148 * 8) * 3
+        self.partials = torch.empty(npart, dtype=torch.float64, device="cuda")
+        self.counter = torch.zeros(4, dtype=torch.int32, device="cuda")
+
+    def spmv_dot(self, p_ext, x_offset, q, pq):
+        call("psfem_pcg_spmv_dot", C.byref(self.A), ptr(p_ext), x_offset, ptr(q), ptr(pq), ptr(self.partials),
+             ptr(self.counter), stream_ptr())
+
+    def update(self, x, r, p_own, q, dinv, rz, pq, out2):
+        call("psfem_pcg_update", self.n, ptr(x), ptr(r), ptr(p_own), ptr(q), ptr(dinv), ptr(rz), ptr(pq), ptr(out2),
+             ptr(self.partials), C.c_void_p(self.counter.data_ptr() + 4), stream_ptr())
+
+    def pupdate(self, p_own, r, dinv, rz_old, rz_new):
+        call("psfem_pcg_pupdate", self.n, ptr(p_own), ptr(r), ptr(dinv), ptr(rz_old), ptr(rz_new), stream_ptr())
+
+    def init(self, r, dinv, b, p_own, out3):
+        call("psfem_pcg_init", self.n, ptr(r), ptr(dinv), ptr(b), ptr(p_own), ptr(out3), ptr(self.partials),
+             C.c_void_p(self.counter.data_ptr() + 8), stream_ptr())
+
+    @staticmethod
+    def copy_scalar(src, dst):
+        call("psfem_axpby", 1, 1.0, ptr(src), 0.0, ptr(None), ptr(dst), stream_ptr())
+
+
+class StripProblem:
+    """Clamped-left / loaded-right Q4 plate of BASELINE configs[3]/[4] on `world` GPUs: strip mesh,
+    symbolic pattern, numeric assembly, BC reduction, distributed Jacobi-PCG.  Also the single-GPU
+    benchmark object (world = 1)."""
+
+    def __init__(self, L, l, N, M, rank=0, world=1, E=210e9, nu=0.3, t=0.1, element_type="quad", mesh_type="coarse",
+                 load=(0.0, -1e6)):
+        self.L, self.l, self.N, self.M = L, l, N, M
+        self.rank, self.world = rank, world
+        self.E, self.nu, self.t = E, nu, t
+        self.element_type, self.mesh_type, self.load = element_type, mesh_type, load
+        self.part = StripPartition(N, M, world, rank, fine=(mesh_type == "fine"))
+
+    # -- set-up ---------------------------------------------------------------------------------
+    def setup(self, nodes_conn=None):
+        from .device import Assembler, FreeMap, device_mesh
+        from ._capi import ETYPE
+        torch = _capi.torch_cuda()
+        _capi.bind_device()
+        p = self.part
+        if nodes_conn is None:
+            self.nodes, self.conn = device_mesh(self.L, self.l, self.N, self.M, 0, 0, self.element_type, self.mesh_type,
+                                                col0=p.e0, ncols=p.e1 - p.e0, cell0=p.cell0, ncells=p.cell1 - p.cell0)
+        else:
+            self.nodes, self.conn = nodes_conn
+        et = ETYPE[(self.element_type, self.mesh_type)]
+        self.asm = Assembler(self.conn, p.n_ext_nodes, et)
+        f64 = dict(dtype=torch.float64, device="cuda")
+        self.K_vals = torch.empty(self.asm.nnz, **f64)
+        self.asm.assemble(self.nodes, E=self.E, nu=self.nu, t=self.t, what=1, K_out=self.K_vals)
+        K_ext = self.asm.pattern_csr(self.K_vals)
+        # boundary conditions: left edge clamped (global node column 0), Polygones.boundary('left',[0,0],...)
+        m = p.m
+        cd_global = np.arange(2 * m, dtype=np.int64)              # DOFs 2k, 2k+1 of nodes k = 0..m-1
+        self.fm = FreeMap(p.n_ext_dof, p.local_constrained(cd_global))
+        self.K_ext_red = self.fm.reduce_csr(K_ext)
+        free = self.fm.free_dofs                                   # sorted extended-local ids of free DOFs
+
+        def count_free(a, b):
+            lo_ = int(torch.searchsorted(free, torch.tensor([a], dtype=free.dtype, device="cuda")).item())
+            hi_ = int(torch.searchsorted(free, torch.tensor([b], dtype=free.dtype, device="cuda")).item())
+            return hi_ - lo_
+        self.plan = p.halo_plan(count_free=count_free)
+        lo, hi = self.plan["own"]
+        self.n_owned_free = hi - lo
+        self.n_ext_free = self.plan["n_ext_free"]
+        # owned rows of the reduced extended matrix: a row slice (pointer offset), columns stay extended
+        from .device import DeviceCSR
+        rp = self.K_ext_red.row_ptr[lo:hi + 1]
+        self.K_red = DeviceCSR(hi - lo, self.n_ext_free, rp, self.K_ext_red.col_idx, self.K_ext_red.vals, nnz=None)
+        self.K_red.nnz = int((rp[-1] - rp[0]).item())
+        self.A = self.K_red.struct()
+        _, nb, _ = self.K_red.plan()
+        # load: edgeForces(F,[0,-1e6],'right',l,N,M): f*l/(m-1) on every node of the right edge (global column n-1)
+        F_ext = torch.zeros(p.n_ext_dof, **f64)
+        if p.e1 == p.n:
+            k0 = (p.n - 1 - p.e0) * m
+            F_ext[2 * k0:2 * (k0 + m):2] = self.load[0] * self.l / (m - 1)
+            F_ext[2 * k0 + 1:2 * (k0 + m):2] = self.load[1] * self.l / (m - 1)
+        self.b_own = self.fm.reduce_vec(F_ext)[lo:hi].contiguous()
+        # global sizes
+        self.n_dof_global = 2 * p.n * p.m
+        self.n_free_global = self.n_dof_global - 2 * m
+        per_cell = 2 if self.element_type == "tri" else 1
+        self.nel_global = self.N * self.M * per_cell
+        self.nel_owned = self.asm.nel
+        # PCG state
+        self.ops = CudaOps(self.A, self.n_owned_free, nb)
+        import torch.distributed as dist
+        self.comm = Comm(p, self.plan, dist if self.world > 1 else None)
+        n = self.n_owned_free
+        self.st = dict(x=torch.zeros(n, **f64), r=self.b_own.clone(), q=torch.empty(n, **f64),
+                       dinv=torch.empty(n, **f64), p_ext=torch.zeros(self.n_ext_free, **f64),
+                       rz=torch.zeros(2, **f64), pq=torch.zeros(1, **f64), out2=torch.zeros(2, **f64),
+                       out3=torch.zeros(3, **f64), parity=0, iters=0)
+        call("psfem_extract_diag", C.byref(self.A), lo, 1, ptr(self.st["dinv"]), stream_ptr())
+        pcg_start(self.ops, self.comm, self.st, self.b_own)
+        torch.cuda.synchronize()
+        return self
+
+    # -- timed pieces -----------------------------------------------------------------------------
+    def assemble(self):
+        self.asm.assemble(self.nodes, E=self.E, nu=self.nu, t=self.t, what=1, K_out=self.K_vals)
+
+    def cg_iterations(self, k):
+        pcg_iterations(self.ops, self.comm, self.st, k)
+
+    def spmv_only(self, k):
+        lo, _ = self.plan["own"]
+        for _ in range(k):
+            self.ops.spmv_dot(self.st["p_ext"], lo, self.st["q"], self.st["pq"])
+
+    def residual(self):
+        """(||r||, ||b||) from the recurrence (global)."""
+        rr = self.st["out2"][1].item() if self.st["iters"] else self.st["out3"][1].item()
+        bb = self.st["out3"][2].item()
+        return float(np.sqrt(rr)), float(np.sqrt(bb))
+
+    def solve(self, rtol=1e-8, maxit=200000, check_every=100):
+        """Continue the PCG until ||r|| <= rtol ||b|| (host checks every check_every iterations)."""
+        torch = _capi.torch_cuda()
+        t0 = time.perf_counter()
+        while self.st["iters"] < maxit:
+            r, b = self.residual()
+            if r <= rtol * b:
+                break
+            self.cg_iterations(check_every)
+        torch.cuda.synchronize()
+        r, b = self.residual()
+        return dict(iterations=self.st["iters"], relres=r / b if b > 0 else 0.0, seconds=time.perf_counter() - t0)
+
+    def full_solve(self, rtol):
+        torch = _capi.torch_cuda()
+        self.st["x"].zero_()
+        self.st["r"].copy_(self.b_own)
+        pcg_start(self.ops, self.comm, self.st, self.b_own)
+        torch.cuda.synchronize()
+        return self.solve(rtol)
+
+    def e2e_distributed(self, iters, steps):
+        """End-to-end at N>1: every step uploads the rank's strip mesh from pinned host memory,
+        assembles, reduces, runs `iters` PCG iterations and reads the residual norm back."""
+        torch = _capi.torch_cuda()
+        import torch.distributed as dist
+        nodes_h = self.nodes.cpu().pin_memory()
+        conn_h = self.conn.cpu().pin_memory()
+        self.release()
+        torch.cuda.empty_cache()
+        times = []
+        for s in range(steps + 1):
+            if self.world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            nodes = nodes_h.cuda(non_blocking=True)
+            conn = conn_h.cuda(non_blocking=True)
+            self.setup((nodes, conn))
+            self.cg_iterations(iters)
+            r, b = self.residual()
+            torch.cuda.synchronize()
+            if self.world > 1:
+                dist.barrier()
+            times.append(time.perf_counter() - t0)
+            self.release()
+        t = torch.tensor([sum(times[1:])], dtype=torch.float64, device="cuda")
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return {"value": self.n_free_global * iters * steps / float(t.item()), "unit": "DOF*iter/s",
+                "h2d_bytes_per_step": int(nodes_h.numel() * 8 + conn_h.numel() * 4), "d2h_bytes_per_step": 16,
+                "steps": steps, "pcg_iters_per_call": iters,
+                "calls": "per rank: pinned host strip mesh -> H2D -> pattern + assembly + BC reduction -> PCG iterations -> residual D2H"}
+
+    def release(self):
+        for k in ("asm", "K_vals", "K_ext_red", "K_red", "fm", "st", "ops", "A", "b_own", "nodes", "conn"):
+            if hasattr(self, k):
+                delattr(self, k)

@@ -1,0 +1,154 @@
+"""CPU tests of the multi-GPU path: strip-partition index logic and the rank-local PCG loop
+(`psfem_b200.dist.pcg_iterations`) run at world_size 2 and 3 over gloo, with NumPy/SciPy ops from the
+oracle standing in for the CUDA kernels.  The control flow (halo exchange, all-reduces, scalar
+ping-pong) is the product's; only the local arithmetic is the oracle's."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("N,M,world,fine", [(8, 3, 1, False), (8, 3, 2, False), (9, 4, 4, False), (16, 2, 8, False),
+                                            (6, 2, 3, True), (5, 3, 2, True)])
+def test_partition_covers_everything_once(psfem, N, M, world, fine):
+    from psfem_b200.dist import StripPartition
+    parts = [StripPartition(N, M, world, r, fine) for r in range(world)]
+    n, m = parts[0].n, parts[0].m
+    owned = np.zeros(n, int)
+    step = 2 if fine else 1
+    for p in parts:
+        owned[p.c0:p.c1] += 1
+        assert p.e0 <= p.c0 < p.c1 <= p.e1 <= n
+        assert p.e0 == step * p.cell0 and p.e1 == step * p.cell1 + 1
+        # every cell touching an owned node column is meshed
+        for c in range(p.c0, p.c1):
+            cells = {c // step} | ({c // step - 1} if c % step == 0 else set())
+            cells = {k for k in cells if 0 <= k < N}
+            assert all(p.cell0 <= k < p.cell1 for k in cells)
+        assert p.own_hi - p.own_lo == 2 * m * (p.c1 - p.c0)
+        cd = p.local_constrained(np.arange(2 * m))
+        assert (len(cd) == 2 * m) == (p.e0 == 0)
+    assert np.all(owned == 1)
+    # halo message sizes agree between neighbours, with a few constrained DOFs scattered around
+    rng = np.random.default_rng(0)
+    free_global = np.ones(2 * n * m, bool)
+    free_global[rng.choice(2 * n * m, size=min(7, n * m), replace=False)] = False
+    plans = [p.halo_plan(free_mask_ext=free_global[p.dof_shift:p.dof_shift + p.n_ext_dof]) for p in parts]
+    for r in range(world - 1):
+        a, b = plans[r]["send_right"]
+        c, d = plans[r + 1]["recv_left"]
+        assert b - a == d - c
+        a, b = plans[r + 1]["send_left"]
+        c, d = plans[r]["recv_right"]
+        assert b - a == d - c
+    assert sum(pl["own"][1] - pl["own"][0] for pl in plans) == free_global.sum()
+
+
+class NumpyOps:
+    """The three PCG kernels + init on torch CPU tensors (oracle arithmetic)."""
+
+    def __init__(self, A_own):
+        self.A = A_own
+
+    def spmv_dot(self, p_ext, lo, q, pq):
+        qn = self.A @ p_ext.numpy()
+        q.numpy()[:] = qn
+        pq.numpy()[0] = p_ext.numpy()[lo:lo + len(qn)] @ qn
+
+    @staticmethod
+    def update(x, r, p_own, q, dinv, rz, pq, out2):
+        alpha = rz.numpy()[0] / pq.numpy()[0]
+        x.numpy()[:] += alpha * p_own.numpy()
+        r.numpy()[:] -= alpha * q.numpy()
+        out2.numpy()[0] = r.numpy() @ (dinv.numpy() * r.numpy())
+        out2.numpy()[1] = r.numpy() @ r.numpy()
+
+    @staticmethod
+    def pupdate(p_own, r, dinv, rz_old, rz_new):
+        beta = rz_new.numpy()[0] / rz_old.numpy()[0]
+        p_own.numpy()[:] = dinv.numpy() * r.numpy() + beta * p_own.numpy()
+
+    @staticmethod
+    def init(r, dinv, b, p_own, out3):
+        p_own.numpy()[:] = dinv.numpy() * r.numpy()
+        out3.numpy()[:] = [r.numpy() @ p_own.numpy(), r.numpy() @ r.numpy(), b.numpy() @ b.numpy()]
+
+    @staticmethod
+    def copy_scalar(src, dst):
+        dst.numpy()[:] = src.numpy()
+
+
+def _worker(rank, world, port, N, M, iters, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import torch
+    import torch.distributed as dist
+    import psfem_b200  # noqa
+    from psfem_b200.dist import Comm, StripPartition, pcg_iterations, pcg_start
+    import psfem_oracle as O
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    part = StripPartition(N, M, world, rank)
+    L, l = 0.001 * N, 0.001 * M
+    nodes, conn = O.mesh(L, l, N, M, element_type="quad")
+    m = part.m
+    # the strip: nodes of columns [e0,e1), elements of cell columns [cell0,cell1), ids made local
+    nodes_s = nodes[part.e0 * m:part.e1 * m]
+    conn_s = conn[part.cell0 * M:part.cell1 * M] - part.e0 * m
+    K_ext = O.global_stiffness_matrix(nodes_s, conn_s, 210e9, 0.3, 0.1, "quad")
+    mask = np.ones(part.n_ext_dof, bool)
+    mask[part.local_constrained(np.arange(2 * m))] = False
+    free = np.nonzero(mask)[0]
+    K_red = K_ext[free][:, free]
+    plan = part.halo_plan(free_mask_ext=mask)
+    lo, hi = plan["own"]
+    A_own = K_red[lo:hi]
+    F = O.edge_forces(np.zeros(2 * len(nodes)), [0, -1e6], "right", l, N, M)
+    b_own = F[part.dof_shift:part.dof_shift + part.n_ext_dof][free][lo:hi]
+    f64 = torch.float64
+    st = dict(x=torch.zeros(hi - lo, dtype=f64), r=torch.from_numpy(b_own.copy()), q=torch.zeros(hi - lo, dtype=f64),
+              dinv=torch.from_numpy(1.0 / A_own[:, lo:hi].diagonal()), p_ext=torch.zeros(plan["n_ext_free"], dtype=f64),
+              rz=torch.zeros(2, dtype=f64), pq=torch.zeros(1, dtype=f64), out2=torch.zeros(2, dtype=f64),
+              out3=torch.zeros(3, dtype=f64), parity=0, iters=0)
+    ops = NumpyOps(A_own)
+    comm = Comm(part, plan, dist)
+    pcg_start(ops, comm, st, torch.from_numpy(b_own.copy()))
+    pcg_iterations(ops, comm, st, iters)
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), x=st["x"].numpy(), rr=st["out2"].numpy()[1],
+             rows=A_own.toarray() if A_own.shape[0] * A_own.shape[1] < 4e6 else np.zeros(1), lo=lo, hi=hi)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_strip_pcg_over_gloo_matches_single_process(tmp_path, psfem, world):
+    import torch.multiprocessing as mp
+    import psfem_oracle as O
+    N, M, iters = 12, 5, 40
+    port = 29500 + os.getpid() % 2000 + world
+    mp.spawn(_worker, args=(world, port, N, M, iters, str(tmp_path)), nprocs=world, join=True)
+    # single-process reference: same recurrence, same number of iterations
+    nodes, conn = O.mesh(0.001 * N, 0.001 * M, N, M, element_type="quad")
+    K = O.global_stiffness_matrix(nodes, conn, 210e9, 0.3, 0.1, "quad")
+    F = O.edge_forces(np.zeros(K.shape[0]), [0, -1e6], "right", 0.001 * M, N, M)
+    K_red, F_red, _ = O.apply_boundary_conditions(K, F, O.boundary("left", [0, 0], N, M))
+    x_ref, it, rel = O.jacobi_pcg(K_red, F_red, rtol=0.0, maxit=iters)
+    xs = [np.load(tmp_path / f"rank{r}.npz") for r in range(world)]
+    x = np.concatenate([d["x"] for d in xs])
+    assert x.shape == x_ref.shape
+    # unconverged CG iterates amplify the different dot-product summation order; 1e-7 after 40 iterations
+    assert np.abs(x - x_ref).max() <= 1e-7 * np.abs(x_ref).max()
+    # owned rows of every strip are bit-identical to the same rows of the single-process matrix
+    row0 = 0
+    Kd = K_red.toarray()
+    for r, d in enumerate(xs):
+        rows = d["rows"]
+        nr = rows.shape[0]
+        # columns of the strip are a contiguous window of the global reduced numbering
+        col0 = row0 - int(d["lo"])
+        assert np.array_equal(rows, Kd[row0:row0 + nr, col0:col0 + rows.shape[1]])
+        row0 += nr
