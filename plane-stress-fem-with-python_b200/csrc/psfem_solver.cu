@@ -157,6 +157,170 @@ spmv_kernel(const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// SpMV v2: persistent, warp-specialised, TMA-staged.
+//
+// One producer warp streams the vals / col_idx / row_ptr slices of the CTA's row blocks into a ring
+// of shared-memory stages with bulk async copies (cp.async.bulk + mbarrier complete_tx), running
+// SPMV2_STAGES blocks ahead of the eight consumer warps, so HBM latency is off the critical path
+// (v1 was long-scoreboard bound at 41 % of DRAM peak, profiles/r1a_summary.md).  Consumers turn a
+// landed stage into products in place (x gathered through L1/L2), then reduce one row per thread in
+// column order.  Row blocks are dealt round-robin to a grid of 2 CTAs per SM; the dot-product partial
+// of a CTA is accumulated in registers over all its blocks (296 partials, fixed order).
+// ---------------------------------------------------------------------------------------------
+constexpr int SPMV2_CONSUMERS = 256;
+constexpr int SPMV2_THREADS = SPMV2_CONSUMERS + 32;
+constexpr int SPMV2_STAGES = 2;
+constexpr int SPMV2_ROWCAP = 1024;  // row_ptr entries staged per block (blocks with more rows read row_ptr from global)
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+struct Spmv2Meta {  // per stage, written by the producer before the stage's bulk copies complete
+    int r0, r1, k0a, r0a, rows_staged, kb /* absolute end of the bulk-copied non-zeros */, pad[2];
+};
+
+template <bool DOT>
+__global__ void __launch_bounds__(SPMV2_THREADS, 2)
+spmv2_kernel(const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col_idx, const double *__restrict__ vals,
+             const int32_t *__restrict__ rowblk, int n_blocks, int n_rows, int cap, const double *__restrict__ x, double alpha,
+             double gamma, const double *__restrict__ z, double *__restrict__ y, const double *__restrict__ xdot,
+             double *__restrict__ dot_out, double *__restrict__ partials, unsigned int *counter, const int *__restrict__ done) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint64_t full_bar[SPMV2_STAGES], empty_bar[SPMV2_STAGES];
+    __shared__ Spmv2Meta meta[SPMV2_STAGES];
+    __shared__ double red[SPMV2_THREADS / 32];
+    if (done && *done) return;
+    // stage layout: vals[cap] | cols[cap] | rp[ROWCAP+8]
+    const size_t stage_bytes = (size_t)cap * 12 + (SPMV2_ROWCAP + 8) * 4;
+    auto vals_s = [&](int s) { return reinterpret_cast<double *>(smem_raw + s * stage_bytes); };
+    auto cols_s = [&](int s) { return reinterpret_cast<int *>(smem_raw + s * stage_bytes + (size_t)cap * 8); };
+    auto rp_s = [&](int s) { return reinterpret_cast<int *>(smem_raw + s * stage_bytes + (size_t)cap * 12); };
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        for (int s = 0; s < SPMV2_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], SPMV2_CONSUMERS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int n_mine = (n_blocks - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    double dot[1] = {0.0};
+    if (tid >= SPMV2_CONSUMERS) {
+        // ---------------- producer warp ----------------
+        // The 32 lanes fetch the (row, non-zero) ranges of the CTA's next 32 row blocks with two batched
+        // loads (rowblk, then row_ptr), so the dependent global-load latency is paid once per 32 blocks
+        // instead of once per block; lane 0 then issues the bulk copies block by block.
+        const int lane = tid & 31;
+        const int kend4 = row_ptr[n_rows] & ~3;
+        const int rp_mis = (int)((reinterpret_cast<uintptr_t>(row_ptr) >> 2) & 3);  // row_ptr may be a row slice
+        for (int base = 0; base < n_mine; base += 32) {
+            int r0_l = 0, r1_l = 0, k0_l = 0, k1_l = 0;
+            if (base + lane < n_mine) {
+                const int b = blockIdx.x + (base + lane) * gridDim.x;
+                r0_l = rowblk[b]; r1_l = rowblk[b + 1];
+                k0_l = row_ptr[r0_l]; k1_l = row_ptr[r1_l];
+            }
+            const int nj = min(32, n_mine - base);
+            for (int j = 0; j < nj; ++j) {
+                const int r0 = __shfl_sync(0xffffffffu, r0_l, j), r1 = __shfl_sync(0xffffffffu, r1_l, j);
+                const int k0 = __shfl_sync(0xffffffffu, k0_l, j), k1 = __shfl_sync(0xffffffffu, k1_l, j);
+                if (lane == 0) {
+                    // bulk copies need 16-byte aligned addresses and sizes: slices are widened to multiples of
+                    // 4 elements but never past the last offset this operand references (row_ptr[n_rows]); the
+                    // few non-zeros beyond the last aligned boundary are read from global memory by consumers.
+                    const int i = base + j;
+                    const int s = i % SPMV2_STAGES, n = i / SPMV2_STAGES;
+                    mbar_wait(&empty_bar[s], (n & 1) ^ 1);       // consumers are done with this stage
+                    const int k0a = k0 & ~3;
+                    int kb = (k1 + 3) & ~3;
+                    if (kb > kend4) kb = kend4;
+                    if (kb < k0a) kb = k0a;
+                    const int r0a = r0 - ((r0 + rp_mis) & 3);        // (row_ptr + r0a) is 16-byte aligned
+                    int rows_staged = r1 - r0a + 1;                  // row_ptr[r0a .. r1]
+                    int rp_cnt = (rows_staged + 3) & ~3;
+                    if (rows_staged > SPMV2_ROWCAP || r0a + rp_cnt > n_rows + 1) { rows_staged = 0; rp_cnt = 0; }
+                    Spmv2Meta m;
+                    m.r0 = r0; m.r1 = r1; m.k0a = k0a; m.r0a = r0a; m.rows_staged = rows_staged; m.kb = kb;
+                    meta[s] = m;
+                    const uint32_t nb = (uint32_t)(kb - k0a);
+                    mbar_expect_tx(&full_bar[s], nb * 12u + (uint32_t)rp_cnt * 4u);
+                    if (nb) {
+                        bulk_g2s(vals_s(s), vals + k0a, nb * 8u, &full_bar[s]);
+                        bulk_g2s(cols_s(s), col_idx + k0a, nb * 4u, &full_bar[s]);
+                    }
+                    if (rp_cnt) bulk_g2s(rp_s(s), row_ptr + r0a, (uint32_t)rp_cnt * 4u, &full_bar[s]);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ---------------- consumer warps ----------------
+        for (int i = 0; i < n_mine; ++i) {
+            const int s = i % SPMV2_STAGES, n = i / SPMV2_STAGES;
+            mbar_wait(&full_bar[s], n & 1);
+            const Spmv2Meta m = meta[s];
+            double *vs = vals_s(s);
+            const int *cs = cols_s(s);
+            const int *rp = rp_s(s);
+            // one row per thread straight from the staged slices: the gathers of a warp hit consecutive x
+            // entries (adjacent rows share / neighbour their columns), every gather of a batch is in flight
+            // together, and the row is summed in column order (the order of scipy's CSR mat-vec).
+            constexpr int U = 9;
+            for (int r = m.r0 + tid; r < m.r1; r += SPMV2_CONSUMERS) {
+                int a, b;
+                if (m.rows_staged) { a = rp[r - m.r0a]; b = rp[r + 1 - m.r0a]; }
+                else { a = row_ptr[r]; b = row_ptr[r + 1]; }
+                double sum = 0.0;
+                for (int q = a; q < b; q += U) {
+                    int c[U];
+                    double v[U], xv[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const int kk = q + u;
+                        if (kk < b) {
+                            const bool staged = kk < m.kb;   // beyond kb: unaligned tail of the last block
+                            c[u] = staged ? cs[kk - m.k0a] : col_idx[kk];
+                            v[u] = staged ? vs[kk - m.k0a] : vals[kk];
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+                        if (q + u < b) xv[u] = __ldg(x + c[u]);
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+                        if (q + u < b) sum += alpha * v[u] * xv[u];
+                }
+                if (z) sum += gamma * z[r];
+                y[r] = sum;
+                if (DOT) dot[0] += xdot[r] * sum;
+            }
+            mbar_arrive(&empty_bar[s]);
+        }
+    }
+    if (DOT) {
+        double total[1];
+        if (grid_sum<SPMV2_THREADS, 1>(dot, partials, counter, red, total)) *dot_out = total[0];
+    }
+}
+
 int launch_spmv(const psfem_csr *A, const double *v2, const double *x1, const double *x2, double alpha, double beta,
                 double gamma, const double *z, double *y, const double *xdot, double *dot_out, double *partials,
                 unsigned int *counter, const int *done, cudaStream_t stream) {
@@ -164,6 +328,30 @@ int launch_spmv(const psfem_csr *A, const double *v2, const double *x1, const do
     const size_t smem = (size_t)(SPMV_T + A->max_row_nnz + 8) * sizeof(double);
     PSFEM_REQUIRE(smem <= 200 * 1024, "spmv: a row with %lld non-zeros does not fit the shared-memory stage", (long long)A->max_row_nnz);
     const bool dual = v2 != nullptr, dot = dot_out != nullptr;
+    if (!dual && A->n_blocks >= 8 && ((reinterpret_cast<uintptr_t>(A->vals) | reinterpret_cast<uintptr_t>(A->col_idx)) & 15) == 0) {
+        // v2: persistent TMA-staged kernel (vals / col_idx base pointers must be 16-byte aligned)
+        const int cap = (int)((SPMV_T + A->max_row_nnz + 8 + 3) & ~3ll);
+        const size_t stage_bytes = (size_t)cap * 12 + (SPMV2_ROWCAP + 8) * 4;
+        const size_t smem2 = SPMV2_STAGES * stage_bytes;
+        if (smem2 <= 110 * 1024) {
+            int dev = 0, sms = 148;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            int64_t grid = 2ll * sms;
+            if (grid > A->n_blocks) grid = A->n_blocks;
+            if (dot) {
+                PSFEM_CUDA_CHECK(cudaFuncSetAttribute(spmv2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+                spmv2_kernel<true><<<(unsigned)grid, SPMV2_THREADS, smem2, stream>>>(A->row_ptr, A->col_idx, A->vals, A->rowblk, (int)A->n_blocks, (int)A->n_rows, cap,
+                    x1, alpha, gamma, z, y, xdot, dot_out, partials, counter, done);
+            } else {
+                PSFEM_CUDA_CHECK(cudaFuncSetAttribute(spmv2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+                spmv2_kernel<false><<<(unsigned)grid, SPMV2_THREADS, smem2, stream>>>(A->row_ptr, A->col_idx, A->vals, A->rowblk, (int)A->n_blocks, (int)A->n_rows, cap,
+                    x1, alpha, gamma, z, y, xdot, dot_out, partials, counter, done);
+            }
+            PSFEM_LAUNCH_CHECK();
+            return PSFEM_OK;
+        }
+    }
 #define PSFEM_SPMV_LAUNCH(D, O)                                                                                      \
     do {                                                                                                             \
         if (smem > 48 * 1024)                                                                                        \
