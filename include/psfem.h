@@ -107,36 +107,38 @@ int psfem_assemble(const double *d_nodes, const int32_t *d_conn, int64_t nel, in
                    const int32_t *d_perm, double *d_K_vals, double *d_M_vals,
                    void *d_ws, size_t ws_bytes, int64_t *h_bad_element, void *stream);
 
-/* ---- tile-fused numeric assembly for T3 / Q4 (the fast path of the two calls above) ----------
- * A CTA owns a tile of tile_nodes_R (32..256) node rows that are neighbours in space (Morton order of
- * the coordinates): every element touching the tile is computed once into shared memory, then one
- * thread per CSR node pair sums its contributions in ascending element id and writes the CSR values
- * once.  psfem_tileplan_build derives the tiles from the coordinates and the pattern plan
- * (d_node_ptr / d_pair_ptr / d_perm of psfem_pattern_*), re-ordered tile by tile, padded and 16-byte
- * aligned so that a CTA receives its whole plan through a few bulk async copies:
- *   d_tile_nodes    n_nodes            node ids sorted by (tile, id); tile t = entries [t*R, (t+1)*R)
- *   d_tile_elem_ptr n_tiles+1          n_tiles = ceil(n_nodes / R)
- *   d_tile_elems    nel*npe            (upper bound) element ids of every tile, ascending; h_info[0] used
- *   d_tile_hdr      8*n_tiles          {e0, ne, q0, npairs, c0, ncodes, nn, 0} per tile
- *   d_tile_conn     4*nel*npe          (upper bound) int4 connectivity of every tile element
- *   d_nmeta         2*n_tiles*R        {first CSR pair of the node, pair prefix inside its tile}
- *   d_tp_cnt        n_pairs+16*n_tiles uint8 contributions per pair, tile order, tiles padded to 16
- *   d_tcodes        nel*npe^2+8*n_tiles uint16 codes slot*16 + i*npe + j, tile order, tiles padded to 8
- *   h_info[6]       {tile elements used, max elements, max pairs, max codes per tile, usable (1/0), mean elements}
- * The kernel is persistent and software pipelined (cp.async coordinate gathers + TMA bulk copies of the
- * plan, one tile ahead).  Summation order per CSR entry is that of psfem_assemble (ascending element id).
+/* ---- tile-fused numeric assembly for T3 / Q4 (the fast path of psfem_assemble) ------------------
+ * A CTA owns a tile of tile_nodes_R (even, 32..256) node rows that are neighbours in space (Morton order
+ * of the coordinates, so any mesh tiles well).  Every element touching the tile is computed once, in
+ * registers; the tile's block of CSR values lives in shared memory and the elements add their matrix rows
+ * into it in rounds (round r of a node = its r-th incident element in ascending id: all rows of a round
+ * belong to distinct nodes, so it is race-free without atomics, and every entry is summed in ascending
+ * element id like Polygones.py:717-726 => bit-reproducible); the finished rows are written to HBM once.  The kernel is persistent and software pipelined (cp.async coordinate gathers + TMA bulk
+ * copies of the plan, one tile ahead).
+ * psfem_tileplan_build derives the plan from the coordinates, the connectivity and the CSR pattern
+ * (d_node_ptr of psfem_pattern_fill, d_col_idx):
+ *   d_tile_nodes    n_nodes       node ids sorted by (tile, id); tile t = entries [t*R, (t+1)*R)
+ *   d_tile_elem_ptr n_tiles+1     n_tiles = ceil(n_nodes / R)
+ *   d_tile_elems    nel*npe       (upper bound) element ids per tile, ascending; h_info[0] used
+ *   d_tile_hdr      8*n_tiles     {e0, ne, nn, npairs, nrounds, 0,0,0}
+ *   d_tile_conn     4*nel*npe     (upper bound) int4 connectivity of every tile element; bits 28..31 of
+ *                                 entry i = scatter round of row i (15 = row node not owned by the tile)
+ *   d_tile_off      16*nel*npe    (upper bound) u16 tile-local CSR pair of block (i,j); 0xFFFF = row not owned
+ *   d_nmeta         2*n_tiles*R   {first CSR pair of the node, pair prefix inside its tile}
+ *   h_info[6]       {tile elements used, max elements, max pairs, max rounds per tile, usable (1/0), mean elements}
+ * Same summation order as psfem_assemble (ascending element id).
  * Work space of psfem_assemble_tiled: 16 bytes. */
 int psfem_tileplan_workspace(int64_t nel, int npe, int64_t n_nodes, int tile_nodes_R, size_t *bytes);
 int psfem_tileplan_build(const double *d_nodes, const int32_t *d_conn, int64_t nel, int npe, int64_t n_nodes,
-                         int tile_nodes_R, int64_t n_pairs, const int32_t *d_node_ptr, const int32_t *d_pair_ptr,
-                         const int32_t *d_perm, int32_t *d_tile_nodes, int32_t *d_tile_elem_ptr, int32_t *d_tile_elems,
-                         int32_t *d_tile_hdr, int32_t *d_tile_conn, int32_t *d_nmeta, uint8_t *d_tp_cnt,
-                         uint16_t *d_tcodes, int64_t *h_info, void *d_ws, size_t ws_bytes, void *stream);
+                         int tile_nodes_R, const int32_t *d_node_ptr, const int32_t *d_col_idx,
+                         int32_t *d_tile_nodes, int32_t *d_tile_elem_ptr, int32_t *d_tile_elems, int32_t *d_tile_hdr,
+                         int32_t *d_tile_conn, uint16_t *d_tile_off, int32_t *d_nmeta, int64_t *h_info,
+                         void *d_ws, size_t ws_bytes, void *stream);
 int psfem_assemble_tiled(const double *d_nodes, int64_t nel, int etype, int64_t n_nodes,
                          double E, double nu, double rho, double t, int what, int tile_nodes_R,
                          const int64_t *h_plan_info, const int32_t *d_tile_hdr, const int32_t *d_tile_conn,
-                         const int32_t *d_tile_elems, const int32_t *d_nmeta, const uint8_t *d_tp_cnt,
-                         const uint16_t *d_tcodes, double *d_K_vals, double *d_M_vals, void *d_ws, size_t ws_bytes,
+                         const uint16_t *d_tile_off, const int32_t *d_tile_elems, const int32_t *d_nmeta,
+                         double *d_K_vals, double *d_M_vals, void *d_ws, size_t ws_bytes,
                          int64_t *h_bad_element, void *stream);
 
 /* element matrices only: Polygones.element_stiffness_matrix :566, element_mass_matrix :1250.

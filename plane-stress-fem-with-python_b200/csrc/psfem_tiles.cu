@@ -5,19 +5,22 @@
 // set-up (profiles/r1a_summary.md).  Here a CTA owns a TILE of node rows that are close in space
 // (consecutive nodes of a Morton ordering of the coordinates, so the tiling works for any mesh, not
 // only structured ones):
-//   phase 1  one thread per element touching the tile: Ke (symmetric 2x2-block form) / Me computed ONCE
-//            per tile into shared memory (elements on tile borders are recomputed by the neighbour tile:
-//            (9*17)/(8*16) = 1.2x for a structured Q4 mesh and 128-node tiles);
-//   phase 2  one thread per CSR node pair of the tile: sums its contributions from shared memory in
-//            ascending element id (same deterministic order as v1 / as Polygones.py:717) and writes the
-//            four CSR values exactly once, in runs of consecutive rows (coalesced).
+//   phase 1  one thread per element touching the tile: the gradient products of Ke / Me are computed ONCE
+//            per tile and stay in registers (elements on tile borders are recomputed by the neighbour
+//            tile: (9*17)/(8*16) = 1.2x for a structured Q4 mesh and 128-node tiles);
+//   scatter  the tile's block of CSR values lives in shared memory; elements add their matrix rows into it
+//            in ROUNDS: round r of a node is its r-th incident element (ascending id), so all rows added
+//            in one round belong to distinct nodes -- plain read-modify-write is race-free, every thread
+//            is busy in every round, and each entry is summed in ascending element id (reference order);
+//   copy-out the finished rows go to HBM exactly once, in runs of consecutive rows (coalesced).
 // No atomics, no intermediate HBM round trip.  The kernel is persistent (2 CTAs per SM) and software
 // pipelined: while tile i is computed, the coordinates of tile i+1 are gathered into shared memory with
-// cp.async, its plan (pair counts, contribution codes, row offsets) arrives by bulk async copies (TMA)
+// cp.async, its plan (scatter offsets, row offsets) arrives by bulk async copies (TMA)
 // on an mbarrier, and the connectivity of tile i+2 / the header of tile i+3 are already in registers --
 // so no global-memory latency sits on the critical path.  The symbolic side (psfem_tileplan_build)
 // derives the tiles and stores each tile's plan contiguously and 16-byte aligned for those copies.
 #include <cstdlib>
+#include <type_traits>
 #include <cub/cub.cuh>
 #include "psfem_common.cuh"
 
@@ -114,93 +117,134 @@ __global__ void unpack_elems_kernel(const unsigned long long *__restrict__ ukeys
     if (i < n) tile_elems[i] = (int32_t)(ukeys[i] & 0xffffffffull);
 }
 
-// per tile-ordered node u (a = tile_nodes[u]): number of CSR pairs (degree) and of contributions
+// per tile-ordered node u (a = tile_nodes[u]): number of CSR pairs (degree)
 __global__ void tnode_counts_kernel(int64_t n_nodes, const int32_t *__restrict__ tile_nodes, const int32_t *__restrict__ node_ptr,
-                                    const int32_t *__restrict__ pair_ptr, int32_t *__restrict__ deg, int32_t *__restrict__ ncodes) {
+                                    int32_t *__restrict__ deg) {
     int64_t u = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (u > n_nodes) return;
-    if (u == n_nodes) { deg[u] = 0; ncodes[u] = 0; return; }
-    const int a = tile_nodes[u];
-    const int p0 = node_ptr[a], p1 = node_ptr[a + 1];
-    deg[u] = p1 - p0;
-    ncodes[u] = pair_ptr[p1] - pair_ptr[p0];
+    deg[u] = (u == n_nodes) ? 0 : node_ptr[tile_nodes[u] + 1] - node_ptr[tile_nodes[u]];
 }
 
-// padded per-tile sizes (pairs to a multiple of 16 bytes of uint8, codes to 16 bytes of uint16) + maxima
-__global__ void tile_sizes_kernel(int32_t n_tiles, int64_t n_nodes, int R, const int32_t *__restrict__ gp, const int32_t *__restrict__ gc,
-                                  const int32_t *__restrict__ tile_elem_ptr, int32_t *__restrict__ qsz, int32_t *__restrict__ csz,
-                                  int *__restrict__ maxima) {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t > n_tiles) return;
-    if (t == n_tiles) { qsz[t] = 0; csz[t] = 0; return; }
-    const int64_t u0 = (int64_t)t * R, u1 = (u0 + R < n_nodes) ? u0 + R : n_nodes;
-    const int np = gp[u1] - gp[u0], nc = gc[u1] - gc[u0];
-    qsz[t] = (np + 15) & ~15;
-    csz[t] = (nc + 7) & ~7;
-    atomicMax(maxima + 0, tile_elem_ptr[t + 1] - tile_elem_ptr[t]);
-    atomicMax(maxima + 1, np);
-    atomicMax(maxima + 2, nc);
-}
-
-__global__ void tile_hdr_kernel(int32_t n_tiles, int64_t n_nodes, int R, const int32_t *__restrict__ gp, const int32_t *__restrict__ gc,
-                                const int32_t *__restrict__ tile_elem_ptr, const int32_t *__restrict__ q0, const int32_t *__restrict__ c0,
-                                int32_t *__restrict__ hdr) {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_tiles) return;
-    const int64_t u0 = (int64_t)t * R, u1 = (u0 + R < n_nodes) ? u0 + R : n_nodes;
-    int32_t *h = hdr + 8ll * t;
-    h[0] = tile_elem_ptr[t]; h[1] = tile_elem_ptr[t + 1] - tile_elem_ptr[t];
-    h[2] = q0[t]; h[3] = gp[u1] - gp[u0];
-    h[4] = c0[t]; h[5] = gc[u1] - gc[u0];
-    h[6] = (int)(u1 - u0); h[7] = 0;
-}
-
-// tile-ordered compact plan of one node: nmeta = {first CSR pair of the node, pair prefix inside the tile},
-// tp_cnt[q] = contributions of pair q (uint8), tcodes = slot*16 + i*npe + j (uint16)
-__global__ void tmeta_fill_kernel(int64_t n_nodes, int npe2, int R, const int32_t *__restrict__ tile_nodes,
-                                  const int32_t *__restrict__ node_ptr, const int32_t *__restrict__ pair_ptr,
-                                  const int32_t *__restrict__ perm, const int32_t *__restrict__ tile_elem_ptr,
-                                  const int32_t *__restrict__ tile_elems, const int32_t *__restrict__ gp, const int32_t *__restrict__ gc,
-                                  const int32_t *__restrict__ q0, const int32_t *__restrict__ c0, int2 *__restrict__ nmeta,
-                                  uint8_t *__restrict__ tp_cnt, uint16_t *__restrict__ tcodes, int *__restrict__ flags) {
+// nmeta[u] = {first CSR pair of the node (global), pair prefix inside its tile}
+__global__ void nmeta_kernel(int64_t n_nodes, int R, const int32_t *__restrict__ tile_nodes, const int32_t *__restrict__ node_ptr,
+                             const int32_t *__restrict__ gp, int2 *__restrict__ nmeta) {
     int64_t u = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (u >= n_nodes) return;
-    const int t = (int)(u / R);
+    const int64_t u0 = (u / R) * R;
+    nmeta[u] = make_int2(node_ptr[tile_nodes[u]], gp[u] - gp[u0]);
+}
+
+__device__ __forceinline__ int find_sorted(const int32_t *__restrict__ a, int n, int key) {  // index of key in sorted a[0..n), or -1
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (a[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    return (lo < n && a[lo] == key) ? lo : -1;
+}
+
+// Scatter rounds of one tile.  Element e adds row i of its matrix (the 2x2 blocks (i, j=0..npe-1)) to the
+// CSR rows of node a = conn[e][i].  Rows of the same node must not be added concurrently, so every owned
+// node hands out round numbers to its incident (element, i) items in ASCENDING ELEMENT ID: round r of
+// node a is its r-th incident element.  All items of one round touch distinct nodes => race-free plain
+// read-modify-write, all threads busy in every round (one row per element per round on a structured
+// mesh), and each CSR entry is summed in ascending element id -- the order of Polygones.py:717-726.
+// The round of (e,i) is packed into the 4 spare high bits of the node id in tile_conn (0xF = row not owned).
+template <int NPE>
+__global__ void tile_rounds_kernel(int32_t n_tiles, int64_t n_nodes, int R, const int32_t *__restrict__ tile_nodes,
+                                   const int32_t *__restrict__ tile_elem_ptr, const int32_t *__restrict__ tile_elems,
+                                   const int32_t *__restrict__ conn, const int32_t *__restrict__ gp, int4 *__restrict__ tile_conn,
+                                   int32_t *__restrict__ hdr, int *__restrict__ flags) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tiles) return;
     const int64_t u0 = (int64_t)t * R;
-    const int a = tile_nodes[u];
-    const int e0 = tile_elem_ptr[t], e1 = tile_elem_ptr[t + 1];
-    const int p0 = node_ptr[a], p1 = node_ptr[a + 1];
-    nmeta[u] = make_int2(p0, gp[u] - gp[u0]);
-    int q = q0[t] + (gp[u] - gp[u0]), c = c0[t] + (gc[u] - gc[u0]);
-    for (int s = p0; s < p1; ++s) {
-        const int k0 = pair_ptr[s], k1 = pair_ptr[s + 1];
-        if (k1 - k0 > 255) atomicExch(flags, 1);
-        tp_cnt[q++] = (uint8_t)(k1 - k0);
-        for (int k = k0; k < k1; ++k) {
-            const int code = perm[k];
-            const int e = code / npe2, ij = code - e * npe2;
-            int lo = e0, hi = e1;
-            while (lo < hi) {
-                int mid = (lo + hi) >> 1;
-                if (tile_elems[mid] < e) lo = mid + 1; else hi = mid;
+    const int nn = (int)((n_nodes - u0) < R ? (n_nodes - u0) : R);
+    const int32_t *tn = tile_nodes + u0;
+    const int e0 = tile_elem_ptr[t], ne = tile_elem_ptr[t + 1] - e0;
+    uint8_t cnt[256];
+    for (int s = 0; s < nn; ++s) cnt[s] = 0;
+    int nrounds = 0;
+    for (int k = 0; k < ne; ++k) {
+        const int32_t *c = conn + (int64_t)tile_elems[e0 + k] * NPE;
+        int v[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int i = 0; i < NPE; ++i) {
+            const int s = find_sorted(tn, nn, c[i]);
+            int r = 15;
+            if (s >= 0) {
+                r = cnt[s]++;
+                if (r >= 15) { atomicExch(flags, 1); r = 14; }
+                if (r + 1 > nrounds) nrounds = r + 1;
             }
-            tcodes[c++] = (uint16_t)((lo - e0) * 16 + ij);
+            v[i] = (int)((uint32_t)c[i] | ((uint32_t)r << 28));
+        }
+        tile_conn[e0 + k] = make_int4(v[0], v[1], v[2], v[3]);
+    }
+    int32_t *h = hdr + 8ll * t;
+    h[0] = e0; h[1] = ne; h[2] = nn; h[3] = gp[u0 + nn] - gp[u0]; h[4] = nrounds; h[5] = 0; h[6] = 0; h[7] = 0;
+}
+
+// per tile element: connectivity and, for every (i,j), the tile-local CSR pair index its 2x2 block adds to
+// (0xFFFF when row node i is not owned by the tile)
+template <int NPE>
+__global__ void tile_scatter_plan_kernel(int32_t n_tiles, int64_t n_nodes, int R, const int32_t *__restrict__ tile_nodes,
+                                         const int32_t *__restrict__ tile_elem_ptr, const int32_t *__restrict__ sorted_elems,
+                                         const int32_t *__restrict__ conn, const int32_t *__restrict__ node_ptr,
+                                         const int32_t *__restrict__ col_idx, const int32_t *__restrict__ gp,
+                                         uint16_t *__restrict__ tile_off) {
+    // one thread per (tile element); the tile is found by binary search on tile_elem_ptr
+    int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int n_te = tile_elem_ptr[n_tiles];
+    if (k >= n_te) return;
+    int lo = 0, hi = n_tiles;   // last t with tile_elem_ptr[t] <= k
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (tile_elem_ptr[mid] <= k) lo = mid; else hi = mid;
+    }
+    const int t = lo;
+    const int64_t u0 = (int64_t)t * R;
+    const int nn = (int)((n_nodes - u0) < R ? (n_nodes - u0) : R);
+    const int32_t *tn = tile_nodes + u0;
+    const int32_t *c = conn + (int64_t)sorted_elems[k] * NPE;
+    int nd[NPE];
+#pragma unroll
+    for (int i = 0; i < NPE; ++i) nd[i] = c[i];
+    uint16_t *o = tile_off + 16 * k;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) o[q] = 0xFFFF;
+#pragma unroll
+    for (int i = 0; i < NPE; ++i) {
+        const int s = find_sorted(tn, nn, nd[i]);
+        if (s < 0) continue;
+        const int pfx = gp[u0 + s] - gp[u0];
+        const int p0 = node_ptr[nd[i]], deg = node_ptr[nd[i] + 1] - p0;
+#pragma unroll
+        for (int j = 0; j < NPE; ++j) {
+            // position of node nd[j] among the column nodes of row node nd[i]: columns 2b of DOF row 2a
+            int l = 0, h = deg;
+            const int32_t *cols = col_idx + 4ll * p0;   // row 2a: 2*deg entries {2b, 2b+1}
+            const int want = 2 * nd[j];
+            while (l < h) {
+                int mid = (l + h) >> 1;
+                if (cols[2 * mid] < want) l = mid + 1; else h = mid;
+            }
+            o[i * NPE + j] = (uint16_t)(pfx + l);
         }
     }
 }
 
-template <int NPE>
-__global__ void tile_conn_kernel(int32_t n, const int32_t *__restrict__ tile_elems, const int32_t *__restrict__ conn, int4 *__restrict__ tile_conn) {
-    int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    const int32_t *c = conn + (int64_t)tile_elems[k] * NPE;
-    tile_conn[k] = make_int4(c[0], c[1], c[2], NPE == 4 ? c[NPE - 1] : 0);
+__global__ void tile_max_kernel(int32_t n_tiles, const int32_t *__restrict__ hdr, int *__restrict__ maxima) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tiles) return;
+    atomicMax(maxima + 0, hdr[8ll * t + 1]);
+    atomicMax(maxima + 1, hdr[8ll * t + 3]);
+    atomicMax(maxima + 2, hdr[8ll * t + 4]);
 }
 
 struct TileWs {
     unsigned long long *box, *k64a, *k64b;
     uint32_t *k32a, *k32b;
-    int32_t *v32a, *v32b, *tile_of, *deg, *ncd, *gp, *gc, *qsz, *csz, *q0, *c0;
+    int32_t *v32a, *v32b, *tile_of, *deg, *gp;
     int *scal;
     void *cub_tmp;
     size_t cub_bytes, total;
@@ -220,7 +264,7 @@ size_t tile_cub_bytes(int64_t n_nodes, int64_t ninc) {
     return align_up(r > d ? r : d) + 256;
 }
 
-TileWs carve_tiles(void *ws, int64_t n_nodes, int64_t ninc, int64_t n_tiles) {
+TileWs carve_tiles(void *ws, int64_t n_nodes, int64_t ninc) {
     TileWs w;
     Carver c(ws);
     w.box = c.take<unsigned long long>(4);
@@ -232,13 +276,7 @@ TileWs carve_tiles(void *ws, int64_t n_nodes, int64_t ninc, int64_t n_tiles) {
     w.v32b = c.take<int32_t>(n_nodes);
     w.tile_of = c.take<int32_t>(n_nodes);
     w.deg = c.take<int32_t>(n_nodes + 1);
-    w.ncd = c.take<int32_t>(n_nodes + 1);
     w.gp = c.take<int32_t>(n_nodes + 1);
-    w.gc = c.take<int32_t>(n_nodes + 1);
-    w.qsz = c.take<int32_t>(n_tiles + 1);
-    w.csz = c.take<int32_t>(n_tiles + 1);
-    w.q0 = c.take<int32_t>(n_tiles + 1);
-    w.c0 = c.take<int32_t>(n_tiles + 1);
     w.scal = c.take<int>(8);
     w.cub_bytes = tile_cub_bytes(n_nodes, ninc);
     w.cub_tmp = c.take<char>(w.cub_bytes);
@@ -253,145 +291,116 @@ struct Mat {
     double d00, d01, d22, t, rho;
 };
 
-// upper-triangular block index of (i,j), i<=j, for NPE nodes
 template <int NPE> __host__ __device__ constexpr int tri_index(int i, int j) { return i * NPE - (i * (i - 1)) / 2 + (j - i); }
 
-template <int NPE> struct TileLayout {
-    static constexpr int NB = NPE * (NPE + 1) / 2;                  // stored blocks per element
-    static constexpr int K_STRIDE = NB * 4 + 2;                      // doubles per element (padded: odd number of 16-byte units)
-    static constexpr int M_STRIDE = NB + 1;
-};
-
-// Q4 element stiffness / mass in symmetric block form.  Same arithmetic as gauss_kernel (Polygones.py:582-595,
-// :657-708, :1266-1291) with the element computed once: per Gauss point the 36 gradient products
-// Gxx(i<=j), Gyy(i<=j), Gxy(i,j) are accumulated, D is applied once at the end.
-template <bool DO_K, bool DO_M>
-__device__ __forceinline__ bool q4_element(const double2 (&p)[4], const Mat &mat, double *__restrict__ kout, double *__restrict__ mout) {
-    constexpr double A = 0.7745966692414834;  // sqrt(0.6)  (Polygones.py:549)
-    const double gp[3] = {-A, 0.0, A};
-    const double gw[3] = {5.0 / 9, 8.0 / 9, 5.0 / 9};
-    const double sx[4] = {-1, 1, 1, -1}, sy[4] = {-1, -1, 1, 1};
+// Q4: gradient products of the element, integrated with the 3x3 rule.  Same arithmetic as gauss_kernel
+// (Polygones.py:582-595, :657-708, :1266-1291) with the element computed once; D is applied when a 2x2
+// block is scattered.
+template <bool DO_K, bool DO_M> struct ElemQ4 {
     double gxx[10], gyy[10], gxy[16], mm[10];
+    __device__ __forceinline__ bool compute(const double2 (&p)[4], const Mat &mat) {
+        constexpr double A = 0.7745966692414834;  // sqrt(0.6)  (Polygones.py:549)
+        const double gp[3] = {-A, 0.0, A};
+        const double gw[3] = {5.0 / 9, 8.0 / 9, 5.0 / 9};
+        const double sx[4] = {-1, 1, 1, -1}, sy[4] = {-1, -1, 1, 1};
 #pragma unroll
-    for (int q = 0; q < 10; ++q) { gxx[q] = 0; gyy[q] = 0; mm[q] = 0; }
+        for (int q = 0; q < 10; ++q) { gxx[q] = 0; gyy[q] = 0; mm[q] = 0; }
 #pragma unroll
-    for (int q = 0; q < 16; ++q) gxy[q] = 0;
-    bool ok = true;
+        for (int q = 0; q < 16; ++q) gxy[q] = 0;
+        bool ok = true;
 #pragma unroll
-    for (int r = 0; r < 3; ++r) {      // eta (outer, Polygones.py:551-553)
+        for (int r = 0; r < 3; ++r) {      // eta (outer, Polygones.py:551-553)
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {  // xi
-            const double xi = gp[c], eta = gp[r];
-            double dnx[4], dne[4], nn[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                dnx[i] = sx[i] * (1 + sy[i] * eta) / 4;
-                dne[i] = sy[i] * (1 + sx[i] * xi) / 4;
-                nn[i] = (1 + sx[i] * xi) * (1 + sy[i] * eta) / 4;
-            }
-            double j00 = 0, j01 = 0, j10 = 0, j11 = 0;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                j00 += dnx[i] * p[i].x; j01 += dnx[i] * p[i].y;
-                j10 += dne[i] * p[i].x; j11 += dne[i] * p[i].y;
-            }
-            const double detJ = j00 * j11 - j01 * j10;
-            const double ad = fabs(detJ);
-            if (ad < 1e-10) ok = false;  // Polygones.py:686-687
-            const double w = gw[r] * gw[c];
-            if (DO_K) {
-                const double inv = 1.0 / detJ;
-                const double pp = j11 * inv, qq = -j01 * inv, rr = -j10 * inv, ss = j00 * inv;
-                const double cc = w * ad * mat.t;
-                double dx[4], dy[4], cx[4], cy[4];
+            for (int c = 0; c < 3; ++c) {  // xi
+                const double xi = gp[c], eta = gp[r];
+                double dnx[4], dne[4], nn[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    dx[i] = pp * dnx[i] + qq * dne[i];
-                    dy[i] = rr * dnx[i] + ss * dne[i];
-                    cx[i] = cc * dx[i];
-                    cy[i] = cc * dy[i];
+                    dnx[i] = sx[i] * (1 + sy[i] * eta) / 4;
+                    dne[i] = sy[i] * (1 + sx[i] * xi) / 4;
+                    nn[i] = (1 + sx[i] * xi) * (1 + sy[i] * eta) / 4;
                 }
+                double j00 = 0, j01 = 0, j10 = 0, j11 = 0;
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
+                for (int i = 0; i < 4; ++i) {
+                    j00 += dnx[i] * p[i].x; j01 += dnx[i] * p[i].y;
+                    j10 += dne[i] * p[i].x; j11 += dne[i] * p[i].y;
+                }
+                const double detJ = j00 * j11 - j01 * j10;
+                const double ad = fabs(detJ);
+                if (ad < 1e-10) ok = false;  // Polygones.py:686-687
+                const double w = gw[r] * gw[c];
+                if (DO_K) {
+                    const double inv = 1.0 / detJ;
+                    const double pp = j11 * inv, qq = -j01 * inv, rr = -j10 * inv, ss = j00 * inv;
+                    const double cc = w * ad * mat.t;
+                    double dx[4], dy[4], cx[4], cy[4];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        if (j >= i) {
-                            gxx[tri_index<4>(i, j)] += cx[i] * dx[j];
-                            gyy[tri_index<4>(i, j)] += cy[i] * dy[j];
-                        }
-                        gxy[i * 4 + j] += cx[i] * dy[j];
+                    for (int i = 0; i < 4; ++i) {
+                        dx[i] = pp * dnx[i] + qq * dne[i];
+                        dy[i] = rr * dnx[i] + ss * dne[i];
+                        cx[i] = cc * dx[i];
+                        cy[i] = cc * dy[i];
                     }
-            }
-            if (DO_M) {
-                const double cm = w * mat.rho * mat.t * ad;
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
+                    for (int i = 0; i < 4; ++i)
 #pragma unroll
-                    for (int j = i; j < 4; ++j) mm[tri_index<4>(i, j)] += (cm * nn[i]) * nn[j];
+                        for (int j = 0; j < 4; ++j) {
+                            if (j >= i) {
+                                gxx[tri_index<4>(i, j)] += cx[i] * dx[j];
+                                gyy[tri_index<4>(i, j)] += cy[i] * dy[j];
+                            }
+                            gxy[i * 4 + j] += cx[i] * dy[j];
+                        }
+                }
+                if (DO_M) {
+                    const double cm = w * mat.rho * mat.t * ad;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int j = i; j < 4; ++j) mm[tri_index<4>(i, j)] += (cm * nn[i]) * nn[j];
+                }
             }
         }
+        return ok;
     }
-    if (DO_K) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = i; j < 4; ++j) {
-                const int b = tri_index<4>(i, j);
-                double *o = kout + 4 * b;
-                o[0] = mat.d00 * gxx[b] + mat.d22 * gyy[b];                    // K(2i,2j)
-                o[1] = mat.d01 * gxy[i * 4 + j] + mat.d22 * gxy[j * 4 + i];    // K(2i,2j+1)
-                o[2] = mat.d01 * gxy[j * 4 + i] + mat.d22 * gxy[i * 4 + j];    // K(2i+1,2j)
-                o[3] = mat.d00 * gyy[b] + mat.d22 * gxx[b];                    // K(2i+1,2j+1)
-            }
+    // {K(2i,2j), K(2i,2j+1), K(2i+1,2j), K(2i+1,2j+1)}
+    __device__ __forceinline__ double4 kblock(int i, int j, const Mat &mat) const {
+        const int b = i <= j ? tri_index<4>(i, j) : tri_index<4>(j, i);
+        return make_double4(mat.d00 * gxx[b] + mat.d22 * gyy[b], mat.d01 * gxy[i * 4 + j] + mat.d22 * gxy[j * 4 + i],
+                            mat.d01 * gxy[j * 4 + i] + mat.d22 * gxy[i * 4 + j], mat.d00 * gyy[b] + mat.d22 * gxx[b]);
     }
-    if (DO_M) {
-#pragma unroll
-        for (int b = 0; b < 10; ++b) mout[b] = mm[b];
-    }
-    return ok;
-}
+    __device__ __forceinline__ double mval(int i, int j) const { return mm[i <= j ? tri_index<4>(i, j) : tri_index<4>(j, i)]; }
+};
 
 // T3 closed form (Polygones.py:840-883, :1218-1235), signed area
-template <bool DO_K, bool DO_M>
-__device__ __forceinline__ bool t3_element(const double2 (&p)[3], const Mat &mat, double *__restrict__ kout, double *__restrict__ mout) {
-    const double delta = p[0].x * (p[1].y - p[2].y) + p[1].x * (p[2].y - p[0].y) + p[2].x * (p[0].y - p[1].y);
-    const double vol = 0.5 * delta * mat.t;
-    if (DO_K) {
-        double b[3], g[3];
+template <bool DO_K, bool DO_M> struct ElemT3 {
+    double b[3], g[3], vol, mbase;
+    __device__ __forceinline__ bool compute(const double2 (&p)[3], const Mat &mat) {
+        const double delta = p[0].x * (p[1].y - p[2].y) + p[1].x * (p[2].y - p[0].y) + p[2].x * (p[0].y - p[1].y);
+        vol = 0.5 * delta * mat.t;
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
             b[i] = (p[(i + 1) % 3].y - p[(i + 2) % 3].y) / delta;
             g[i] = (p[(i + 2) % 3].x - p[(i + 1) % 3].x) / delta;
         }
-#pragma unroll
-        for (int i = 0; i < 3; ++i)
-#pragma unroll
-            for (int j = i; j < 3; ++j) {
-                double *o = kout + 4 * tri_index<3>(i, j);
-                o[0] = (mat.d00 * b[i] * b[j] + mat.d22 * g[i] * g[j]) * vol;
-                o[1] = (mat.d01 * b[i] * g[j] + mat.d22 * g[i] * b[j]) * vol;
-                o[2] = (mat.d01 * g[i] * b[j] + mat.d22 * b[i] * g[j]) * vol;
-                o[3] = (mat.d00 * g[i] * g[j] + mat.d22 * b[i] * b[j]) * vol;
-            }
+        mbase = mat.rho * vol / 12;
+        return true;
     }
-    if (DO_M) {
-        const double base = mat.rho * vol / 12;
-#pragma unroll
-        for (int i = 0; i < 3; ++i)
-#pragma unroll
-            for (int j = i; j < 3; ++j) mout[tri_index<3>(i, j)] = (i == j ? 2.0 : 1.0) * base;
+    __device__ __forceinline__ double4 kblock(int i, int j, const Mat &mat) const {
+        return make_double4((mat.d00 * b[i] * b[j] + mat.d22 * g[i] * g[j]) * vol, (mat.d01 * b[i] * g[j] + mat.d22 * g[i] * b[j]) * vol,
+                            (mat.d01 * g[i] * b[j] + mat.d22 * b[i] * g[j]) * vol, (mat.d00 * g[i] * g[j] + mat.d22 * b[i] * b[j]) * vol);
     }
-    return true;
-}
+    __device__ __forceinline__ double mval(int i, int j) const { return (i == j ? 2.0 : 1.0) * mbase; }
+};
 
 struct TilePlanDev {  // device pointers of the tile plan (see psfem_tileplan_build)
-    const int4 *hdr;        // 2 x int4 per tile: {e0, ne, q0, npairs}, {c0, ncodes, nn, 0}
-    const int4 *tile_conn;  // connectivity of every tile element (tile order)
-    const int2 *nmeta;      // n_tiles*R: {first CSR pair of the node, pair prefix inside the tile}
+    const int4 *hdr;            // 2 x int4 per tile: {e0, ne, nn, npairs}, {nrounds,0,0,0}
+    const int4 *tile_conn;      // connectivity of every tile element (ascending id); bits 28..31 = scatter round of row i
+    const uint16_t *tile_off;   // 16 x u16 per tile element: tile-local CSR pair of block (i,j), 0xFFFF = row not owned
+    const int2 *nmeta;          // n_tiles*R: {first CSR pair of the node, pair prefix inside the tile}
     const int32_t *tile_elems;  // element id of every tile element (error reporting only)
-    const uint8_t *tp_cnt;
-    const uint16_t *tcodes;
-    int R, max_elems, max_pairs, max_codes;
+    int R, max_elems, max_pairs;
 };
 
 __device__ __forceinline__ uint32_t t_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -410,32 +419,28 @@ __device__ __forceinline__ void t_mbar_wait(uint64_t *bar, uint32_t parity) {
     } while (!ok);
 }
 
-struct TileHdr { int e0, ne, q0, npairs, c0, ncodes, nn, pad; };
+struct TileHdr { int e0, ne, nn, npairs, nrounds; };
 
 template <int ETYPE, int NPE, bool DO_K, bool DO_M, int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB)
 assemble_tile_kernel(const double2 *__restrict__ nodes, Mat mat, int n_tiles, TilePlanDev tp, double *__restrict__ K_vals,
                      double *__restrict__ M_vals, unsigned long long *__restrict__ bad) {
-    using L = TileLayout<NPE>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint64_t meta_bar[2];
-    __shared__ int s_wsum[THREADS / 32 + 1];
     const int tid = threadIdx.x, R = tp.R;
     // ---- shared-memory carve-up (sizes from the plan's per-tile maxima; every region 16-byte aligned) ----
-    const int cap_e = (tp.max_elems + 1) & ~1, cap_p = (tp.max_pairs + 15) & ~15, cap_c = (tp.max_codes + 7) & ~7;
+    const int cap_e = tp.max_elems, cap_p = (tp.max_pairs + 15) & ~15;
     unsigned char *sp = smem_raw;
-    double *kb = reinterpret_cast<double *>(sp); sp += DO_K ? (size_t)cap_e * L::K_STRIDE * 8 : 0;
-    double *mb = reinterpret_cast<double *>(sp); sp += DO_M ? (((size_t)cap_e * L::M_STRIDE * 8 + 15) & ~(size_t)15) : 0;
-    double2 *xy_s[2]; int2 *nm_s[2]; uint8_t *cnt_s[2]; uint16_t *cod_s[2];
+    double *kbuf = reinterpret_cast<double *>(sp); sp += DO_K ? (size_t)cap_p * 32 : 0;   // 4 doubles per tile pair
+    double *mbuf = reinterpret_cast<double *>(sp); sp += DO_M ? (size_t)cap_p * 8 : 0;    // 1 double per tile pair
+    double2 *xy_s[2]; int2 *nm_s[2]; uint16_t *off_s[2];
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
         xy_s[s] = reinterpret_cast<double2 *>(sp); sp += (size_t)THREADS * NPE * 16;
         nm_s[s] = reinterpret_cast<int2 *>(sp); sp += (size_t)R * 8;
-        cnt_s[s] = sp; sp += cap_p;
-        cod_s[s] = reinterpret_cast<uint16_t *>(sp); sp += (size_t)cap_c * 2;
+        off_s[s] = reinterpret_cast<uint16_t *>(sp); sp += (size_t)cap_e * 32;
     }
-    int *s_coff = reinterpret_cast<int *>(sp); sp += (size_t)(cap_p + 4) * 4;
-    uint8_t *s_slot = sp;
+    uint8_t *s_slot = sp;   // node slot of every tile pair
 
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(t_smem_u32(&meta_bar[0])));
@@ -446,10 +451,10 @@ assemble_tile_kernel(const double2 *__restrict__ nodes, Mat mat, int n_tiles, Ti
     const int n_mine = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     auto tile_id = [&](int i) { return (int)blockIdx.x + i * (int)gridDim.x; };
     auto load_hdr = [&](int i) -> TileHdr {
-        TileHdr h = {0, 0, 0, 0, 0, 0, 0, 0};
+        TileHdr h = {0, 0, 0, 0, 0};
         if (i < n_mine) {
-            const int4 a = tp.hdr[2 * tile_id(i)], b = tp.hdr[2 * tile_id(i) + 1];
-            h.e0 = a.x; h.ne = a.y; h.q0 = a.z; h.npairs = a.w; h.c0 = b.x; h.ncodes = b.y; h.nn = b.z;
+            const int4 a = tp.hdr[2 * (size_t)tile_id(i)], b = tp.hdr[2 * (size_t)tile_id(i) + 1];
+            h.e0 = a.x; h.ne = a.y; h.nn = a.z; h.npairs = a.w; h.nrounds = b.x;
         }
         return h;
     };
@@ -461,18 +466,17 @@ assemble_tile_kernel(const double2 *__restrict__ nodes, Mat mat, int n_tiles, Ti
         if (i < n_mine) {
             if (tid < h.ne) {
                 double2 *dst = xy_s[stage] + (size_t)tid * NPE;
-                t_cp_async16(dst + 0, nodes + c.x);
-                t_cp_async16(dst + 1, nodes + c.y);
-                t_cp_async16(dst + 2, nodes + c.z);
-                if (NPE == 4) t_cp_async16(dst + 3, nodes + c.w);
+                t_cp_async16(dst + 0, nodes + (c.x & 0x0fffffff));
+                t_cp_async16(dst + 1, nodes + (c.y & 0x0fffffff));
+                t_cp_async16(dst + 2, nodes + (c.z & 0x0fffffff));
+                if (NPE == 4) t_cp_async16(dst + 3, nodes + (c.w & 0x0fffffff));
             }
             if (tid == 0) {
-                const uint32_t b_nm = (uint32_t)R * 8, b_cnt = (uint32_t)((h.npairs + 15) & ~15), b_cod = (uint32_t)((h.ncodes + 7) & ~7) * 2;
+                const uint32_t b_nm = (uint32_t)R * 8, b_off = (uint32_t)h.ne * 32;
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(t_smem_u32(&meta_bar[stage])), "r"(b_nm + b_cnt + b_cod) : "memory");
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(t_smem_u32(&meta_bar[stage])), "r"(b_nm + b_off) : "memory");
                 t_bulk_g2s(nm_s[stage], tp.nmeta + (size_t)tile_id(i) * R, b_nm, &meta_bar[stage]);
-                if (b_cnt) t_bulk_g2s(cnt_s[stage], tp.tp_cnt + h.q0, b_cnt, &meta_bar[stage]);
-                if (b_cod) t_bulk_g2s(cod_s[stage], tp.tcodes + h.c0, b_cod, &meta_bar[stage]);
+                if (b_off) t_bulk_g2s(off_s[stage], tp.tile_off + 16 * (size_t)h.e0, b_off, &meta_bar[stage]);
             }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
@@ -480,115 +484,110 @@ assemble_tile_kernel(const double2 *__restrict__ nodes, Mat mat, int n_tiles, Ti
 
     // ---- prologue: tile 0 staged, connectivity of tile 1 and headers up to tile 2 in registers ----
     TileHdr h0 = load_hdr(0), h1 = load_hdr(1), h2 = load_hdr(2);
+    auto rounds_of = [](const int4 &c) -> uint32_t {   // 4 x 4-bit scatter rounds of the element's rows
+        return ((uint32_t)c.x >> 28) | (((uint32_t)c.y >> 28) << 4) | (((uint32_t)c.z >> 28) << 8) | (((uint32_t)c.w >> 28) << 12);
+    };
     int4 conn_a = load_conn(h0);
     prefetch(0, 0, h0, conn_a);
+    uint32_t rnd_next = rounds_of(conn_a);
     conn_a = load_conn(h1);
 
     for (int i = 0; i < n_mine; ++i) {
         const int st = i & 1;
         // ---- software pipeline: inputs of tile i+1, connectivity of tile i+2, header of tile i+3 ----
         prefetch(i + 1, st ^ 1, h1, conn_a);
+        const uint32_t rnd_cur = rnd_next;
+        rnd_next = rounds_of(conn_a);
         const int4 conn_b = load_conn(h2);
         const TileHdr h3 = load_hdr(i + 3);
+        // zero the tile's CSR block while the inputs land
+        const int ne = h0.ne, nn = h0.nn, npairs = h0.npairs;
+        if (DO_K)
+            for (int q = tid; q < 2 * npairs; q += THREADS) reinterpret_cast<double2 *>(kbuf)[q] = make_double2(0.0, 0.0);
+        if (DO_M)
+            for (int q = tid; q < npairs; q += THREADS) mbuf[q] = 0.0;
         asm volatile("cp.async.wait_group 1;" ::: "memory");          // everything but the newest group: tile i is in
         t_mbar_wait(&meta_bar[st], (uint32_t)((i >> 1) & 1));
         __syncthreads();
-        const int ne = h0.ne, nn = h0.nn, npairs = h0.npairs;
         const double2 *xy = xy_s[st];
         const int2 *nm = nm_s[st];
-        const uint8_t *cnt = cnt_s[st];
-        const uint16_t *cod = cod_s[st];
-        // ---- phase 1: element matrices of the tile, each computed once ----
-        for (int slot = tid; slot < ne; slot += THREADS) {
-            double2 p[NPE];
-            if (slot < THREADS) {
-#pragma unroll
-                for (int q = 0; q < NPE; ++q) p[q] = xy[(size_t)slot * NPE + q];
-            } else {  // rare: a tile with more elements than threads reads the overflow directly
-                const int4 c = tp.tile_conn[h0.e0 + slot];
-                p[0] = nodes[c.x]; p[1] = nodes[c.y]; p[2] = nodes[c.z];
-                if (NPE == 4) p[NPE - 1] = nodes[c.w];
-            }
-            bool ok;
-            if (ETYPE == PSFEM_Q4)
-                ok = q4_element<DO_K, DO_M>(reinterpret_cast<const double2(&)[4]>(p), mat, kb + (size_t)slot * L::K_STRIDE, mb + (size_t)slot * L::M_STRIDE);
-            else
-                ok = t3_element<DO_K, DO_M>(reinterpret_cast<const double2(&)[3]>(p), mat, kb + (size_t)slot * L::K_STRIDE, mb + (size_t)slot * L::M_STRIDE);
-            if (!ok) atomicMin(bad, (unsigned long long)tp.tile_elems[h0.e0 + slot]);   // lowest failing element id, like Polygones.py:686-687
-        }
-        // node slot of every pair
+        const uint16_t *off = off_s[st];
+        // node slot of every pair (for the copy-out)
         for (int s = tid; s < nn; s += THREADS) {
             const int b0 = nm[s].y, b1 = (s + 1 < nn) ? nm[s + 1].y : npairs;
             for (int q = b0; q < b1; ++q) s_slot[q] = (uint8_t)s;
         }
-        // exclusive scan of the pair counts -> offset of every pair's codes (chunk per thread + block scan)
-        {
-            const int chunk = (npairs + THREADS - 1) / THREADS;
-            const int b0 = min(tid * chunk, npairs), b1 = min(b0 + chunk, npairs);
-            int sum = 0;
-            for (int q = b0; q < b1; ++q) sum += cnt[q];
-            int v = sum;
+        // ---- element pass(es): compute once, scatter row by row in rounds ----
+        for (int base = 0; base < ne; base += THREADS) {
+            const int slot = base + tid;
+            const bool active = slot < ne;
+            typename std::conditional<ETYPE == PSFEM_Q4, ElemQ4<DO_K, DO_M>, ElemT3<DO_K, DO_M>>::type el;
+            uint32_t rnd = 0xffffu;   // all rows "not owned"
+            if (active) {
+                double2 p[NPE];
+                if (base == 0) {
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                int u = __shfl_up_sync(0xffffffffu, v, o);
-                if ((tid & 31) >= o) v += u;
-            }
-            if ((tid & 31) == 31) s_wsum[tid >> 5] = v;
-            __syncthreads();
-            if (tid == 0) {
-                int run = 0;
-                for (int w = 0; w < THREADS / 32; ++w) { int x = s_wsum[w]; s_wsum[w] = run; run += x; }
-            }
-            __syncthreads();
-            int off = s_wsum[tid >> 5] + v - sum;
-            for (int q = b0; q < b1; ++q) { s_coff[q] = off; off += cnt[q]; }
-        }
-        __syncthreads();
-        // ---- phase 2: one thread per CSR node pair, everything but the output in shared memory ----
-        for (int idx = tid; idx < npairs; idx += THREADS) {
-            const int s = s_slot[idx];
-            const int2 m = nm[s];
-            const int pos = idx - m.y;
-            const int deg = ((s + 1 < nn) ? nm[s + 1].y : npairs) - m.y;
-            const int k0 = s_coff[idx], k1 = k0 + cnt[idx];
-            double a0 = 0, a1 = 0, a2 = 0, a3 = 0, mm = 0;
-            for (int k = k0; k < k1; ++k) {  // ascending element id
-                const int code = cod[k];
-                const int slot = code >> 4, ij = code & 15;
-                const int ii = ij / NPE, jj = ij - ii * NPE;
-                const bool up = ii <= jj;
-                const int b = up ? tri_index<NPE>(ii, jj) : tri_index<NPE>(jj, ii);
-                if (DO_K) {
-                    const double2 *src = reinterpret_cast<const double2 *>(kb + (size_t)slot * L::K_STRIDE + 4 * b);
-                    const double2 u = src[0], v = src[1];
-                    a0 += u.x; a3 += v.y;
-                    a1 += up ? u.y : v.x;   // transpose of the stored block when i > j
-                    a2 += up ? v.x : u.y;
+                    for (int q = 0; q < NPE; ++q) p[q] = xy[(size_t)slot * NPE + q];
+                    rnd = rnd_cur;
+                } else {  // rare: a tile with more elements than threads reads the overflow directly
+                    const int4 c = tp.tile_conn[h0.e0 + slot];
+                    p[0] = nodes[c.x & 0x0fffffff]; p[1] = nodes[c.y & 0x0fffffff]; p[2] = nodes[c.z & 0x0fffffff];
+                    if (NPE == 4) p[NPE - 1] = nodes[c.w & 0x0fffffff];
+                    rnd = rounds_of(c);
                 }
-                if (DO_M) mm += mb[(size_t)slot * L::M_STRIDE + b];
+                if (!el.compute(p, mat)) atomicMin(bad, (unsigned long long)tp.tile_elems[h0.e0 + slot]);  // lowest id, Polygones.py:686
             }
+            const uint16_t *o = off + 16 * (size_t)(active ? slot : 0);
+            for (int r = 0; r < h0.nrounds; ++r) {
+#pragma unroll
+                for (int ii = 0; ii < NPE; ++ii) {
+                    if (((rnd >> (4 * ii)) & 15u) == (uint32_t)r) {
+#pragma unroll
+                        for (int jj = 0; jj < NPE; ++jj) {
+                            const int q = o[ii * NPE + jj];
+                            if (DO_K) {
+                                const double4 v = el.kblock(ii, jj, mat);
+                                double2 *dst = reinterpret_cast<double2 *>(kbuf + 4 * (size_t)q);
+                                double2 a = dst[0], b = dst[1];
+                                a.x += v.x; a.y += v.y; b.x += v.z; b.y += v.w;
+                                dst[0] = a; dst[1] = b;
+                            }
+                            if (DO_M) mbuf[q] += el.mval(ii, jj);
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        if (h0.nrounds == 0) __syncthreads();
+        // ---- copy-out: every CSR value of the tile's rows is written exactly once ----
+        for (int q = tid; q < npairs; q += THREADS) {
+            const int s = s_slot[q];
+            const int2 m = nm[s];
+            const int pos = q - m.y;
+            const int deg = ((s + 1 < nn) ? nm[s + 1].y : npairs) - m.y;
             const int64_t r0 = 4ll * m.x + 2 * pos, r1 = r0 + 2 * deg;
             if (DO_K) {
-                *reinterpret_cast<double2 *>(K_vals + r0) = make_double2(a0, a1);
-                *reinterpret_cast<double2 *>(K_vals + r1) = make_double2(a2, a3);
+                const double2 *src = reinterpret_cast<const double2 *>(kbuf + 4 * (size_t)q);
+                *reinterpret_cast<double2 *>(K_vals + r0) = src[0];
+                *reinterpret_cast<double2 *>(K_vals + r1) = src[1];
             }
             if (DO_M) {
-                *reinterpret_cast<double2 *>(M_vals + r0) = make_double2(mm, 0.0);
-                *reinterpret_cast<double2 *>(M_vals + r1) = make_double2(0.0, mm);
+                const double mv = mbuf[q];
+                *reinterpret_cast<double2 *>(M_vals + r0) = make_double2(mv, 0.0);
+                *reinterpret_cast<double2 *>(M_vals + r1) = make_double2(0.0, mv);
             }
         }
-        __syncthreads();   // kb / s_coff / stage st are free again
+        __syncthreads();   // kbuf / mbuf / s_slot / stage st are free again
         h0 = h1; h1 = h2; h2 = h3; conn_a = conn_b;
     }
 }
 
 template <int NPE, bool DO_K, bool DO_M> size_t tile_smem_bytes(const TilePlanDev &tp, int threads) {
-    using L = TileLayout<NPE>;
-    const size_t cap_e = (tp.max_elems + 1) & ~1, cap_p = (tp.max_pairs + 15) & ~15, cap_c = (tp.max_codes + 7) & ~7;
-    size_t b = DO_K ? cap_e * L::K_STRIDE * 8 : 0;
-    b += DO_M ? ((cap_e * L::M_STRIDE * 8 + 15) & ~(size_t)15) : 0;
-    b += 2 * ((size_t)threads * NPE * 16 + (size_t)tp.R * 8 + cap_p + cap_c * 2);
-    b += (cap_p + 4) * 4 + cap_p + 16;
+    const size_t cap_e = tp.max_elems, cap_p = (tp.max_pairs + 15) & ~15;
+    size_t b = (DO_K ? cap_p * 32 : 0) + (DO_M ? cap_p * 8 : 0);
+    b += 2 * ((size_t)threads * NPE * 16 + (size_t)tp.R * 8 + cap_e * 32);
+    b += cap_p + 32;
     return b;
 }
 
@@ -616,18 +615,17 @@ int launch_tiles(const double *d_nodes, Mat mat, int64_t n_tiles, const TilePlan
 extern "C" int psfem_tileplan_workspace(int64_t nel, int npe, int64_t n_nodes, int tile_nodes_R, size_t *bytes) {
     PSFEM_REQUIRE(bytes && nel >= 0 && n_nodes > 0 && npe > 0 && tile_nodes_R >= 32, "tileplan_workspace: bad arguments");
     PSFEM_REQUIRE(nel * npe < (int64_t)INT32_MAX, "tileplan: nel*npe exceeds int32");
-    *bytes = carve_tiles(nullptr, n_nodes, nel * npe > 0 ? nel * npe : 1, ceil_div(n_nodes, tile_nodes_R)).total;
+    *bytes = carve_tiles(nullptr, n_nodes, nel * npe > 0 ? nel * npe : 1).total;
     return PSFEM_OK;
 }
 
 extern "C" int psfem_tileplan_build(const double *d_nodes, const int32_t *d_conn, int64_t nel, int npe, int64_t n_nodes,
-                                    int tile_nodes_R, int64_t n_pairs, const int32_t *d_node_ptr, const int32_t *d_pair_ptr,
-                                    const int32_t *d_perm, int32_t *d_tile_nodes /* n_nodes */,
-                                    int32_t *d_tile_elem_ptr /* n_tiles+1 */, int32_t *d_tile_elems /* nel*npe (upper bound) */,
-                                    int32_t *d_tile_hdr /* 8*n_tiles */, int32_t *d_tile_conn /* 4*nel*npe (upper bound) */,
-                                    int32_t *d_nmeta /* 2*n_tiles*R */, uint8_t *d_tp_cnt /* n_pairs + 16*n_tiles */,
-                                    uint16_t *d_tcodes /* nel*npe^2 + 8*n_tiles */,
-                                    int64_t *h_info /* tile elements, max elems, max pairs, max codes, usable, mean elems */,
+                                    int tile_nodes_R, const int32_t *d_node_ptr, const int32_t *d_col_idx,
+                                    int32_t *d_tile_nodes /* n_nodes */, int32_t *d_tile_elem_ptr /* n_tiles+1 */,
+                                    int32_t *d_tile_elems /* nel*npe (upper bound) */, int32_t *d_tile_hdr /* 8*n_tiles */,
+                                    int32_t *d_tile_conn /* 4*nel*npe (upper bound) */, uint16_t *d_tile_off /* 16*nel*npe (upper bound) */,
+                                    int32_t *d_nmeta /* 2*n_tiles*R */,
+                                    int64_t *h_info /* tile elements, max elems, max pairs, max colours, usable, mean elems */,
                                     void *d_ws, size_t ws_bytes, void *stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     PSFEM_REQUIRE(npe == 3 || npe == 4, "tileplan_build: tiled assembly covers T3 and Q4");
@@ -635,10 +633,9 @@ extern "C" int psfem_tileplan_build(const double *d_nodes, const int32_t *d_conn
     PSFEM_REQUIRE(h_info, "tileplan_build: null output");
     const int64_t ninc = nel * npe;
     PSFEM_REQUIRE(ninc > 0 && ninc < (int64_t)INT32_MAX, "tileplan_build: bad element count");
-    PSFEM_REQUIRE(nel * npe * npe + 8 * ceil_div(n_nodes, tile_nodes_R) < (int64_t)INT32_MAX, "tileplan_build: too many contributions");
     const int R = tile_nodes_R;
     const int64_t n_tiles = ceil_div(n_nodes, R);
-    TileWs w = carve_tiles(d_ws, n_nodes, ninc, n_tiles);
+    TileWs w = carve_tiles(d_ws, n_nodes, ninc);
     PSFEM_REQUIRE(ws_bytes >= w.total, "tileplan_build: workspace too small");
     const int T = 256;
     const double2 *nodes = reinterpret_cast<const double2 *>(d_nodes);
@@ -667,7 +664,7 @@ extern "C" int psfem_tileplan_build(const double *d_nodes, const int32_t *d_conn
         PSFEM_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, tk2, tv2, (int)n_nodes, 0, tile_bits, stream));
         PSFEM_CUDA_CHECK(cudaMemcpyAsync(d_tile_nodes, tv2.Current(), n_nodes * sizeof(int32_t), cudaMemcpyDeviceToDevice, stream));
     }
-    // 3. per-tile unique element lists
+    // 3. per-tile unique element lists (ascending element id)
     unsigned grid = (unsigned)ceil_div(ninc, T);
     if (npe == 3) incidence_keys_kernel<3><<<grid, T, 0, stream>>>(d_conn, nel, w.tile_of, w.k64a);
     else incidence_keys_kernel<4><<<grid, T, 0, stream>>>(d_conn, nel, w.tile_of, w.k64a);
@@ -689,44 +686,47 @@ extern "C" int psfem_tileplan_build(const double *d_nodes, const int32_t *d_conn
     PSFEM_LAUNCH_CHECK();
     unpack_elems_kernel<<<(unsigned)ceil_div(h_unique, T), T, 0, stream>>>(uniq, h_unique, d_tile_elems);
     PSFEM_LAUNCH_CHECK();
-    if (npe == 3) tile_conn_kernel<3><<<(unsigned)ceil_div(h_unique, T), T, 0, stream>>>(h_unique, d_tile_elems, d_conn, reinterpret_cast<int4 *>(d_tile_conn));
-    else tile_conn_kernel<4><<<(unsigned)ceil_div(h_unique, T), T, 0, stream>>>(h_unique, d_tile_elems, d_conn, reinterpret_cast<int4 *>(d_tile_conn));
-    PSFEM_LAUNCH_CHECK();
-    // 4. tile-ordered, padded plan: global prefixes per tile-ordered node, padded per-tile bases, fill
+    // 4. pair prefix per tile-ordered node, row metadata
     PSFEM_CUDA_CHECK(cudaMemsetAsync(w.scal + 2, 0, 6 * sizeof(int), stream));
-    tnode_counts_kernel<<<(unsigned)ceil_div(n_nodes + 1, T), T, 0, stream>>>(n_nodes, d_tile_nodes, d_node_ptr, d_pair_ptr, w.deg, w.ncd);
+    tnode_counts_kernel<<<(unsigned)ceil_div(n_nodes + 1, T), T, 0, stream>>>(n_nodes, d_tile_nodes, d_node_ptr, w.deg);
     PSFEM_LAUNCH_CHECK();
     tb = w.cub_bytes;
     PSFEM_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(w.cub_tmp, tb, w.deg, w.gp, (int)n_nodes + 1, stream));
-    tb = w.cub_bytes;
-    PSFEM_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(w.cub_tmp, tb, w.ncd, w.gc, (int)n_nodes + 1, stream));
-    tile_sizes_kernel<<<(unsigned)ceil_div(n_tiles + 1, T), T, 0, stream>>>((int32_t)n_tiles, n_nodes, R, w.gp, w.gc, d_tile_elem_ptr, w.qsz, w.csz, w.scal + 2);
-    PSFEM_LAUNCH_CHECK();
-    tb = w.cub_bytes;
-    PSFEM_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(w.cub_tmp, tb, w.qsz, w.q0, (int)n_tiles + 1, stream));
-    tb = w.cub_bytes;
-    PSFEM_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(w.cub_tmp, tb, w.csz, w.c0, (int)n_tiles + 1, stream));
-    tile_hdr_kernel<<<(unsigned)ceil_div(n_tiles, T), T, 0, stream>>>((int32_t)n_tiles, n_nodes, R, w.gp, w.gc, d_tile_elem_ptr, w.q0, w.c0, d_tile_hdr);
-    PSFEM_LAUNCH_CHECK();
     PSFEM_CUDA_CHECK(cudaMemsetAsync(d_nmeta, 0, (size_t)n_tiles * R * 8, stream));
-    tmeta_fill_kernel<<<(unsigned)ceil_div(n_nodes, T), T, 0, stream>>>(n_nodes, npe * npe, R, d_tile_nodes, d_node_ptr, d_pair_ptr, d_perm,
-                                                                       d_tile_elem_ptr, d_tile_elems, w.gp, w.gc, w.q0, w.c0,
-                                                                       reinterpret_cast<int2 *>(d_nmeta), d_tp_cnt, d_tcodes, w.scal + 5);
+    nmeta_kernel<<<(unsigned)ceil_div(n_nodes, T), T, 0, stream>>>(n_nodes, R, d_tile_nodes, d_node_ptr, w.gp, reinterpret_cast<int2 *>(d_nmeta));
+    PSFEM_LAUNCH_CHECK();
+    // 5. scatter rounds of every (tile element, row), packed into the tile connectivity; headers
+    PSFEM_REQUIRE(n_nodes < (1ll << 28), "tileplan_build: node ids need 28 bits");
+    if (npe == 3)
+        tile_rounds_kernel<3><<<(unsigned)ceil_div(n_tiles, 64), 64, 0, stream>>>((int32_t)n_tiles, n_nodes, R, d_tile_nodes, d_tile_elem_ptr, d_tile_elems,
+                                                                                d_conn, w.gp, reinterpret_cast<int4 *>(d_tile_conn), d_tile_hdr, w.scal + 5);
+    else
+        tile_rounds_kernel<4><<<(unsigned)ceil_div(n_tiles, 64), 64, 0, stream>>>((int32_t)n_tiles, n_nodes, R, d_tile_nodes, d_tile_elem_ptr, d_tile_elems,
+                                                                                d_conn, w.gp, reinterpret_cast<int4 *>(d_tile_conn), d_tile_hdr, w.scal + 5);
+    PSFEM_LAUNCH_CHECK();
+    // 6. scatter offsets of every tile element
+    if (npe == 3)
+        tile_scatter_plan_kernel<3><<<(unsigned)ceil_div(h_unique, T), T, 0, stream>>>((int32_t)n_tiles, n_nodes, R, d_tile_nodes, d_tile_elem_ptr, d_tile_elems,
+                                                                                      d_conn, d_node_ptr, d_col_idx, w.gp, d_tile_off);
+    else
+        tile_scatter_plan_kernel<4><<<(unsigned)ceil_div(h_unique, T), T, 0, stream>>>((int32_t)n_tiles, n_nodes, R, d_tile_nodes, d_tile_elem_ptr, d_tile_elems,
+                                                                                      d_conn, d_node_ptr, d_col_idx, w.gp, d_tile_off);
+    PSFEM_LAUNCH_CHECK();
+    tile_max_kernel<<<(unsigned)ceil_div(n_tiles, T), T, 0, stream>>>((int32_t)n_tiles, d_tile_hdr, w.scal + 2);
     PSFEM_LAUNCH_CHECK();
     int h[4] = {0, 0, 0, 0};
     PSFEM_CUDA_CHECK(cudaMemcpyAsync(h, w.scal + 2, sizeof(h), cudaMemcpyDeviceToHost, stream));
     PSFEM_CUDA_CHECK(cudaStreamSynchronize(stream));
     h_info[0] = h_unique; h_info[1] = h[0]; h_info[2] = h[1]; h_info[3] = h[2];
-    h_info[4] = (h[3] == 0 && h[0] <= 4095) ? 1 : 0;   // a pair with > 255 contributions / a huge tile: use psfem_assemble
+    h_info[4] = (h[3] == 0 && h[0] <= 4095 && h[1] < 65535) ? 1 : 0;   // a node with > 14 elements / a huge tile: use psfem_assemble
     h_info[5] = ceil_div(h_unique, n_tiles);
-    (void)n_pairs;
     return PSFEM_OK;
 }
 
 extern "C" int psfem_assemble_tiled(const double *d_nodes, int64_t nel, int etype, int64_t n_nodes,
                                     double E, double nu, double rho, double t, int what, int tile_nodes_R,
                                     const int64_t *h_plan_info, const int32_t *d_tile_hdr, const int32_t *d_tile_conn,
-                                    const int32_t *d_tile_elems, const int32_t *d_nmeta, const uint8_t *d_tp_cnt, const uint16_t *d_tcodes,
+                                    const uint16_t *d_tile_off, const int32_t *d_tile_elems, const int32_t *d_nmeta,
                                     double *d_K_vals, double *d_M_vals, void *d_ws, size_t ws_bytes,
                                     int64_t *h_bad_element, void *stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -745,18 +745,18 @@ extern "C" int psfem_assemble_tiled(const double *d_nodes, int64_t nel, int etyp
     PSFEM_CUDA_CHECK(cudaMemsetAsync(bad, 0xff, sizeof(unsigned long long), stream));
     TilePlanDev tp;
     tp.hdr = reinterpret_cast<const int4 *>(d_tile_hdr); tp.tile_conn = reinterpret_cast<const int4 *>(d_tile_conn);
-    tp.nmeta = reinterpret_cast<const int2 *>(d_nmeta); tp.tp_cnt = d_tp_cnt; tp.tcodes = d_tcodes; tp.tile_elems = d_tile_elems;
-    tp.R = tile_nodes_R; tp.max_elems = (int)h_plan_info[1]; tp.max_pairs = (int)h_plan_info[2]; tp.max_codes = (int)h_plan_info[3];
+    tp.tile_off = d_tile_off; tp.nmeta = reinterpret_cast<const int2 *>(d_nmeta); tp.tile_elems = d_tile_elems;
+    tp.R = tile_nodes_R; tp.max_elems = (int)h_plan_info[1]; tp.max_pairs = (int)h_plan_info[2];
     const int64_t n_tiles = ceil_div(n_nodes, tp.R);
-    const int mean = (int)h_plan_info[5];   // threads follow the TYPICAL tile; bigger tiles take a second round
+    const int mean = (int)h_plan_info[5];   // threads follow the TYPICAL tile; bigger tiles take a second pass
     int rc;
 #define PSFEM_TILE_CASE(ET, NPE, TH, MB)                                                                              \
     (what == 3 ? launch_tiles<ET, NPE, true, true, TH, MB>(d_nodes, mat, n_tiles, tp, d_K_vals, d_M_vals, bad, stream) \
      : what == 1 ? launch_tiles<ET, NPE, true, false, TH, MB>(d_nodes, mat, n_tiles, tp, d_K_vals, d_M_vals, bad, stream) \
                  : launch_tiles<ET, NPE, false, true, TH, MB>(d_nodes, mat, n_tiles, tp, d_K_vals, d_M_vals, bad, stream))
     if (etype == PSFEM_Q4) {
-        if (mean <= 96) rc = PSFEM_TILE_CASE(PSFEM_Q4, 4, 96, 3);
-        else if (mean <= 160) rc = PSFEM_TILE_CASE(PSFEM_Q4, 4, 160, 2);
+        if (mean <= 96) rc = PSFEM_TILE_CASE(PSFEM_Q4, 4, 96, 4);
+        else if (mean <= 160) rc = PSFEM_TILE_CASE(PSFEM_Q4, 4, 160, 3);
         else rc = PSFEM_TILE_CASE(PSFEM_Q4, 4, 320, 1);
     } else {
         if (mean <= 160) rc = PSFEM_TILE_CASE(PSFEM_T3, 3, 160, 3);

@@ -200,25 +200,26 @@ class Assembler:
             sz = C.c_size_t(0)
             call("psfem_tileplan_workspace", self.nel, self.npe, self.n_nodes, R, C.byref(sz))
             ws = workspace(sz.value)
-            ninc, nk = self.nel * self.npe, self.nel * self.npe * self.npe
+            ninc = self.nel * self.npe
             tile_nodes = torch.empty(self.n_nodes, **i32)
             tile_elem_ptr = torch.empty(n_tiles + 1, **i32)
             tile_elems = torch.empty(max(ninc, 1), **i32)
             tile_hdr = torch.empty(8 * n_tiles, **i32)
             tile_conn = torch.empty(4 * max(ninc, 1), **i32)
+            tile_off = torch.empty(16 * max(ninc, 1), dtype=torch.int16, device="cuda")
             nmeta = torch.empty(2 * n_tiles * R, **i32)
-            tp_cnt = torch.zeros(self.n_pairs + 16 * n_tiles + 16, dtype=torch.uint8, device="cuda")
-            tcodes = torch.zeros(nk + 8 * n_tiles + 8, dtype=torch.int16, device="cuda")
             info = (C.c_int64 * 8)()
-            call("psfem_tileplan_build", ptr(nodes_dev), ptr(self.conn), self.nel, self.npe, self.n_nodes, R, self.n_pairs,
-                 ptr(self.node_ptr), ptr(self.pair_ptr), ptr(self.perm), ptr(tile_nodes), ptr(tile_elem_ptr), ptr(tile_elems),
-                 ptr(tile_hdr), ptr(tile_conn), ptr(nmeta), ptr(tp_cnt), ptr(tcodes), info, ptr(ws), sz.value, stream_ptr())
+            call("psfem_tileplan_build", ptr(nodes_dev), ptr(self.conn), self.nel, self.npe, self.n_nodes, R,
+                 ptr(self.node_ptr), ptr(self.col_idx), ptr(tile_nodes), ptr(tile_elem_ptr), ptr(tile_elems), ptr(tile_hdr),
+                 ptr(tile_conn), ptr(tile_off), ptr(nmeta), info, ptr(ws), sz.value, stream_ptr())
             n_te = int(info[0])
             tile_elems = tile_elems[:n_te].clone()                  # drop the upper-bound slack
             tile_conn = tile_conn[: 4 * n_te].clone()
+            tile_off = tile_off[: 16 * n_te].clone()
             del ws
-            self._tiles = dict(R=R, tile_hdr=tile_hdr, tile_conn=tile_conn, tile_elems=tile_elems, nmeta=nmeta, tp_cnt=tp_cnt,
-                               tcodes=tcodes, info=info, max_elems=int(info[1]), mean_elems=int(info[5]), ws=workspace(256))
+            self._tiles = dict(R=R, tile_hdr=tile_hdr, tile_conn=tile_conn, tile_off=tile_off, tile_elems=tile_elems, nmeta=nmeta,
+                               info=info, max_elems=int(info[1]), max_rounds=int(info[3]), mean_elems=int(info[5]),
+                               ws=workspace(256))
             if info[4] != 1:
                 self.use_tiles = False
         return self._tiles
@@ -253,7 +254,7 @@ class Assembler:
         if self.use_tiles and self.nel > 0:
             rc = lib.psfem_assemble_tiled(ptr(nodes_dev), self.nel, self.etype, self.n_nodes, float(E), float(nu), float(rho),
                                           float(t), what, tp["R"], tp["info"], ptr(tp["tile_hdr"]), ptr(tp["tile_conn"]),
-                                          ptr(tp["tile_elems"]), ptr(tp["nmeta"]), ptr(tp["tp_cnt"]), ptr(tp["tcodes"]),
+                                          ptr(tp["tile_off"]), ptr(tp["tile_elems"]), ptr(tp["nmeta"]),
                                           ptr(K_vals), ptr(M_vals), ptr(tp["ws"]), 256, C.byref(bad), stream_ptr())
             check(rc, bad.value)
             return K_vals, M_vals
