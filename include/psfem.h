@@ -123,7 +123,8 @@ int psfem_assemble(const double *d_nodes, const int32_t *d_conn, int64_t nel, in
  *   d_tile_hdr      8*n_tiles     {e0, ne, nn, npairs, nrounds, 0,0,0}
  *   d_tile_conn     4*nel*npe     (upper bound) int4 connectivity of every tile element; bits 28..31 of
  *                                 entry i = scatter round of row i (15 = row node not owned by the tile)
- *   d_tile_off      16*nel*npe    (upper bound) u16 tile-local CSR pair of block (i,j); 0xFFFF = row not owned
+ *   d_tile_rec      32 B*nel*npe  (upper bound) scatter record of every tile element: double2 offsets of its
+ *                                 rows inside the tile's value block (kept in shared memory in the global layout)
  *   d_nmeta         2*n_tiles*R   {first CSR pair of the node, pair prefix inside its tile}
  *   h_info[6]       {tile elements used, max elements, max pairs, max rounds per tile, usable (1/0), mean elements}
  * Same summation order as psfem_assemble (ascending element id).
@@ -132,12 +133,12 @@ int psfem_tileplan_workspace(int64_t nel, int npe, int64_t n_nodes, int tile_nod
 int psfem_tileplan_build(const double *d_nodes, const int32_t *d_conn, int64_t nel, int npe, int64_t n_nodes,
                          int tile_nodes_R, const int32_t *d_node_ptr, const int32_t *d_col_idx,
                          int32_t *d_tile_nodes, int32_t *d_tile_elem_ptr, int32_t *d_tile_elems, int32_t *d_tile_hdr,
-                         int32_t *d_tile_conn, uint16_t *d_tile_off, int32_t *d_nmeta, int64_t *h_info,
+                         int32_t *d_tile_conn, void *d_tile_rec, int32_t *d_nmeta, int64_t *h_info,
                          void *d_ws, size_t ws_bytes, void *stream);
 int psfem_assemble_tiled(const double *d_nodes, int64_t nel, int etype, int64_t n_nodes,
                          double E, double nu, double rho, double t, int what, int tile_nodes_R,
                          const int64_t *h_plan_info, const int32_t *d_tile_hdr, const int32_t *d_tile_conn,
-                         const uint16_t *d_tile_off, const int32_t *d_tile_elems, const int32_t *d_nmeta,
+                         const void *d_tile_rec, const int32_t *d_tile_elems, const int32_t *d_nmeta,
                          double *d_K_vals, double *d_M_vals, void *d_ws, size_t ws_bytes,
                          int64_t *h_bad_element, void *stream);
 

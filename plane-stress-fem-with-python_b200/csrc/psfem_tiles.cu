@@ -184,15 +184,24 @@ __global__ void tile_rounds_kernel(int32_t n_tiles, int64_t n_nodes, int R, cons
     h[0] = e0; h[1] = ne; h[2] = nn; h[3] = gp[u0 + nn] - gp[u0]; h[4] = nrounds; h[5] = 0; h[6] = 0; h[7] = 0;
 }
 
-// per tile element: connectivity and, for every (i,j), the tile-local CSR pair index its 2x2 block adds to
-// (0xFFFF when row node i is not owned by the tile)
+// Scatter record of a tile element (32 bytes): the tile's CSR block is kept in shared memory in EXACTLY the
+// global layout (per node: row 2a = 2*deg doubles, then row 2a+1), nodes in tile order, so that runs of
+// consecutive nodes leave with one bulk copy.  Block (i,j) adds {K(2a,2b),K(2a,2b+1)} at double2 index
+// base[i]+pos[i][j] and {K(2a+1,2b),K(2a+1,2b+1)} deg[i] double2 further.
+struct __align__(16) TileRec {
+    uint16_t base[4];   // 2*prefix of row node i inside the tile (double2 units); unused rows: anything
+    uint8_t deg[4];     // CSR pairs of row node i
+    uint8_t pos[16];    // position of node j among the column nodes of row node i
+    uint8_t pad[4];
+};
+
 template <int NPE>
 __global__ void tile_scatter_plan_kernel(int32_t n_tiles, int64_t n_nodes, int R, const int32_t *__restrict__ tile_nodes,
                                          const int32_t *__restrict__ tile_elem_ptr, const int32_t *__restrict__ sorted_elems,
                                          const int32_t *__restrict__ conn, const int32_t *__restrict__ node_ptr,
                                          const int32_t *__restrict__ col_idx, const int32_t *__restrict__ gp,
-                                         uint16_t *__restrict__ tile_off) {
-    // one thread per (tile element); the tile is found by binary search on tile_elem_ptr
+                                         TileRec *__restrict__ tile_rec, int *__restrict__ flags) {
+    // one thread per tile element; the tile is found by binary search on tile_elem_ptr
     int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int n_te = tile_elem_ptr[n_tiles];
     if (k >= n_te) return;
@@ -209,15 +218,20 @@ __global__ void tile_scatter_plan_kernel(int32_t n_tiles, int64_t n_nodes, int R
     int nd[NPE];
 #pragma unroll
     for (int i = 0; i < NPE; ++i) nd[i] = c[i];
-    uint16_t *o = tile_off + 16 * k;
+    TileRec rec;
 #pragma unroll
-    for (int q = 0; q < 16; ++q) o[q] = 0xFFFF;
+    for (int q = 0; q < 4; ++q) { rec.base[q] = 0; rec.deg[q] = 0; rec.pad[q] = 0; }
+#pragma unroll
+    for (int q = 0; q < 16; ++q) rec.pos[q] = 0;
 #pragma unroll
     for (int i = 0; i < NPE; ++i) {
         const int s = find_sorted(tn, nn, nd[i]);
         if (s < 0) continue;
         const int pfx = gp[u0 + s] - gp[u0];
         const int p0 = node_ptr[nd[i]], deg = node_ptr[nd[i] + 1] - p0;
+        if (deg > 255 || 2 * pfx > 65535) atomicExch(flags, 1);
+        rec.base[i] = (uint16_t)(2 * pfx);
+        rec.deg[i] = (uint8_t)deg;
 #pragma unroll
         for (int j = 0; j < NPE; ++j) {
             // position of node nd[j] among the column nodes of row node nd[i]: columns 2b of DOF row 2a
@@ -228,9 +242,10 @@ __global__ void tile_scatter_plan_kernel(int32_t n_tiles, int64_t n_nodes, int R
                 int mid = (l + h) >> 1;
                 if (cols[2 * mid] < want) l = mid + 1; else h = mid;
             }
-            o[i * NPE + j] = (uint16_t)(pfx + l);
+            rec.pos[i * NPE + j] = (uint8_t)l;
         }
     }
+    tile_rec[k] = rec;
 }
 
 __global__ void tile_max_kernel(int32_t n_tiles, const int32_t *__restrict__ hdr, int *__restrict__ maxima) {
@@ -291,6 +306,15 @@ struct Mat {
     double d00, d01, d22, t, rho;
 };
 
+// 1/d without the IEEE division slow path: fp32 reciprocal seed + two Newton steps (relative error ~1e-16;
+// |d| >= 1e-10 is guaranteed by the Jacobian guard, far inside the fp32 exponent range)
+__device__ __forceinline__ double fast_rcp(double d) {
+    double x = (double)(1.0f / (float)d);
+    x = x * (2.0 - d * x);
+    x = x * (2.0 - d * x);
+    return x;
+}
+
 template <int NPE> __host__ __device__ constexpr int tri_index(int i, int j) { return i * NPE - (i * (i - 1)) / 2 + (j - i); }
 
 // Q4: gradient products of the element, integrated with the 3x3 rule.  Same arithmetic as gauss_kernel
@@ -310,9 +334,11 @@ template <bool DO_K, bool DO_M> struct ElemQ4 {
         bool ok = true;
 #pragma unroll
         for (int r = 0; r < 3; ++r) {      // eta (outer, Polygones.py:551-553)
+            const double eta = gp[r];
+            const double wr = gw[r];
 #pragma unroll
             for (int c = 0; c < 3; ++c) {  // xi
-                const double xi = gp[c], eta = gp[r];
+                const double xi = gp[c];
                 double dnx[4], dne[4], nn[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -329,29 +355,29 @@ template <bool DO_K, bool DO_M> struct ElemQ4 {
                 const double detJ = j00 * j11 - j01 * j10;
                 const double ad = fabs(detJ);
                 if (ad < 1e-10) ok = false;  // Polygones.py:686-687
-                const double w = gw[r] * gw[c];
+                const double w = wr * gw[c];
                 if (DO_K) {
-                    const double inv = 1.0 / detJ;
+                    const double inv = fast_rcp(detJ);
                     const double pp = j11 * inv, qq = -j01 * inv, rr = -j10 * inv, ss = j00 * inv;
                     const double cc = w * ad * mat.t;
-                    double dx[4], dy[4], cx[4], cy[4];
+                    double dx[4], dy[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         dx[i] = pp * dnx[i] + qq * dne[i];
                         dy[i] = rr * dnx[i] + ss * dne[i];
-                        cx[i] = cc * dx[i];
-                        cy[i] = cc * dy[i];
                     }
 #pragma unroll
-                    for (int i = 0; i < 4; ++i)
+                    for (int i = 0; i < 4; ++i) {
+                        const double cxi = cc * dx[i], cyi = cc * dy[i];
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             if (j >= i) {
-                                gxx[tri_index<4>(i, j)] += cx[i] * dx[j];
-                                gyy[tri_index<4>(i, j)] += cy[i] * dy[j];
+                                gxx[tri_index<4>(i, j)] += cxi * dx[j];
+                                gyy[tri_index<4>(i, j)] += cyi * dy[j];
                             }
-                            gxy[i * 4 + j] += cx[i] * dy[j];
+                            gxy[i * 4 + j] += cxi * dy[j];
                         }
+                    }
                 }
                 if (DO_M) {
                     const double cm = w * mat.rho * mat.t * ad;
@@ -384,7 +410,7 @@ template <bool DO_K, bool DO_M> struct ElemT3 {
             b[i] = (p[(i + 1) % 3].y - p[(i + 2) % 3].y) / delta;
             g[i] = (p[(i + 2) % 3].x - p[(i + 1) % 3].x) / delta;
         }
-        mbase = mat.rho * vol / 12;
+        mbase = mat.rho * vol / 12;   // T3 keeps IEEE divisions: the arithmetic of Polygones.py:848-850 verbatim
         return true;
     }
     __device__ __forceinline__ double4 kblock(int i, int j, const Mat &mat) const {
@@ -397,7 +423,7 @@ template <bool DO_K, bool DO_M> struct ElemT3 {
 struct TilePlanDev {  // device pointers of the tile plan (see psfem_tileplan_build)
     const int4 *hdr;            // 2 x int4 per tile: {e0, ne, nn, npairs}, {nrounds,0,0,0}
     const int4 *tile_conn;      // connectivity of every tile element (ascending id); bits 28..31 = scatter round of row i
-    const uint16_t *tile_off;   // 16 x u16 per tile element: tile-local CSR pair of block (i,j), 0xFFFF = row not owned
+    const TileRec *tile_rec;    // scatter record of every tile element
     const int2 *nmeta;          // n_tiles*R: {first CSR pair of the node, pair prefix inside the tile}
     const int32_t *tile_elems;  // element id of every tile element (error reporting only)
     int R, max_elems, max_pairs;
@@ -428,19 +454,23 @@ assemble_tile_kernel(const double2 *__restrict__ nodes, Mat mat, int n_tiles, Ti
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint64_t meta_bar[2];
     const int tid = threadIdx.x, R = tp.R;
-    // ---- shared-memory carve-up (sizes from the plan's per-tile maxima; every region 16-byte aligned) ----
+    // ---- shared-memory carve-up (sizes from the plan's per-tile maxima; every region 16-byte aligned).
+    // Buffers are addressed as smem_raw + offset (never through an array of pointers) so that the compiler
+    // keeps them in the shared address space (LDS/STS instead of generic LD/ST).
     const int cap_e = tp.max_elems, cap_p = (tp.max_pairs + 15) & ~15;
-    unsigned char *sp = smem_raw;
-    double *kbuf = reinterpret_cast<double *>(sp); sp += DO_K ? (size_t)cap_p * 32 : 0;   // 4 doubles per tile pair
-    double *mbuf = reinterpret_cast<double *>(sp); sp += DO_M ? (size_t)cap_p * 8 : 0;    // 1 double per tile pair
-    double2 *xy_s[2]; int2 *nm_s[2]; uint16_t *off_s[2];
-#pragma unroll
-    for (int s = 0; s < 2; ++s) {
-        xy_s[s] = reinterpret_cast<double2 *>(sp); sp += (size_t)THREADS * NPE * 16;
-        nm_s[s] = reinterpret_cast<int2 *>(sp); sp += (size_t)R * 8;
-        off_s[s] = reinterpret_cast<uint16_t *>(sp); sp += (size_t)cap_e * 32;
-    }
-    uint8_t *s_slot = sp;   // node slot of every tile pair
+    const uint32_t vbuf_bytes = (uint32_t)cap_p * 32;                       // one tile block of CSR values (K or M)
+    const uint32_t nbuf = (DO_K ? 1u : 0u) + (DO_M ? 1u : 0u);
+    const uint32_t stage0_off = 2 * nbuf * vbuf_bytes;                       // value blocks are double buffered
+    const uint32_t xy_bytes = (uint32_t)THREADS * NPE * 16, nm_bytes = (uint32_t)R * 8, rec_bytes = (uint32_t)cap_e * 32;
+    const uint32_t cn_bytes = (uint32_t)THREADS * 16;
+    const uint32_t stage_bytes = xy_bytes + nm_bytes + rec_bytes + cn_bytes;
+    __shared__ __align__(16) int4 s_hdr[4][2];                               // ring of tile headers
+#define PSFEM_KBUF(st) reinterpret_cast<double2 *>(smem_raw + (st) * nbuf * vbuf_bytes)
+#define PSFEM_MBUF(st) reinterpret_cast<double2 *>(smem_raw + (st) * nbuf * vbuf_bytes + (DO_K ? vbuf_bytes : 0))
+#define PSFEM_STAGE_XY(st) reinterpret_cast<double2 *>(smem_raw + stage0_off + (st) * stage_bytes)
+#define PSFEM_STAGE_NM(st) reinterpret_cast<int2 *>(smem_raw + stage0_off + (st) * stage_bytes + xy_bytes)
+#define PSFEM_STAGE_REC(st) reinterpret_cast<TileRec *>(smem_raw + stage0_off + (st) * stage_bytes + xy_bytes + nm_bytes)
+#define PSFEM_STAGE_CONN(st) reinterpret_cast<int4 *>(smem_raw + stage0_off + (st) * stage_bytes + xy_bytes + nm_bytes + rec_bytes)
 
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(t_smem_u32(&meta_bar[0])));
@@ -450,79 +480,112 @@ assemble_tile_kernel(const double2 *__restrict__ nodes, Mat mat, int n_tiles, Ti
     __syncthreads();
     const int n_mine = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     auto tile_id = [&](int i) { return (int)blockIdx.x + i * (int)gridDim.x; };
-    auto load_hdr = [&](int i) -> TileHdr {
+    auto read_hdr = [&](int i) -> TileHdr {        // header of my i-th tile from the shared ring (zeros past the end)
         TileHdr h = {0, 0, 0, 0, 0};
         if (i < n_mine) {
-            const int4 a = tp.hdr[2 * (size_t)tile_id(i)], b = tp.hdr[2 * (size_t)tile_id(i) + 1];
+            const int4 a = s_hdr[i & 3][0], b = s_hdr[i & 3][1];
             h.e0 = a.x; h.ne = a.y; h.nn = a.z; h.npairs = a.w; h.nrounds = b.x;
         }
         return h;
     };
-    auto load_conn = [&](const TileHdr &h) -> int4 {
-        return (tid < h.ne) ? tp.tile_conn[h.e0 + tid] : make_int4(0, 0, 0, 0);
+    // Everything below is asynchronous and lands in shared memory: no register is held across a tile.
+    auto fetch_hdr = [&](int i) {                  // header of tile i -> ring
+        if (i < n_mine && tid < 2) t_cp_async16(&s_hdr[i & 3][tid], tp.hdr + 2 * (size_t)tile_id(i) + tid);
     };
-    // coordinates of the first THREADS elements of a tile -> stage (cp.async), its plan -> stage (bulk copies)
-    auto prefetch = [&](int i, int stage, const TileHdr &h, const int4 &c) {
+    auto fetch_conn = [&](int i, const TileHdr &h) {   // connectivity of the first THREADS elements of tile i
+        if (i < n_mine && tid < h.ne) t_cp_async16(PSFEM_STAGE_CONN(i & 1) + tid, tp.tile_conn + h.e0 + tid);
+    };
+    auto fetch_inputs = [&](int i, const TileHdr &h) {  // coordinates (needs conn(i) in smem) + plan of tile i
         if (i < n_mine) {
+            const int stage = i & 1;
             if (tid < h.ne) {
-                double2 *dst = xy_s[stage] + (size_t)tid * NPE;
+                const int4 c = PSFEM_STAGE_CONN(stage)[tid];
+                double2 *dst = PSFEM_STAGE_XY(stage) + (size_t)tid * NPE;
                 t_cp_async16(dst + 0, nodes + (c.x & 0x0fffffff));
                 t_cp_async16(dst + 1, nodes + (c.y & 0x0fffffff));
                 t_cp_async16(dst + 2, nodes + (c.z & 0x0fffffff));
                 if (NPE == 4) t_cp_async16(dst + 3, nodes + (c.w & 0x0fffffff));
             }
             if (tid == 0) {
-                const uint32_t b_nm = (uint32_t)R * 8, b_off = (uint32_t)h.ne * 32;
+                const uint32_t b_nm = (uint32_t)R * 8, b_rec = (uint32_t)h.ne * 32;
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(t_smem_u32(&meta_bar[stage])), "r"(b_nm + b_off) : "memory");
-                t_bulk_g2s(nm_s[stage], tp.nmeta + (size_t)tile_id(i) * R, b_nm, &meta_bar[stage]);
-                if (b_off) t_bulk_g2s(off_s[stage], tp.tile_off + 16 * (size_t)h.e0, b_off, &meta_bar[stage]);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(t_smem_u32(&meta_bar[stage])), "r"(b_nm + b_rec) : "memory");
+                t_bulk_g2s(PSFEM_STAGE_NM(stage), tp.nmeta + (size_t)tile_id(i) * R, b_nm, &meta_bar[stage]);
+                if (b_rec) t_bulk_g2s(PSFEM_STAGE_REC(stage), tp.tile_rec + h.e0, b_rec, &meta_bar[stage]);
             }
         }
-        asm volatile("cp.async.commit_group;" ::: "memory");
     };
-
-    // ---- prologue: tile 0 staged, connectivity of tile 1 and headers up to tile 2 in registers ----
-    TileHdr h0 = load_hdr(0), h1 = load_hdr(1), h2 = load_hdr(2);
+    auto commit_wait_sync = [&]() {
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+    };
     auto rounds_of = [](const int4 &c) -> uint32_t {   // 4 x 4-bit scatter rounds of the element's rows
         return ((uint32_t)c.x >> 28) | (((uint32_t)c.y >> 28) << 4) | (((uint32_t)c.z >> 28) << 8) | (((uint32_t)c.w >> 28) << 12);
     };
-    int4 conn_a = load_conn(h0);
-    prefetch(0, 0, h0, conn_a);
-    uint32_t rnd_next = rounds_of(conn_a);
-    conn_a = load_conn(h1);
+    // one matrix row of an element -> the tile block: the NPE destinations of a row are distinct CSR pairs,
+    // so all loads are issued before the adds and stores (the compiler cannot prove it and would serialise)
+    auto scatter_row = [&](double2 *vb, const TileRec &rec, int ii, auto &&block) {
+        double2 r0[NPE], r1[NPE];
+        int q0[NPE];
+#pragma unroll
+        for (int jj = 0; jj < NPE; ++jj) {
+            q0[jj] = (int)rec.base[ii] + (int)rec.pos[ii * NPE + jj];
+            r0[jj] = vb[q0[jj]];
+            r1[jj] = vb[q0[jj] + rec.deg[ii]];
+        }
+#pragma unroll
+        for (int jj = 0; jj < NPE; ++jj) {
+            const double4 v = block(ii, jj);
+            r0[jj].x += v.x; r0[jj].y += v.y; r1[jj].x += v.z; r1[jj].y += v.w;
+        }
+#pragma unroll
+        for (int jj = 0; jj < NPE; ++jj) {
+            vb[q0[jj]] = r0[jj];
+            vb[q0[jj] + rec.deg[ii]] = r1[jj];
+        }
+    };
+
+    // ---- prologue (latency exposed once per CTA): headers 0..2, conn 0..1, inputs of tile 0 ----
+    fetch_hdr(0); fetch_hdr(1); fetch_hdr(2);
+    commit_wait_sync();
+    fetch_conn(0, read_hdr(0)); fetch_conn(1, read_hdr(1));
+    commit_wait_sync();
+    fetch_inputs(0, read_hdr(0));
+    asm volatile("cp.async.commit_group;" ::: "memory");
 
     for (int i = 0; i < n_mine; ++i) {
         const int st = i & 1;
-        // ---- software pipeline: inputs of tile i+1, connectivity of tile i+2, header of tile i+3 ----
-        prefetch(i + 1, st ^ 1, h1, conn_a);
-        const uint32_t rnd_cur = rnd_next;
-        rnd_next = rounds_of(conn_a);
-        const int4 conn_b = load_conn(h2);
-        const TileHdr h3 = load_hdr(i + 3);
-        // zero the tile's CSR block while the inputs land
-        const int ne = h0.ne, nn = h0.nn, npairs = h0.npairs;
-        if (DO_K)
-            for (int q = tid; q < 2 * npairs; q += THREADS) reinterpret_cast<double2 *>(kbuf)[q] = make_double2(0.0, 0.0);
-        if (DO_M)
-            for (int q = tid; q < npairs; q += THREADS) mbuf[q] = 0.0;
-        asm volatile("cp.async.wait_group 1;" ::: "memory");          // everything but the newest group: tile i is in
+        // inputs of tile i were issued one tile ago; the bulk stores that read value buffer `st` two tiles ago are done
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         t_mbar_wait(&meta_bar[st], (uint32_t)((i >> 1) & 1));
         __syncthreads();
-        const double2 *xy = xy_s[st];
-        const int2 *nm = nm_s[st];
-        const uint16_t *off = off_s[st];
-        // node slot of every pair (for the copy-out)
-        for (int s = tid; s < nn; s += THREADS) {
-            const int b0 = nm[s].y, b1 = (s + 1 < nn) ? nm[s + 1].y : npairs;
-            for (int q = b0; q < b1; ++q) s_slot[q] = (uint8_t)s;
+        const TileHdr h0 = read_hdr(i);
+        const int ne = h0.ne, nn = h0.nn, npairs = h0.npairs;
+        const uint32_t rnd_cur = (tid < ne) ? rounds_of(PSFEM_STAGE_CONN(st)[tid]) : 0xffffu;
+        double2 *kbuf = PSFEM_KBUF(st), *mbuf = PSFEM_MBUF(st);
+        // zero the tile's value block(s)
+        for (int q = tid; q < 2 * npairs; q += THREADS) {
+            if (DO_K) kbuf[q] = make_double2(0.0, 0.0);
+            if (DO_M) mbuf[q] = make_double2(0.0, 0.0);
         }
+        __syncthreads();   // conn(i) read by everyone before its buffer is refilled with conn(i+2); zero-fill done
+        // ---- software pipeline: inputs of tile i+1, connectivity of tile i+2, header of tile i+3 ----
+        fetch_inputs(i + 1, read_hdr(i + 1));
+        fetch_conn(i + 2, read_hdr(i + 2));
+        fetch_hdr(i + 3);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        const double2 *xy = PSFEM_STAGE_XY(st);
+        const int2 *nm = PSFEM_STAGE_NM(st);
+        const TileRec *recs = PSFEM_STAGE_REC(st);
         // ---- element pass(es): compute once, scatter row by row in rounds ----
         for (int base = 0; base < ne; base += THREADS) {
             const int slot = base + tid;
             const bool active = slot < ne;
             typename std::conditional<ETYPE == PSFEM_Q4, ElemQ4<DO_K, DO_M>, ElemT3<DO_K, DO_M>>::type el;
             uint32_t rnd = 0xffffu;   // all rows "not owned"
+            TileRec rec;
             if (active) {
                 double2 p[NPE];
                 if (base == 0) {
@@ -535,60 +598,73 @@ assemble_tile_kernel(const double2 *__restrict__ nodes, Mat mat, int n_tiles, Ti
                     if (NPE == 4) p[NPE - 1] = nodes[c.w & 0x0fffffff];
                     rnd = rounds_of(c);
                 }
+                rec = recs[slot];
                 if (!el.compute(p, mat)) atomicMin(bad, (unsigned long long)tp.tile_elems[h0.e0 + slot]);  // lowest id, Polygones.py:686
             }
-            const uint16_t *o = off + 16 * (size_t)(active ? slot : 0);
             for (int r = 0; r < h0.nrounds; ++r) {
 #pragma unroll
                 for (int ii = 0; ii < NPE; ++ii) {
                     if (((rnd >> (4 * ii)) & 15u) == (uint32_t)r) {
-#pragma unroll
-                        for (int jj = 0; jj < NPE; ++jj) {
-                            const int q = o[ii * NPE + jj];
-                            if (DO_K) {
-                                const double4 v = el.kblock(ii, jj, mat);
-                                double2 *dst = reinterpret_cast<double2 *>(kbuf + 4 * (size_t)q);
-                                double2 a = dst[0], b = dst[1];
-                                a.x += v.x; a.y += v.y; b.x += v.z; b.y += v.w;
-                                dst[0] = a; dst[1] = b;
-                            }
-                            if (DO_M) mbuf[q] += el.mval(ii, jj);
-                        }
+                        if (DO_K) scatter_row(kbuf, rec, ii, [&](int a, int b) { return el.kblock(a, b, mat); });
+                        if (DO_M) scatter_row(mbuf, rec, ii, [&](int a, int b) { const double m = el.mval(a, b); return make_double4(m, 0.0, 0.0, m); });
                     }
                 }
                 __syncthreads();
             }
         }
-        if (h0.nrounds == 0) __syncthreads();
-        // ---- copy-out: every CSR value of the tile's rows is written exactly once ----
-        for (int q = tid; q < npairs; q += THREADS) {
-            const int s = s_slot[q];
-            const int2 m = nm[s];
-            const int pos = q - m.y;
-            const int deg = ((s + 1 < nn) ? nm[s + 1].y : npairs) - m.y;
-            const int64_t r0 = 4ll * m.x + 2 * pos, r1 = r0 + 2 * deg;
-            if (DO_K) {
-                const double2 *src = reinterpret_cast<const double2 *>(kbuf + 4 * (size_t)q);
-                *reinterpret_cast<double2 *>(K_vals + r0) = src[0];
-                *reinterpret_cast<double2 *>(K_vals + r1) = src[1];
+        // ---- copy-out: runs of consecutive nodes leave with one bulk (TMA) store each; nothing waits for them ----
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes of the block -> visible to the async proxy
+        __syncthreads();
+        if (tid < 32) {
+            for (int b0 = 0; b0 < nn; b0 += 32) {
+                const int s = b0 + tid;
+                int p0 = 0, pfx = 0, deg = 0;
+                bool start = false;
+                if (s < nn) {
+                    const int2 m = nm[s];
+                    p0 = m.x; pfx = m.y;
+                    deg = ((s + 1 < nn) ? nm[s + 1].y : npairs) - pfx;
+                    if (tid == 0) start = true;
+                    else { const int2 mp = nm[s - 1]; start = (mp.x + (pfx - mp.y) != p0); }
+                }
+                const unsigned starts = __ballot_sync(0xffffffffu, start);
+                const unsigned valid = __ballot_sync(0xffffffffu, s < nn);
+                if (start) {
+                    // run = [tid, next start or end of the valid lanes)
+                    const unsigned later = starts & ~((2u << tid) - 1u);
+                    const int end_lane = later ? (__ffs(later) - 1) : (32 - __clz(valid));
+                    const int s_end = b0 + end_lane;   // first node after the run (within this group of 32)
+                    const int pfx_end = (s_end < nn) ? nm[s_end].y : npairs;
+                    const uint32_t bytes = (uint32_t)(pfx_end - pfx) * 32;
+                    if (bytes) {
+                        if (DO_K)
+                            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(K_vals + 4ll * p0), "r"(t_smem_u32(kbuf + 2 * pfx)), "r"(bytes) : "memory");
+                        if (DO_M)
+                            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(M_vals + 4ll * p0), "r"(t_smem_u32(mbuf + 2 * pfx)), "r"(bytes) : "memory");
+                    }
+                }
+                (void)deg;
             }
-            if (DO_M) {
-                const double mv = mbuf[q];
-                *reinterpret_cast<double2 *>(M_vals + r0) = make_double2(mv, 0.0);
-                *reinterpret_cast<double2 *>(M_vals + r1) = make_double2(0.0, mv);
-            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
-        __syncthreads();   // kbuf / mbuf / s_slot / stage st are free again
-        h0 = h1; h1 = h2; h2 = h3; conn_a = conn_b;
+        // the barrier at the top of the next iteration orders everything else
     }
+    if (tid < 32) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all stores complete before the CTA exits
 }
+
+#undef PSFEM_STAGE_XY
+#undef PSFEM_STAGE_NM
+#undef PSFEM_STAGE_REC
+#undef PSFEM_STAGE_CONN
+#undef PSFEM_KBUF
+#undef PSFEM_MBUF
 
 template <int NPE, bool DO_K, bool DO_M> size_t tile_smem_bytes(const TilePlanDev &tp, int threads) {
     const size_t cap_e = tp.max_elems, cap_p = (tp.max_pairs + 15) & ~15;
-    size_t b = (DO_K ? cap_p * 32 : 0) + (DO_M ? cap_p * 8 : 0);
-    b += 2 * ((size_t)threads * NPE * 16 + (size_t)tp.R * 8 + cap_e * 32);
-    b += cap_p + 32;
-    return b;
+    const size_t nbuf = (DO_K ? 1 : 0) + (DO_M ? 1 : 0);
+    size_t b = 2 * nbuf * cap_p * 32;
+    b += 2 * ((size_t)threads * NPE * 16 + (size_t)tp.R * 8 + cap_e * 32 + (size_t)threads * 16);
+    return b + 32;
 }
 
 template <int ETYPE, int NPE, bool DO_K, bool DO_M, int THREADS, int MINB>
@@ -623,7 +699,7 @@ extern "C" int psfem_tileplan_build(const double *d_nodes, const int32_t *d_conn
                                     int tile_nodes_R, const int32_t *d_node_ptr, const int32_t *d_col_idx,
                                     int32_t *d_tile_nodes /* n_nodes */, int32_t *d_tile_elem_ptr /* n_tiles+1 */,
                                     int32_t *d_tile_elems /* nel*npe (upper bound) */, int32_t *d_tile_hdr /* 8*n_tiles */,
-                                    int32_t *d_tile_conn /* 4*nel*npe (upper bound) */, uint16_t *d_tile_off /* 16*nel*npe (upper bound) */,
+                                    int32_t *d_tile_conn /* 4*nel*npe (upper bound) */, void *d_tile_rec /* 32 bytes * nel*npe (upper bound) */,
                                     int32_t *d_nmeta /* 2*n_tiles*R */,
                                     int64_t *h_info /* tile elements, max elems, max pairs, max colours, usable, mean elems */,
                                     void *d_ws, size_t ws_bytes, void *stream_) {
@@ -704,13 +780,13 @@ extern "C" int psfem_tileplan_build(const double *d_nodes, const int32_t *d_conn
         tile_rounds_kernel<4><<<(unsigned)ceil_div(n_tiles, 64), 64, 0, stream>>>((int32_t)n_tiles, n_nodes, R, d_tile_nodes, d_tile_elem_ptr, d_tile_elems,
                                                                                 d_conn, w.gp, reinterpret_cast<int4 *>(d_tile_conn), d_tile_hdr, w.scal + 5);
     PSFEM_LAUNCH_CHECK();
-    // 6. scatter offsets of every tile element
+    // 6. scatter record of every tile element
     if (npe == 3)
         tile_scatter_plan_kernel<3><<<(unsigned)ceil_div(h_unique, T), T, 0, stream>>>((int32_t)n_tiles, n_nodes, R, d_tile_nodes, d_tile_elem_ptr, d_tile_elems,
-                                                                                      d_conn, d_node_ptr, d_col_idx, w.gp, d_tile_off);
+                                                                                      d_conn, d_node_ptr, d_col_idx, w.gp, static_cast<TileRec *>(d_tile_rec), w.scal + 5);
     else
         tile_scatter_plan_kernel<4><<<(unsigned)ceil_div(h_unique, T), T, 0, stream>>>((int32_t)n_tiles, n_nodes, R, d_tile_nodes, d_tile_elem_ptr, d_tile_elems,
-                                                                                      d_conn, d_node_ptr, d_col_idx, w.gp, d_tile_off);
+                                                                                      d_conn, d_node_ptr, d_col_idx, w.gp, static_cast<TileRec *>(d_tile_rec), w.scal + 5);
     PSFEM_LAUNCH_CHECK();
     tile_max_kernel<<<(unsigned)ceil_div(n_tiles, T), T, 0, stream>>>((int32_t)n_tiles, d_tile_hdr, w.scal + 2);
     PSFEM_LAUNCH_CHECK();
@@ -726,7 +802,7 @@ extern "C" int psfem_tileplan_build(const double *d_nodes, const int32_t *d_conn
 extern "C" int psfem_assemble_tiled(const double *d_nodes, int64_t nel, int etype, int64_t n_nodes,
                                     double E, double nu, double rho, double t, int what, int tile_nodes_R,
                                     const int64_t *h_plan_info, const int32_t *d_tile_hdr, const int32_t *d_tile_conn,
-                                    const uint16_t *d_tile_off, const int32_t *d_tile_elems, const int32_t *d_nmeta,
+                                    const void *d_tile_rec, const int32_t *d_tile_elems, const int32_t *d_nmeta,
                                     double *d_K_vals, double *d_M_vals, void *d_ws, size_t ws_bytes,
                                     int64_t *h_bad_element, void *stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -745,7 +821,7 @@ extern "C" int psfem_assemble_tiled(const double *d_nodes, int64_t nel, int etyp
     PSFEM_CUDA_CHECK(cudaMemsetAsync(bad, 0xff, sizeof(unsigned long long), stream));
     TilePlanDev tp;
     tp.hdr = reinterpret_cast<const int4 *>(d_tile_hdr); tp.tile_conn = reinterpret_cast<const int4 *>(d_tile_conn);
-    tp.tile_off = d_tile_off; tp.nmeta = reinterpret_cast<const int2 *>(d_nmeta); tp.tile_elems = d_tile_elems;
+    tp.tile_rec = static_cast<const TileRec *>(d_tile_rec); tp.nmeta = reinterpret_cast<const int2 *>(d_nmeta); tp.tile_elems = d_tile_elems;
     tp.R = tile_nodes_R; tp.max_elems = (int)h_plan_info[1]; tp.max_pairs = (int)h_plan_info[2];
     const int64_t n_tiles = ceil_div(n_nodes, tp.R);
     const int mean = (int)h_plan_info[5];   // threads follow the TYPICAL tile; bigger tiles take a second pass
@@ -756,7 +832,11 @@ extern "C" int psfem_assemble_tiled(const double *d_nodes, int64_t nel, int etyp
                  : launch_tiles<ET, NPE, false, true, TH, MB>(d_nodes, mat, n_tiles, tp, d_K_vals, d_M_vals, bad, stream))
     if (etype == PSFEM_Q4) {
         if (mean <= 96) rc = PSFEM_TILE_CASE(PSFEM_Q4, 4, 96, 4);
-        else if (mean <= 160) rc = PSFEM_TILE_CASE(PSFEM_Q4, 4, 160, 3);
+        else if (mean <= 160) {
+            static const char *minb_env = getenv("PSFEM_TILE_MINB");   // tuning knob
+            if (minb_env && minb_env[0] == '2') rc = PSFEM_TILE_CASE(PSFEM_Q4, 4, 160, 2);
+            else rc = PSFEM_TILE_CASE(PSFEM_Q4, 4, 160, 3);
+        }
         else rc = PSFEM_TILE_CASE(PSFEM_Q4, 4, 320, 1);
     } else {
         if (mean <= 160) rc = PSFEM_TILE_CASE(PSFEM_T3, 3, 160, 3);

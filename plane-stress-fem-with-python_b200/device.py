@@ -188,7 +188,7 @@ class Assembler:
         self._csr = None
         self._tiles = None            # tile plan of the fused T3/Q4 path, built at the first assembly
         self.use_tiles = etype in (_capi.T3, _capi.Q4)
-        self.tile_nodes_R = 128
+        self.tile_nodes_R = 64        # 8x8-node Morton tiles: best measured on B200 (profiles/r1_tiles.md)
 
     def tile_plan(self, nodes_dev):
         """Symbolic side of the tile-fused assembly (psfem_tileplan_build); needs coordinates once."""
@@ -206,18 +206,18 @@ class Assembler:
             tile_elems = torch.empty(max(ninc, 1), **i32)
             tile_hdr = torch.empty(8 * n_tiles, **i32)
             tile_conn = torch.empty(4 * max(ninc, 1), **i32)
-            tile_off = torch.empty(16 * max(ninc, 1), dtype=torch.int16, device="cuda")
+            tile_rec = torch.empty(32 * max(ninc, 1), dtype=torch.uint8, device="cuda")
             nmeta = torch.empty(2 * n_tiles * R, **i32)
             info = (C.c_int64 * 8)()
             call("psfem_tileplan_build", ptr(nodes_dev), ptr(self.conn), self.nel, self.npe, self.n_nodes, R,
                  ptr(self.node_ptr), ptr(self.col_idx), ptr(tile_nodes), ptr(tile_elem_ptr), ptr(tile_elems), ptr(tile_hdr),
-                 ptr(tile_conn), ptr(tile_off), ptr(nmeta), info, ptr(ws), sz.value, stream_ptr())
+                 ptr(tile_conn), ptr(tile_rec), ptr(nmeta), info, ptr(ws), sz.value, stream_ptr())
             n_te = int(info[0])
             tile_elems = tile_elems[:n_te].clone()                  # drop the upper-bound slack
             tile_conn = tile_conn[: 4 * n_te].clone()
-            tile_off = tile_off[: 16 * n_te].clone()
+            tile_rec = tile_rec[: 32 * n_te].clone()
             del ws
-            self._tiles = dict(R=R, tile_hdr=tile_hdr, tile_conn=tile_conn, tile_off=tile_off, tile_elems=tile_elems, nmeta=nmeta,
+            self._tiles = dict(R=R, tile_hdr=tile_hdr, tile_conn=tile_conn, tile_rec=tile_rec, tile_elems=tile_elems, nmeta=nmeta,
                                info=info, max_elems=int(info[1]), max_rounds=int(info[3]), mean_elems=int(info[5]),
                                ws=workspace(256))
             if info[4] != 1:
@@ -254,10 +254,13 @@ class Assembler:
         if self.use_tiles and self.nel > 0:
             rc = lib.psfem_assemble_tiled(ptr(nodes_dev), self.nel, self.etype, self.n_nodes, float(E), float(nu), float(rho),
                                           float(t), what, tp["R"], tp["info"], ptr(tp["tile_hdr"]), ptr(tp["tile_conn"]),
-                                          ptr(tp["tile_off"]), ptr(tp["tile_elems"]), ptr(tp["nmeta"]),
+                                          ptr(tp["tile_rec"]), ptr(tp["tile_elems"]), ptr(tp["nmeta"]),
                                           ptr(K_vals), ptr(M_vals), ptr(tp["ws"]), 256, C.byref(bad), stream_ptr())
-            check(rc, bad.value)
-            return K_vals, M_vals
+            if rc == _capi.EINVAL and "shared memory" in _capi.last_error():
+                self.use_tiles = False          # tile too large for one SM: use the two-kernel path below
+            else:
+                check(rc, bad.value)
+                return K_vals, M_vals
         ws, nbytes = self._ws(what)
         rc = lib.psfem_assemble(ptr(nodes_dev), ptr(self.conn), self.nel, self.etype, self.n_nodes, float(E), float(nu),
                                 float(rho), float(t), what, self.n_pairs, ptr(self.node_ptr), ptr(self.pair_row),
