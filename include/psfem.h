@@ -142,6 +142,21 @@ int psfem_assemble_tiled(const double *d_nodes, int64_t nel, int etype, int64_t 
                          double *d_K_vals, double *d_M_vals, void *d_ws, size_t ws_bytes,
                          int64_t *h_bad_element, void *stream);
 
+/* ---- lattice assembly: the fast path for meshes with the topology of Polygones.mesh (Polygones.py:62-108) ----
+ * psfem_lattice_detect: h_nm = {n, m} (node columns, nodes per column) when EVERY element equals the formula of
+ * Polygones.py:83-85 (T3) / :100 (Q4) for node id = i*m+j, else {0, 0}.  Coordinates are not looked at: a
+ * jittered or otherwise deformed structured mesh is still a lattice.  d_ws: >= 16 bytes.  Synchronises.
+ * psfem_assemble_lattice (Q4): same result as psfem_assemble / psfem_assemble_tiled (values summed in ascending
+ * element id, Polygones.py:717-726) on the pattern of psfem_pattern_fill, but plan-free: a warp marches along i
+ * over a strip of 31 node rows, element matrices and the open node column live in registers, the rows owned by the
+ * neighbour lane travel by shuffle, finished node columns leave by bulk async stores.  d_ws: >= 32 bytes. */
+int psfem_lattice_detect(const int32_t *d_conn, int64_t nel, int etype, int64_t n_nodes, int64_t *h_nm /* [2] */,
+                         void *d_ws, size_t ws_bytes, void *stream);
+int psfem_assemble_lattice(const double *d_nodes, int64_t n, int64_t m, int etype,
+                           double E, double nu, double rho, double t, int what,
+                           double *d_K_vals, double *d_M_vals, void *d_ws, size_t ws_bytes,
+                           int64_t *h_bad_element, void *stream);
+
 /* element matrices only: Polygones.element_stiffness_matrix :566, element_mass_matrix :1250.
  * d_Ke / d_Me: nel*(2npe)^2 doubles, one row-major (2npe x 2npe) matrix per element.
  * Work space: psfem_assemble_workspace(nel, etype, what). */

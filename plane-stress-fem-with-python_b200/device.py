@@ -189,6 +189,12 @@ class Assembler:
         self._tiles = None            # tile plan of the fused T3/Q4 path, built at the first assembly
         self.use_tiles = etype in (_capi.T3, _capi.Q4)
         self.tile_nodes_R = 64        # 8x8-node Morton tiles: best measured on B200 (profiles/r1_tiles.md)
+        # lattice topology of Polygones.mesh (any coordinates): plan-free marching-warp assembly
+        nm = (C.c_int64 * 2)()
+        self._small_ws = workspace(256)
+        call("psfem_lattice_detect", ptr(conn_dev), self.nel, etype, self.n_nodes, nm, ptr(self._small_ws), 256, stream_ptr())
+        self.lattice = (int(nm[0]), int(nm[1])) if nm[0] > 0 else None
+        self.use_lattice = self.lattice is not None and etype == _capi.Q4
 
     def tile_plan(self, nodes_dev):
         """Symbolic side of the tile-fused assembly (psfem_tileplan_build); needs coordinates once."""
@@ -249,6 +255,12 @@ class Assembler:
         K_vals = (K_out if K_out is not None else torch.empty(max(self.nnz, 1), **f64)[: self.nnz]) if what & 1 else None
         M_vals = (M_out if M_out is not None else torch.empty(max(self.nnz, 1), **f64)[: self.nnz]) if what & 2 else None
         bad = C.c_int64(-1)
+        if self.use_lattice and self.nel > 0:
+            n, m = self.lattice
+            rc = lib.psfem_assemble_lattice(ptr(nodes_dev), n, m, self.etype, float(E), float(nu), float(rho), float(t), what,
+                                            ptr(K_vals), ptr(M_vals), ptr(self._small_ws), 256, C.byref(bad), stream_ptr())
+            check(rc, bad.value)
+            return K_vals, M_vals
         if self.use_tiles and self.nel > 0:
             tp = self.tile_plan(nodes_dev)
         if self.use_tiles and self.nel > 0:
