@@ -12,7 +12,9 @@ struct Mat {
 // 1/d without the IEEE division slow path: fp32 reciprocal seed + two Newton steps (relative error ~1e-16;
 // |d| >= 1e-10 is guaranteed by the Jacobian guard, far inside the fp32 exponent range)
 __device__ __forceinline__ double fast_rcp(double d) {
-    double x = (double)(1.0f / (float)d);
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"((float)d));   // one MUFU.RCP, relative error 2^-23
+    double x = (double)r;
     x = x * (2.0 - d * x);
     x = x * (2.0 - d * x);
     return x;

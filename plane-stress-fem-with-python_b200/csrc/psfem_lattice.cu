@@ -133,6 +133,10 @@ lattice_q4_kernel(const double2 *__restrict__ nodes, Mat mat, int n, int m, int 
         for (; ci < ib; ++ci) {
             const int64_t cpf = min(ci + 2, N);                  // coordinates of the step after this one
             const double2 f1 = nodes[cpf * m + jc0], f2 = nodes[cpf * m + jc1];
+            // ptxas consumes f1/f2 right away (it rotates the coordinate registers early), so the column after that
+            // is pulled into L1 one step ahead: the loads above then hit L1 instead of waiting for HBM
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(nodes + (int64_t)min(ci + 3, N) * m + jc0));
+            if (lane == 31) asm volatile("prefetch.global.L1 [%0];" ::"l"(nodes + (int64_t)min(ci + 3, N) * m + jc1));
             const bool el_ok = el_j_ok && ci < N;
             ElemQ4<IS_K, !IS_K> el;
             {
