@@ -69,6 +69,26 @@ def as_element_table(elements, npe_expected=None) -> ElementTable:
     return tab
 
 
+PIN_THRESHOLD = 1 << 20    # elements; smaller arrays are not worth a page-locked allocation
+
+
+def to_host(t):
+    """Device tensor -> host tensor (asynchronous into pinned memory when large; caller synchronises)."""
+    torch = _capi.torch_cuda()
+    if t.numel() < PIN_THRESHOLD:
+        return t.cpu()
+    h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    h.copy_(t, non_blocking=True)
+    return h
+
+
+def to_device(a, dtype=None):
+    """Host ndarray -> device tensor; page-locked sources (e.g. arrays this package returned) go by DMA."""
+    torch = _capi.torch_cuda()
+    a = np.ascontiguousarray(a, dtype=dtype)
+    return torch.from_numpy(a).to("cuda", non_blocking=False)
+
+
 # --------------------------------------------------------------------------------------------
 # CSR on the device
 # --------------------------------------------------------------------------------------------
@@ -113,10 +133,13 @@ class DeviceCSR:
         return s
 
     def to_scipy(self):
+        """Host scipy CSR.  Large arrays land in page-locked host memory (torch's caching host allocator), so the
+        7 GB of a 33.6 M-DOF matrix cross PCIe at DMA speed instead of through the pageable staging path; the
+        arrays are ordinary NumPy arrays for the caller (and upload at DMA speed when handed back to a driver)."""
         torch = _capi.torch_cuda()
+        parts = [to_host(t) for t in (self.vals, self.col_idx, self.row_ptr)]
         torch.cuda.current_stream().synchronize()
-        return sparse.csr_matrix((self.vals.cpu().numpy(), self.col_idx.cpu().numpy(), self.row_ptr.cpu().numpy()),
-                                 shape=self.shape)
+        return sparse.csr_matrix(tuple(h.numpy() for h in parts), shape=self.shape)
 
     @classmethod
     def from_scipy(cls, A):
