@@ -225,6 +225,44 @@ int psfem_pcg_update(int64_t n, double *d_x, double *d_r, const double *d_p, con
 int psfem_pcg_pupdate(int64_t n, double *d_p, const double *d_r, const double *d_dinv,
                       const double *d_rz_old, const double *d_rz_new, void *stream);
 
+/* ---- strip-partitioned Jacobi-PCG with the collectives FUSED into its kernels (multi-GPU, one process per GPU) ----
+ * Replaces, per iteration, two NCCL all-reduces and one halo send/recv by stores over NVLink/NVSwitch peer memory:
+ *   - every rank owns a small "board" and its extended p vector in memory that the other ranks map
+ *     (psfem_peer_alloc -> 64-byte CUDA IPC handle, exchanged by the host through torch.distributed;
+ *     psfem_peer_open on the other ranks);
+ *   - the SpMV kernel publishes its p.q partial to every board, the update kernel spins on its OWN board, adds the
+ *     partials in rank order (bit-identical on every rank) and publishes {r.z, r.r}; the p-update kernel reads them,
+ *     computes p and stores the first / last owned node column straight into the neighbours' extended vectors,
+ *     then raises their halo flag, which the next SpMV waits for.
+ * Sequence numbers only grow: psfem_dist_pcg_start takes seq >= 1, the following iterations seq+1, seq+2, ...
+ * (the host keeps the counter; it is never reset while the boards live).  Same recurrence and the same per-rank
+ * kernels as psfem_pcg_spmv_dot / _update / _pupdate. */
+#define PSFEM_MAX_RANKS 8
+typedef struct psfem_dist_ctx {
+    int32_t rank, world, has_left, has_right;
+    void *board[PSFEM_MAX_RANKS];         /* board[w] of rank w (peer mapped); board[rank] is this rank's own        */
+    double *p_ext;                         /* this rank's extended p vector (peer-visible allocation)                */
+    double *left_p_ext, *right_p_ext;      /* the neighbours' extended p vectors (peer mapped) or NULL                */
+    int64_t own_lo, n_own;                 /* owned entries of p_ext: [own_lo, own_lo + n_own)                        */
+    int64_t send_left_n, left_dst_off;     /* first send_left_n owned entries -> left_p_ext[left_dst_off ...]         */
+    int64_t send_right_n, right_dst_off;   /* last send_right_n owned entries -> right_p_ext[right_dst_off ...]       */
+    double *x, *r, *q, *dinv;              /* owned rows                                                              */
+    double *out3;                          /* 4 doubles of local device memory (psfem_dist_pcg_residual + scratch)    */
+    double *partials;                      /* max(n_blocks, 1184)*3 doubles                                           */
+    uint32_t *counter;                     /* 4 zero-initialised uint32                                               */
+} psfem_dist_ctx;
+int psfem_peer_board_bytes(size_t *bytes);
+int psfem_peer_alloc(size_t bytes, void **d_ptr, unsigned char *handle64);   /* zero-filled */
+int psfem_peer_open(const unsigned char *handle64, void **d_ptr);
+int psfem_peer_close(void *d_ptr);
+int psfem_peer_free(void *d_ptr);
+/* x = 0, r = b, p = D^-1 r (halo pushed), {r.z, r.r, b.b} published with sequence number seq */
+int psfem_dist_pcg_start(const psfem_dist_ctx *ctx, const double *d_b, uint64_t seq, void *stream);
+/* k iterations with sequence numbers seq_first .. seq_first+k-1 (seq_first = previous sequence number + 1) */
+int psfem_dist_pcg_iterations(const psfem_csr *A, const psfem_dist_ctx *ctx, int64_t k, uint64_t seq_first, void *stream);
+/* global {r.z, r.r, b.b} of the step with sequence number seq (b.b is valid for the start step only); synchronises */
+int psfem_dist_pcg_residual(const psfem_dist_ctx *ctx, uint64_t seq, double *h_out3, void *stream);
+
 /* ---- BLAS-1 helpers for the drivers (Lanczos, K_eff = K + c M, energies) ------------------ */
 int psfem_axpby(int64_t n, double a, const double *d_x, double b, const double *d_y /* may be NULL */,
                 double *d_out, void *stream);

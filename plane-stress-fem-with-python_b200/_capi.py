@@ -27,6 +27,18 @@ class psfem_csr(C.Structure):
                 ("vals", C.c_void_p), ("rowblk", C.c_void_p), ("n_blocks", C.c_int64), ("max_row_nnz", C.c_int64)]
 
 
+MAX_RANKS = 8
+
+
+class psfem_dist_ctx(C.Structure):
+    _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("has_left", C.c_int32), ("has_right", C.c_int32),
+                ("board", C.c_void_p * MAX_RANKS), ("p_ext", C.c_void_p), ("left_p_ext", C.c_void_p), ("right_p_ext", C.c_void_p),
+                ("own_lo", C.c_int64), ("n_own", C.c_int64), ("send_left_n", C.c_int64), ("left_dst_off", C.c_int64),
+                ("send_right_n", C.c_int64), ("right_dst_off", C.c_int64),
+                ("x", C.c_void_p), ("r", C.c_void_p), ("q", C.c_void_p), ("dinv", C.c_void_p), ("out3", C.c_void_p),
+                ("partials", C.c_void_p), ("counter", C.c_void_p)]
+
+
 if not os.path.exists(LIB_PATH):
     raise ImportError(
         f"{LIB_PATH} is missing: build the CUDA library first (python -c 'import __graft_entry__ as g; g.build()' "
@@ -39,6 +51,8 @@ _pi64 = C.POINTER(C.c_int64)
 _pdbl = C.POINTER(C.c_double)
 _psz = C.POINTER(C.c_size_t)
 _pcsr = C.POINTER(psfem_csr)
+_pctx = C.POINTER(psfem_dist_ctx)
+_u64 = C.c_uint64
 
 # name -> argtypes; must list every symbol include/psfem.h declares (tests/test_capi_symbols.py checks)
 SIGNATURES = {
@@ -77,6 +91,14 @@ SIGNATURES = {
     "psfem_pcg_spmv_dot": [_pcsr, _ptr, _i64, _ptr, _ptr, _ptr, _ptr, _ptr],
     "psfem_pcg_update": [_i64, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr],
     "psfem_pcg_pupdate": [_i64, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr],
+    "psfem_peer_board_bytes": [_psz],
+    "psfem_peer_alloc": [_sz, C.POINTER(C.c_void_p), _ptr],
+    "psfem_peer_open": [_ptr, C.POINTER(C.c_void_p)],
+    "psfem_peer_close": [_ptr],
+    "psfem_peer_free": [_ptr],
+    "psfem_dist_pcg_start": [_pctx, _ptr, _u64, _ptr],
+    "psfem_dist_pcg_iterations": [_pcsr, _pctx, _i64, _u64, _ptr],
+    "psfem_dist_pcg_residual": [_pctx, _u64, _pdbl, _ptr],
     "psfem_axpby": [_i64, _dbl, _ptr, _dbl, _ptr, _ptr, _ptr],
     "psfem_dot_workspace": [_i64, _psz],
     "psfem_dot": [_i64, _ptr, _ptr, _pdbl, _ptr, _sz, _ptr],

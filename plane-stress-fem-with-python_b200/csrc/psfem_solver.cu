@@ -10,6 +10,7 @@
 // Replaces: np.linalg.solve / scipy.linalg.solve / lu_factor+lu_solve (Statictest.py:69,
 // StaticTest2.py:71, Beamexemple.py:63, main.py:286,295,314) and the dense mat-vecs of
 // main.py:310,383-384.
+#include <cstring>
 #include "psfem_common.cuh"
 
 using namespace psfem;
@@ -98,6 +99,73 @@ struct PcgCtl {
     int done;
     int parity;
 };
+
+// ---------------------------------------------------------------------------------------------
+// peer boards: the collectives of the strip-partitioned PCG, fused into its three kernels.
+//
+// Every rank owns a PeerBoard in memory that all ranks map (CUDA IPC over NVLink/NVSwitch).  A reduction is
+// "everybody stores its partial into everybody's board, then a sequence number" (st.release.sys); the consumer
+// kernel spins on ITS OWN board (ld.acquire.sys, local HBM) and adds the partials in rank order, so every rank
+// gets the bit-identical sum without a collective launch.  The halo of p is stored straight into the
+// neighbours' extended p vectors by the kernel that computes p.  Sequence numbers only grow (one per PCG
+// iteration / solve start), values are double buffered by sequence parity.
+// ---------------------------------------------------------------------------------------------
+struct PeerBoard {
+    double val[2][2][PSFEM_MAX_RANKS][4];           // [0: p.q | 1: {r.z, r.r, b.b}][seq parity][source rank][slot]
+    unsigned long long flag[2][PSFEM_MAX_RANKS];    // seq of the value last published by a rank
+    unsigned long long halo_flag[2];                 // [0] left / [1] right neighbour's halo for iteration seq is in
+};
+struct PeerSync {
+    PeerBoard *board[PSFEM_MAX_RANKS];               // board[w] of rank w (peer mapped), board[rank] is local
+    int world, rank, has_left, has_right;
+    unsigned long long seq;
+    int *err;                                        // local flag: set when a wait gave up (a peer died), never hangs the GPU
+};
+constexpr long long PEER_SPIN_LIMIT = 1ll << 26;     // polls of local memory (~ tens of seconds) before giving up
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ double ld_relaxed_sys(const double *p) {
+    double v;
+    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+// one thread: store my partial(s) into every rank's board, then the sequence number
+template <int NV> __device__ __forceinline__ void peer_publish(const PeerSync &ps, int stage, const double (&v)[NV]) {
+    const int par = (int)(ps.seq & 1);
+    for (int w = 0; w < ps.world; ++w) {
+#pragma unroll
+        for (int q = 0; q < NV; ++q) ps.board[w]->val[stage][par][ps.rank][q] = v[q];
+    }
+    __threadfence_system();
+    for (int w = 0; w < ps.world; ++w) st_release_sys(&ps.board[w]->flag[stage][ps.rank], ps.seq);
+}
+// one thread: wait until every rank's partial of sequence `seq` is on my board, add them in rank order
+template <int NV> __device__ __forceinline__ void peer_wait_sum(const PeerSync &ps, int stage, unsigned long long seq, double (&out)[NV]) {
+    PeerBoard *me = ps.board[ps.rank];
+    long long spins = 0;
+    for (int w = 0; w < ps.world; ++w)
+        while (ld_acquire_sys(&me->flag[stage][w]) < seq)
+            if (++spins > PEER_SPIN_LIMIT) { *ps.err = 1; break; }
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+        double s = 0.0;
+        for (int w = 0; w < ps.world; ++w) s += ld_relaxed_sys(&me->val[stage][(int)(seq & 1)][w][q]);
+        out[q] = s;
+    }
+}
+__device__ __forceinline__ void peer_wait_halo(const PeerSync &ps) {   // one thread
+    PeerBoard *me = ps.board[ps.rank];
+    long long spins = 0;
+    if (ps.has_left) while (ld_acquire_sys(&me->halo_flag[0]) < ps.seq) if (++spins > PEER_SPIN_LIMIT) { *ps.err = 1; break; }
+    if (ps.has_right) while (ld_acquire_sys(&me->halo_flag[1]) < ps.seq) if (++spins > PEER_SPIN_LIMIT) { *ps.err = 1; break; }
+}
 
 // ---------------------------------------------------------------------------------------------
 // SpMV
@@ -204,7 +272,8 @@ __global__ void __launch_bounds__(SPMV2_THREADS, 2)
 spmv2_kernel(const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col_idx, const double *__restrict__ vals,
              const int32_t *__restrict__ rowblk, int n_blocks, int n_rows, int cap, const double *__restrict__ x, double alpha,
              double gamma, const double *__restrict__ z, double *__restrict__ y, const double *__restrict__ xdot,
-             double *__restrict__ dot_out, double *__restrict__ partials, unsigned int *counter, const int *__restrict__ done) {
+             double *__restrict__ dot_out, double *__restrict__ partials, unsigned int *counter, const int *__restrict__ done,
+             const PeerSync ps) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t full_bar[SPMV2_STAGES], empty_bar[SPMV2_STAGES];
     __shared__ Spmv2Meta meta[SPMV2_STAGES];
@@ -219,6 +288,7 @@ spmv2_kernel(const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ co
     if (tid == 0) {
         for (int s = 0; s < SPMV2_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], SPMV2_CONSUMERS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (ps.world) peer_wait_halo(ps);   // the neighbours' p values of this iteration sit in my extended vector
     }
     __syncthreads();
     const int n_mine = (n_blocks - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -317,14 +387,20 @@ spmv2_kernel(const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ co
     }
     if (DOT) {
         double total[1];
-        if (grid_sum<SPMV2_THREADS, 1>(dot, partials, counter, red, total)) *dot_out = total[0];
+        if (grid_sum<SPMV2_THREADS, 1>(dot, partials, counter, red, total)) {
+            *dot_out = total[0];
+            if (ps.world) peer_publish<1>(ps, 0, total);   // my p.q partial -> every rank's board
+        }
     }
 }
 
 int launch_spmv(const psfem_csr *A, const double *v2, const double *x1, const double *x2, double alpha, double beta,
                 double gamma, const double *z, double *y, const double *xdot, double *dot_out, double *partials,
-                unsigned int *counter, const int *done, cudaStream_t stream) {
+                unsigned int *counter, const int *done, cudaStream_t stream, const PeerSync *peer = nullptr) {
     PSFEM_REQUIRE(A && A->rowblk && A->n_blocks > 0, "spmv: matrix has no row-block plan (psfem_spmv_plan)");
+    PeerSync ps;
+    memset(&ps, 0, sizeof(ps));
+    if (peer) ps = *peer;
     const size_t smem = (size_t)(SPMV_T + A->max_row_nnz + 8) * sizeof(double);
     PSFEM_REQUIRE(smem <= 200 * 1024, "spmv: a row with %lld non-zeros does not fit the shared-memory stage", (long long)A->max_row_nnz);
     const bool dual = v2 != nullptr, dot = dot_out != nullptr;
@@ -342,16 +418,17 @@ int launch_spmv(const psfem_csr *A, const double *v2, const double *x1, const do
             if (dot) {
                 PSFEM_CUDA_CHECK(cudaFuncSetAttribute(spmv2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
                 spmv2_kernel<true><<<(unsigned)grid, SPMV2_THREADS, smem2, stream>>>(A->row_ptr, A->col_idx, A->vals, A->rowblk, (int)A->n_blocks, (int)A->n_rows, cap,
-                    x1, alpha, gamma, z, y, xdot, dot_out, partials, counter, done);
+                    x1, alpha, gamma, z, y, xdot, dot_out, partials, counter, done, ps);
             } else {
                 PSFEM_CUDA_CHECK(cudaFuncSetAttribute(spmv2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
                 spmv2_kernel<false><<<(unsigned)grid, SPMV2_THREADS, smem2, stream>>>(A->row_ptr, A->col_idx, A->vals, A->rowblk, (int)A->n_blocks, (int)A->n_rows, cap,
-                    x1, alpha, gamma, z, y, xdot, dot_out, partials, counter, done);
+                    x1, alpha, gamma, z, y, xdot, dot_out, partials, counter, done, ps);
             }
             PSFEM_LAUNCH_CHECK();
             return PSFEM_OK;
         }
     }
+    PSFEM_REQUIRE(!peer, "spmv: the peer-synchronised SpMV needs the TMA-staged kernel (>= 8 row blocks, 16-byte aligned CSR arrays)");
 #define PSFEM_SPMV_LAUNCH(D, O)                                                                                      \
     do {                                                                                                             \
         if (smem > 48 * 1024)                                                                                        \
@@ -595,6 +672,133 @@ __global__ void multi_axpy_kernel(int64_t m, int64_t n, const double *__restrict
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// strip-partitioned PCG with the collectives fused into the kernels (see PeerBoard above)
+// ---------------------------------------------------------------------------------------------
+struct HaloPush {   // where the first / last owned entries of p go in the neighbours' extended vectors
+    double *left, *right;
+    long long left_n, right_n, n;
+    __device__ __forceinline__ void operator()(long long i, double v) const {
+        if (left && i < left_n) left[i] = v;
+        if (right && i >= n - right_n) right[i - (n - right_n)] = v;
+    }
+};
+__device__ __forceinline__ void halo_signal(const PeerSync &ps) {   // one thread, after every block fenced its stores
+    if (ps.has_left) st_release_sys(&ps.board[ps.rank - 1]->halo_flag[1], ps.seq + 1);
+    if (ps.has_right) st_release_sys(&ps.board[ps.rank + 1]->halo_flag[0], ps.seq + 1);
+}
+
+// x = 0, r = b, p = dinv r (+ halo push), publishes {r.z, r.r, b.b}
+__global__ void __launch_bounds__(EW_THREADS)
+dist_init_kernel(int64_t n, const double *__restrict__ b, const double *__restrict__ dinv, double *__restrict__ x,
+                 double *__restrict__ r, double *__restrict__ p, HaloPush halo, PeerSync ps, double *__restrict__ partials,
+                 unsigned int *counter) {
+    __shared__ double red[EW_THREADS / 32];
+    double v[3] = {0, 0, 0};
+    for (int64_t i = blockIdx.x * (int64_t)EW_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * EW_THREADS) {
+        const double bi = b[i], zi = dinv[i] * bi;
+        x[i] = 0.0; r[i] = bi; p[i] = zi;
+        halo(i, zi);
+        v[0] += bi * zi;
+        v[1] += bi * bi;
+    }
+    v[2] = v[1];
+    __threadfence_system();
+    double tot[3];
+    if (grid_sum<EW_THREADS, 3>(v, partials, counter, red, tot)) {
+        peer_publish<3>(ps, 1, tot);
+        halo_signal(ps);
+    }
+}
+
+// alpha = (r.z)/(p.q) from the boards; x += alpha p; r -= alpha q; publishes {r.z, r.r}
+__global__ void __launch_bounds__(EW_THREADS)
+dist_update_kernel(int64_t n, double *__restrict__ x, double *__restrict__ r, const double *__restrict__ p,
+                   const double *__restrict__ q, const double *__restrict__ dinv, PeerSync ps, double *__restrict__ partials,
+                   unsigned int *counter) {
+    __shared__ double red[EW_THREADS / 32];
+    __shared__ double sc[2];
+    if (threadIdx.x == 0) {
+        double pq[1], rz[1];
+        peer_wait_sum<1>(ps, 0, ps.seq, pq);
+        peer_wait_sum<1>(ps, 1, ps.seq - 1, rz);
+        sc[0] = rz[0]; sc[1] = pq[0];
+    }
+    __syncthreads();
+    const double alpha = sc[0] / sc[1];
+    double v[2] = {0, 0};
+    for (int64_t i = blockIdx.x * (int64_t)EW_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * EW_THREADS) {
+        const double pi = p[i], qi = q[i];
+        x[i] += alpha * pi;
+        const double ri = r[i] - alpha * qi;
+        r[i] = ri;
+        v[0] += ri * (dinv[i] * ri);
+        v[1] += ri * ri;
+    }
+    double tot[2];
+    if (grid_sum<EW_THREADS, 2>(v, partials, counter, red, tot)) {
+        const double t3[3] = {tot[0], tot[1], 0.0};
+        peer_publish<3>(ps, 1, t3);
+    }
+}
+
+// beta = (r.z)_new/(r.z)_old from the boards; p = dinv r + beta p, halo entries stored into the neighbours' vectors
+__global__ void __launch_bounds__(EW_THREADS)
+dist_pupdate_kernel(int64_t n, double *__restrict__ p, const double *__restrict__ r, const double *__restrict__ dinv,
+                    HaloPush halo, PeerSync ps, unsigned int *counter) {
+    __shared__ double sc[2];
+    __shared__ bool is_last;
+    if (threadIdx.x == 0) {
+        double nw[1], old[1];
+        peer_wait_sum<1>(ps, 1, ps.seq, nw);
+        peer_wait_sum<1>(ps, 1, ps.seq - 1, old);
+        sc[0] = nw[0]; sc[1] = old[0];
+    }
+    __syncthreads();
+    const double beta = sc[0] / sc[1];
+    for (int64_t i = blockIdx.x * (int64_t)EW_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * EW_THREADS) {
+        const double v = dinv[i] * r[i] + beta * p[i];
+        p[i] = v;
+        halo(i, v);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int ticket = atomicAdd(counter, 1u);
+        is_last = (ticket == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last && threadIdx.x == 0) {
+        *counter = 0;
+        __threadfence_system();
+        halo_signal(ps);
+    }
+}
+
+// global {r.z, r.r, b.b} of sequence `seq` from my board
+__global__ void dist_read_kernel(PeerSync ps, double *out3) {
+    double t[3];
+    peer_wait_sum<3>(ps, 1, ps.seq, t);
+    out3[0] = t[0]; out3[1] = t[1]; out3[2] = t[2];
+}
+
+PeerSync make_peer(const psfem_dist_ctx *c, unsigned long long seq) {
+    PeerSync ps;
+    memset(&ps, 0, sizeof(ps));
+    for (int w = 0; w < c->world && w < PSFEM_MAX_RANKS; ++w) ps.board[w] = static_cast<PeerBoard *>(c->board[w]);
+    ps.world = c->world; ps.rank = c->rank; ps.has_left = c->has_left; ps.has_right = c->has_right;
+    ps.seq = seq;
+    ps.err = reinterpret_cast<int *>(c->counter + 3);
+    return ps;
+}
+HaloPush make_halo(const psfem_dist_ctx *c) {
+    HaloPush h;
+    h.left = c->has_left ? c->left_p_ext + c->left_dst_off : nullptr;
+    h.right = c->has_right ? c->right_p_ext + c->right_dst_off : nullptr;
+    h.left_n = c->send_left_n; h.right_n = c->send_right_n; h.n = c->n_own;
+    return h;
+}
+
 struct PcgWs {
     double *r, *p, *q, *dinv, *partials, *scal;
     PcgCtl *ctl;
@@ -709,6 +913,102 @@ extern "C" int psfem_pcg_pupdate(int64_t n, double *d_p, const double *d_r, cons
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     pcg_pupdate_kernel<<<ew_grid(n), EW_THREADS, 0, stream>>>(n, d_p, d_r, d_dinv, d_rz_old, d_rz_new, nullptr, nullptr);
     PSFEM_LAUNCH_CHECK();
+    return PSFEM_OK;
+}
+
+// ---- peer memory + fused strip-partitioned PCG ------------------------------------------------
+extern "C" int psfem_peer_board_bytes(size_t *bytes) {
+    PSFEM_REQUIRE(bytes, "peer_board_bytes: null output");
+    *bytes = align_up(sizeof(PeerBoard));
+    return PSFEM_OK;
+}
+
+extern "C" int psfem_peer_alloc(size_t bytes, void **d_ptr, unsigned char *handle64) {
+    PSFEM_REQUIRE(d_ptr && handle64 && bytes > 0, "peer_alloc: bad arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    void *p = nullptr;
+    PSFEM_CUDA_CHECK(cudaMalloc(&p, bytes));
+    cudaError_t e = cudaMemset(p, 0, bytes);
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        set_error("peer_alloc: %s", cudaGetErrorString(e));
+        return PSFEM_ECUDA;
+    }
+    memcpy(handle64, &h, 64);
+    *d_ptr = p;
+    return PSFEM_OK;
+}
+
+extern "C" int psfem_peer_open(const unsigned char *handle64, void **d_ptr) {
+    PSFEM_REQUIRE(d_ptr && handle64, "peer_open: bad arguments");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    PSFEM_CUDA_CHECK(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return PSFEM_OK;
+}
+
+extern "C" int psfem_peer_close(void *d_ptr) {
+    if (d_ptr) PSFEM_CUDA_CHECK(cudaIpcCloseMemHandle(d_ptr));
+    return PSFEM_OK;
+}
+
+extern "C" int psfem_peer_free(void *d_ptr) {
+    if (d_ptr) PSFEM_CUDA_CHECK(cudaFree(d_ptr));
+    return PSFEM_OK;
+}
+
+static int dist_check(const psfem_dist_ctx *c) {
+    PSFEM_REQUIRE(c && c->world >= 1 && c->world <= PSFEM_MAX_RANKS && c->rank >= 0 && c->rank < c->world, "dist_pcg: bad rank/world");
+    PSFEM_REQUIRE(c->p_ext && c->x && c->r && c->q && c->dinv && c->partials && c->counter && c->n_own > 0, "dist_pcg: null buffers");
+    PSFEM_REQUIRE(!c->has_left || (c->left_p_ext && c->rank > 0), "dist_pcg: left neighbour not mapped");
+    PSFEM_REQUIRE(!c->has_right || (c->right_p_ext && c->rank < c->world - 1), "dist_pcg: right neighbour not mapped");
+    for (int w = 0; w < c->world; ++w) PSFEM_REQUIRE(c->board[w], "dist_pcg: board of rank %d not mapped", w);
+    return PSFEM_OK;
+}
+
+extern "C" int psfem_dist_pcg_start(const psfem_dist_ctx *c, const double *d_b, uint64_t seq, void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (int rc = dist_check(c)) return rc;
+    PSFEM_REQUIRE(d_b && seq >= 1, "dist_pcg_start: bad arguments");
+    dist_init_kernel<<<ew_grid(c->n_own), EW_THREADS, 0, stream>>>(c->n_own, d_b, c->dinv, c->x, c->r, c->p_ext + c->own_lo, make_halo(c),
+                                                                  make_peer(c, seq), c->partials, c->counter + 2);
+    PSFEM_LAUNCH_CHECK();
+    return PSFEM_OK;
+}
+
+extern "C" int psfem_dist_pcg_iterations(const psfem_csr *A, const psfem_dist_ctx *c, int64_t k, uint64_t seq_first, void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (int rc = dist_check(c)) return rc;
+    PSFEM_REQUIRE(A && A->n_rows == c->n_own && seq_first >= 2, "dist_pcg_iterations: bad arguments");
+    double *p_own = c->p_ext + c->own_lo;
+    for (int64_t j = 0; j < k; ++j) {
+        const PeerSync ps = make_peer(c, seq_first + (uint64_t)j);
+        // q = A p_ext (waits for the neighbours' halo), p.q partial -> all boards
+        int rc = launch_spmv(A, nullptr, c->p_ext, nullptr, 1.0, 0.0, 0.0, nullptr, c->q, p_own, c->out3 + 3 /* local p.q, unused */, c->partials,
+                             c->counter, nullptr, stream, &ps);
+        if (rc) return rc;
+        dist_update_kernel<<<ew_grid(c->n_own), EW_THREADS, 0, stream>>>(c->n_own, c->x, c->r, p_own, c->q, c->dinv, ps, c->partials, c->counter + 1);
+        dist_pupdate_kernel<<<ew_grid(c->n_own), EW_THREADS, 0, stream>>>(c->n_own, p_own, c->r, c->dinv, make_halo(c), ps, c->counter + 2);
+    }
+    PSFEM_LAUNCH_CHECK();
+    return PSFEM_OK;
+}
+
+extern "C" int psfem_dist_pcg_residual(const psfem_dist_ctx *c, uint64_t seq, double *h_out3, void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (int rc = dist_check(c)) return rc;
+    PSFEM_REQUIRE(h_out3 && c->out3, "dist_pcg_residual: null output");
+    dist_read_kernel<<<1, 1, 0, stream>>>(make_peer(c, seq), c->out3);
+    PSFEM_LAUNCH_CHECK();
+    double h[4] = {0, 0, 0, 0};
+    PSFEM_CUDA_CHECK(cudaMemcpyAsync(h, c->out3, 3 * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    int err = 0;
+    PSFEM_CUDA_CHECK(cudaMemcpyAsync(&err, c->counter + 3, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    PSFEM_CUDA_CHECK(cudaStreamSynchronize(stream));
+    h_out3[0] = h[0]; h_out3[1] = h[1]; h_out3[2] = h[2];
+    if (err) { set_error("dist_pcg: a wait on a peer rank timed out"); return PSFEM_ECUDA; }
     return PSFEM_OK;
 }
 

@@ -160,6 +160,91 @@ def pcg_start(ops, comm: Comm, st: dict, b_own):
 
 
 # ------------------------------------------------------------------------------------------------
+# peer memory (CUDA IPC over NVLink / NVSwitch) for the fused strip solver
+# ------------------------------------------------------------------------------------------------
+class _RawDeviceArray:
+    """__cuda_array_interface__ view of library-owned device memory (torch.as_tensor aliases it)."""
+
+    def __init__(self, ptr_, n, typestr="<f8"):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": typestr, "data": (int(ptr_), False), "version": 2}
+
+
+class PeerFabric:
+    """This rank's board and extended p vector live in memory that the other ranks map (psfem_peer_alloc /
+    psfem_peer_open); the PCG kernels then exchange their scalars and halo columns with plain stores over
+    NVLink instead of NCCL calls (include/psfem.h, psfem_dist_*).  The host only swaps the 64-byte IPC
+    handles and the halo sizes once, through torch.distributed."""
+
+    def __init__(self, part: StripPartition, plan: dict, dist_module):
+        torch = _capi.torch_cuda()
+        self.part, self.plan, self.dist = part, plan, dist_module
+        self.opened = []
+        self.own = []
+        world, rank = part.world, part.rank
+        if world > _capi.MAX_RANKS:
+            raise RuntimeError(f"fused strip solver supports up to {_capi.MAX_RANKS} ranks")
+        sz = C.c_size_t(0)
+        call("psfem_peer_board_bytes", C.byref(sz))
+        self.board_ptr, hb = self._alloc(sz.value)
+        self.n_ext_free = plan["n_ext_free"]
+        self.p_ptr, hp = self._alloc(max(self.n_ext_free, 1) * 8)
+        lo, hi = plan["own"]
+        mine = dict(board=hb, p=hp, lo=lo, hi=hi, n_ext_free=self.n_ext_free,
+                    send_left=plan["send_left"], send_right=plan["send_right"])
+        everyone = [None] * world
+        dist_module.all_gather_object(everyone, mine)
+        self.boards = [None] * world
+        for w in range(world):
+            self.boards[w] = self.board_ptr if w == rank else self._open(everyone[w]["board"])
+        self.left_p = self.right_p = None
+        self.left_dst_off = self.right_dst_off = 0
+        self.send_left_n = self.send_right_n = 0
+        if part.left is not None:
+            nb = everyone[part.left]
+            self.left_p = self._open(nb["p"])
+            self.left_dst_off = nb["hi"]                                   # its recv_right region [hi, n_ext_free)
+            self.send_left_n = plan["send_left"][1] - plan["send_left"][0]
+            if self.send_left_n != nb["n_ext_free"] - nb["hi"] or plan["send_left"][0] != lo:
+                raise RuntimeError("halo plan mismatch with the left neighbour")
+        if part.right is not None:
+            nb = everyone[part.right]
+            self.right_p = self._open(nb["p"])
+            self.right_dst_off = 0                                           # its recv_left region [0, lo)
+            self.send_right_n = plan["send_right"][1] - plan["send_right"][0]
+            if self.send_right_n != nb["lo"] or plan["send_right"][1] != hi:
+                raise RuntimeError("halo plan mismatch with the right neighbour")
+        self.p_ext = torch.as_tensor(_RawDeviceArray(self.p_ptr, self.n_ext_free), device="cuda")
+        dist_module.barrier()
+
+    def _alloc(self, nbytes):
+        p = C.c_void_p(0)
+        h = (C.c_ubyte * 64)()
+        call("psfem_peer_alloc", int(nbytes), C.byref(p), h)
+        self.own.append(p.value)
+        return p.value, bytes(h)
+
+    def _open(self, handle):
+        p = C.c_void_p(0)
+        h = (C.c_ubyte * 64).from_buffer_copy(handle)
+        call("psfem_peer_open", h, C.byref(p))
+        self.opened.append(p.value)
+        return p.value
+
+    def close(self):
+        torch = _capi.torch_cuda()
+        torch.cuda.synchronize()
+        self.dist.barrier()                       # nobody still stores into / reads from a mapping
+        self.p_ext = None
+        for q in self.opened:
+            call("psfem_peer_close", C.c_void_p(q))
+        self.opened = []
+        self.dist.barrier()
+        for q in self.own:
+            call("psfem_peer_free", C.c_void_p(q))
+        self.own = []
+
+
+# ------------------------------------------------------------------------------------------------
 # CUDA backend
 # ------------------------------------------------------------------------------------------------
 class CudaOps:
@@ -197,7 +282,13 @@ class StripProblem:
     benchmark object (world = 1)."""
 
     def __init__(self, L, l, N, M, rank=0, world=1, E=210e9, nu=0.3, t=0.1, element_type="quad", mesh_type="coarse",
-                 load=(0.0, -1e6)):
+                 load=(0.0, -1e6), transport=None):
+        import os
+        # "peer": collectives fused into the PCG kernels over CUDA-IPC peer memory (default for world > 1);
+        # "nccl": torch.distributed all-reduce + send/recv between the kernels
+        self.transport = transport or os.environ.get("PSFEM_DIST_TRANSPORT", "peer")
+        self.fabric = None
+        self.seq = 0
         self.L, self.l, self.N, self.M = L, l, N, M
         self.rank, self.world = rank, world
         self.E, self.nu, self.t = E, nu, t
@@ -262,21 +353,62 @@ class StripProblem:
         import torch.distributed as dist
         self.comm = Comm(p, self.plan, dist if self.world > 1 else None)
         n = self.n_owned_free
+        if self.world > 1 and self.transport == "peer":
+            try:
+                self.fabric = PeerFabric(p, self.plan, dist)
+            except Exception as e:                      # no P2P / IPC on this box: keep the NCCL transport
+                import warnings
+                warnings.warn(f"peer-memory transport unavailable ({e}); using NCCL")
+                self.fabric, self.transport = None, "nccl"
+        p_ext = self.fabric.p_ext if self.fabric else torch.zeros(self.n_ext_free, **f64)
         self.st = dict(x=torch.zeros(n, **f64), r=self.b_own.clone(), q=torch.empty(n, **f64),
-                       dinv=torch.empty(n, **f64), p_ext=torch.zeros(self.n_ext_free, **f64),
+                       dinv=torch.empty(n, **f64), p_ext=p_ext,
                        rz=torch.zeros(2, **f64), pq=torch.zeros(1, **f64), out2=torch.zeros(2, **f64),
-                       out3=torch.zeros(3, **f64), parity=0, iters=0)
+                       out3=torch.zeros(4, **f64), parity=0, iters=0)
         call("psfem_extract_diag", C.byref(self.A), lo, 1, ptr(self.st["dinv"]), stream_ptr())
-        pcg_start(self.ops, self.comm, self.st, self.b_own)
+        if self.fabric:
+            fb, st = self.fabric, self.st
+            c = self.ctx = _capi.psfem_dist_ctx()
+            c.rank, c.world = self.rank, self.world
+            c.has_left, c.has_right = int(p.left is not None), int(p.right is not None)
+            for w in range(self.world):
+                c.board[w] = fb.boards[w]
+            c.p_ext, c.left_p_ext, c.right_p_ext = fb.p_ptr, fb.left_p, fb.right_p
+            c.own_lo, c.n_own = lo, n
+            c.send_left_n, c.left_dst_off = fb.send_left_n, fb.left_dst_off
+            c.send_right_n, c.right_dst_off = fb.send_right_n, fb.right_dst_off
+            c.x, c.r, c.q, c.dinv = st["x"].data_ptr(), st["r"].data_ptr(), st["q"].data_ptr(), st["dinv"].data_ptr()
+            c.out3 = st["out3"].data_ptr()
+            c.partials, c.counter = self.ops.partials.data_ptr(), self.ops.counter.data_ptr()
+        self.start()
         torch.cuda.synchronize()
         return self
+
+    def start(self):
+        """x = 0, r = b, p = D^-1 r with its halo, r.z / r.r / b.b."""
+        if self.fabric:
+            self.seq += 1
+            call("psfem_dist_pcg_start", C.byref(self.ctx), ptr(self.b_own), self.seq, stream_ptr())
+            self.st["iters"] = 0
+            h = (C.c_double * 3)()
+            call("psfem_dist_pcg_residual", C.byref(self.ctx), self.seq, h, stream_ptr())
+            self._bb = float(h[2])
+        else:
+            self.st["x"].zero_()
+            self.st["r"].copy_(self.b_own)
+            pcg_start(self.ops, self.comm, self.st, self.b_own)
 
     # -- timed pieces -----------------------------------------------------------------------------
     def assemble(self):
         self.asm.assemble(self.nodes, E=self.E, nu=self.nu, t=self.t, what=1, K_out=self.K_vals)
 
     def cg_iterations(self, k):
-        pcg_iterations(self.ops, self.comm, self.st, k)
+        if self.fabric:   # three kernels per iteration, no collective launches: scalars and halo go through peer memory
+            call("psfem_dist_pcg_iterations", C.byref(self.A), C.byref(self.ctx), int(k), self.seq + 1, stream_ptr())
+            self.seq += int(k)
+            self.st["iters"] += int(k)
+        else:
+            pcg_iterations(self.ops, self.comm, self.st, k)
 
     def spmv_only(self, k):
         lo, _ = self.plan["own"]
@@ -285,6 +417,10 @@ class StripProblem:
 
     def residual(self):
         """(||r||, ||b||) from the recurrence (global)."""
+        if self.fabric:
+            h = (C.c_double * 3)()
+            call("psfem_dist_pcg_residual", C.byref(self.ctx), self.seq, h, stream_ptr())
+            return float(np.sqrt(h[1])), float(np.sqrt(self._bb))
         rr = self.st["out2"][1].item() if self.st["iters"] else self.st["out3"][1].item()
         bb = self.st["out3"][2].item()
         return float(np.sqrt(rr)), float(np.sqrt(bb))
@@ -304,9 +440,7 @@ class StripProblem:
 
     def full_solve(self, rtol):
         torch = _capi.torch_cuda()
-        self.st["x"].zero_()
-        self.st["r"].copy_(self.b_own)
-        pcg_start(self.ops, self.comm, self.st, self.b_own)
+        self.start()
         torch.cuda.synchronize()
         return self.solve(rtol)
 
@@ -344,6 +478,10 @@ class StripProblem:
                 "calls": "per rank: pinned host strip mesh -> H2D -> pattern + assembly + BC reduction -> PCG iterations -> residual D2H"}
 
     def release(self):
-        for k in ("asm", "K_vals", "K_ext_red", "K_red", "fm", "st", "ops", "A", "b_own", "nodes", "conn"):
+        if getattr(self, "fabric", None) is not None:
+            self.st["p_ext"] = None
+            self.fabric.close()
+            self.fabric = None
+        for k in ("asm", "K_vals", "K_ext_red", "K_red", "fm", "st", "ops", "A", "b_own", "nodes", "conn", "ctx"):
             if hasattr(self, k):
                 delattr(self, k)
