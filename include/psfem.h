@@ -247,7 +247,7 @@ typedef struct psfem_dist_ctx {
     int64_t send_left_n, left_dst_off;     /* first send_left_n owned entries -> left_p_ext[left_dst_off ...]         */
     int64_t send_right_n, right_dst_off;   /* last send_right_n owned entries -> right_p_ext[right_dst_off ...]       */
     double *x, *r, *q, *dinv;              /* owned rows                                                              */
-    double *out3;                          /* 4 doubles of local device memory (psfem_dist_pcg_residual + scratch)    */
+    double *out3;                          /* 8 doubles of local device memory: global scalars of the recurrence      */
     double *partials;                      /* max(n_blocks, 1184)*3 doubles                                           */
     uint32_t *counter;                     /* 4 zero-initialised uint32                                               */
 } psfem_dist_ctx;
@@ -260,6 +260,9 @@ int psfem_peer_free(void *d_ptr);
 int psfem_dist_pcg_start(const psfem_dist_ctx *ctx, const double *d_b, uint64_t seq, void *stream);
 /* k iterations with sequence numbers seq_first .. seq_first+k-1 (seq_first = previous sequence number + 1) */
 int psfem_dist_pcg_iterations(const psfem_csr *A, const psfem_dist_ctx *ctx, int64_t k, uint64_t seq_first, void *stream);
+/* diagnostic twin of psfem_dist_pcg_iterations: mean milliseconds of {SpMV+dot, update, p-update} (CUDA events
+ * around every kernel; synchronises) */
+int psfem_dist_pcg_profile(const psfem_csr *A, const psfem_dist_ctx *ctx, int64_t k, uint64_t seq_first, double *h_ms3, void *stream);
 /* global {r.z, r.r, b.b} of the step with sequence number seq (b.b is valid for the start step only); synchronises */
 int psfem_dist_pcg_residual(const psfem_dist_ctx *ctx, uint64_t seq, double *h_out3, void *stream);
 

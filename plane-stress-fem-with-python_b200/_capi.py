@@ -98,6 +98,7 @@ SIGNATURES = {
     "psfem_peer_free": [_ptr],
     "psfem_dist_pcg_start": [_pctx, _ptr, _u64, _ptr],
     "psfem_dist_pcg_iterations": [_pcsr, _pctx, _i64, _u64, _ptr],
+    "psfem_dist_pcg_profile": [_pcsr, _pctx, _i64, _u64, _pdbl, _ptr],
     "psfem_dist_pcg_residual": [_pctx, _u64, _pdbl, _ptr],
     "psfem_axpby": [_i64, _dbl, _ptr, _dbl, _ptr, _ptr, _ptr],
     "psfem_dot_workspace": [_i64, _psz],

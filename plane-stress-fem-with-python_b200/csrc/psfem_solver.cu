@@ -11,6 +11,7 @@
 // StaticTest2.py:71, Beamexemple.py:63, main.py:286,295,314) and the dense mat-vecs of
 // main.py:310,383-384.
 #include <cstring>
+#include <vector>
 #include "psfem_common.cuh"
 
 using namespace psfem;
@@ -59,7 +60,7 @@ __global__ void max_row_kernel(const int32_t *__restrict__ row_ptr, int64_t n, i
 // deterministic grid-wide sums: per-block partials, the last block to finish adds them in a fixed
 // order (no floating-point atomics).
 // ---------------------------------------------------------------------------------------------
-template <int THREADS, int NV>
+template <int THREADS, int NV, bool SYS_FENCE = false>
 __device__ __forceinline__ bool grid_sum(double (&v)[NV], double *__restrict__ partials, unsigned int *counter,
                                          double *smem, double (&total)[NV]) {
     __shared__ bool is_last;
@@ -69,9 +70,9 @@ __device__ __forceinline__ bool grid_sum(double (&v)[NV], double *__restrict__ p
         double s = block_sum<THREADS>(v[q], smem);
         if (threadIdx.x == 0) partials[(int64_t)q * nb + blockIdx.x] = s;
     }
-    __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
+        if (SYS_FENCE) __threadfence_system(); else __threadfence();
         unsigned int ticket = atomicAdd(counter, 1u);
         is_last = (ticket == (unsigned)nb - 1);
     }
@@ -104,9 +105,10 @@ struct PcgCtl {
 // peer boards: the collectives of the strip-partitioned PCG, fused into its three kernels.
 //
 // Every rank owns a PeerBoard in memory that all ranks map (CUDA IPC over NVLink/NVSwitch).  A reduction is
-// "everybody stores its partial into everybody's board, then a sequence number" (st.release.sys); the consumer
-// kernel spins on ITS OWN board (ld.acquire.sys, local HBM) and adds the partials in rank order, so every rank
-// gets the bit-identical sum without a collective launch.  The halo of p is stored straight into the
+// "everybody stores its partial into everybody's board, then a sequence number"; the LAST block of the producing
+// kernel then spins on ITS OWN board (one thread, ld.acquire.sys on local HBM), adds the partials in rank order --
+// every rank gets the bit-identical sum -- and leaves the result in local memory for the next kernel, so no
+// collective is launched and no consumer block ever polls.  The halo of p is stored straight into the
 // neighbours' extended p vectors by the kernel that computes p.  Sequence numbers only grow (one per PCG
 // iteration / solve start), values are double buffered by sequence parity.
 // ---------------------------------------------------------------------------------------------
@@ -120,6 +122,7 @@ struct PeerSync {
     int world, rank, has_left, has_right;
     unsigned long long seq;
     int *err;                                        // local flag: set when a wait gave up (a peer died), never hangs the GPU
+    double *scal;                                    // local scalars: [0] r.z [1] r.r [2] b.b [3] scratch [4] p.q [5+parity] r.z by sequence parity
 };
 constexpr long long PEER_SPIN_LIMIT = 1ll << 26;     // polls of local memory (~ tens of seconds) before giving up
 
@@ -128,8 +131,10 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+// flag stores are RELAXED: the publisher issues ONE system-scope fence after its data stores and before all of
+// its flag stores (fence + relaxed store = release); a st.release per flag would drain the store queues per flag
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ double ld_relaxed_sys(const double *p) {
     double v;
@@ -144,7 +149,7 @@ template <int NV> __device__ __forceinline__ void peer_publish(const PeerSync &p
         for (int q = 0; q < NV; ++q) ps.board[w]->val[stage][par][ps.rank][q] = v[q];
     }
     __threadfence_system();
-    for (int w = 0; w < ps.world; ++w) st_release_sys(&ps.board[w]->flag[stage][ps.rank], ps.seq);
+    for (int w = 0; w < ps.world; ++w) st_relaxed_sys(&ps.board[w]->flag[stage][ps.rank], ps.seq);
 }
 // one thread: wait until every rank's partial of sequence `seq` is on my board, add them in rank order
 template <int NV> __device__ __forceinline__ void peer_wait_sum(const PeerSync &ps, int stage, unsigned long long seq, double (&out)[NV]) {
@@ -288,7 +293,6 @@ spmv2_kernel(const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ co
     if (tid == 0) {
         for (int s = 0; s < SPMV2_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], SPMV2_CONSUMERS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        if (ps.world) peer_wait_halo(ps);   // the neighbours' p values of this iteration sit in my extended vector
     }
     __syncthreads();
     const int n_mine = (n_blocks - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -389,7 +393,12 @@ spmv2_kernel(const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ co
         double total[1];
         if (grid_sum<SPMV2_THREADS, 1>(dot, partials, counter, red, total)) {
             *dot_out = total[0];
-            if (ps.world) peer_publish<1>(ps, 0, total);   // my p.q partial -> every rank's board
+            if (ps.world) {   // my p.q partial -> every rank's board; the global sum (rank order) stays in local memory
+                peer_publish<1>(ps, 0, total);
+                double pq[1];
+                peer_wait_sum<1>(ps, 0, ps.seq, pq);
+                ps.scal[4] = pq[0];
+            }
         }
     }
 }
@@ -678,14 +687,25 @@ __global__ void multi_axpy_kernel(int64_t m, int64_t n, const double *__restrict
 struct HaloPush {   // where the first / last owned entries of p go in the neighbours' extended vectors
     double *left, *right;
     long long left_n, right_n, n;
-    __device__ __forceinline__ void operator()(long long i, double v) const {
-        if (left && i < left_n) left[i] = v;
-        if (right && i >= n - right_n) right[i - (n - right_n)] = v;
+    // Called by every thread AFTER its grid-stride loop over i = base, base + stride, ...: the thread re-reads the
+    // halo entries it wrote itself (same index mapping, so program order suffices) and stores them into the
+    // neighbours' vectors.  Kept out of the streaming loop so that loop stays free of possibly aliasing stores.
+    __device__ __forceinline__ bool operator()(const double *p, long long base, long long stride) const {
+        bool sent = false;
+        if (left)
+            for (long long i = base; i < left_n; i += stride) { left[i] = p[i]; sent = true; }
+        if (right) {
+            const long long first = n - right_n;
+            long long i = base;
+            if (i < first) i += (first - i + stride - 1) / stride * stride;
+            for (; i < n; i += stride) { right[i - first] = p[i]; sent = true; }
+        }
+        return sent;
     }
 };
-__device__ __forceinline__ void halo_signal(const PeerSync &ps) {   // one thread, after every block fenced its stores
-    if (ps.has_left) st_release_sys(&ps.board[ps.rank - 1]->halo_flag[1], ps.seq + 1);
-    if (ps.has_right) st_release_sys(&ps.board[ps.rank + 1]->halo_flag[0], ps.seq + 1);
+__device__ __forceinline__ void halo_signal(const PeerSync &ps) {   // one thread, after a system-scope fence that follows every block's halo stores
+    if (ps.has_left) st_relaxed_sys(&ps.board[ps.rank - 1]->halo_flag[1], ps.seq + 1);
+    if (ps.has_right) st_relaxed_sys(&ps.board[ps.rank + 1]->halo_flag[0], ps.seq + 1);
 }
 
 // x = 0, r = b, p = dinv r (+ halo push), publishes {r.z, r.r, b.b}
@@ -698,16 +718,23 @@ dist_init_kernel(int64_t n, const double *__restrict__ b, const double *__restri
     for (int64_t i = blockIdx.x * (int64_t)EW_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * EW_THREADS) {
         const double bi = b[i], zi = dinv[i] * bi;
         x[i] = 0.0; r[i] = bi; p[i] = zi;
-        halo(i, zi);
         v[0] += bi * zi;
         v[1] += bi * bi;
     }
     v[2] = v[1];
-    __threadfence_system();
+    halo(p, blockIdx.x * (long long)EW_THREADS + threadIdx.x, (long long)gridDim.x * EW_THREADS);
+    // the block barriers inside grid_sum order every thread's halo stores before thread 0's system-scope fence
+    // below (cumulativity), so one fence per block suffices
     double tot[3];
-    if (grid_sum<EW_THREADS, 3>(v, partials, counter, red, tot)) {
+    if (grid_sum<EW_THREADS, 3, true>(v, partials, counter, red, tot)) {
         peer_publish<3>(ps, 1, tot);
         halo_signal(ps);
+        double g[3];
+        peer_wait_sum<3>(ps, 1, ps.seq, g);
+        ps.scal[0] = g[0]; ps.scal[1] = g[1]; ps.scal[2] = g[2]; ps.scal[5 + (int)(ps.seq & 1)] = g[0];
+        PeerSync nxt = ps;
+        nxt.seq = ps.seq + 1;
+        peer_wait_halo(nxt);   // the neighbours' first p columns are in my extended vector before the first SpMV starts
     }
 }
 
@@ -717,15 +744,7 @@ dist_update_kernel(int64_t n, double *__restrict__ x, double *__restrict__ r, co
                    const double *__restrict__ q, const double *__restrict__ dinv, PeerSync ps, double *__restrict__ partials,
                    unsigned int *counter) {
     __shared__ double red[EW_THREADS / 32];
-    __shared__ double sc[2];
-    if (threadIdx.x == 0) {
-        double pq[1], rz[1];
-        peer_wait_sum<1>(ps, 0, ps.seq, pq);
-        peer_wait_sum<1>(ps, 1, ps.seq - 1, rz);
-        sc[0] = rz[0]; sc[1] = pq[0];
-    }
-    __syncthreads();
-    const double alpha = sc[0] / sc[1];
+    const double alpha = ps.scal[5 + (int)((ps.seq - 1) & 1)] / ps.scal[4];   // global sums left by the previous kernels' last blocks
     double v[2] = {0, 0};
     for (int64_t i = blockIdx.x * (int64_t)EW_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * EW_THREADS) {
         const double pi = p[i], qi = q[i];
@@ -739,6 +758,9 @@ dist_update_kernel(int64_t n, double *__restrict__ x, double *__restrict__ r, co
     if (grid_sum<EW_THREADS, 2>(v, partials, counter, red, tot)) {
         const double t3[3] = {tot[0], tot[1], 0.0};
         peer_publish<3>(ps, 1, t3);
+        double g[3];
+        peer_wait_sum<3>(ps, 1, ps.seq, g);
+        ps.scal[0] = g[0]; ps.scal[1] = g[1]; ps.scal[5 + (int)(ps.seq & 1)] = g[0];
     }
 }
 
@@ -746,24 +768,15 @@ dist_update_kernel(int64_t n, double *__restrict__ x, double *__restrict__ r, co
 __global__ void __launch_bounds__(EW_THREADS)
 dist_pupdate_kernel(int64_t n, double *__restrict__ p, const double *__restrict__ r, const double *__restrict__ dinv,
                     HaloPush halo, PeerSync ps, unsigned int *counter) {
-    __shared__ double sc[2];
     __shared__ bool is_last;
+    const double beta = ps.scal[5 + (int)(ps.seq & 1)] / ps.scal[5 + (int)((ps.seq - 1) & 1)];
+    for (int64_t i = blockIdx.x * (int64_t)EW_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * EW_THREADS)
+        p[i] = dinv[i] * r[i] + beta * p[i];
+    const bool sent = halo(p, blockIdx.x * (long long)EW_THREADS + threadIdx.x, (long long)gridDim.x * EW_THREADS);
+    const int block_sent = __syncthreads_or(sent ? 1 : 0);
     if (threadIdx.x == 0) {
-        double nw[1], old[1];
-        peer_wait_sum<1>(ps, 1, ps.seq, nw);
-        peer_wait_sum<1>(ps, 1, ps.seq - 1, old);
-        sc[0] = nw[0]; sc[1] = old[0];
-    }
-    __syncthreads();
-    const double beta = sc[0] / sc[1];
-    for (int64_t i = blockIdx.x * (int64_t)EW_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * EW_THREADS) {
-        const double v = dinv[i] * r[i] + beta * p[i];
-        p[i] = v;
-        halo(i, v);
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) {
+        // after the barrier one fence covers the halo stores of the whole block; blocks without halo entries skip it
+        if (block_sent) __threadfence_system(); else __threadfence();
         unsigned int ticket = atomicAdd(counter, 1u);
         is_last = (ticket == gridDim.x - 1);
     }
@@ -772,14 +785,10 @@ dist_pupdate_kernel(int64_t n, double *__restrict__ p, const double *__restrict_
         *counter = 0;
         __threadfence_system();
         halo_signal(ps);
+        PeerSync nxt = ps;
+        nxt.seq = ps.seq + 1;
+        peer_wait_halo(nxt);   // my neighbours' columns for the next SpMV are in before this kernel ends
     }
-}
-
-// global {r.z, r.r, b.b} of sequence `seq` from my board
-__global__ void dist_read_kernel(PeerSync ps, double *out3) {
-    double t[3];
-    peer_wait_sum<3>(ps, 1, ps.seq, t);
-    out3[0] = t[0]; out3[1] = t[1]; out3[2] = t[2];
 }
 
 PeerSync make_peer(const psfem_dist_ctx *c, unsigned long long seq) {
@@ -789,6 +798,7 @@ PeerSync make_peer(const psfem_dist_ctx *c, unsigned long long seq) {
     ps.world = c->world; ps.rank = c->rank; ps.has_left = c->has_left; ps.has_right = c->has_right;
     ps.seq = seq;
     ps.err = reinterpret_cast<int *>(c->counter + 3);
+    ps.scal = c->out3;
     return ps;
 }
 HaloPush make_halo(const psfem_dist_ctx *c) {
@@ -996,12 +1006,45 @@ extern "C" int psfem_dist_pcg_iterations(const psfem_csr *A, const psfem_dist_ct
     return PSFEM_OK;
 }
 
+// diagnostic twin of psfem_dist_pcg_iterations: CUDA events around every kernel, mean milliseconds of
+// {SpMV+dot, update, p-update} over the k iterations (synchronises)
+extern "C" int psfem_dist_pcg_profile(const psfem_csr *A, const psfem_dist_ctx *c, int64_t k, uint64_t seq_first, double *h_ms3,
+                                      void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (int rc = dist_check(c)) return rc;
+    PSFEM_REQUIRE(A && A->n_rows == c->n_own && seq_first >= 2 && h_ms3 && k > 0 && k <= 4096, "dist_pcg_profile: bad arguments");
+    double *p_own = c->p_ext + c->own_lo;
+    std::vector<cudaEvent_t> ev(3 * k + 1);
+    for (auto &e : ev) PSFEM_CUDA_CHECK(cudaEventCreate(&e));
+    PSFEM_CUDA_CHECK(cudaEventRecord(ev[0], stream));
+    for (int64_t j = 0; j < k; ++j) {
+        const PeerSync ps = make_peer(c, seq_first + (uint64_t)j);
+        int rc = launch_spmv(A, nullptr, c->p_ext, nullptr, 1.0, 0.0, 0.0, nullptr, c->q, p_own, c->out3 + 3, c->partials, c->counter, nullptr, stream, &ps);
+        if (rc) return rc;
+        cudaEventRecord(ev[3 * j + 1], stream);
+        dist_update_kernel<<<ew_grid(c->n_own), EW_THREADS, 0, stream>>>(c->n_own, c->x, c->r, p_own, c->q, c->dinv, ps, c->partials, c->counter + 1);
+        cudaEventRecord(ev[3 * j + 2], stream);
+        dist_pupdate_kernel<<<ew_grid(c->n_own), EW_THREADS, 0, stream>>>(c->n_own, p_own, c->r, c->dinv, make_halo(c), ps, c->counter + 2);
+        cudaEventRecord(ev[3 * j + 3], stream);
+    }
+    PSFEM_LAUNCH_CHECK();
+    PSFEM_CUDA_CHECK(cudaStreamSynchronize(stream));
+    h_ms3[0] = h_ms3[1] = h_ms3[2] = 0.0;
+    for (int64_t j = 0; j < k; ++j)
+        for (int q = 0; q < 3; ++q) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ev[3 * j + q], ev[3 * j + q + 1]);
+            h_ms3[q] += ms / (double)k;
+        }
+    for (auto &e : ev) cudaEventDestroy(e);
+    return PSFEM_OK;
+}
+
 extern "C" int psfem_dist_pcg_residual(const psfem_dist_ctx *c, uint64_t seq, double *h_out3, void *stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (int rc = dist_check(c)) return rc;
     PSFEM_REQUIRE(h_out3 && c->out3, "dist_pcg_residual: null output");
-    dist_read_kernel<<<1, 1, 0, stream>>>(make_peer(c, seq), c->out3);
-    PSFEM_LAUNCH_CHECK();
+    (void)seq;   // the sums of the last completed step were left in local memory by its last block
     double h[4] = {0, 0, 0, 0};
     PSFEM_CUDA_CHECK(cudaMemcpyAsync(h, c->out3, 3 * sizeof(double), cudaMemcpyDeviceToHost, stream));
     int err = 0;

@@ -364,7 +364,7 @@ class StripProblem:
         self.st = dict(x=torch.zeros(n, **f64), r=self.b_own.clone(), q=torch.empty(n, **f64),
                        dinv=torch.empty(n, **f64), p_ext=p_ext,
                        rz=torch.zeros(2, **f64), pq=torch.zeros(1, **f64), out2=torch.zeros(2, **f64),
-                       out3=torch.zeros(4, **f64), parity=0, iters=0)
+                       out3=torch.zeros(8, **f64), parity=0, iters=0)
         call("psfem_extract_diag", C.byref(self.A), lo, 1, ptr(self.st["dinv"]), stream_ptr())
         if self.fabric:
             fb, st = self.fabric, self.st
