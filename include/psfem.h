@@ -146,12 +146,17 @@ int psfem_assemble_tiled(const double *d_nodes, int64_t nel, int etype, int64_t 
  * psfem_lattice_detect: h_nm = {n, m} (node columns, nodes per column) when EVERY element equals the formula of
  * Polygones.py:83-85 (T3) / :100 (Q4) for node id = i*m+j, else {0, 0}.  Coordinates are not looked at: a
  * jittered or otherwise deformed structured mesh is still a lattice.  d_ws: >= 16 bytes.  Synchronises.
- * psfem_assemble_lattice (Q4): same result as psfem_assemble / psfem_assemble_tiled (values summed in ascending
+ * psfem_assemble_lattice (T3, Q4): same result as psfem_assemble / psfem_assemble_tiled (values summed in ascending
  * element id, Polygones.py:717-726) on the pattern of psfem_pattern_fill, but plan-free: a warp marches along i
  * over a strip of 31 node rows, element matrices and the open node column live in registers, the rows owned by the
  * neighbour lane travel by shuffle, finished node columns leave by bulk async stores.  d_ws: >= 32 bytes. */
 int psfem_lattice_detect(const int32_t *d_conn, int64_t nel, int etype, int64_t n_nodes, int64_t *h_nm /* [2] */,
                          void *d_ws, size_t ws_bytes, void *stream);
+/* Symbolic phase of a lattice in closed form (no sort): the same row_ptr / col_idx / node_ptr that
+ * psfem_pattern_count + psfem_pattern_fill produce for that connectivity (tests compare them bit for bit), written
+ * by one kernel at HBM speed.  d_row_ptr == NULL: only returns n_pairs (nnz = 4*n_pairs) for sizing. */
+int psfem_lattice_pattern(int64_t n, int64_t m, int etype, int32_t *d_row_ptr /* 2nm+1 */, int32_t *d_col_idx /* 4*n_pairs */,
+                          int32_t *d_node_ptr /* nm+1 */, int64_t *h_n_pairs, void *stream);
 int psfem_assemble_lattice(const double *d_nodes, int64_t n, int64_t m, int etype,
                            double E, double nu, double rho, double t, int what,
                            double *d_K_vals, double *d_M_vals, void *d_ws, size_t ws_bytes,

@@ -99,7 +99,8 @@ __global__ void t3_kernel(const double2 *__restrict__ nodes, const int32_t *__re
     const int32_t *c = conn + e * 3;
     double2 p[3] = {nodes[c[0]], nodes[c[1]], nodes[c[2]]};
     // delta = signed 2*area (:843-845)
-    double delta = p[0].x * (p[1].y - p[2].y) + p[1].x * (p[2].y - p[0].y) + p[2].x * (p[0].y - p[1].y);
+    double delta = __dadd_rn(__dadd_rn(__dmul_rn(p[0].x, p[1].y - p[2].y), __dmul_rn(p[1].x, p[2].y - p[0].y)),
+                             __dmul_rn(p[2].x, p[0].y - p[1].y));   // no FMA contraction: the reference rounds every product
     double vol = 0.5 * delta * mat.t;  // :877-879
     if (DO_K) {
         double b[3], g[3];
@@ -113,10 +114,11 @@ __global__ void t3_kernel(const double2 *__restrict__ nodes, const int32_t *__re
 #pragma unroll
             for (int j = 0; j < 3; ++j) {
                 double4 v;
-                v.x = (mat.d00 * b[i] * b[j] + mat.d22 * g[i] * g[j]) * vol;
-                v.y = (mat.d01 * b[i] * g[j] + mat.d22 * g[i] * b[j]) * vol;
-                v.z = (mat.d01 * g[i] * b[j] + mat.d22 * b[i] * g[j]) * vol;
-                v.w = (mat.d00 * g[i] * g[j] + mat.d22 * b[i] * b[j]) * vol;
+                // np.dot(B.T, np.dot(D, B)) * Volume in the reference's operation order (see ElemT3 in psfem_elem.cuh)
+                v.x = __dmul_rn(fma(g[i], __dmul_rn(mat.d22, g[j]), __dmul_rn(b[i], __dmul_rn(mat.d00, b[j]))), vol);
+                v.y = __dmul_rn(fma(g[i], __dmul_rn(mat.d22, b[j]), __dmul_rn(b[i], __dmul_rn(mat.d01, g[j]))), vol);
+                v.z = __dmul_rn(fma(b[i], __dmul_rn(mat.d22, g[j]), __dmul_rn(g[i], __dmul_rn(mat.d01, b[j]))), vol);
+                v.w = __dmul_rn(fma(b[i], __dmul_rn(mat.d22, b[j]), __dmul_rn(g[i], __dmul_rn(mat.d00, g[j]))), vol);
                 kblk[e * 9 + i * 3 + j] = v;
             }
     }
@@ -310,12 +312,18 @@ AsmWs carve_asm(void *ws, int64_t nel, int npe, int what) {
     return w;
 }
 
-Material make_material(double E, double nu, double rho, double t) {
+Material make_material(double E, double nu, double rho, double t, int etype) {
+    // the T3 closed form and the Gauss path round D differently in the reference (Polygones.py:881 vs :582-584)
     Material m;
-    const double f = E / (1 - nu * nu);
-    m.d00 = f;
-    m.d01 = nu * f;
-    m.d22 = (1 - nu) / 2 * f;
+    const double den = 1 - nu * nu;
+    m.d00 = E / den;
+    if (etype == PSFEM_T3) {
+        m.d01 = (nu * E) / den;
+        m.d22 = (((1 - nu) / 2) * E) / den;
+    } else {
+        m.d01 = nu * m.d00;
+        m.d22 = ((1 - nu) / 2) * m.d00;
+    }
     m.t = t;
     m.rho = rho;
     return m;
@@ -358,7 +366,7 @@ extern "C" int psfem_assemble(const double *d_nodes, const int32_t *d_conn, int6
     if (nel == 0 || n_pairs == 0) return PSFEM_OK;
     AsmWs w = carve_asm(d_ws, nel, npe, what);
     PSFEM_REQUIRE(ws_bytes >= w.total, "assemble: workspace too small (%zu < %zu)", ws_bytes, w.total);
-    int rc = run_elements(d_nodes, d_conn, nel, etype, make_material(E, nu, rho, t), what, w.kblk, w.mblk, w.bad, stream);
+    int rc = run_elements(d_nodes, d_conn, nel, etype, make_material(E, nu, rho, t, etype), what, w.kblk, w.mblk, w.bad, stream);
     if (rc) return rc;
     const int T = 256;
     unsigned grid = (unsigned)ceil_div(n_pairs, T);
@@ -383,7 +391,7 @@ extern "C" int psfem_element_matrices(const double *d_nodes, const int32_t *d_co
     if (nel == 0) return PSFEM_OK;
     AsmWs w = carve_asm(d_ws, nel, npe, what);
     PSFEM_REQUIRE(ws_bytes >= w.total, "element_matrices: workspace too small");
-    int rc = run_elements(d_nodes, d_conn, nel, etype, make_material(E, nu, rho, t), what, w.kblk, w.mblk, w.bad, stream);
+    int rc = run_elements(d_nodes, d_conn, nel, etype, make_material(E, nu, rho, t, etype), what, w.kblk, w.mblk, w.bad, stream);
     if (rc) return rc;
     int64_t nb = nel * npe * npe;
     expand_blocks_kernel<<<(unsigned)ceil_div(nb, 256), 256, 0, stream>>>(nb, npe, (what & 1) ? w.kblk : nullptr,

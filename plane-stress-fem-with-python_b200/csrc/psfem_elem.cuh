@@ -9,6 +9,25 @@ struct Mat {
     double d00, d01, d22, t, rho;
 };
 
+// Plane-stress D with the reference's own rounding.  The generic path scales the pattern matrix by the
+// precomputed factor, [[1,nu,0],[nu,1,0],[0,0,(1-nu)/2]] * (E/(1-nu**2)) (Polygones.py:582-584); the T3 closed
+// form multiplies by E first and divides afterwards, [[..]]*E/(1-nu**2) (:881) -- different last bits.
+inline Mat make_mat(double E, double nu, double rho, double t, int etype) {
+    Mat m;
+    const double den = 1 - nu * nu;
+    m.d00 = E / den;
+    if (etype == PSFEM_T3) {
+        m.d01 = (nu * E) / den;
+        m.d22 = (((1 - nu) / 2) * E) / den;
+    } else {
+        m.d01 = nu * m.d00;
+        m.d22 = ((1 - nu) / 2) * m.d00;
+    }
+    m.t = t;
+    m.rho = rho;
+    return m;
+}
+
 // 1/d without the IEEE division slow path: fp32 reciprocal seed + two Newton steps (relative error ~1e-16;
 // |d| >= 1e-10 is guaranteed by the Jacobian guard, far inside the fp32 exponent range)
 __device__ __forceinline__ double fast_rcp(double d) {
@@ -213,20 +232,45 @@ template <bool DO_K, bool DO_M> struct ElemQ4 {
 // T3 closed form (Polygones.py:840-883, :1218-1235), signed area
 template <bool DO_K, bool DO_M> struct ElemT3 {
     double b[3], g[3], vol, mbase;
+    double db0[3], db1[3], db2[3], dg0[3], dg1[3], dg2[3];   // D B: {d00, d01, d22} x {b_j, c_j}
     __device__ __forceinline__ bool compute(const double2 (&p)[3], const Mat &mat) {
-        const double delta = p[0].x * (p[1].y - p[2].y) + p[1].x * (p[2].y - p[0].y) + p[2].x * (p[0].y - p[1].y);
+        // signed 2*area, Polygones.py:843-845, products and sums rounded one by one like the reference (no FMA contraction)
+        const double delta = __dadd_rn(__dadd_rn(__dmul_rn(p[0].x, p[1].y - p[2].y), __dmul_rn(p[1].x, p[2].y - p[0].y)),
+                                       __dmul_rn(p[2].x, p[0].y - p[1].y));
         vol = 0.5 * delta * mat.t;
+        // b_i = (y_j - y_k)/delta, c_i = (x_k - x_j)/delta (Polygones.py:848-850): ONE IEEE division for the
+        // correctly rounded reciprocal, then a Markstein correction step per quotient (q' = q + (a - q*delta)*inv),
+        // which returns the correctly rounded a/delta -- the reference's six divisions bit for bit, at 3 operations
+        // each instead of the ~20 of the division subroutine.  Signed delta as the reference.
+        const double inv = 1.0 / delta;
+        auto quot = [&](double a) {
+            const double q = a * inv;
+            return fma(fma(-q, delta, a), inv, q);
+        };
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
-            b[i] = (p[(i + 1) % 3].y - p[(i + 2) % 3].y) / delta;
-            g[i] = (p[(i + 2) % 3].x - p[(i + 1) % 3].x) / delta;
+            b[i] = quot(p[(i + 1) % 3].y - p[(i + 2) % 3].y);
+            g[i] = quot(p[(i + 2) % 3].x - p[(i + 1) % 3].x);
         }
-        mbase = mat.rho * vol / 12;   // T3 keeps IEEE divisions: the arithmetic of Polygones.py:848-850 verbatim
+        if (DO_K) {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {   // columns 2j, 2j+1 of D B (:881): single rounded products
+                db0[j] = __dmul_rn(mat.d00, b[j]); db1[j] = __dmul_rn(mat.d01, b[j]); db2[j] = __dmul_rn(mat.d22, b[j]);
+                dg0[j] = __dmul_rn(mat.d00, g[j]); dg1[j] = __dmul_rn(mat.d01, g[j]); dg2[j] = __dmul_rn(mat.d22, g[j]);
+            }
+        }
+        mbase = mat.rho * vol / 12;   // Me*rho*Volume/12, Polygones.py:1234
         return true;
     }
-    __device__ __forceinline__ double4 kblock(int i, int j, const Mat &mat) const {
-        return make_double4((mat.d00 * b[i] * b[j] + mat.d22 * g[i] * g[j]) * vol, (mat.d01 * b[i] * g[j] + mat.d22 * g[i] * b[j]) * vol,
-                            (mat.d01 * g[i] * b[j] + mat.d22 * b[i] * g[j]) * vol, (mat.d00 * g[i] * g[j] + mat.d22 * b[i] * b[j]) * vol);
+    // Ke = np.dot(B.T, np.dot(D, B)) * Volume (Polygones.py:877-882) with the operation order of the reference's
+    // BLAS: every entry of B^T (D B) is a 3-term dot product accumulated with FMAs in k order, one term of which is a
+    // structural zero; the product with the volume is rounded separately (never contracted into the assembly add).
+    // The assembled T3 matrix equals the reference's bit for bit (tests/test_gpu_parity.py, golden README mesh).
+    __device__ __forceinline__ double4 kblock(int i, int j, const Mat &) const {
+        return make_double4(__dmul_rn(fma(g[i], dg2[j], __dmul_rn(b[i], db0[j])), vol),
+                            __dmul_rn(fma(g[i], db2[j], __dmul_rn(b[i], dg1[j])), vol),
+                            __dmul_rn(fma(b[i], dg2[j], __dmul_rn(g[i], db1[j])), vol),
+                            __dmul_rn(fma(b[i], db2[j], __dmul_rn(g[i], dg0[j])), vol));
     }
     __device__ __forceinline__ double mval(int i, int j) const { return (i == j ? 2.0 : 1.0) * mbase; }
 };

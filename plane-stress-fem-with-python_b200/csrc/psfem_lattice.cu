@@ -1,4 +1,4 @@
-// psfem_lattice.cu -- numeric assembly for meshes with the LATTICE TOPOLOGY of Polygones.mesh (Q4).
+// psfem_lattice.cu -- symbolic and numeric assembly for meshes with the LATTICE TOPOLOGY of Polygones.mesh (T3, Q4).
 //
 // Polygones.mesh (Polygones.py:62-108) is the reference's only mesh generator: node id = i*m + j, Q4 element
 // (i,j) = [i*m+j, (i+1)*m+j, (i+1)*m+j+1, i*m+j+1] (:100).  When the symbolic phase finds that topology
@@ -50,6 +50,77 @@ template <int ETYPE> __global__ void lattice_check_kernel(const int32_t *__restr
                      : (c[0] == b && c[1] == b + m && c[2] == b + 1);                            // Polygones.py:83
     }
     if (!ok) atomicExch(flag, 1);
+}
+
+// ---- arithmetic symbolic phase -----------------------------------------------------------------
+// Neighbour stencil of a lattice node (i,j): Q4 couples the full 3x3 block; the two triangles per cell of
+// Polygones.py:83-85 couple all but the (-1,-1) and (+1,+1) diagonals.  Columns ascend with the node id i*m+j,
+// so the slots are visited di-major.  pairs_before(i,j) is the closed-form prefix of the slot counts.
+template <int ETYPE> struct Stencil {
+    // number of neighbours in node column i+di (di = -1, 0, +1) of the node in row j
+    __host__ __device__ static int count(int di, int j, int m) {
+        const int jm = j > 0, jp = j < m - 1;
+        if (ETYPE == PSFEM_Q4 || di == 0) return 1 + jm + jp;
+        return di < 0 ? 1 + jp : 1 + jm;   // T3: (-1,0),(-1,+1) / (+1,-1),(+1,0)
+    }
+    __host__ __device__ static bool has(int di, int dj) {
+        return ETYPE == PSFEM_Q4 || !((di < 0 && dj < 0) || (di > 0 && dj > 0));
+    }
+    // sum of count(di, j') over j' < j (0 <= j <= m)
+    __host__ __device__ static long long prefix(int di, int j, int m) {
+        if (ETYPE == PSFEM_Q4 || di == 0) return 3ll * j - (j > 0) - (j == m);
+        return di < 0 ? 2ll * j - (j == m) : 2ll * j - (j > 0);
+    }
+    __host__ __device__ static long long column_total(int i, int n, int m) {
+        return (i > 0 ? prefix(-1, m, m) : 0) + prefix(0, m, m) + (i < n - 1 ? prefix(1, m, m) : 0);
+    }
+    __host__ __device__ static long long pairs_before(int i, int j, int n, int m) {
+        // whole columns 0..i-1: column 0 and column n-1 miss one neighbour column
+        long long full = 0;
+        if (i > 0) {
+            const long long inner = prefix(-1, m, m) + prefix(0, m, m) + prefix(1, m, m);
+            full = column_total(0, n, m) + (long long)(i - 1) * inner;
+        }
+        return full + (i > 0 ? prefix(-1, j, m) : 0) + prefix(0, j, m) + (i < n - 1 ? prefix(1, j, m) : 0);
+    }
+};
+
+template <int ETYPE>
+__global__ void lattice_pattern_kernel(int n, int m, int32_t *__restrict__ row_ptr, int32_t *__restrict__ col_idx,
+                                       int32_t *__restrict__ node_ptr) {
+    const int64_t a = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t n_nodes = (int64_t)n * m;
+    if (a > n_nodes) return;
+    using S = Stencil<ETYPE>;
+    if (a == n_nodes) {   // closing entries
+        const long long tot = S::pairs_before(n - 1, m, n, m);
+        node_ptr[a] = (int32_t)tot;
+        row_ptr[2 * a] = (int32_t)(4 * tot);
+        return;
+    }
+    const int i = (int)(a / m), j = (int)(a % m);
+    const long long p0 = S::pairs_before(i, j, n, m);
+    int deg = 0;
+#pragma unroll
+    for (int di = -1; di <= 1; ++di)
+        if (i + di >= 0 && i + di < n) deg += S::count(di, j, m);
+    node_ptr[a] = (int32_t)p0;
+    row_ptr[2 * a] = (int32_t)(4 * p0);
+    row_ptr[2 * a + 1] = (int32_t)(4 * p0 + 2 * deg);
+    int2 *r0 = reinterpret_cast<int2 *>(col_idx + 4 * p0);   // 4*p0 and 2*deg are even: 8-byte aligned
+    int2 *r1 = r0 + deg;
+    int q = 0;
+#pragma unroll
+    for (int di = -1; di <= 1; ++di)
+#pragma unroll
+        for (int dj = -1; dj <= 1; ++dj) {
+            if (!S::has(di, dj) || i + di < 0 || i + di >= n || j + dj < 0 || j + dj >= m) continue;
+            const int b = (int)(a + (int64_t)di * m + dj);
+            const int2 c = make_int2(2 * b, 2 * b + 1);
+            r0[q] = c;
+            r1[q] = c;
+            ++q;
+        }
 }
 
 // ---- 2x2 blocks: {K(2a,2b), K(2a,2b+1), K(2a+1,2b), K(2a+1,2b+1)}; the mass block is m*I2 -> one scalar ----
@@ -208,6 +279,140 @@ lattice_q4_kernel(const double2 *__restrict__ nodes, Mat mat, int n, int m, int 
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all stores complete before the warp exits
 }
 
+// ---- T3: two triangles per cell, A = [n00, n10, n01] (element 2c) and B = [n11, n01, n10] (2c+1), Polygones.py:83-85.
+// Same marching scheme as Q4; the node rows a cell contributes to are
+//   n00: A row 0            n01 (the lane above): A row 2, then B row 1
+//   n10: A row 1, B row 2   n11 (the lane above): B row 0
+// and every entry is summed in ascending element id: cell(i-1,j-1).B, cell(i-1,j).A, .B, cell(i,j-1).A, .B, cell(i,j).A.
+template <bool IS_K, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
+lattice_t3_kernel(const double2 *__restrict__ nodes, Mat mat, int n, int m, int seg_len, int n_seg, int n_strips,
+                  double *__restrict__ vals, unsigned int *__restrict__ counter) {
+    using B = typename BlockOf<IS_K>::type;
+    using S = Stencil<PSFEM_T3>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned char *wbuf = smem_raw + (size_t)wid * 2 * LBUF_BYTES;
+    const int N = n - 1, M = m - 1;
+    const int n_items = n_seg * n_strips;
+    int parity = 0;
+    for (;;) {
+        int item = 0;
+        if (lane == 0) item = (int)atomicAdd(counter, 1u);
+        item = __shfl_sync(FULL, item, 0);
+        if (item >= n_items) break;
+        const int s = item % n_strips, g = item / n_strips;
+        const int ia = g * seg_len, ib = min(ia + seg_len, n);
+        const int js = STRIP * s, je = min(js + STRIP, m);
+        const int jl = js - 1 + lane;
+        const bool el_j_ok = jl >= 0 && jl < M;
+        const bool node_out = lane >= 1 && jl < m;
+        const bool has_jm = jl > 0, has_jp = jl < M;
+        const int jn = max(jl, js);
+        const int64_t jc0 = min(max(jl, 0), M), jc1 = min(max(jl + 1, 0), M);
+        int ci = max(ia - 1, 0);
+        double2 p0 = nodes[(int64_t)ci * m + jc0], p3 = nodes[(int64_t)ci * m + jc1];
+        double2 p1 = nodes[(int64_t)min(ci + 1, N) * m + jc0], p2 = nodes[(int64_t)min(ci + 1, N) * m + jc1];
+        B acc[9];
+#pragma unroll
+        for (int q = 0; q < 9; ++q) zero(acc[q]);
+        for (; ci < ib; ++ci) {
+            const int64_t cpf = min(ci + 2, N);
+            const double2 f1 = nodes[cpf * m + jc0], f2 = nodes[cpf * m + jc1];
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(nodes + (int64_t)min(ci + 3, N) * m + jc0));
+            if (lane == 31) asm volatile("prefetch.global.L1 [%0];" ::"l"(nodes + (int64_t)min(ci + 3, N) * m + jc1));
+            const bool el_ok = el_j_ok && ci < N;
+            ElemT3<IS_K, !IS_K> ea, eb;
+            {
+                // lanes without a cell integrate unit triangles of zero thickness: exact zeros
+                const double2 q0 = el_ok ? p0 : make_double2(0.0, 0.0), q1 = el_ok ? p1 : make_double2(1.0, 0.0);
+                const double2 q2 = el_ok ? p2 : make_double2(1.0, 1.0), q3 = el_ok ? p3 : make_double2(0.0, 1.0);
+                Mat ml = mat;
+                ml.t = el_ok ? mat.t : 0.0;
+                const double2 pa[3] = {q0, q1, q3}, pb[3] = {q2, q3, q1};
+                ea.compute(pa, ml);
+                eb.compute(pb, ml);
+            }
+            if (ci >= ia) {   // ---- finish node column ci ----
+                const B a20 = up1(blk<IS_K>(ea, 2, 0, mat)), a21 = up1(blk<IS_K>(ea, 2, 1, mat)), a22 = up1(blk<IS_K>(ea, 2, 2, mat));
+                const B b10 = up1(blk<IS_K>(eb, 1, 0, mat)), b11 = up1(blk<IS_K>(eb, 1, 1, mat)), b12 = up1(blk<IS_K>(eb, 1, 2, mat));
+                add(acc[3], a20);
+                add(acc[4], a22); add(acc[4], b11); add(acc[4], blk<IS_K>(ea, 0, 0, mat));
+                add(acc[5], blk<IS_K>(ea, 0, 2, mat));
+                acc[6] = sum(a21, b12);
+                acc[7] = sum(b10, blk<IS_K>(ea, 0, 1, mat));
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                __syncwarp();
+                const bool has_im = ci > 0, has_ip = ci < N;
+                double2 *buf = reinterpret_cast<double2 *>(wbuf + parity * LBUF_BYTES);
+                long long q_node = S::prefix(0, jn, m) - S::prefix(0, js, m), q_all = S::prefix(0, je, m) - S::prefix(0, js, m);
+                if (has_im) { q_node += S::prefix(-1, jn, m) - S::prefix(-1, js, m); q_all += S::prefix(-1, je, m) - S::prefix(-1, js, m); }
+                if (has_ip) { q_node += S::prefix(1, jn, m) - S::prefix(1, js, m); q_all += S::prefix(1, je, m) - S::prefix(1, js, m); }
+                if (node_out) {
+                    const int deg = (has_im ? S::count(-1, jl, m) : 0) + S::count(0, jl, m) + (has_ip ? S::count(1, jl, m) : 0);
+                    double2 *row0 = buf + 2 * q_node;
+                    int q = 0;
+                    if (has_im) {
+                        put(row0, deg, q++, acc[1]);
+                        if (has_jp) put(row0, deg, q++, acc[2]);
+                    }
+                    if (has_jm) put(row0, deg, q++, acc[3]);
+                    put(row0, deg, q++, acc[4]);
+                    if (has_jp) put(row0, deg, q++, acc[5]);
+                    if (has_ip) {
+                        if (has_jm) put(row0, deg, q++, acc[6]);
+                        put(row0, deg, q++, acc[7]);
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) {
+                    const long long pair0 = S::pairs_before(ci, js, n, m);
+                    const uint32_t bytes = (uint32_t)q_all * 32u;
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                 ::"l"(vals + 4 * pair0), "r"(l_smem_u32(buf)), "r"(bytes) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                parity ^= 1;
+            }
+            {   // ---- open node column ci+1 ----
+                const B b00 = up1(blk<IS_K>(eb, 0, 0, mat)), b01 = up1(blk<IS_K>(eb, 0, 1, mat)), b02 = up1(blk<IS_K>(eb, 0, 2, mat));
+                acc[1] = sum(b01, blk<IS_K>(ea, 1, 0, mat));
+                acc[2] = sum(blk<IS_K>(ea, 1, 2, mat), blk<IS_K>(eb, 2, 1, mat));
+                acc[3] = b02;
+                acc[4] = sum(sum(b00, blk<IS_K>(ea, 1, 1, mat)), blk<IS_K>(eb, 2, 2, mat));
+                acc[5] = blk<IS_K>(eb, 2, 0, mat);
+            }
+            p0 = p1; p3 = p2; p1 = f1; p2 = f2;
+        }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+template <bool IS_K, int WARPS, int MINB>
+int launch_lattice_t3(const double *d_nodes, const Mat &mat, int n, int m, int seg_len, double *vals, unsigned int *counter,
+                      cudaStream_t stream) {
+    auto kern = lattice_t3_kernel<IS_K, WARPS, MINB>;
+    const size_t smem = (size_t)WARPS * 2 * LBUF_BYTES;
+    PSFEM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int dev = 0, sms = 148, per_sm = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    PSFEM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem));
+    if (per_sm < 1) per_sm = 1;
+    const int n_strips = (int)ceil_div(m, STRIP);
+    int n_seg = (int)ceil_div(n, seg_len);
+    seg_len = (int)ceil_div(n, n_seg);
+    n_seg = (int)ceil_div(n, seg_len);
+    const int64_t n_items = (int64_t)n_seg * n_strips;
+    int64_t grid = (int64_t)sms * per_sm;
+    if (grid * WARPS > n_items) grid = ceil_div(n_items, WARPS);
+    PSFEM_CUDA_CHECK(cudaMemsetAsync(counter, 0, sizeof(unsigned int), stream));
+    kern<<<(unsigned)grid, WARPS * 32, smem, stream>>>(reinterpret_cast<const double2 *>(d_nodes), mat, n, m, seg_len, n_seg, n_strips, vals, counter);
+    PSFEM_LAUNCH_CHECK();
+    return PSFEM_OK;
+}
+
 template <bool IS_K, int WARPS, int MINB>
 int launch_lattice_q4(const double *d_nodes, const Mat &mat, int n, int m, int seg_len, double *vals, unsigned long long *bad,
                       unsigned int *counter, cudaStream_t stream) {
@@ -263,21 +468,38 @@ extern "C" int psfem_lattice_detect(const int32_t *d_conn, int64_t nel, int etyp
     return PSFEM_OK;
 }
 
+extern "C" int psfem_lattice_pattern(int64_t n, int64_t m, int etype, int32_t *d_row_ptr, int32_t *d_col_idx,
+                                     int32_t *d_node_ptr, int64_t *h_n_pairs, void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    PSFEM_REQUIRE(etype == PSFEM_Q4 || etype == PSFEM_T3, "lattice_pattern: T3 and Q4 only");
+    PSFEM_REQUIRE(n >= 2 && m >= 2 && n * m < (1ll << 30) && h_n_pairs, "lattice_pattern: bad lattice");
+    const long long np = etype == PSFEM_Q4 ? Stencil<PSFEM_Q4>::pairs_before((int)n - 1, (int)m, (int)n, (int)m)
+                                           : Stencil<PSFEM_T3>::pairs_before((int)n - 1, (int)m, (int)n, (int)m);
+    PSFEM_REQUIRE(4 * np < (long long)INT32_MAX, "lattice_pattern: more than 2^31 non-zeros on one GPU: partition the mesh");
+    *h_n_pairs = np;
+    if (!d_row_ptr) return PSFEM_OK;   // size query
+    PSFEM_REQUIRE(d_col_idx && d_node_ptr, "lattice_pattern: null output");
+    const int T = 128;
+    const unsigned grid = (unsigned)ceil_div(n * m + 1, T);
+    if (etype == PSFEM_Q4) lattice_pattern_kernel<PSFEM_Q4><<<grid, T, 0, stream>>>((int)n, (int)m, d_row_ptr, d_col_idx, d_node_ptr);
+    else lattice_pattern_kernel<PSFEM_T3><<<grid, T, 0, stream>>>((int)n, (int)m, d_row_ptr, d_col_idx, d_node_ptr);
+    PSFEM_LAUNCH_CHECK();
+    return PSFEM_OK;
+}
+
 extern "C" int psfem_assemble_lattice(const double *d_nodes, int64_t n, int64_t m, int etype,
                                       double E, double nu, double rho, double t, int what,
                                       double *d_K_vals, double *d_M_vals, void *d_ws, size_t ws_bytes,
                                       int64_t *h_bad_element, void *stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    PSFEM_REQUIRE(etype == PSFEM_Q4, "assemble_lattice: Q4 only");
+    PSFEM_REQUIRE(etype == PSFEM_Q4 || etype == PSFEM_T3, "assemble_lattice: T3 and Q4 only");
     PSFEM_REQUIRE(what >= 1 && what <= 3, "assemble_lattice: what must be 1 (K), 2 (M) or 3 (both)");
     PSFEM_REQUIRE(!(what & 1) || d_K_vals, "assemble_lattice: K requested but d_K_vals is null");
     PSFEM_REQUIRE(!(what & 2) || d_M_vals, "assemble_lattice: M requested but d_M_vals is null");
     PSFEM_REQUIRE(d_nodes && n >= 2 && m >= 2 && n * m < (1ll << 31), "assemble_lattice: bad lattice");
     PSFEM_REQUIRE(d_ws && ws_bytes >= 32, "assemble_lattice: workspace too small");
     if (h_bad_element) *h_bad_element = -1;
-    Mat mat;
-    const double f = E / (1 - nu * nu);
-    mat.d00 = f; mat.d01 = nu * f; mat.d22 = (1 - nu) / 2 * f; mat.t = t; mat.rho = rho;
+    const Mat mat = make_mat(E, nu, rho, t, etype);
     unsigned long long *bad = static_cast<unsigned long long *>(d_ws);
     unsigned int *counter = reinterpret_cast<unsigned int *>(bad + 1);
     PSFEM_CUDA_CHECK(cudaMemsetAsync(bad, 0xff, sizeof(unsigned long long), stream));
@@ -287,6 +509,11 @@ extern "C" int psfem_assemble_lattice(const double *d_nodes, int64_t n, int64_t 
     if (seg_len < 1) seg_len = 64;
     const int occ = occ_env ? atoi(occ_env) : 2;
     int rc = PSFEM_OK;
+    if (etype == PSFEM_T3) {   // closed form, no Jacobian guard in the reference (Polygones.py:875-883): nothing to report
+        if (what & 1) rc = launch_lattice_t3<true, 4, 3>(d_nodes, mat, (int)n, (int)m, seg_len, d_K_vals, counter, stream);
+        if (!rc && (what & 2)) rc = launch_lattice_t3<false, 4, 3>(d_nodes, mat, (int)n, (int)m, seg_len, d_M_vals, counter, stream);
+        return rc;
+    }
     if (what & 1) {
         rc = occ == 3 ? launch_lattice_q4<true, 4, 3>(d_nodes, mat, (int)n, (int)m, seg_len, d_K_vals, bad, counter, stream)
                       : launch_lattice_q4<true, 4, 2>(d_nodes, mat, (int)n, (int)m, seg_len, d_K_vals, bad, counter, stream);

@@ -698,9 +698,7 @@ extern "C" int psfem_assemble_tiled(const double *d_nodes, int64_t nel, int etyp
     PSFEM_REQUIRE(h_plan_info && h_plan_info[4] == 1, "assemble_tiled: the tile plan is not usable for this mesh");
     if (h_bad_element) *h_bad_element = -1;
     if (nel == 0) return PSFEM_OK;
-    Mat mat;
-    const double f = E / (1 - nu * nu);
-    mat.d00 = f; mat.d01 = nu * f; mat.d22 = (1 - nu) / 2 * f; mat.t = t; mat.rho = rho;
+    const Mat mat = make_mat(E, nu, rho, t, etype);
     unsigned long long *bad = static_cast<unsigned long long *>(d_ws);
     PSFEM_CUDA_CHECK(cudaMemsetAsync(bad, 0xff, sizeof(unsigned long long), stream));
     TilePlanDev tp;

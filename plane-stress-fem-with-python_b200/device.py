@@ -187,37 +187,63 @@ class Assembler:
         self.conn = conn_dev
         self.nel = int(conn_dev.shape[0])
         self.n_nodes = int(n_nodes)
+        self._asm_ws = {}
+        self._csr = None
+        self._tiles = None            # tile plan of the fused T3/Q4 path, built at the first assembly
+        self.use_tiles = etype in (_capi.T3, _capi.Q4)
+        self.tile_nodes_R = 64        # 8x8-node Morton tiles: best measured on B200 (profiles/r1_tiles.md)
+        self.perm = self.pair_row = self.pair_ptr = None
+        # lattice topology of Polygones.mesh (any coordinates): closed-form pattern, plan-free marching-warp assembly
+        nm = (C.c_int64 * 2)()
+        self._small_ws = workspace(256)
+        call("psfem_lattice_detect", ptr(conn_dev), self.nel, etype, self.n_nodes, nm, ptr(self._small_ws), 256, stream_ptr())
+        self.lattice = (int(nm[0]), int(nm[1])) if nm[0] > 0 else None
+        self.use_lattice = self.lattice is not None
+        i32 = dict(dtype=torch.int32, device="cuda")
+        if self.lattice is not None:
+            n, m = self.lattice
+            npairs = C.c_int64(0)
+            call("psfem_lattice_pattern", n, m, etype, None, None, None, C.byref(npairs), stream_ptr())
+            self.n_pairs = npairs.value
+            self.nnz = 4 * self.n_pairs
+            self.row_ptr = torch.empty(2 * self.n_nodes + 1, **i32)
+            self.col_idx = torch.empty(self.nnz, **i32)
+            self.node_ptr = torch.empty(self.n_nodes + 1, **i32)
+            call("psfem_lattice_pattern", n, m, etype, ptr(self.row_ptr), ptr(self.col_idx), ptr(self.node_ptr),
+                 C.byref(npairs), stream_ptr())
+        else:
+            self._sort_pattern(keep_pattern=True)
+
+    def _sort_pattern(self, keep_pattern):
+        """General symbolic phase (radix sort of the node-pair keys): pattern + segmented-reduction plan.
+        A lattice already has its pattern in closed form and only needs the plan when the two-kernel path
+        is asked for (keep_pattern=False: the sorted pattern is identical and is dropped)."""
+        torch = _capi.torch_cuda()
         nk = self.nel * self.npe * self.npe
         sz = C.c_size_t(0)
         call("psfem_pattern_workspace", self.nel, self.npe, self.n_nodes, C.byref(sz))
         ws = workspace(sz.value)
         self.perm = torch.empty(max(nk, 1), dtype=torch.int32, device="cuda")
         npairs = C.c_int64(0)
-        call("psfem_pattern_count", ptr(conn_dev), self.nel, self.npe, self.n_nodes, ptr(self.perm), ptr(ws), sz.value,
+        call("psfem_pattern_count", ptr(self.conn), self.nel, self.npe, self.n_nodes, ptr(self.perm), ptr(ws), sz.value,
              C.byref(npairs), stream_ptr())
-        self.n_pairs = npairs.value
-        self.nnz = 4 * self.n_pairs
         i32 = dict(dtype=torch.int32, device="cuda")
-        self.row_ptr = torch.empty(2 * self.n_nodes + 1, **i32)
-        self.col_idx = torch.empty(max(self.nnz, 1), **i32)[: self.nnz]
-        self.node_ptr = torch.empty(self.n_nodes + 1, **i32)
-        self.pair_row = torch.empty(max(self.n_pairs, 1), **i32)
-        self.pair_ptr = torch.empty(self.n_pairs + 1, **i32)
-        call("psfem_pattern_fill", self.nel, self.npe, self.n_nodes, self.n_pairs, ptr(ws), sz.value, ptr(self.row_ptr),
-             ptr(self.col_idx), ptr(self.node_ptr), ptr(self.pair_row), ptr(self.pair_ptr), stream_ptr())
+        n_pairs = npairs.value
+        row_ptr = torch.empty(2 * self.n_nodes + 1, **i32)
+        col_idx = torch.empty(max(4 * n_pairs, 1), **i32)[: 4 * n_pairs]
+        node_ptr = torch.empty(self.n_nodes + 1, **i32)
+        self.pair_row = torch.empty(max(n_pairs, 1), **i32)
+        self.pair_ptr = torch.empty(n_pairs + 1, **i32)
+        call("psfem_pattern_fill", self.nel, self.npe, self.n_nodes, n_pairs, ptr(ws), sz.value, ptr(row_ptr),
+             ptr(col_idx), ptr(node_ptr), ptr(self.pair_row), ptr(self.pair_ptr), stream_ptr())
         torch.cuda.current_stream().synchronize()
         del ws
-        self._asm_ws = {}
-        self._csr = None
-        self._tiles = None            # tile plan of the fused T3/Q4 path, built at the first assembly
-        self.use_tiles = etype in (_capi.T3, _capi.Q4)
-        self.tile_nodes_R = 64        # 8x8-node Morton tiles: best measured on B200 (profiles/r1_tiles.md)
-        # lattice topology of Polygones.mesh (any coordinates): plan-free marching-warp assembly
-        nm = (C.c_int64 * 2)()
-        self._small_ws = workspace(256)
-        call("psfem_lattice_detect", ptr(conn_dev), self.nel, etype, self.n_nodes, nm, ptr(self._small_ws), 256, stream_ptr())
-        self.lattice = (int(nm[0]), int(nm[1])) if nm[0] > 0 else None
-        self.use_lattice = self.lattice is not None and etype == _capi.Q4
+        if keep_pattern:
+            self.n_pairs, self.nnz = n_pairs, 4 * n_pairs
+            self.row_ptr, self.col_idx, self.node_ptr = row_ptr, col_idx, node_ptr
+        else:
+            assert n_pairs == self.n_pairs
+        return row_ptr, col_idx, node_ptr
 
     def tile_plan(self, nodes_dev):
         """Symbolic side of the tile-fused assembly (psfem_tileplan_build); needs coordinates once."""
@@ -296,6 +322,8 @@ class Assembler:
             else:
                 check(rc, bad.value)
                 return K_vals, M_vals
+        if self.perm is None:
+            self._sort_pattern(keep_pattern=False)
         ws, nbytes = self._ws(what)
         rc = lib.psfem_assemble(ptr(nodes_dev), ptr(self.conn), self.nel, self.etype, self.n_nodes, float(E), float(nu),
                                 float(rho), float(t), what, self.n_pairs, ptr(self.node_ptr), ptr(self.pair_row),
