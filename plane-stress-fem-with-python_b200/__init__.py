@@ -17,5 +17,6 @@ from . import Polygones  # noqa: F401
 from ._capi import ConvergenceError  # noqa: F401
 from .device import (Assembler, DeviceCSR, ElementTable, FreeMap, device_mesh, pcg_jacobi)  # noqa: F401
 from .drivers import modal, newmark, ramp_load, static_solve  # noqa: F401
+from .matio import load_matrix, save_matrix  # noqa: F401
 
 __version__ = "0.1.0"
