@@ -8,8 +8,9 @@ For N>1 every rank owns a strip of 4096 cell columns of a (4096*N)x4096 plate (w
 N=4 is BASELINE's configs[4], the 16384x4096 strip), halo columns exchanged over NCCL each SpMV,
 CG dot products all-reduced.
 
-One STEP = one numeric assembly of K over all elements of the rank + `--cg-iters` Jacobi-PCG
-iterations on the clamped system.  `value` = CG DOF*iterations/s (whole job); the assembly rate is
+One STEP = one numeric assembly of K over all elements of the rank (one launch of the lattice kernel) +
+`--cg-iters` Jacobi-PCG iterations on the clamped system (three kernels each; for N>1 the reductions and the
+halo exchange are fused into those kernels over peer memory, PSFEM_DIST_TRANSPORT=nccl selects NCCL instead).  `value` = CG DOF*iterations/s (whole job); the assembly rate is
 in the `assembly` object.  Device timing with CUDA events on the launching stream, max over ranks.
 All inputs (> 7 GB of CSR per rank) are far larger than the 126 MB L2, so no explicit L2 flush.
 
@@ -199,7 +200,7 @@ def main():
             t_wall0 = time.perf_counter()
         e0, e1, e2, e3 = ev(), ev(), ev(), ev()
         e0.record()
-        prob.assemble()                                    # numeric assembly of K (element kernel + segmented reduction)
+        prob.assemble()                                    # numeric assembly of K (one marching-warp lattice kernel)
         e1.record()
         prob.cg_iterations(args.cg_iters)                  # 3 kernels per iteration (+ halo / all-reduce when world > 1)
         e2.record()
@@ -210,7 +211,7 @@ def main():
             asm_ms.append(e0.elapsed_time(e1))
             cg_ms.append(e1.elapsed_time(e2))
             spmv_ms.append(e2.elapsed_time(e3))
-            launches += 2 + 3 * args.cg_iters + args.cg_iters
+            launches += 1 + 3 * args.cg_iters + args.cg_iters   # assembly + PCG kernels + the SpMV-only leg
     barrier()
     wall = time.perf_counter() - t_wall0
     clocks = sampler.stop()
@@ -237,6 +238,11 @@ def main():
     iter_gbs = iter_bytes / (t_cg / (K_ * args.cg_iters)) / 1e9
     asm_bytes = 320 * nel_local                                           # 16 conn + 16 coords + 288 CSR values
     asm_gbs = asm_bytes / (t_asm / K_) / 1e9
+    asm_traffic = None
+    try:
+        asm_traffic = json.load(open(os.path.join(ROOT, "profiles", "asm_traffic.json"))).get("dram_bytes_per_launch")
+    except Exception:
+        pass
 
     line = {
         "metric": METRIC, "value": cg_rate, "unit": UNIT, "n_gpus": world, "steps": K_, "warmup": args.warmup,
@@ -245,11 +251,12 @@ def main():
         "config": {"workload": workload_name(world, cells), "dof": int(prob.n_dof_global), "free_dof": int(n_free_global),
                    "elements": int(prob.nel_global), "nnz_per_gpu": int(nnz), "cg_iters_per_step": args.cg_iters,
                    "l2": "inputs (>7 GB CSR per GPU) exceed the 126 MB L2; no flush",
-                   "parallelism": f"strip{world}"},
+                   "parallelism": f"strip{world}", "transport": prob.transport if world > 1 else "single GPU"},
         "assembly": {"value": asm_rate, "unit": "elements/s", "ms": 1e3 * t_asm / K_,
                      "roofline": {"bound": "hbm", "achieved": asm_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": asm_gbs / hbm_peak,
-                                  "bytes_per_element": 320}},
-        "roofline": {"kernel": "spmv_kernel<false,true> (PCG SpMV + dot)", "bound": "hbm", "achieved": spmv_gbs, "peak": hbm_peak,
+                                  "bytes_per_element": 320, "kernel": "lattice_q4_kernel<true> (marching warps, TMA bulk stores)",
+                                  "traffic": asm_traffic}},
+        "roofline": {"kernel": "spmv2_kernel<true> (PCG SpMV + dot, TMA-staged)", "bound": "hbm", "achieved": spmv_gbs, "peak": hbm_peak,
                      "unit": "GB/s", "frac": spmv_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
                      "bytes_per_launch": spmv_bytes, "ms_per_launch": 1e3 * spmv_t},
         "pcg_iteration": {"achieved": iter_gbs, "unit": "GB/s", "frac": iter_gbs / hbm_peak, "bytes_per_dof_iter": iter_bytes / n,
@@ -263,13 +270,13 @@ def main():
         except Exception:
             pass
 
+    if args.full_solve:                                    # before the e2e legs, which release the device-resident state
+        line["full_solve"] = prob.full_solve(1e-8)
     # ---- end to end through the public API with HOST buffers ------------------------------------
     if not args.no_e2e and world == 1:
         line["e2e"] = e2e_leg(psfem_b200, prob, args, cells)
     elif world > 1:
         line["e2e"] = prob.e2e_distributed(args.e2e_iters, min(K_, 2))
-    if args.full_solve:
-        line["full_solve"] = prob.full_solve(1e-8)
     if rank == 0 and not args.no_cpu and world == 1:
         r = cpu_run(1, 0)
         line["cpu_baseline"] = {"value": r["cg_rate"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"],
