@@ -47,34 +47,49 @@ def peaks():
 # clocks during the timed region
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """nvidia-smi in loop mode.  The process needs about a second to produce its first row, so it is started (and
+    waited for) BEFORE the warm-up; rows are time-stamped and only those taken while the benchmark loop (warm-up +
+    timed steps, the same load) was running are reported."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
         self.rows, self.proc, self.index = [], None, index
+        self.t_load0 = None
 
-    def start(self):
+    def start(self, wait_s=5.0):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "200"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.index), "-lms", "50"], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
+            t0 = time.perf_counter()
+            while not self.rows and time.perf_counter() - t0 < wait_s:
+                time.sleep(0.01)
         except Exception:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def mark_load(self):
+        self.t_load0 = time.perf_counter()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        t_end = time.perf_counter()
+        time.sleep(0.06)                      # let the row that covers the end of the loop arrive
         self.proc.terminate()
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        rows = [r for t, r in self.rows if self.t_load0 is None or t >= self.t_load0]
+        rows = rows or [r for _, r in self.rows[-1:]]
+        sm = [float(r[0]) for r in rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == "Active" for r in self.rows)]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == "Active" for r in rows)]
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "window": "warm-up + timed steps (same load)",
+                "window_s": t_end - (self.t_load0 or t_end)}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -190,13 +205,14 @@ def main():
         torch.cuda.synchronize()
 
     sampler = ClockSampler(local)
+    sampler.start()                                        # nvidia-smi is up before the first warm-up step
     asm_ms, cg_ms, spmv_ms = [], [], []
     launches = 0
     barrier()
+    sampler.mark_load()
     for s in range(args.warmup + args.steps):
         if s == args.warmup:
             barrier()
-            sampler.start()
             t_wall0 = time.perf_counter()
         e0, e1, e2, e3 = ev(), ev(), ev(), ev()
         e0.record()
@@ -231,10 +247,13 @@ def main():
 
     # roofline of the dominant kernel (SpMV+dot of the PCG iteration), per rank
     nnz, n = prob.K_red.nnz, prob.n_owned_free
-    spmv_bytes = 12 * nnz + 4 * (n + 1) + 16 * n
+    csr_bytes = 12 * nnz + 4 * (n + 1) + 16 * n                          # CSR SpMV
+    node_block = prob.K_red.plan()[3] is not None and not os.environ.get("PSFEM_NO_NODEBLOCK")
+    # node-block SpMV: 8 B value + one 4-byte node id per 2x2 block, node_ptr, x, y
+    spmv_bytes = (9 * nnz + 4 * (n // 2 + 1) + 16 * n) if node_block else csr_bytes
     spmv_t = t_spmv / (K_ * args.cg_iters)
     spmv_gbs = spmv_bytes / spmv_t / 1e9
-    iter_bytes = 12 * nnz + 4 * (n + 1) + 13 * 8 * n
+    iter_bytes = spmv_bytes + (13 - 2) * 8 * n
     iter_gbs = iter_bytes / (t_cg / (K_ * args.cg_iters)) / 1e9
     asm_bytes = 320 * nel_local                                           # 16 conn + 16 coords + 288 CSR values
     asm_gbs = asm_bytes / (t_asm / K_) / 1e9
@@ -256,9 +275,13 @@ def main():
                      "roofline": {"bound": "hbm", "achieved": asm_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": asm_gbs / hbm_peak,
                                   "bytes_per_element": 320, "kernel": "lattice_q4_kernel<true> (marching warps, TMA bulk stores)",
                                   "traffic": asm_traffic}},
-        "roofline": {"kernel": "spmv2_kernel<true> (PCG SpMV + dot, TMA-staged)", "bound": "hbm", "achieved": spmv_gbs, "peak": hbm_peak,
+        "roofline": {"kernel": ("spmv_nb_kernel<true> (PCG SpMV + dot on the 2x2 node-block structure, TMA-staged, 9 B/non-zero)" if node_block
+                                else "spmv2_kernel<true> (PCG SpMV + dot, CSR, TMA-staged, 12 B/non-zero)"),
+                     "bound": "hbm", "achieved": spmv_gbs, "peak": hbm_peak,
                      "unit": "GB/s", "frac": spmv_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
-                     "bytes_per_launch": spmv_bytes, "ms_per_launch": 1e3 * spmv_t},
+                     "bytes_per_launch": spmv_bytes, "ms_per_launch": 1e3 * spmv_t,
+                     "csr_equivalent": {"bytes_per_launch": csr_bytes, "gbs": csr_bytes / spmv_t / 1e9,
+                                        "note": "SURVEY 8d counts the CSR formulation, 12 B per non-zero"}},
         "pcg_iteration": {"achieved": iter_gbs, "unit": "GB/s", "frac": iter_gbs / hbm_peak, "bytes_per_dof_iter": iter_bytes / n,
                           "ms": 1e3 * t_cg / (K_ * args.cg_iters)},
         "gpu_launches": launches, "clocks": clocks, "timed_region_wall_s": wall,
@@ -266,7 +289,8 @@ def main():
     traffic_file = os.path.join(ROOT, "profiles", "spmv_traffic.json")
     if os.path.exists(traffic_file):
         try:
-            line["roofline"]["traffic"] = json.load(open(traffic_file)).get("dram_bytes_per_launch")
+            tj = json.load(open(traffic_file))
+            line["roofline"]["traffic"] = (tj.get("node_block") if node_block else tj.get("csr") or tj).get("dram_bytes_per_launch")
         except Exception:
             pass
 

@@ -61,6 +61,14 @@ typedef struct psfem_csr {
     const int32_t *rowblk;  /* n_blocks + 2 ints (plan + one scratch slot) */
     int64_t n_blocks;
     int64_t max_row_nnz;
+    /* optional node-block view (psfem_spmv_nb_plan; all NULL / 0 when the matrix has no 2x2 node-block structure):
+     * rows 2a and 2a+1 share the columns {2b, 2b+1}, so one node id per 2x2 block replaces four column indices
+     * and the SpMV streams 9 instead of 12 bytes per non-zero.  Results are bit-identical to the CSR kernels. */
+    const int32_t *nb_node_ptr; /* n_rows/2 + 1 (+8 padding): first 2x2 block of node a, absolute (= row_ptr[2a]/4) */
+    const int32_t *nb_pcol;     /* nnz/4 (+8 padding): column node of each block, entry k belongs to block nb_node_ptr[0]+k */
+    const int32_t *nb_nodeblk;  /* nb_n_blocks + 3 ints */
+    int64_t nb_n_blocks;
+    int64_t nb_max_pairs;
 } psfem_csr;
 
 /* ---- mesh: Polygones.mesh, Polygones.py:62-108 ------------------------------------------
@@ -195,6 +203,13 @@ int psfem_scatter_free(const double *d_red, const int32_t *d_free_dofs, int64_t 
 int psfem_spmv_plan_size(int64_t n, int64_t nnz, int64_t *n_blocks);
 int psfem_spmv_plan(int64_t n, const int32_t *d_row_ptr, int64_t nnz, int32_t *d_rowblk /* n_blocks+2 */,
                     int64_t n_blocks, int64_t *h_max_row_nnz, void *stream);
+/* node-block view of a CSR operand: h_info[0] = 1 if the matrix has the structure (else the outputs are unused),
+ * h_info[1] = largest number of 2x2 blocks in a node row.  d_node_ptr: n/2+9 ints, d_pcol: nnz/4+8 ints,
+ * d_nodeblk: n_blocks+3 ints with n_blocks from psfem_spmv_nb_plan_size.  Synchronises. */
+int psfem_spmv_nb_plan_size(int64_t n, int64_t nnz, int64_t *n_blocks);
+int psfem_spmv_nb_plan(int64_t n, const int32_t *d_row_ptr, const int32_t *d_col_idx, int64_t nnz,
+                       int32_t *d_node_ptr, int32_t *d_pcol, int32_t *d_nodeblk, int64_t n_blocks,
+                       int64_t *h_info /* [2] */, void *stream);
 /* y = alpha*A*x + gamma*z   (z may be NULL; y may alias z) */
 int psfem_spmv(const psfem_csr *A, const double *d_x, double alpha, double gamma, const double *d_z,
                double *d_y, void *stream);

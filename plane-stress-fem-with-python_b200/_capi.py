@@ -24,7 +24,9 @@ class ConvergenceError(RuntimeError):
 
 class psfem_csr(C.Structure):
     _fields_ = [("n_rows", C.c_int64), ("nnz", C.c_int64), ("row_ptr", C.c_void_p), ("col_idx", C.c_void_p),
-                ("vals", C.c_void_p), ("rowblk", C.c_void_p), ("n_blocks", C.c_int64), ("max_row_nnz", C.c_int64)]
+                ("vals", C.c_void_p), ("rowblk", C.c_void_p), ("n_blocks", C.c_int64), ("max_row_nnz", C.c_int64),
+                ("nb_node_ptr", C.c_void_p), ("nb_pcol", C.c_void_p), ("nb_nodeblk", C.c_void_p),
+                ("nb_n_blocks", C.c_int64), ("nb_max_pairs", C.c_int64)]
 
 
 MAX_RANKS = 8
@@ -83,6 +85,8 @@ SIGNATURES = {
     "psfem_scatter_free": [_ptr, _ptr, _i64, _i64, _i64, _ptr, _ptr],
     "psfem_spmv_plan_size": [_i64, _i64, _pi64],
     "psfem_spmv_plan": [_i64, _ptr, _i64, _ptr, _i64, _pi64, _ptr],
+    "psfem_spmv_nb_plan_size": [_i64, _i64, _pi64],
+    "psfem_spmv_nb_plan": [_i64, _ptr, _ptr, _i64, _ptr, _ptr, _ptr, _i64, _pi64, _ptr],
     "psfem_spmv": [_pcsr, _ptr, _dbl, _dbl, _ptr, _ptr, _ptr],
     "psfem_spmv2": [_pcsr, _ptr, _ptr, _ptr, _dbl, _dbl, _dbl, _ptr, _ptr, _ptr],
     "psfem_extract_diag": [_pcsr, _i64, _i32, _ptr, _ptr],

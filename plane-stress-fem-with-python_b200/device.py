@@ -120,16 +120,38 @@ class DeviceCSR:
             rowblk = torch.empty(nb.value + 2, dtype=torch.int32, device="cuda")
             mx = C.c_int64(0)
             call("psfem_spmv_plan", self.n_rows, ptr(self.row_ptr), self.nnz, ptr(rowblk), nb.value, C.byref(mx), stream_ptr())
-            self._plan = (rowblk, nb.value, mx.value)
+            self._plan = (rowblk, nb.value, mx.value, self._node_block_plan())
         return self._plan
 
+    def _node_block_plan(self):
+        """Node-block view for the 9-byte-per-non-zero SpMV (psfem_spmv_nb_plan); None if the matrix does not
+        have the 2x2 node-block structure (e.g. a reduction that removed single DOFs of a node)."""
+        torch = _capi.torch_cuda()
+        if self.n_rows == 0 or self.n_rows % 2 or self.nnz % 4 or self.nnz == 0:
+            return None
+        nb = C.c_int64(0)
+        call("psfem_spmv_nb_plan_size", self.n_rows, self.nnz, C.byref(nb))
+        i32 = dict(dtype=torch.int32, device="cuda")
+        node_ptr = torch.empty(self.n_rows // 2 + 9, **i32)
+        pcol = torch.empty(self.nnz // 4 + 8, **i32)
+        nodeblk = torch.empty(nb.value + 3, **i32)
+        info = (C.c_int64 * 2)()
+        call("psfem_spmv_nb_plan", self.n_rows, ptr(self.row_ptr), ptr(self.col_idx), self.nnz, ptr(node_ptr), ptr(pcol),
+             ptr(nodeblk), nb.value, info, stream_ptr())
+        if info[0] != 1:
+            return None
+        return (node_ptr, pcol, nodeblk, nb.value, int(info[1]))
+
     def struct(self, vals=None):
-        rowblk, nb, mx = self.plan()
+        rowblk, nb, mx, nbp = self.plan()
         s = _capi.psfem_csr()
         s.n_rows, s.nnz = self.n_rows, self.nnz
         s.row_ptr, s.col_idx = self.row_ptr.data_ptr(), self.col_idx.data_ptr()
         s.vals = (self.vals if vals is None else vals).data_ptr()
         s.rowblk, s.n_blocks, s.max_row_nnz = rowblk.data_ptr(), nb, mx
+        if nbp is not None:
+            s.nb_node_ptr, s.nb_pcol, s.nb_nodeblk = nbp[0].data_ptr(), nbp[1].data_ptr(), nbp[2].data_ptr()
+            s.nb_n_blocks, s.nb_max_pairs = nbp[3], nbp[4]
         return s
 
     def to_scipy(self):

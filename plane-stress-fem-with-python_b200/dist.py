@@ -334,7 +334,7 @@ class StripProblem:
         self.K_red = DeviceCSR(hi - lo, self.n_ext_free, rp, self.K_ext_red.col_idx, self.K_ext_red.vals, nnz=None)
         self.K_red.nnz = int((rp[-1] - rp[0]).item())
         self.A = self.K_red.struct()
-        _, nb, _ = self.K_red.plan()
+        nb = self.K_red.plan()[1]
         # load: edgeForces(F,[0,-1e6],'right',l,N,M): f*l/(m-1) on every node of the right edge (global column n-1)
         F_ext = torch.zeros(p.n_ext_dof, **f64)
         if p.e1 == p.n:
