@@ -2,7 +2,8 @@
 test_gpu_parity.py::test_fused_strip_pcg_multi_gpu):
   1. the peer-memory transport (collectives fused into the PCG kernels) and the NCCL transport give the same
      iterates (bit-identical for 2 ranks: the scalar sums have two addends);
-  2. both match the single-GPU solver on the owned rows;
+  2. both match the single-GPU solver on the owned rows, and the assembled, reduced matrix rows a rank owns are
+     the single-GPU rows bit for bit;
   3. a restarted solve (sequence numbers keep growing) converges to the requested residual.
 """
 import os
@@ -30,6 +31,10 @@ def main():
         prob = StripProblem(rank=rank, world=world, transport=transport, **kw).setup()
         assert prob.transport == transport, f"transport {transport} not available: fell back to {prob.transport}"
         assert (prob.fabric is not None) == (transport == "peer")
+        if transport == "peer":                                    # assembled + reduced rows this rank owns
+            rp = prob.K_red.row_ptr.cpu().numpy().astype(np.int64)
+            res["K_rows"] = (rp - rp[0], prob.K_red.vals[int(rp[0]):int(rp[-1])].cpu().numpy().copy(),
+                             prob.K_red.col_idx[int(rp[0]):int(rp[-1])].cpu().numpy().astype(np.int64) - prob.plan["own"][0])
         prob.cg_iterations(iters)
         r, b = prob.residual()
         res[transport] = (prob.st["x"].cpu().numpy().copy(), r, b)
@@ -58,6 +63,13 @@ def main():
     dist.all_gather_object(sizes, len(xp))
     off = sum(sizes[:rank])
     assert sum(sizes) == len(x1)
+    # the strip's owned rows of K are the single-GPU rows BIT FOR BIT (pattern, values; columns up to the strip offset)
+    rp1 = one.K_red.row_ptr.cpu().numpy().astype(np.int64)
+    a, b_ = int(rp1[off]), int(rp1[off + len(xp)])
+    rel_ptr, vals, cols = res["K_rows"]
+    assert np.array_equal(rel_ptr, rp1[off:off + len(xp) + 1] - a)
+    assert np.array_equal(vals, one.K_red.vals[a:b_].cpu().numpy())
+    assert np.array_equal(cols + off, one.K_red.col_idx[a:b_].cpu().numpy().astype(np.int64))
     assert np.abs(xp - x1[off:off + len(xp)]).max() <= 1e-8 * np.abs(x1).max()
     assert abs(rp - r1) <= 1e-5 * r1 and abs(bp - b1) <= 1e-12 * b1
     dist.barrier()
