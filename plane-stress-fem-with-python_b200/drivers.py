@@ -116,14 +116,18 @@ def newmark(K, M, bc, f_shape, f_scale, dt=1e-3, gamma=0.5, beta=0.25, alpha_R=0
     ws = workspace(sz.value)
     info = (C.c_double * 4)()
     scale_c = f_scale.ctypes.data_as(C.POINTER(C.c_double))
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
     rc = lib.psfem_newmark_run(C.byref(s), ptr(M_red.vals), ptr(Keff_vals), ptr(fshape_red), scale_c, n_steps,
                                float(dt), float(gamma), float(beta), float(alpha_R), float(beta_R), ptr(a0),
                                int(store_every), ptr(U), ptr(V), ptr(A), ptr(E), float(rtol),
                                int(maxit if maxit is not None else 10 * n + 100), info, ptr(ws), sz.value, stream_ptr())
+    ev1.record()
     check(rc)
     torch.cuda.current_stream().synchronize()
     out = dict(U=U.cpu().numpy().T, V=V.cpu().numpy().T, A=A.cpu().numpy().T, constrained_dofs=constrained,
-               info=dict(pcg_iterations=int(info[0]), max_relres=float(info[1]), stabiliser_triggers=int(info[2])))
+               info=dict(pcg_iterations=int(info[0]), max_relres=float(info[1]), stabiliser_triggers=int(info[2]),
+                         run_ms=float(ev0.elapsed_time(ev1))))
     if energies:
         e = E.cpu().numpy()
         out.update(kinetic_energy=e[:, 0].copy(), potential_energy=e[:, 1].copy(), total_energy=e[:, 2].copy())
