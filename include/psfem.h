@@ -192,6 +192,11 @@ int psfem_reduce_count(int64_t n, const int32_t *d_row_ptr, const int32_t *d_col
                        void *d_ws, size_t ws_bytes, void *stream);
 int psfem_reduce_fill(int64_t n, const int32_t *d_row_ptr, const int32_t *d_col_idx, const int32_t *d_new_id,
                       const int32_t *d_row_ptr_red, int32_t *d_col_idx_red, int32_t *d_keep, void *stream);
+/* sanity of a CSR operand that arrives from the host (replaces scipy's host-side has_sorted_indices scan):
+ * *h_flags bit0 = columns not strictly ascending within a row, bit1 = column out of [0, n_cols), bit2 = row_ptr not
+ * monotone.  d_ws: >= 16 bytes.  Synchronises. */
+int psfem_csr_check(int64_t n, int64_t n_cols, const int32_t *d_row_ptr, const int32_t *d_col_idx, int64_t nnz,
+                    int64_t *h_flags, void *d_ws, size_t ws_bytes, void *stream);
 int psfem_gather(const double *d_src, const int32_t *d_index, int64_t n, double *d_dst, void *stream);
 /* reconstruct_full_vector(s) Polygones.py:913-936: d_full[v, free[i]] = d_red[v, i], zeros elsewhere */
 int psfem_scatter_free(const double *d_red, const int32_t *d_free_dofs, int64_t n_free, int64_t n_full,

@@ -81,6 +81,7 @@ SIGNATURES = {
     "psfem_free_map": [_i64, _ptr, _i64, _ptr, _ptr, _pi64, _ptr, _sz, _ptr],
     "psfem_reduce_count": [_i64, _ptr, _ptr, _ptr, _i64, _ptr, _pi64, _ptr, _sz, _ptr],
     "psfem_reduce_fill": [_i64, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr],
+    "psfem_csr_check": [_i64, _i64, _ptr, _ptr, _i64, _pi64, _ptr, _sz, _ptr],
     "psfem_gather": [_ptr, _ptr, _i64, _ptr, _ptr],
     "psfem_scatter_free": [_ptr, _ptr, _i64, _i64, _i64, _ptr, _ptr],
     "psfem_spmv_plan_size": [_i64, _i64, _pi64],

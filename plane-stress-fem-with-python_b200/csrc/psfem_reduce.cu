@@ -64,6 +64,29 @@ __global__ void reduce_fill_kernel(int64_t n, const int32_t *__restrict__ row_pt
     }
 }
 
+// CSR sanity of a matrix that arrives from the host: row_ptr non-decreasing, columns inside [0, n_cols) and strictly
+// ascending within each row (what the SpMV / reduction kernels assume).  flags: bit0 = unsorted or duplicate columns,
+// bit1 = column out of range, bit2 = row_ptr not monotone.  One pass over col_idx at HBM speed instead of a host scan.
+__global__ void csr_check_kernel(int64_t n, int64_t n_cols, const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col_idx,
+                                 int *__restrict__ flags) {
+    const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t nnz = row_ptr[n] - row_ptr[0];
+    int f = 0;
+    if (k < n && row_ptr[k + 1] < row_ptr[k]) f |= 4;
+    if (k < nnz) {
+        const int64_t q = row_ptr[0] + k;
+        const int32_t c = col_idx[q];
+        if (c < 0 || c >= n_cols) f |= 2;
+        if (k + 1 < nnz && col_idx[q + 1] <= c) {
+            // a descent is fine only at a row boundary: find whether q+1 starts a row (binary search in row_ptr)
+            int64_t lo = 0, hi = n;
+            while (lo < hi) { const int64_t mid = lo + ((hi - lo) >> 1); if (row_ptr[mid] < q + 1) lo = mid + 1; else hi = mid; }
+            if (lo > n || row_ptr[lo] != q + 1) f |= 1;
+        }
+    }
+    if (f) atomicOr(flags, f);
+}
+
 __global__ void gather_kernel(const double *__restrict__ src, const int32_t *__restrict__ index, int64_t n, double *__restrict__ dst) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i < n) dst[i] = src[index[i]];
@@ -148,6 +171,24 @@ extern "C" int psfem_reduce_fill(int64_t n, const int32_t *d_row_ptr, const int3
     const int T = 256;
     reduce_fill_kernel<<<(unsigned)ceil_div(n, T), T, 0, stream>>>(n, d_row_ptr, d_col_idx, d_new_id, d_row_ptr_red, d_col_idx_red, d_keep);
     PSFEM_LAUNCH_CHECK();
+    return PSFEM_OK;
+}
+
+extern "C" int psfem_csr_check(int64_t n, int64_t n_cols, const int32_t *d_row_ptr, const int32_t *d_col_idx, int64_t nnz,
+                               int64_t *h_flags, void *d_ws, size_t ws_bytes, void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    PSFEM_REQUIRE(n >= 0 && d_row_ptr && h_flags && d_ws && ws_bytes >= 16, "csr_check: bad arguments");
+    int *flags = static_cast<int *>(d_ws);
+    PSFEM_CUDA_CHECK(cudaMemsetAsync(flags, 0, sizeof(int), stream));
+    const int64_t work = nnz > n ? nnz : n;
+    if (work > 0) {
+        csr_check_kernel<<<(unsigned)ceil_div(work, 256), 256, 0, stream>>>(n, n_cols, d_row_ptr, d_col_idx, flags);
+        PSFEM_LAUNCH_CHECK();
+    }
+    int h = 0;
+    PSFEM_CUDA_CHECK(cudaMemcpyAsync(&h, flags, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    PSFEM_CUDA_CHECK(cudaStreamSynchronize(stream));
+    *h_flags = h;
     return PSFEM_OK;
 }
 

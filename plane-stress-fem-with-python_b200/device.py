@@ -166,15 +166,29 @@ class DeviceCSR:
     @classmethod
     def from_scipy(cls, A):
         torch = _capi.torch_cuda()
+        _capi.bind_device()
         A = sparse.csr_matrix(A)
-        if not A.has_sorted_indices:
-            A = A.sorted_indices()
         if A.nnz >= 2 ** 31 - 8192:
             raise ValueError("matrix has too many non-zeros for one GPU (int32 indices): partition it")
-        return cls(A.shape[0], A.shape[1],
-                   torch.from_numpy(np.ascontiguousarray(A.indptr, dtype=np.int32)).cuda(),
-                   torch.from_numpy(np.ascontiguousarray(A.indices, dtype=np.int32)).cuda(),
-                   torch.from_numpy(np.ascontiguousarray(A.data, dtype=np.float64)).cuda())
+
+        def upload(M):
+            return cls(M.shape[0], M.shape[1], to_device(M.indptr, np.int32), to_device(M.indices, np.int32),
+                       to_device(M.data, np.float64), nnz=M.nnz)
+        dev = upload(A)
+        # sorted / in-range columns are checked on the device (one pass at HBM speed) instead of scipy's
+        # has_sorted_indices host scan -- 0.3 s for the 604 M indices of the 33.6 M-DOF plate
+        flags = C.c_int64(0)
+        ws = workspace(256)
+        call("psfem_csr_check", dev.n_rows, dev.n_cols, ptr(dev.row_ptr), ptr(dev.col_idx), dev.nnz, C.byref(flags), ptr(ws), 256,
+             stream_ptr())
+        if flags.value & 6:
+            raise ValueError("malformed CSR matrix (row pointers not monotone or column index out of range)")
+        if flags.value & 1:                       # rare: unsorted or duplicated columns -> canonical form on the host
+            A = A.copy()
+            A.sum_duplicates()
+            A.sort_indices()
+            dev = upload(A)
+        return dev
 
     # y = alpha*A@x + gamma*z
     def matvec(self, x, alpha=1.0, gamma=0.0, z=None, out=None):

@@ -14,7 +14,7 @@ import numpy as np
 
 from . import _capi
 from ._capi import call, check, lib, ptr, stream_ptr, workspace
-from .device import Blas, DeviceCSR, FreeMap, constrained_dofs_of, pcg_jacobi
+from .device import Blas, DeviceCSR, FreeMap, constrained_dofs_of, pcg_jacobi, to_host
 from .Polygones import device_copy
 
 
@@ -54,8 +54,9 @@ def static_solve(K, F, bc, rtol=1e-8, maxit=None, check_every=50, return_device=
     U = fm.expand(U_red)
     if return_device:
         return U, U_red, constrained, info
+    Uh, Urh = to_host(U), to_host(U_red)          # page-locked landing buffers: DMA instead of the pageable path
     torch.cuda.current_stream().synchronize()
-    return U.cpu().numpy(), U_red.cpu().numpy(), constrained, info
+    return Uh.numpy(), Urh.numpy(), constrained, info
 
 
 # ---------------------------------------------------------------------------------------------
