@@ -355,7 +355,8 @@ def e2e_leg(psfem_b200, prob, args, cells):
             "d2h_bytes_per_step": int(d2h), "steps": steps, "pcg_iters_per_call": args.e2e_iters,
             "assembly_elements_per_s": cells * cells * steps / t_asm,
             "calls": "Polygones.global_stiffness_matrix(host nodes, elements) -> host scipy CSR; "
-                     "static_solve(host CSR, host F, bc, maxit) -> host U (pageable host memory, as a user has it)"}
+                     "static_solve(host CSR, host F, bc, maxit) -> host U (nodes, F: the caller's pageable arrays; the CSR arrays are the "
+                     "page-locked buffers global_stiffness_matrix returned)"}
 
 
 if __name__ == "__main__":
