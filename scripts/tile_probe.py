@@ -7,6 +7,7 @@ nodes, conn = psfem_b200.device_mesh(N * 1e-3, N * 1e-3, N, N, element_type='qua
 for R in (64, 128):
     asm = psfem_b200.Assembler(conn, (N + 1) ** 2, _capi.Q4)
     asm.tile_nodes_R = R
+    asm.use_lattice = False            # force the general tile-fused path on this lattice mesh
     K, _ = asm.assemble(nodes, E=210e9, nu=.3, t=.1, what=1)
     ts = []
     for rep in range(3):
