@@ -282,8 +282,13 @@ class StripProblem:
     benchmark object (world = 1)."""
 
     def __init__(self, L, l, N, M, rank=0, world=1, E=210e9, nu=0.3, t=0.1, element_type="quad", mesh_type="coarse",
-                 load=(0.0, -1e6), transport=None):
+                 load=(0.0, -1e6), transport=None, bc=None, F=None):
+        """bc: boundary conditions like the reference's lists [(global node, [ux, uy]), ...] (None entries = free
+        component); default Polygones.boundary('left', [0, 0], N, M).  F: global load, either a callable
+        (dof_lo, dof_hi) -> ndarray of that DOF range (so no rank builds the whole vector) or a full-length array;
+        default Polygones.edgeForces(zeros, load, 'right', l, N, M)."""
         import os
+        self.bc, self.F = bc, F
         # "peer": collectives fused into the PCG kernels over CUDA-IPC peer memory (default for world > 1);
         # "nccl": torch.distributed all-reduce + send/recv between the kernels
         self.transport = transport or os.environ.get("PSFEM_DIST_TRANSPORT", "peer")
@@ -315,7 +320,12 @@ class StripProblem:
         K_ext = self.asm.pattern_csr(self.K_vals)
         # boundary conditions: left edge clamped (global node column 0), Polygones.boundary('left',[0,0],...)
         m = p.m
-        cd_global = np.arange(2 * m, dtype=np.int64)              # DOFs 2k, 2k+1 of nodes k = 0..m-1
+        if self.bc is None:
+            cd_global = np.arange(2 * m, dtype=np.int64)          # DOFs 2k, 2k+1 of nodes k = 0..m-1
+        else:
+            from .device import constrained_dofs_of
+            cd_global = np.asarray(constrained_dofs_of(self.bc), dtype=np.int64)
+        self.constrained_global = cd_global
         self.fm = FreeMap(p.n_ext_dof, p.local_constrained(cd_global))
         self.K_ext_red = self.fm.reduce_csr(K_ext)
         free = self.fm.free_dofs                                   # sorted extended-local ids of free DOFs
@@ -336,15 +346,21 @@ class StripProblem:
         self.A = self.K_red.struct()
         nb = self.K_red.plan()[1]
         # load: edgeForces(F,[0,-1e6],'right',l,N,M): f*l/(m-1) on every node of the right edge (global column n-1)
-        F_ext = torch.zeros(p.n_ext_dof, **f64)
-        if p.e1 == p.n:
-            k0 = (p.n - 1 - p.e0) * m
-            F_ext[2 * k0:2 * (k0 + m):2] = self.load[0] * self.l / (m - 1)
-            F_ext[2 * k0 + 1:2 * (k0 + m):2] = self.load[1] * self.l / (m - 1)
+        if self.F is None:
+            F_ext = torch.zeros(p.n_ext_dof, **f64)
+            if p.e1 == p.n:
+                k0 = (p.n - 1 - p.e0) * m
+                F_ext[2 * k0:2 * (k0 + m):2] = self.load[0] * self.l / (m - 1)
+                F_ext[2 * k0 + 1:2 * (k0 + m):2] = self.load[1] * self.l / (m - 1)
+        else:
+            a, b = p.dof_shift, p.dof_shift + p.n_ext_dof
+            Fh = self.F(a, b) if callable(self.F) else np.asarray(self.F)[a:b]
+            F_ext = torch.from_numpy(np.ascontiguousarray(Fh, dtype=np.float64)).cuda()
         self.b_own = self.fm.reduce_vec(F_ext)[lo:hi].contiguous()
         # global sizes
         self.n_dof_global = 2 * p.n * p.m
-        self.n_free_global = self.n_dof_global - 2 * m
+        cdg = cd_global[(cd_global >= 0) & (cd_global < self.n_dof_global)]
+        self.n_free_global = self.n_dof_global - len(np.unique(cdg))
         per_cell = 2 if self.element_type == "tri" else 1
         self.nel_global = self.N * self.M * per_cell
         self.nel_owned = self.asm.nel
@@ -437,6 +453,27 @@ class StripProblem:
         torch.cuda.synchronize()
         r, b = self.residual()
         return dict(iterations=self.st["iters"], relres=r / b if b > 0 else 0.0, seconds=time.perf_counter() - t0)
+
+    def gather_solution(self, dst=0):
+        """Global displacement vector (zeros at constrained DOFs, like reconstruct_full_vector Polygones.py:913-921)
+        on rank `dst` (None elsewhere): every rank contributes the free DOFs of its owned node columns."""
+        torch = _capi.torch_cuda()
+        lo, hi = self.plan["own"]
+        torch.cuda.synchronize()
+        ids = (self.fm.free_dofs[lo:hi].cpu().numpy().astype(np.int64) + self.part.dof_shift)
+        vals = self.st["x"].cpu().numpy()
+        if self.world == 1:
+            parts = [(ids, vals)]
+        else:
+            import torch.distributed as dist
+            parts = [None] * self.world if self.rank == dst else None
+            dist.gather_object((ids, vals), parts, dst=dst)
+            if self.rank != dst:
+                return None
+        U = np.zeros(self.n_dof_global)
+        for i, v in parts:
+            U[i] = v
+        return U
 
     def full_solve(self, rtol):
         torch = _capi.torch_cuda()

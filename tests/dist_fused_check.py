@@ -4,7 +4,8 @@ test_gpu_parity.py::test_fused_strip_pcg_multi_gpu):
      iterates (bit-identical for 2 ranks: the scalar sums have two addends);
   2. both match the single-GPU solver on the owned rows, and the assembled, reduced matrix rows a rank owns are
      the single-GPU rows bit for bit;
-  3. a restarted solve (sequence numbers keep growing) converges to the requested residual.
+  3. a restarted solve (sequence numbers keep growing) converges to the requested residual;
+  4. a problem with general boundary conditions (rollers, a pinned node) and loads gives the single-GPU solution.
 """
 import os
 import sys
@@ -72,6 +73,24 @@ def main():
     assert np.array_equal(cols + off, one.K_red.col_idx[a:b_].cpu().numpy().astype(np.int64))
     assert np.abs(xp - x1[off:off + len(xp)]).max() <= 1e-8 * np.abs(x1).max()
     assert abs(rp - r1) <= 1e-5 * r1 and abs(bp - b1) <= 1e-12 * b1
+    # 4. general boundary conditions and loads: rollers along the bottom edge (single DOFs constrained: the reduced
+    #    matrix loses its node-block structure, CSR kernels), one pinned node, load on the top edge; the gathered
+    #    solution against the single-GPU static_solve of the same problem
+    from psfem_b200 import Polygones as P
+    nodes, elements = P.mesh(kw["L"], kw["l"], N, M, element_type="quad")
+    bc = [(0, [0, 0])] + P.boundary("bottom", [None, 0], N, M)[1:]
+    Fg = P.edgeForces(np.zeros(2 * len(nodes)), [2e5, -1e6], "top", kw["L"], N, M)
+    prob = StripProblem(rank=rank, world=world, transport="peer", bc=bc, F=lambda a, b: Fg[a:b], **kw).setup()
+    assert prob.fabric is not None
+    info = prob.solve(rtol=1e-11, maxit=40000, check_every=200)
+    assert info["relres"] <= 1e-11, info
+    Ug = prob.gather_solution(dst=0)
+    prob.release()
+    if rank == 0:
+        K = P.global_stiffness_matrix(nodes, elements, kw["E"], kw["nu"], kw["t"], "quad")
+        U1, _, cd, _ = psfem_b200.static_solve(K, Fg, bc, rtol=1e-11, check_every=200)
+        assert np.all(Ug[cd] == 0)
+        assert np.abs(Ug - U1).max() <= 1e-8 * np.abs(U1).max(), np.abs(Ug - U1).max() / np.abs(U1).max()
     dist.barrier()
     if rank == 0:
         print(f"dist_fused_check OK: world={world} iters={iters} relres={rp / bp:.3e} full-solve iterations={res['solve_iters']}")
