@@ -259,7 +259,7 @@ def main():
     spmv_bytes = (9 * nnz + 4 * (n // 2 + 1) + 16 * n) if node_block else csr_bytes
     spmv_t = t_spmv / (K_ * args.cg_iters)
     spmv_gbs = spmv_bytes / spmv_t / 1e9
-    iter_bytes = spmv_bytes + (13 - 2) * 8 * n
+    iter_bytes = spmv_bytes + (4 + 6) * 8 * n                            # update: q, r, dinv, r' ; p-update: p, x, r, dinv, p', x'
     iter_gbs = iter_bytes / (t_cg / (K_ * args.cg_iters)) / 1e9
     asm_bytes = 320 * nel_local                                           # 16 conn + 16 coords + 288 CSR values
     asm_gbs = asm_bytes / (t_asm / K_) / 1e9

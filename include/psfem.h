@@ -237,18 +237,19 @@ int psfem_pcg_jacobi(const psfem_csr *A, const double *d_b, double *d_x, double 
  * halo exchange and all-reduces between them (scalars stay on the device):
  *   init    : p = dinv*r ; out3 = {r.dinv r, r.r, b.b}  (local sums)
  *   spmv_dot: q = A p_ext ; *d_pq = p_own . q  (p_own = p_ext + x_offset)
- *   update  : alpha = *d_rz / *d_pq ; x += alpha p ; r -= alpha q ; out2 = {r.dinv r, r.r}
- *   pupdate : beta = *d_rz_new / *d_rz_old ; p = dinv*r + beta p
+ *   update  : alpha = *d_rz / *d_pq ; r -= alpha q ; out2 = {r.dinv r, r.r}
+ *   pupdate : alpha = *d_rz_old / *d_pq ; beta = *d_rz_new / *d_rz_old ; x += alpha p ; p = dinv*r + beta p
+ *             (the x step lives here because this kernel streams p anyway: 80 instead of 88 bytes per DOF and iteration)
  * d_partials: max(n_blocks, 1184)*3 doubles, d_counter: zero-initialised uint32. */
 int psfem_pcg_init(int64_t n, const double *d_r, const double *d_dinv, const double *d_b, double *d_p,
                    double *d_out3, double *d_partials, uint32_t *d_counter, void *stream);
 int psfem_pcg_spmv_dot(const psfem_csr *A, const double *d_p_ext, int64_t x_offset, double *d_q, double *d_pq,
                        double *d_partials, uint32_t *d_counter, void *stream);
-int psfem_pcg_update(int64_t n, double *d_x, double *d_r, const double *d_p, const double *d_q,
+int psfem_pcg_update(int64_t n, double *d_r, const double *d_q,
                      const double *d_dinv, const double *d_rz, const double *d_pq, double *d_out2,
                      double *d_partials, uint32_t *d_counter, void *stream);
-int psfem_pcg_pupdate(int64_t n, double *d_p, const double *d_r, const double *d_dinv,
-                      const double *d_rz_old, const double *d_rz_new, void *stream);
+int psfem_pcg_pupdate(int64_t n, double *d_p, double *d_x, const double *d_r, const double *d_dinv,
+                      const double *d_rz_old, const double *d_rz_new, const double *d_pq, void *stream);
 
 /* ---- strip-partitioned Jacobi-PCG with the collectives FUSED into its kernels (multi-GPU, one process per GPU) ----
  * Replaces, per iteration, two NCCL all-reduces and one halo send/recv by stores over NVLink/NVSwitch peer memory:

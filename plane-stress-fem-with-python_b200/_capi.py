@@ -95,8 +95,8 @@ SIGNATURES = {
     "psfem_pcg_jacobi": [_pcsr, _ptr, _ptr, _dbl, _i64, _i64, _pdbl, _ptr, _sz, _ptr],
     "psfem_pcg_init": [_i64, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr],
     "psfem_pcg_spmv_dot": [_pcsr, _ptr, _i64, _ptr, _ptr, _ptr, _ptr, _ptr],
-    "psfem_pcg_update": [_i64, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr],
-    "psfem_pcg_pupdate": [_i64, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr],
+    "psfem_pcg_update": [_i64, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr],
+    "psfem_pcg_pupdate": [_i64, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr],
     "psfem_peer_board_bytes": [_psz],
     "psfem_peer_alloc": [_sz, C.POINTER(C.c_void_p), _ptr],
     "psfem_peer_open": [_ptr, C.POINTER(C.c_void_p)],

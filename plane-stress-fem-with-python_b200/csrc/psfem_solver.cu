@@ -689,9 +689,11 @@ pcg_init_kernel(int64_t n, const double *__restrict__ r, const double *__restric
     }
 }
 
-// x += alpha p; r -= alpha q; rz_new = r.(dinv r); rr = r.r      alpha = rz/pq
+// r -= alpha q; rz_new = r.(dinv r); rr = r.r      alpha = rz/pq
+// (x += alpha p is done by the p-update kernel, which streams p anyway: 8 B per DOF and iteration less than
+//  reading p here as well)
 __global__ void __launch_bounds__(EW_THREADS)
-pcg_update_kernel(int64_t n, double *__restrict__ x, double *__restrict__ r, const double *__restrict__ p,
+pcg_update_kernel(int64_t n, double *__restrict__ r,
                   const double *__restrict__ q, const double *__restrict__ dinv, const double *__restrict__ rz_in,
                   const double *__restrict__ pq_in, double *__restrict__ out2, double *__restrict__ partials,
                   unsigned int *counter, PcgCtl *ctl) {
@@ -706,9 +708,7 @@ pcg_update_kernel(int64_t n, double *__restrict__ x, double *__restrict__ r, con
     const double alpha = rz / pq;
     double v[2] = {0, 0};
     for (int64_t i = blockIdx.x * (int64_t)EW_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * EW_THREADS) {
-        const double pi = p[i], qi = q[i];
-        x[i] += alpha * pi;
-        const double ri = r[i] - alpha * qi;
+        const double ri = r[i] - alpha * q[i];
         r[i] = ri;
         v[0] += ri * (dinv[i] * ri);
         v[1] += ri * ri;
@@ -727,21 +727,24 @@ pcg_update_kernel(int64_t n, double *__restrict__ x, double *__restrict__ r, con
     }
 }
 
-// p = dinv*r + beta p     beta = rz_new/rz_old
+// x += alpha p (the step of THIS iteration, with the old p); p = dinv*r + beta p     alpha = rz_old/pq, beta = rz_new/rz_old
 __global__ void __launch_bounds__(EW_THREADS)
-pcg_pupdate_kernel(int64_t n, double *__restrict__ p, const double *__restrict__ r, const double *__restrict__ dinv,
-                   const double *__restrict__ rz_old_in, const double *__restrict__ rz_new_in, PcgCtl *ctl,
-                   unsigned int *counter) {
-    double rz_old, rz_new;
+pcg_pupdate_kernel(int64_t n, double *__restrict__ p, double *__restrict__ x, const double *__restrict__ r,
+                   const double *__restrict__ dinv, const double *__restrict__ rz_old_in, const double *__restrict__ rz_new_in,
+                   const double *__restrict__ pq_in, PcgCtl *ctl, unsigned int *counter) {
+    double rz_old, rz_new, pq;
     if (ctl) {
         if (ctl->done) return;
-        rz_old = ctl->rz[ctl->parity]; rz_new = ctl->rz[ctl->parity ^ 1];
+        rz_old = ctl->rz[ctl->parity]; rz_new = ctl->rz[ctl->parity ^ 1]; pq = ctl->pq;
     } else {
-        rz_old = *rz_old_in; rz_new = *rz_new_in;
+        rz_old = *rz_old_in; rz_new = *rz_new_in; pq = *pq_in;
     }
-    const double beta = rz_new / rz_old;
-    for (int64_t i = blockIdx.x * (int64_t)EW_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * EW_THREADS)
-        p[i] = dinv[i] * r[i] + beta * p[i];
+    const double beta = rz_new / rz_old, alpha = rz_old / pq;
+    for (int64_t i = blockIdx.x * (int64_t)EW_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * EW_THREADS) {
+        const double pi = p[i];
+        x[i] += alpha * pi;
+        p[i] = dinv[i] * r[i] + beta * pi;
+    }
     if (ctl) {
         // last block flips parity / sets done after every block has read the old state
         __shared__ bool is_last;
@@ -933,18 +936,16 @@ dist_init_kernel(int64_t n, const double *__restrict__ b, const double *__restri
     }
 }
 
-// alpha = (r.z)/(p.q) from the boards; x += alpha p; r -= alpha q; publishes {r.z, r.r}
+// alpha = (r.z)/(p.q) from the boards; r -= alpha q; publishes {r.z, r.r}  (x += alpha p: see dist_pupdate_kernel)
 __global__ void __launch_bounds__(EW_THREADS)
-dist_update_kernel(int64_t n, double *__restrict__ x, double *__restrict__ r, const double *__restrict__ p,
+dist_update_kernel(int64_t n, double *__restrict__ r,
                    const double *__restrict__ q, const double *__restrict__ dinv, PeerSync ps, double *__restrict__ partials,
                    unsigned int *counter) {
     __shared__ double red[EW_THREADS / 32];
     const double alpha = ps.scal[5 + (int)((ps.seq - 1) & 1)] / ps.scal[4];   // global sums left by the previous kernels' last blocks
     double v[2] = {0, 0};
     for (int64_t i = blockIdx.x * (int64_t)EW_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * EW_THREADS) {
-        const double pi = p[i], qi = q[i];
-        x[i] += alpha * pi;
-        const double ri = r[i] - alpha * qi;
+        const double ri = r[i] - alpha * q[i];
         r[i] = ri;
         v[0] += ri * (dinv[i] * ri);
         v[1] += ri * ri;
@@ -961,12 +962,16 @@ dist_update_kernel(int64_t n, double *__restrict__ x, double *__restrict__ r, co
 
 // beta = (r.z)_new/(r.z)_old from the boards; p = dinv r + beta p, halo entries stored into the neighbours' vectors
 __global__ void __launch_bounds__(EW_THREADS)
-dist_pupdate_kernel(int64_t n, double *__restrict__ p, const double *__restrict__ r, const double *__restrict__ dinv,
-                    HaloPush halo, PeerSync ps, unsigned int *counter) {
+dist_pupdate_kernel(int64_t n, double *__restrict__ p, double *__restrict__ x, const double *__restrict__ r,
+                    const double *__restrict__ dinv, HaloPush halo, PeerSync ps, unsigned int *counter) {
     __shared__ bool is_last;
-    const double beta = ps.scal[5 + (int)(ps.seq & 1)] / ps.scal[5 + (int)((ps.seq - 1) & 1)];
-    for (int64_t i = blockIdx.x * (int64_t)EW_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * EW_THREADS)
-        p[i] = dinv[i] * r[i] + beta * p[i];
+    const double rz_old = ps.scal[5 + (int)((ps.seq - 1) & 1)];
+    const double beta = ps.scal[5 + (int)(ps.seq & 1)] / rz_old, alpha = rz_old / ps.scal[4];
+    for (int64_t i = blockIdx.x * (int64_t)EW_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * EW_THREADS) {
+        const double pi = p[i];
+        x[i] += alpha * pi;                    // the step of this iteration, with the old p
+        p[i] = dinv[i] * r[i] + beta * pi;
+    }
     const bool sent = halo(p, blockIdx.x * (long long)EW_THREADS + threadIdx.x, (long long)gridDim.x * EW_THREADS);
     const int block_sent = __syncthreads_or(sent ? 1 : 0);
     if (threadIdx.x == 0) {
@@ -1148,19 +1153,19 @@ extern "C" int psfem_pcg_init(int64_t n, const double *d_r, const double *d_dinv
     return PSFEM_OK;
 }
 
-extern "C" int psfem_pcg_update(int64_t n, double *d_x, double *d_r, const double *d_p, const double *d_q,
+extern "C" int psfem_pcg_update(int64_t n, double *d_r, const double *d_q,
                                 const double *d_dinv, const double *d_rz, const double *d_pq, double *d_out2,
                                 double *d_partials, uint32_t *d_counter, void *stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    pcg_update_kernel<<<ew_grid(n), EW_THREADS, 0, stream>>>(n, d_x, d_r, d_p, d_q, d_dinv, d_rz, d_pq, d_out2, d_partials, d_counter, nullptr);
+    pcg_update_kernel<<<ew_grid(n), EW_THREADS, 0, stream>>>(n, d_r, d_q, d_dinv, d_rz, d_pq, d_out2, d_partials, d_counter, nullptr);
     PSFEM_LAUNCH_CHECK();
     return PSFEM_OK;
 }
 
-extern "C" int psfem_pcg_pupdate(int64_t n, double *d_p, const double *d_r, const double *d_dinv, const double *d_rz_old,
-                                 const double *d_rz_new, void *stream_) {
+extern "C" int psfem_pcg_pupdate(int64_t n, double *d_p, double *d_x, const double *d_r, const double *d_dinv,
+                                 const double *d_rz_old, const double *d_rz_new, const double *d_pq, void *stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    pcg_pupdate_kernel<<<ew_grid(n), EW_THREADS, 0, stream>>>(n, d_p, d_r, d_dinv, d_rz_old, d_rz_new, nullptr, nullptr);
+    pcg_pupdate_kernel<<<ew_grid(n), EW_THREADS, 0, stream>>>(n, d_p, d_x, d_r, d_dinv, d_rz_old, d_rz_new, d_pq, nullptr, nullptr);
     PSFEM_LAUNCH_CHECK();
     return PSFEM_OK;
 }
@@ -1238,8 +1243,8 @@ extern "C" int psfem_dist_pcg_iterations(const psfem_csr *A, const psfem_dist_ct
         int rc = launch_spmv(A, nullptr, c->p_ext, nullptr, 1.0, 0.0, 0.0, nullptr, c->q, p_own, c->out3 + 3 /* local p.q, unused */, c->partials,
                              c->counter, nullptr, stream, &ps);
         if (rc) return rc;
-        dist_update_kernel<<<ew_grid(c->n_own), EW_THREADS, 0, stream>>>(c->n_own, c->x, c->r, p_own, c->q, c->dinv, ps, c->partials, c->counter + 1);
-        dist_pupdate_kernel<<<ew_grid(c->n_own), EW_THREADS, 0, stream>>>(c->n_own, p_own, c->r, c->dinv, make_halo(c), ps, c->counter + 2);
+        dist_update_kernel<<<ew_grid(c->n_own), EW_THREADS, 0, stream>>>(c->n_own, c->r, c->q, c->dinv, ps, c->partials, c->counter + 1);
+        dist_pupdate_kernel<<<ew_grid(c->n_own), EW_THREADS, 0, stream>>>(c->n_own, p_own, c->x, c->r, c->dinv, make_halo(c), ps, c->counter + 2);
     }
     PSFEM_LAUNCH_CHECK();
     return PSFEM_OK;
@@ -1261,9 +1266,9 @@ extern "C" int psfem_dist_pcg_profile(const psfem_csr *A, const psfem_dist_ctx *
         int rc = launch_spmv(A, nullptr, c->p_ext, nullptr, 1.0, 0.0, 0.0, nullptr, c->q, p_own, c->out3 + 3, c->partials, c->counter, nullptr, stream, &ps);
         if (rc) return rc;
         cudaEventRecord(ev[3 * j + 1], stream);
-        dist_update_kernel<<<ew_grid(c->n_own), EW_THREADS, 0, stream>>>(c->n_own, c->x, c->r, p_own, c->q, c->dinv, ps, c->partials, c->counter + 1);
+        dist_update_kernel<<<ew_grid(c->n_own), EW_THREADS, 0, stream>>>(c->n_own, c->r, c->q, c->dinv, ps, c->partials, c->counter + 1);
         cudaEventRecord(ev[3 * j + 2], stream);
-        dist_pupdate_kernel<<<ew_grid(c->n_own), EW_THREADS, 0, stream>>>(c->n_own, p_own, c->r, c->dinv, make_halo(c), ps, c->counter + 2);
+        dist_pupdate_kernel<<<ew_grid(c->n_own), EW_THREADS, 0, stream>>>(c->n_own, p_own, c->x, c->r, c->dinv, make_halo(c), ps, c->counter + 2);
         cudaEventRecord(ev[3 * j + 3], stream);
     }
     PSFEM_LAUNCH_CHECK();
@@ -1345,8 +1350,8 @@ int pcg_solve(const psfem_csr *A, const double *d_b, double *d_x, double rtol, i
         for (int64_t it = 0; it < batch; ++it) {
             rc = launch_spmv(A, nullptr, w.p, nullptr, 1.0, 0.0, 0.0, nullptr, w.q, w.p, &w.ctl->pq, w.partials, w.counter, &w.ctl->done, stream);
             if (rc) return rc;
-            pcg_update_kernel<<<g, EW_THREADS, 0, stream>>>(n, d_x, w.r, w.p, w.q, w.dinv, nullptr, nullptr, nullptr, w.partials, w.counter + 1, w.ctl);
-            pcg_pupdate_kernel<<<g, EW_THREADS, 0, stream>>>(n, w.p, w.r, w.dinv, nullptr, nullptr, w.ctl, w.counter + 2);
+            pcg_update_kernel<<<g, EW_THREADS, 0, stream>>>(n, w.r, w.q, w.dinv, nullptr, nullptr, nullptr, w.partials, w.counter + 1, w.ctl);
+            pcg_pupdate_kernel<<<g, EW_THREADS, 0, stream>>>(n, w.p, d_x, w.r, w.dinv, nullptr, nullptr, nullptr, w.ctl, w.counter + 2);
         }
         PSFEM_LAUNCH_CHECK();
         launched += batch;

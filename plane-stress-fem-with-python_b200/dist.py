@@ -139,10 +139,11 @@ def pcg_iterations(ops, comm: Comm, st: dict, k: int):
         cur, nxt = st["parity"], st["parity"] ^ 1
         ops.spmv_dot(st["p_ext"], lo, st["q"], st["pq"])                 # q = A p ; pq = p_own . q (local)
         comm.allreduce(st["pq"])
-        ops.update(st["x"], st["r"], st["p_ext"][lo:hi], st["q"], st["dinv"], st["rz"][cur:cur + 1], st["pq"], st["out2"])
+        ops.update(st["r"], st["q"], st["dinv"], st["rz"][cur:cur + 1], st["pq"], st["out2"])   # r -= alpha q
         comm.allreduce(st["out2"])                                        # {r.z, r.r}
         ops.copy_scalar(st["out2"][0:1], st["rz"][nxt:nxt + 1])
-        ops.pupdate(st["p_ext"][lo:hi], st["r"], st["dinv"], st["rz"][cur:cur + 1], st["rz"][nxt:nxt + 1])
+        # x += alpha p (old p), p = dinv r + beta p
+        ops.pupdate(st["p_ext"][lo:hi], st["x"], st["r"], st["dinv"], st["rz"][cur:cur + 1], st["rz"][nxt:nxt + 1], st["pq"])
         comm.halo(st["p_ext"])
         st["parity"] = nxt
         st["iters"] += 1
@@ -260,12 +261,12 @@ class CudaOps:
         call("psfem_pcg_spmv_dot", C.byref(self.A), ptr(p_ext), x_offset, ptr(q), ptr(pq), ptr(self.partials),
              ptr(self.counter), stream_ptr())
 
-    def update(self, x, r, p_own, q, dinv, rz, pq, out2):
-        call("psfem_pcg_update", self.n, ptr(x), ptr(r), ptr(p_own), ptr(q), ptr(dinv), ptr(rz), ptr(pq), ptr(out2),
+    def update(self, r, q, dinv, rz, pq, out2):
+        call("psfem_pcg_update", self.n, ptr(r), ptr(q), ptr(dinv), ptr(rz), ptr(pq), ptr(out2),
              ptr(self.partials), C.c_void_p(self.counter.data_ptr() + 4), stream_ptr())
 
-    def pupdate(self, p_own, r, dinv, rz_old, rz_new):
-        call("psfem_pcg_pupdate", self.n, ptr(p_own), ptr(r), ptr(dinv), ptr(rz_old), ptr(rz_new), stream_ptr())
+    def pupdate(self, p_own, x, r, dinv, rz_old, rz_new, pq):
+        call("psfem_pcg_pupdate", self.n, ptr(p_own), ptr(x), ptr(r), ptr(dinv), ptr(rz_old), ptr(rz_new), ptr(pq), stream_ptr())
 
     def init(self, r, dinv, b, p_own, out3):
         call("psfem_pcg_init", self.n, ptr(r), ptr(dinv), ptr(b), ptr(p_own), ptr(out3), ptr(self.partials),

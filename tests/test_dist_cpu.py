@@ -59,16 +59,17 @@ class NumpyOps:
         pq.numpy()[0] = p_ext.numpy()[lo:lo + len(qn)] @ qn
 
     @staticmethod
-    def update(x, r, p_own, q, dinv, rz, pq, out2):
+    def update(r, q, dinv, rz, pq, out2):
         alpha = rz.numpy()[0] / pq.numpy()[0]
-        x.numpy()[:] += alpha * p_own.numpy()
         r.numpy()[:] -= alpha * q.numpy()
         out2.numpy()[0] = r.numpy() @ (dinv.numpy() * r.numpy())
         out2.numpy()[1] = r.numpy() @ r.numpy()
 
     @staticmethod
-    def pupdate(p_own, r, dinv, rz_old, rz_new):
+    def pupdate(p_own, x, r, dinv, rz_old, rz_new, pq):
+        alpha = rz_old.numpy()[0] / pq.numpy()[0]
         beta = rz_new.numpy()[0] / rz_old.numpy()[0]
+        x.numpy()[:] += alpha * p_own.numpy()
         p_own.numpy()[:] = dinv.numpy() * r.numpy() + beta * p_own.numpy()
 
     @staticmethod
