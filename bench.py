@@ -254,9 +254,11 @@ def main():
     # roofline of the dominant kernel (SpMV+dot of the PCG iteration), per rank
     nnz, n = prob.K_red.nnz, prob.n_owned_free
     csr_bytes = 12 * nnz + 4 * (n + 1) + 16 * n                          # CSR SpMV
-    node_block = prob.K_red.plan()[3] is not None and not os.environ.get("PSFEM_NO_NODEBLOCK")
-    # node-block SpMV: 8 B value + one 4-byte node id per 2x2 block, node_ptr, x, y
-    spmv_bytes = (9 * nnz + 4 * (n // 2 + 1) + 16 * n) if node_block else csr_bytes
+    nbp = prob.K_red.plan()[3]
+    node_block = nbp is not None and not os.environ.get("PSFEM_NO_NODEBLOCK")
+    idx_bytes = 2 if (node_block and nbp[5] is not None) else 4
+    # node-block SpMV: 8 B value + one node id (16-bit offset or 32-bit) per 2x2 block, node_ptr, x, y
+    spmv_bytes = (8 * nnz + idx_bytes * (nnz // 4) + 4 * (n // 2 + 1) + 16 * n) if node_block else csr_bytes
     spmv_t = t_spmv / (K_ * args.cg_iters)
     spmv_gbs = spmv_bytes / spmv_t / 1e9
     iter_bytes = spmv_bytes + (4 + 6) * 8 * n                            # update: q, r, dinv, r' ; p-update: p, x, r, dinv, p', x'
@@ -281,7 +283,7 @@ def main():
                      "roofline": {"bound": "hbm", "achieved": asm_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": asm_gbs / hbm_peak,
                                   "bytes_per_element": 320, "kernel": "lattice_q4_kernel<true> (marching warps, TMA bulk stores)",
                                   "traffic": asm_traffic}},
-        "roofline": {"kernel": ("spmv_nb_kernel<true> (PCG SpMV + dot on the 2x2 node-block structure, TMA-staged, 9 B/non-zero)" if node_block
+        "roofline": {"kernel": (f"spmv_nb_kernel<true> (PCG SpMV + dot on the 2x2 node-block structure, TMA-staged, {8 + idx_bytes / 4:g} B/non-zero)" if node_block
                                 else "spmv2_kernel<true> (PCG SpMV + dot, CSR, TMA-staged, 12 B/non-zero)"),
                      "bound": "hbm", "achieved": spmv_gbs, "peak": hbm_peak,
                      "unit": "GB/s", "frac": spmv_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,

@@ -66,6 +66,7 @@ typedef struct psfem_csr {
      * and the SpMV streams 9 instead of 12 bytes per non-zero.  Results are bit-identical to the CSR kernels. */
     const int32_t *nb_node_ptr; /* n_rows/2 + 1 (+8 padding): first 2x2 block of node a, absolute (= row_ptr[2a]/4) */
     const int32_t *nb_pcol;     /* nnz/4 (+8 padding): column node of each block, entry k belongs to block nb_node_ptr[0]+k */
+    const int16_t *nb_pcol16;   /* or (preferred when non-NULL) nnz/4 (+16 padding): column node - row node, 16 bits     */
     const int32_t *nb_nodeblk;  /* nb_n_blocks + 3 ints */
     int64_t nb_n_blocks;
     int64_t nb_max_pairs;
@@ -209,12 +210,16 @@ int psfem_spmv_plan_size(int64_t n, int64_t nnz, int64_t *n_blocks);
 int psfem_spmv_plan(int64_t n, const int32_t *d_row_ptr, int64_t nnz, int32_t *d_rowblk /* n_blocks+2 */,
                     int64_t n_blocks, int64_t *h_max_row_nnz, void *stream);
 /* node-block view of a CSR operand: h_info[0] = 1 if the matrix has the structure (else the outputs are unused),
- * h_info[1] = largest number of 2x2 blocks in a node row.  d_node_ptr: n/2+9 ints, d_pcol: nnz/4+8 ints,
- * d_nodeblk: n_blocks+3 ints with n_blocks from psfem_spmv_nb_plan_size.  Synchronises. */
+ * h_info[1] = largest number of 2x2 blocks in a node row, h_info[2] = largest |column node - row node|.
+ * d_node_ptr: n/2+9 ints, d_pcol: nnz/4+8 ints, d_nodeblk: n_blocks+4 ints with n_blocks from
+ * psfem_spmv_nb_plan_size.  Synchronises.  When h_info[2] < 32768, psfem_spmv_nb_compress turns d_pcol into 16-bit
+ * offsets (d_pcol16: nnz/4+16 int16): 8.5 instead of 9 bytes per non-zero. */
 int psfem_spmv_nb_plan_size(int64_t n, int64_t nnz, int64_t *n_blocks);
 int psfem_spmv_nb_plan(int64_t n, const int32_t *d_row_ptr, const int32_t *d_col_idx, int64_t nnz,
                        int32_t *d_node_ptr, int32_t *d_pcol, int32_t *d_nodeblk, int64_t n_blocks,
-                       int64_t *h_info /* [2] */, void *stream);
+                       int64_t *h_info /* [3] */, void *stream);
+int psfem_spmv_nb_compress(int64_t n, const int32_t *d_node_ptr, const int32_t *d_pcol, int64_t nnz,
+                           int16_t *d_pcol16, void *stream);
 /* y = alpha*A*x + gamma*z   (z may be NULL; y may alias z) */
 int psfem_spmv(const psfem_csr *A, const double *d_x, double alpha, double gamma, const double *d_z,
                double *d_y, void *stream);

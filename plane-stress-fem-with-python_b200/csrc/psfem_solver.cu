@@ -12,6 +12,7 @@
 // main.py:310,383-384.
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 #include <vector>
 #include "psfem_common.cuh"
 
@@ -417,9 +418,13 @@ spmv2_kernel(const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ co
 // ---------------------------------------------------------------------------------------------
 constexpr int NB_PAIRS = 1024;      // target 2x2 blocks per node block (4096 non-zeros)
 constexpr int NB_NODECAP = 1024;    // node_ptr entries staged per block
+#ifndef PSFEM_NB_U
+#define PSFEM_NB_U 5
+#endif
+constexpr int NB_U = PSFEM_NB_U;
 
 __global__ void nb_build_kernel(int64_t n_nodes, const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col_idx,
-                                int32_t *__restrict__ node_ptr, int32_t *__restrict__ pcol, int *__restrict__ info /* [0] bad, [1] max pairs */) {
+                                int32_t *__restrict__ node_ptr, int32_t *__restrict__ pcol, int *__restrict__ info /* [0] bad, [1] max pairs, [2] max |column node - row node| */) {
     const int64_t a = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (a > n_nodes) return;
     const int32_t base = row_ptr[0];
@@ -427,6 +432,7 @@ __global__ void nb_build_kernel(int64_t n_nodes, const int32_t *__restrict__ row
     const int32_t r0 = row_ptr[2 * a], r1 = row_ptr[2 * a + 1], r2 = row_ptr[2 * a + 2];
     const int len = r1 - r0;
     bool ok = (r2 - r1 == len) && !(len & 1) && !(r0 & 3);
+    int maxd = 0;
     node_ptr[a] = r0 >> 2;
     if (ok) {
         const int deg = len >> 1;
@@ -435,10 +441,22 @@ __global__ void nb_build_kernel(int64_t n_nodes, const int32_t *__restrict__ row
             const int32_t c0 = col_idx[r0 + 2 * k], c1 = col_idx[r0 + 2 * k + 1];
             ok = ok && !(c0 & 1) && c1 == c0 + 1 && col_idx[r1 + 2 * k] == c0 && col_idx[r1 + 2 * k + 1] == c1;
             pc[k] = c0 >> 1;
+            const long long d = (long long)(c0 >> 1) - a;
+            maxd = max(maxd, (int)min(d < 0 ? -d : d, (long long)INT32_MAX));
         }
         atomicMax(info + 1, deg);
+        atomicMax(info + 2, maxd);
     }
     if (!ok) atomicExch(info, 1);
+}
+
+// 16-bit form of pcol: column node - row node (FEM numberings keep neighbours close; the plan falls back to 32 bits otherwise)
+__global__ void nb_compress_kernel(int64_t n_nodes, const int32_t *__restrict__ node_ptr, const int32_t *__restrict__ pcol,
+                                   int16_t *__restrict__ pcol16) {
+    const int64_t a = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (a >= n_nodes) return;
+    const int base = node_ptr[0];
+    for (int k = node_ptr[a] - base; k < node_ptr[a + 1] - base; ++k) pcol16[k] = (int16_t)(pcol[k] - (int32_t)a);
 }
 
 __global__ void nb_plan_kernel(const int32_t *__restrict__ node_ptr, int64_t n_nodes, int64_t n_blocks, int32_t *__restrict__ nodeblk) {
@@ -459,9 +477,9 @@ struct NbMeta {  // per stage
     int a0, a1, P0, pc0 /* first staged pcol entry, relative to the operand's first pair */, a0a, staged_nodes, pad[2];
 };
 
-template <bool DOT>
+template <bool DOT, bool IDX16>
 __global__ void __launch_bounds__(SPMV2_THREADS, 2)
-spmv_nb_kernel(const int32_t *__restrict__ node_ptr, const int32_t *__restrict__ pcol, const double *__restrict__ vals,
+spmv_nb_kernel(const int32_t *__restrict__ node_ptr, const void *__restrict__ pcol_, const double *__restrict__ vals,
                const int32_t *__restrict__ nodeblk, int n_blocks, int n_nodes, int cap /* pairs per stage */,
                const double *__restrict__ x, double alpha, double gamma, const double *__restrict__ z, double *__restrict__ y,
                const double *__restrict__ xdot, double *__restrict__ dot_out, double *__restrict__ partials, unsigned int *counter,
@@ -471,11 +489,14 @@ spmv_nb_kernel(const int32_t *__restrict__ node_ptr, const int32_t *__restrict__
     __shared__ NbMeta meta[SPMV2_STAGES];
     __shared__ double red[SPMV2_THREADS / 32];
     if (done && *done) return;
-    // stage layout: vals[4*cap] | pcol[cap+8] | np[NB_NODECAP+8]
-    const size_t stage_bytes = (size_t)cap * 32 + (size_t)(cap + 8) * 4 + (NB_NODECAP + 8) * 4;
+    // stage layout: vals[4*cap] | pcol[cap+16] (4- or 2-byte entries, 4 bytes reserved each) | np[NB_NODECAP+8]
+    using PC = typename std::conditional<IDX16, int16_t, int32_t>::type;
+    constexpr int PCA = IDX16 ? 8 : 4;            // pcol entries per 16 bytes: bulk copies start and end on such boundaries
+    const PC *__restrict__ pcol = static_cast<const PC *>(pcol_);
+    const size_t stage_bytes = (size_t)cap * 32 + (size_t)(cap + 16) * 4 + (NB_NODECAP + 8) * 4;
     auto vals_s = [&](int s) { return reinterpret_cast<double *>(smem_raw + s * stage_bytes); };
-    auto pc_s = [&](int s) { return reinterpret_cast<int *>(smem_raw + s * stage_bytes + (size_t)cap * 32); };
-    auto np_s = [&](int s) { return reinterpret_cast<int *>(smem_raw + s * stage_bytes + (size_t)cap * 32 + (size_t)(cap + 8) * 4); };
+    auto pc_s = [&](int s) { return reinterpret_cast<PC *>(smem_raw + s * stage_bytes + (size_t)cap * 32); };
+    auto np_s = [&](int s) { return reinterpret_cast<int *>(smem_raw + s * stage_bytes + (size_t)cap * 32 + (size_t)(cap + 16) * 4); };
     const int tid = threadIdx.x;
     if (tid == 0) {
         for (int s = 0; s < SPMV2_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], SPMV2_CONSUMERS); }
@@ -505,8 +526,8 @@ spmv_nb_kernel(const int32_t *__restrict__ node_ptr, const int32_t *__restrict__
                     const int s = i % SPMV2_STAGES, n = i / SPMV2_STAGES;
                     mbar_wait(&empty_bar[s], (n & 1) ^ 1);
                     // pcol and node_ptr are this plan's own arrays (16-byte aligned, padded by 8 entries): widen freely
-                    const int pc0 = (P0 - pair_base) & ~3;
-                    const int pc1 = (P1 - pair_base + 3) & ~3;
+                    const int pc0 = (P0 - pair_base) & ~(PCA - 1);
+                    const int pc1 = (P1 - pair_base + PCA - 1) & ~(PCA - 1);
                     const int a0a = a0 & ~3;
                     int staged = a1 - a0a + 1;
                     int np_cnt = (staged + 3) & ~3;
@@ -514,7 +535,7 @@ spmv_nb_kernel(const int32_t *__restrict__ node_ptr, const int32_t *__restrict__
                     NbMeta m;
                     m.a0 = a0; m.a1 = a1; m.P0 = P0; m.pc0 = pc0; m.a0a = a0a; m.staged_nodes = staged;
                     meta[s] = m;
-                    const uint32_t vb = (uint32_t)(P1 - P0) * 32u, pb = (uint32_t)(pc1 - pc0) * 4u;
+                    const uint32_t vb = (uint32_t)(P1 - P0) * 32u, pb = (uint32_t)(pc1 - pc0) * (uint32_t)sizeof(PC);
                     mbar_expect_tx(&full_bar[s], vb + pb + (uint32_t)np_cnt * 4u);
                     if (vb) bulk_g2s(vals_s(s), vals + 4ll * P0, vb, &full_bar[s]);
                     if (pb) bulk_g2s(pc_s(s), pcol + pc0, pb, &full_bar[s]);
@@ -530,9 +551,9 @@ spmv_nb_kernel(const int32_t *__restrict__ node_ptr, const int32_t *__restrict__
             mbar_wait(&full_bar[s], n & 1);
             const NbMeta m = meta[s];
             const double *vs = vals_s(s);
-            const int *pc = pc_s(s);
+            const PC *pc = pc_s(s);
             const int *np = np_s(s);
-            constexpr int U = 5;   // 2x2 blocks per batch: 5 double2 gathers in flight
+            constexpr int U = NB_U;   // 2x2 blocks per batch (double2 gathers in flight per thread)
             const int n_rows_blk = 2 * (m.a1 - m.a0);
             for (int rl = tid; rl < n_rows_blk; rl += SPMV2_CONSUMERS) {
                 const int a = m.a0 + (rl >> 1), p = rl & 1;
@@ -541,13 +562,14 @@ spmv_nb_kernel(const int32_t *__restrict__ node_ptr, const int32_t *__restrict__
                 else { q0 = node_ptr[a]; q1 = node_ptr[a + 1]; }
                 const int deg = q1 - q0;
                 const double2 *v = reinterpret_cast<const double2 *>(vs + 4ll * (q0 - m.P0)) + (size_t)p * deg;   // row p of the node block
-                const int *c = pc + (q0 - pair_base - m.pc0);
+                const PC *c = pc + (q0 - pair_base - m.pc0);
+                const int cbase = IDX16 ? a : 0;       // 16-bit entries are offsets from the row node
                 double sum = 0.0;
                 for (int k = 0; k < deg; k += U) {
                     double2 xv[U], vv[U];
 #pragma unroll
                     for (int u = 0; u < U; ++u)
-                        if (k + u < deg) { xv[u] = __ldg(x2 + c[k + u]); vv[u] = v[k + u]; }
+                        if (k + u < deg) { xv[u] = __ldg(x2 + (cbase + (int)c[k + u])); vv[u] = v[k + u]; }
 #pragma unroll
                     for (int u = 0; u < U; ++u)
                         if (k + u < deg) { sum += alpha * vv[u].x * xv[u].x; sum += alpha * vv[u].y * xv[u].y; }
@@ -585,9 +607,11 @@ int launch_spmv(const psfem_csr *A, const double *v2, const double *x1, const do
     PSFEM_REQUIRE(smem <= 200 * 1024, "spmv: a row with %lld non-zeros does not fit the shared-memory stage", (long long)A->max_row_nnz);
     const bool dual = v2 != nullptr, dot = dot_out != nullptr;
     static const bool nb_off = getenv("PSFEM_NO_NODEBLOCK") != nullptr;   // A/B switch for measurements
-    if (!dual && !nb_off && A->nb_node_ptr && A->nb_n_blocks >= 8 && ((reinterpret_cast<uintptr_t>(A->vals) | reinterpret_cast<uintptr_t>(x1)) & 15) == 0) {
+    if (!dual && !nb_off && A->nb_node_ptr && (A->nb_pcol || A->nb_pcol16) && A->nb_n_blocks >= 8 && ((reinterpret_cast<uintptr_t>(A->vals) | reinterpret_cast<uintptr_t>(x1)) & 15) == 0) {
         const int cap = (int)((NB_PAIRS + A->nb_max_pairs + 8 + 3) & ~3ll);
-        const size_t stage_bytes = (size_t)cap * 32 + (size_t)(cap + 8) * 4 + (NB_NODECAP + 8) * 4;
+        const size_t stage_bytes = (size_t)cap * 32 + (size_t)(cap + 16) * 4 + (NB_NODECAP + 8) * 4;
+        const bool idx16 = A->nb_pcol16 != nullptr;
+        const void *pcol = idx16 ? static_cast<const void *>(A->nb_pcol16) : static_cast<const void *>(A->nb_pcol);
         const size_t smem_nb = SPMV2_STAGES * stage_bytes;
         if (smem_nb <= 110 * 1024) {
             int dev = 0, sms = 148;
@@ -595,15 +619,17 @@ int launch_spmv(const psfem_csr *A, const double *v2, const double *x1, const do
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
             int64_t grid = 2ll * sms;
             if (grid > A->nb_n_blocks) grid = A->nb_n_blocks;
-            if (dot) {
-                PSFEM_CUDA_CHECK(cudaFuncSetAttribute(spmv_nb_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_nb));
-                spmv_nb_kernel<true><<<(unsigned)grid, SPMV2_THREADS, smem_nb, stream>>>(A->nb_node_ptr, A->nb_pcol, A->vals, A->nb_nodeblk, (int)A->nb_n_blocks,
-                    (int)(A->n_rows / 2), cap, x1, alpha, gamma, z, y, xdot, dot_out, partials, counter, done, ps);
-            } else {
-                PSFEM_CUDA_CHECK(cudaFuncSetAttribute(spmv_nb_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_nb));
-                spmv_nb_kernel<false><<<(unsigned)grid, SPMV2_THREADS, smem_nb, stream>>>(A->nb_node_ptr, A->nb_pcol, A->vals, A->nb_nodeblk, (int)A->nb_n_blocks,
-                    (int)(A->n_rows / 2), cap, x1, alpha, gamma, z, y, xdot, dot_out, partials, counter, done, ps);
-            }
+#define PSFEM_NB_LAUNCH(D, I)                                                                                              \
+    do {                                                                                                                   \
+        PSFEM_CUDA_CHECK(cudaFuncSetAttribute(spmv_nb_kernel<D, I>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_nb)); \
+        spmv_nb_kernel<D, I><<<(unsigned)grid, SPMV2_THREADS, smem_nb, stream>>>(A->nb_node_ptr, pcol, A->vals, A->nb_nodeblk,  \
+            (int)A->nb_n_blocks, (int)(A->n_rows / 2), cap, x1, alpha, gamma, z, y, xdot, dot_out, partials, counter, done, ps); \
+    } while (0)
+            if (dot && idx16) PSFEM_NB_LAUNCH(true, true);
+            else if (dot) PSFEM_NB_LAUNCH(true, false);
+            else if (idx16) PSFEM_NB_LAUNCH(false, true);
+            else PSFEM_NB_LAUNCH(false, false);
+#undef PSFEM_NB_LAUNCH
             PSFEM_LAUNCH_CHECK();
             return PSFEM_OK;
         }
@@ -1083,19 +1109,30 @@ extern "C" int psfem_spmv_nb_plan(int64_t n, const int32_t *d_row_ptr, const int
     h_info[0] = 0; h_info[1] = 0;
     if (n <= 0 || (n & 1) || (nnz & 3) || nnz == 0) return PSFEM_OK;   // not a node-block matrix
     const int64_t n_nodes = n / 2;
-    int *info = reinterpret_cast<int *>(d_nodeblk + n_blocks + 1);    // two scratch ints after the plan
-    PSFEM_CUDA_CHECK(cudaMemsetAsync(info, 0, 2 * sizeof(int), stream));
+    int *info = reinterpret_cast<int *>(d_nodeblk + n_blocks + 1);    // three scratch ints after the plan
+    PSFEM_CUDA_CHECK(cudaMemsetAsync(info, 0, 3 * sizeof(int), stream));
     PSFEM_CUDA_CHECK(cudaMemsetAsync(d_pcol + nnz / 4, 0, 8 * sizeof(int32_t), stream));            // padding read by widened bulk copies
     PSFEM_CUDA_CHECK(cudaMemsetAsync(d_node_ptr + n_nodes + 1, 0, 8 * sizeof(int32_t), stream));
     nb_build_kernel<<<(unsigned)ceil_div(n_nodes + 1, 256), 256, 0, stream>>>(n_nodes, d_row_ptr, d_col_idx, d_node_ptr, d_pcol, info);
     PSFEM_LAUNCH_CHECK();
     nb_plan_kernel<<<(unsigned)ceil_div(n_blocks + 1, 256), 256, 0, stream>>>(d_node_ptr, n_nodes, n_blocks, d_nodeblk);
     PSFEM_LAUNCH_CHECK();
-    int h[2] = {1, 0};
+    int h[3] = {1, 0, 0};
     PSFEM_CUDA_CHECK(cudaMemcpyAsync(h, info, sizeof(h), cudaMemcpyDeviceToHost, stream));
     PSFEM_CUDA_CHECK(cudaStreamSynchronize(stream));
     h_info[0] = h[0] == 0 ? 1 : 0;
     h_info[1] = h[1];
+    h_info[2] = h[2];
+    return PSFEM_OK;
+}
+
+extern "C" int psfem_spmv_nb_compress(int64_t n, const int32_t *d_node_ptr, const int32_t *d_pcol, int64_t nnz,
+                                      int16_t *d_pcol16, void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    PSFEM_REQUIRE(n > 0 && !(n & 1) && d_node_ptr && d_pcol && d_pcol16, "spmv_nb_compress: bad arguments");
+    PSFEM_CUDA_CHECK(cudaMemsetAsync(d_pcol16 + nnz / 4, 0, 16 * sizeof(int16_t), stream));
+    nb_compress_kernel<<<(unsigned)ceil_div(n / 2, 256), 256, 0, stream>>>(n / 2, d_node_ptr, d_pcol, d_pcol16);
+    PSFEM_LAUNCH_CHECK();
     return PSFEM_OK;
 }
 
@@ -1109,7 +1146,7 @@ extern "C" int psfem_spmv2(const psfem_csr *A, const double *d_vals2, const doub
                            double beta, double gamma, const double *d_z, double *d_y, void *stream_) {
     PSFEM_REQUIRE(d_vals2 && d_x2, "spmv2: second operand missing");
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    if (A && A->nb_node_ptr && A->nb_n_blocks >= 8 && d_y != d_x1 && d_y != d_x2 &&
+    if (A && A->nb_node_ptr && (A->nb_pcol || A->nb_pcol16) && A->nb_n_blocks >= 8 && d_y != d_x1 && d_y != d_x2 &&
         ((reinterpret_cast<uintptr_t>(A->vals) | reinterpret_cast<uintptr_t>(d_vals2) | reinterpret_cast<uintptr_t>(d_x1) |
           reinterpret_cast<uintptr_t>(d_x2)) & 15) == 0) {
         // node-block operands: two passes of the TMA-staged 9-byte kernel (17 B per non-zero pair + 16 B per row for the

@@ -6,6 +6,7 @@ Everything here calls the C ABI of libpsfem.so through `_capi`; torch only owns 
 from __future__ import annotations
 
 import ctypes as C
+import os
 from collections.abc import Mapping
 
 import numpy as np
@@ -134,13 +135,18 @@ class DeviceCSR:
         i32 = dict(dtype=torch.int32, device="cuda")
         node_ptr = torch.empty(self.n_rows // 2 + 9, **i32)
         pcol = torch.empty(self.nnz // 4 + 8, **i32)
-        nodeblk = torch.empty(nb.value + 3, **i32)
-        info = (C.c_int64 * 2)()
+        nodeblk = torch.empty(nb.value + 4, **i32)
+        info = (C.c_int64 * 3)()
         call("psfem_spmv_nb_plan", self.n_rows, ptr(self.row_ptr), ptr(self.col_idx), self.nnz, ptr(node_ptr), ptr(pcol),
              ptr(nodeblk), nb.value, info, stream_ptr())
         if info[0] != 1:
             return None
-        return (node_ptr, pcol, nodeblk, nb.value, int(info[1]))
+        pcol16 = None
+        if info[2] < 32768 and os.environ.get("PSFEM_NB_IDX16"):      # 16-bit offsets, 8.5 B per non-zero (opt-in)
+            pcol16 = torch.empty(self.nnz // 4 + 16, dtype=torch.int16, device="cuda")
+            call("psfem_spmv_nb_compress", self.n_rows, ptr(node_ptr), ptr(pcol), self.nnz, ptr(pcol16), stream_ptr())
+            pcol = None
+        return (node_ptr, pcol, nodeblk, nb.value, int(info[1]), pcol16)
 
     def struct(self, vals=None):
         rowblk, nb, mx, nbp = self.plan()
@@ -150,7 +156,9 @@ class DeviceCSR:
         s.vals = (self.vals if vals is None else vals).data_ptr()
         s.rowblk, s.n_blocks, s.max_row_nnz = rowblk.data_ptr(), nb, mx
         if nbp is not None:
-            s.nb_node_ptr, s.nb_pcol, s.nb_nodeblk = nbp[0].data_ptr(), nbp[1].data_ptr(), nbp[2].data_ptr()
+            s.nb_node_ptr, s.nb_nodeblk = nbp[0].data_ptr(), nbp[2].data_ptr()
+            s.nb_pcol = nbp[1].data_ptr() if nbp[1] is not None else None
+            s.nb_pcol16 = nbp[5].data_ptr() if nbp[5] is not None else None
             s.nb_n_blocks, s.nb_max_pairs = nbp[3], nbp[4]
         return s
 
