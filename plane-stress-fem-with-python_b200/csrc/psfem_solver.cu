@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <type_traits>
+#include <utility>
 #include <vector>
 #include "psfem_common.cuh"
 
@@ -23,6 +24,28 @@ namespace {
 constexpr int SPMV_THREADS = 256;
 constexpr int SPMV_T = 4096;  // target non-zeros per row block (32 KB of fp64 products)
 constexpr int EW_THREADS = 256;
+
+// Programmatic dependent launch: the kernels of a PCG iteration are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, raise griddepcontrol.launch_dependents on entry and wait for
+// their predecessor with griddepcontrol.wait before touching anything it wrote.  The launch of kernel k+1 (command
+// processing, CTA scheduling, prologue) then overlaps the tail of kernel k -- the last block's fixed-order reduction
+// and, across GPUs, its peer exchange -- instead of following it (about 4 us per kernel boundary).  Without the launch
+// attribute both instructions are no-ops.
+__device__ __forceinline__ void pdl_enter() {
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kern)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t stream, Args &&...args) {
+    static const bool off = getenv("PSFEM_NO_PDL") != nullptr;   // A/B switch
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = off ? 0 : 1;
+    return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
 
 int ew_grid(int64_t n) {
     int64_t g = ceil_div(n, EW_THREADS * 4);
@@ -285,6 +308,7 @@ spmv2_kernel(const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ co
     __shared__ uint64_t full_bar[SPMV2_STAGES], empty_bar[SPMV2_STAGES];
     __shared__ Spmv2Meta meta[SPMV2_STAGES];
     __shared__ double red[SPMV2_THREADS / 32];
+    pdl_enter();
     if (done && *done) return;
     // stage layout: vals[cap] | cols[cap] | rp[ROWCAP+8]
     const size_t stage_bytes = (size_t)cap * 12 + (SPMV2_ROWCAP + 8) * 4;
@@ -488,6 +512,7 @@ spmv_nb_kernel(const int32_t *__restrict__ node_ptr, const void *__restrict__ pc
     __shared__ uint64_t full_bar[SPMV2_STAGES], empty_bar[SPMV2_STAGES];
     __shared__ NbMeta meta[SPMV2_STAGES];
     __shared__ double red[SPMV2_THREADS / 32];
+    pdl_enter();
     if (done && *done) return;
     // stage layout: vals[4*cap] | pcol[cap+16] (4- or 2-byte entries, 4 bytes reserved each) | np[NB_NODECAP+8]
     using PC = typename std::conditional<IDX16, int16_t, int32_t>::type;
@@ -622,8 +647,8 @@ int launch_spmv(const psfem_csr *A, const double *v2, const double *x1, const do
 #define PSFEM_NB_LAUNCH(D, I)                                                                                              \
     do {                                                                                                                   \
         PSFEM_CUDA_CHECK(cudaFuncSetAttribute(spmv_nb_kernel<D, I>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_nb)); \
-        spmv_nb_kernel<D, I><<<(unsigned)grid, SPMV2_THREADS, smem_nb, stream>>>(A->nb_node_ptr, pcol, A->vals, A->nb_nodeblk,  \
-            (int)A->nb_n_blocks, (int)(A->n_rows / 2), cap, x1, alpha, gamma, z, y, xdot, dot_out, partials, counter, done, ps); \
+        PSFEM_CUDA_CHECK(launch_pdl(spmv_nb_kernel<D, I>, (unsigned)grid, SPMV2_THREADS, smem_nb, stream, A->nb_node_ptr, pcol, A->vals, A->nb_nodeblk,  \
+            (int)A->nb_n_blocks, (int)(A->n_rows / 2), cap, x1, alpha, gamma, z, y, xdot, dot_out, partials, counter, done, ps)); \
     } while (0)
             if (dot && idx16) PSFEM_NB_LAUNCH(true, true);
             else if (dot) PSFEM_NB_LAUNCH(true, false);
@@ -647,12 +672,12 @@ int launch_spmv(const psfem_csr *A, const double *v2, const double *x1, const do
             if (grid > A->n_blocks) grid = A->n_blocks;
             if (dot) {
                 PSFEM_CUDA_CHECK(cudaFuncSetAttribute(spmv2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-                spmv2_kernel<true><<<(unsigned)grid, SPMV2_THREADS, smem2, stream>>>(A->row_ptr, A->col_idx, A->vals, A->rowblk, (int)A->n_blocks, (int)A->n_rows, cap,
-                    x1, alpha, gamma, z, y, xdot, dot_out, partials, counter, done, ps);
+                PSFEM_CUDA_CHECK(launch_pdl(spmv2_kernel<true>, (unsigned)grid, SPMV2_THREADS, smem2, stream, A->row_ptr, A->col_idx, A->vals, A->rowblk, (int)A->n_blocks, (int)A->n_rows, cap,
+                    x1, alpha, gamma, z, y, xdot, dot_out, partials, counter, done, ps));
             } else {
                 PSFEM_CUDA_CHECK(cudaFuncSetAttribute(spmv2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-                spmv2_kernel<false><<<(unsigned)grid, SPMV2_THREADS, smem2, stream>>>(A->row_ptr, A->col_idx, A->vals, A->rowblk, (int)A->n_blocks, (int)A->n_rows, cap,
-                    x1, alpha, gamma, z, y, xdot, dot_out, partials, counter, done, ps);
+                PSFEM_CUDA_CHECK(launch_pdl(spmv2_kernel<false>, (unsigned)grid, SPMV2_THREADS, smem2, stream, A->row_ptr, A->col_idx, A->vals, A->rowblk, (int)A->n_blocks, (int)A->n_rows, cap,
+                    x1, alpha, gamma, z, y, xdot, dot_out, partials, counter, done, ps));
             }
             PSFEM_LAUNCH_CHECK();
             return PSFEM_OK;
@@ -694,6 +719,7 @@ __global__ void __launch_bounds__(EW_THREADS)
 pcg_init_kernel(int64_t n, const double *__restrict__ r, const double *__restrict__ dinv, const double *__restrict__ b,
                 double *__restrict__ p, double *__restrict__ out3, double *__restrict__ partials, unsigned int *counter,
                 PcgCtl *ctl, double rtol) {
+    pdl_enter();
     __shared__ double red[EW_THREADS / 32];
     double v[3] = {0, 0, 0};
     for (int64_t i = blockIdx.x * (int64_t)EW_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * EW_THREADS) {
@@ -723,6 +749,7 @@ pcg_update_kernel(int64_t n, double *__restrict__ r,
                   const double *__restrict__ q, const double *__restrict__ dinv, const double *__restrict__ rz_in,
                   const double *__restrict__ pq_in, double *__restrict__ out2, double *__restrict__ partials,
                   unsigned int *counter, PcgCtl *ctl) {
+    pdl_enter();
     __shared__ double red[EW_THREADS / 32];
     double rz, pq;
     if (ctl) {
@@ -758,6 +785,7 @@ __global__ void __launch_bounds__(EW_THREADS)
 pcg_pupdate_kernel(int64_t n, double *__restrict__ p, double *__restrict__ x, const double *__restrict__ r,
                    const double *__restrict__ dinv, const double *__restrict__ rz_old_in, const double *__restrict__ rz_new_in,
                    const double *__restrict__ pq_in, PcgCtl *ctl, unsigned int *counter) {
+    pdl_enter();
     double rz_old, rz_new, pq;
     if (ctl) {
         if (ctl->done) return;
@@ -937,6 +965,7 @@ __global__ void __launch_bounds__(EW_THREADS)
 dist_init_kernel(int64_t n, const double *__restrict__ b, const double *__restrict__ dinv, double *__restrict__ x,
                  double *__restrict__ r, double *__restrict__ p, HaloPush halo, PeerSync ps, double *__restrict__ partials,
                  unsigned int *counter) {
+    pdl_enter();
     __shared__ double red[EW_THREADS / 32];
     double v[3] = {0, 0, 0};
     for (int64_t i = blockIdx.x * (int64_t)EW_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * EW_THREADS) {
@@ -967,6 +996,7 @@ __global__ void __launch_bounds__(EW_THREADS)
 dist_update_kernel(int64_t n, double *__restrict__ r,
                    const double *__restrict__ q, const double *__restrict__ dinv, PeerSync ps, double *__restrict__ partials,
                    unsigned int *counter) {
+    pdl_enter();
     __shared__ double red[EW_THREADS / 32];
     const double alpha = ps.scal[5 + (int)((ps.seq - 1) & 1)] / ps.scal[4];   // global sums left by the previous kernels' last blocks
     double v[2] = {0, 0};
@@ -990,6 +1020,7 @@ dist_update_kernel(int64_t n, double *__restrict__ r,
 __global__ void __launch_bounds__(EW_THREADS)
 dist_pupdate_kernel(int64_t n, double *__restrict__ p, double *__restrict__ x, const double *__restrict__ r,
                     const double *__restrict__ dinv, HaloPush halo, PeerSync ps, unsigned int *counter) {
+    pdl_enter();
     __shared__ bool is_last;
     const double rz_old = ps.scal[5 + (int)((ps.seq - 1) & 1)];
     const double beta = ps.scal[5 + (int)(ps.seq & 1)] / rz_old, alpha = rz_old / ps.scal[4];
@@ -1194,7 +1225,7 @@ extern "C" int psfem_pcg_update(int64_t n, double *d_r, const double *d_q,
                                 const double *d_dinv, const double *d_rz, const double *d_pq, double *d_out2,
                                 double *d_partials, uint32_t *d_counter, void *stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    pcg_update_kernel<<<ew_grid(n), EW_THREADS, 0, stream>>>(n, d_r, d_q, d_dinv, d_rz, d_pq, d_out2, d_partials, d_counter, nullptr);
+    PSFEM_CUDA_CHECK(launch_pdl(pcg_update_kernel, ew_grid(n), EW_THREADS, 0, stream, n, d_r, d_q, d_dinv, d_rz, d_pq, d_out2, d_partials, d_counter, (PcgCtl *)nullptr));
     PSFEM_LAUNCH_CHECK();
     return PSFEM_OK;
 }
@@ -1202,7 +1233,7 @@ extern "C" int psfem_pcg_update(int64_t n, double *d_r, const double *d_q,
 extern "C" int psfem_pcg_pupdate(int64_t n, double *d_p, double *d_x, const double *d_r, const double *d_dinv,
                                  const double *d_rz_old, const double *d_rz_new, const double *d_pq, void *stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    pcg_pupdate_kernel<<<ew_grid(n), EW_THREADS, 0, stream>>>(n, d_p, d_x, d_r, d_dinv, d_rz_old, d_rz_new, d_pq, nullptr, nullptr);
+    PSFEM_CUDA_CHECK(launch_pdl(pcg_pupdate_kernel, ew_grid(n), EW_THREADS, 0, stream, n, d_p, d_x, d_r, d_dinv, d_rz_old, d_rz_new, d_pq, (PcgCtl *)nullptr, (unsigned int *)nullptr));
     PSFEM_LAUNCH_CHECK();
     return PSFEM_OK;
 }
@@ -1280,8 +1311,10 @@ extern "C" int psfem_dist_pcg_iterations(const psfem_csr *A, const psfem_dist_ct
         int rc = launch_spmv(A, nullptr, c->p_ext, nullptr, 1.0, 0.0, 0.0, nullptr, c->q, p_own, c->out3 + 3 /* local p.q, unused */, c->partials,
                              c->counter, nullptr, stream, &ps);
         if (rc) return rc;
-        dist_update_kernel<<<ew_grid(c->n_own), EW_THREADS, 0, stream>>>(c->n_own, c->r, c->q, c->dinv, ps, c->partials, c->counter + 1);
-        dist_pupdate_kernel<<<ew_grid(c->n_own), EW_THREADS, 0, stream>>>(c->n_own, p_own, c->x, c->r, c->dinv, make_halo(c), ps, c->counter + 2);
+        PSFEM_CUDA_CHECK(launch_pdl(dist_update_kernel, ew_grid(c->n_own), EW_THREADS, 0, stream, c->n_own, c->r, (const double *)c->q, (const double *)c->dinv, ps, c->partials,
+                                    (unsigned int *)(c->counter + 1)));
+        PSFEM_CUDA_CHECK(launch_pdl(dist_pupdate_kernel, ew_grid(c->n_own), EW_THREADS, 0, stream, c->n_own, p_own, c->x, (const double *)c->r, (const double *)c->dinv, make_halo(c), ps,
+                                    (unsigned int *)(c->counter + 2)));
     }
     PSFEM_LAUNCH_CHECK();
     return PSFEM_OK;
@@ -1387,8 +1420,10 @@ int pcg_solve(const psfem_csr *A, const double *d_b, double *d_x, double rtol, i
         for (int64_t it = 0; it < batch; ++it) {
             rc = launch_spmv(A, nullptr, w.p, nullptr, 1.0, 0.0, 0.0, nullptr, w.q, w.p, &w.ctl->pq, w.partials, w.counter, &w.ctl->done, stream);
             if (rc) return rc;
-            pcg_update_kernel<<<g, EW_THREADS, 0, stream>>>(n, w.r, w.q, w.dinv, nullptr, nullptr, nullptr, w.partials, w.counter + 1, w.ctl);
-            pcg_pupdate_kernel<<<g, EW_THREADS, 0, stream>>>(n, w.p, d_x, w.r, w.dinv, nullptr, nullptr, nullptr, w.ctl, w.counter + 2);
+            PSFEM_CUDA_CHECK(launch_pdl(pcg_update_kernel, (unsigned)g, EW_THREADS, 0, stream, n, w.r, (const double *)w.q, (const double *)w.dinv, (const double *)nullptr,
+                                        (const double *)nullptr, (double *)nullptr, w.partials, w.counter + 1, w.ctl));
+            PSFEM_CUDA_CHECK(launch_pdl(pcg_pupdate_kernel, (unsigned)g, EW_THREADS, 0, stream, n, w.p, d_x, (const double *)w.r, (const double *)w.dinv, (const double *)nullptr,
+                                        (const double *)nullptr, (const double *)nullptr, w.ctl, w.counter + 2));
         }
         PSFEM_LAUNCH_CHECK();
         launched += batch;
