@@ -238,6 +238,15 @@ int psfem_pcg_workspace(int64_t n, int64_t n_blocks, size_t *bytes);
 int psfem_pcg_jacobi(const psfem_csr *A, const double *d_b, double *d_x, double rtol, int64_t maxit,
                      int64_t check_every, double *h_info, void *d_ws, size_t ws_bytes, void *stream);
 
+/* The same solve on the UNREDUCED matrix: DOFs with d_new_id[i] < 0 (psfem_free_map) stay in the system as inert rows
+ * (D^-1 = 0, residual, direction and right-hand side pinned to zero), so the iterates on the free DOFs are those of the
+ * reduced system K[np.ix_(free,free)] (Polygones.py:1003) while the matrix keeps its 2x2 node-block structure for the
+ * 9-byte SpMV whatever the boundary conditions (a roller constrains one DOF of a node), and no reduced copy of the
+ * matrix is built.  d_b: full-length load (entries at constrained DOFs ignored), d_x: full-length start / solution
+ * (zeros at constrained DOFs).  For systems above 16384 rows. */
+int psfem_pcg_jacobi_masked(const psfem_csr *A, const double *d_b, double *d_x, const int32_t *d_new_id, double rtol,
+                            int64_t maxit, int64_t check_every, double *h_info, void *d_ws, size_t ws_bytes, void *stream);
+
 /* The kernels of one PCG iteration, exposed so the strip-partitioned multi-GPU driver can put its
  * halo exchange and all-reduces between them (scalars stay on the device):
  *   init    : p = dinv*r ; out3 = {r.dinv r, r.r, b.b}  (local sums)

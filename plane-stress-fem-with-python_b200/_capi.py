@@ -94,6 +94,7 @@ SIGNATURES = {
     "psfem_extract_diag": [_pcsr, _i64, _i32, _ptr, _ptr],
     "psfem_pcg_workspace": [_i64, _i64, _psz],
     "psfem_pcg_jacobi": [_pcsr, _ptr, _ptr, _dbl, _i64, _i64, _pdbl, _ptr, _sz, _ptr],
+    "psfem_pcg_jacobi_masked": [_pcsr, _ptr, _ptr, _ptr, _dbl, _i64, _i64, _pdbl, _ptr, _sz, _ptr],
     "psfem_pcg_init": [_i64, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr],
     "psfem_pcg_spmv_dot": [_pcsr, _ptr, _i64, _ptr, _ptr, _ptr, _ptr, _ptr],
     "psfem_pcg_update": [_i64, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr],

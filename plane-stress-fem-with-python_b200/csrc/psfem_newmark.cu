@@ -11,7 +11,8 @@
 
 namespace psfem {
 int pcg_solve(const psfem_csr *A, const double *d_b, double *d_x, double rtol, int64_t maxit, int64_t check_every,
-              double *h_info, double *d_info, double *h_acc, void *d_ws, size_t ws_bytes, bool have_dinv, cudaStream_t stream);
+              double *h_info, double *d_info, double *h_acc, void *d_ws, size_t ws_bytes, bool have_dinv, cudaStream_t stream,
+              bool masked);
 double *pcg_dinv_ptr(void *d_ws, int64_t n, int64_t n_blocks);
 }
 using namespace psfem;
@@ -186,7 +187,7 @@ extern "C" int psfem_newmark_run(const psfem_csr *K, const double *d_M_vals, con
         PSFEM_LAUNCH_CHECK();
         int rc = psfem_spmv2(K, d_M_vals, w.w1, w.vp, -1.0, -alpha_R, h_fscale[i], d_fshape, w.rhs, stream);  // :310
         if (rc) return rc;
-        rc = pcg_solve(&Keff, w.rhs, w.a, rtol, maxit, 50, nullptr, w.info, h_acc, w.pcg, w.pcg_bytes, true, stream);  // :314
+        rc = pcg_solve(&Keff, w.rhs, w.a, rtol, maxit, 50, nullptr, w.info, h_acc, w.pcg, w.pcg_bytes, true, stream, false);  // :314
         if (rc && rc != PSFEM_ENOCONV) return rc;
         corrector_kernel<<<g, NT, 0, stream>>>(n, w.up, w.vp, w.a, c_v_corr, c_u_corr, w.u, w.v, w.partials, w.counter, w.ctl, i);
         PSFEM_LAUNCH_CHECK();

@@ -716,18 +716,24 @@ __global__ void extract_diag_kernel(int64_t n, const int32_t *__restrict__ row_p
 
 // z = dinv*r, p = z, rz = r.z, rr = r.r, bb = b.b   (PCG start)
 __global__ void __launch_bounds__(EW_THREADS)
-pcg_init_kernel(int64_t n, const double *__restrict__ r, const double *__restrict__ dinv, const double *__restrict__ b,
+pcg_init_kernel(int64_t n, double *__restrict__ r, const double *__restrict__ dinv, const double *__restrict__ b,
                 double *__restrict__ p, double *__restrict__ out3, double *__restrict__ partials, unsigned int *counter,
-                PcgCtl *ctl, double rtol) {
+                PcgCtl *ctl, double rtol, int masked) {
     pdl_enter();
     __shared__ double red[EW_THREADS / 32];
     double v[3] = {0, 0, 0};
     for (int64_t i = blockIdx.x * (int64_t)EW_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * EW_THREADS) {
-        const double ri = r[i], zi = dinv[i] * ri;
+        const double di = dinv[i];
+        double ri = r[i];
+        // masked solve (psfem_pcg_jacobi_masked): rows with D^-1 = 0 are constrained DOFs that stayed in the matrix;
+        // their residual, search direction and right-hand side are pinned to zero
+        const bool off = masked && di == 0.0;
+        if (off) { ri = 0.0; r[i] = 0.0; }
+        const double zi = di * ri;
         p[i] = zi;
         v[0] += ri * zi;
         v[1] += ri * ri;
-        if (b) { const double bi = b[i]; v[2] += bi * bi; }
+        if (b && !off) { const double bi = b[i]; v[2] += bi * bi; }
     }
     double tot[3];
     if (grid_sum<EW_THREADS, 3>(v, partials, counter, red, tot)) {
@@ -748,7 +754,7 @@ __global__ void __launch_bounds__(EW_THREADS)
 pcg_update_kernel(int64_t n, double *__restrict__ r,
                   const double *__restrict__ q, const double *__restrict__ dinv, const double *__restrict__ rz_in,
                   const double *__restrict__ pq_in, double *__restrict__ out2, double *__restrict__ partials,
-                  unsigned int *counter, PcgCtl *ctl) {
+                  unsigned int *counter, PcgCtl *ctl, int masked) {
     pdl_enter();
     __shared__ double red[EW_THREADS / 32];
     double rz, pq;
@@ -761,9 +767,10 @@ pcg_update_kernel(int64_t n, double *__restrict__ r,
     const double alpha = rz / pq;
     double v[2] = {0, 0};
     for (int64_t i = blockIdx.x * (int64_t)EW_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * EW_THREADS) {
-        const double ri = r[i] - alpha * q[i];
+        const double di = dinv[i];
+        const double ri = (masked && di == 0.0) ? 0.0 : r[i] - alpha * q[i];   // (K p) at a constrained row is not part of the system
         r[i] = ri;
-        v[0] += ri * (dinv[i] * ri);
+        v[0] += ri * (di * ri);
         v[1] += ri * ri;
     }
     double tot[2];
@@ -1216,7 +1223,7 @@ extern "C" int psfem_pcg_spmv_dot(const psfem_csr *A, const double *d_p_ext, int
 extern "C" int psfem_pcg_init(int64_t n, const double *d_r, const double *d_dinv, const double *d_b, double *d_p,
                               double *d_out3, double *d_partials, uint32_t *d_counter, void *stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    pcg_init_kernel<<<ew_grid(n), EW_THREADS, 0, stream>>>(n, d_r, d_dinv, d_b, d_p, d_out3, d_partials, d_counter, nullptr, 0.0);
+    pcg_init_kernel<<<ew_grid(n), EW_THREADS, 0, stream>>>(n, const_cast<double *>(d_r), d_dinv, d_b, d_p, d_out3, d_partials, d_counter, nullptr, 0.0, 0);
     PSFEM_LAUNCH_CHECK();
     return PSFEM_OK;
 }
@@ -1225,7 +1232,7 @@ extern "C" int psfem_pcg_update(int64_t n, double *d_r, const double *d_q,
                                 const double *d_dinv, const double *d_rz, const double *d_pq, double *d_out2,
                                 double *d_partials, uint32_t *d_counter, void *stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    PSFEM_CUDA_CHECK(launch_pdl(pcg_update_kernel, ew_grid(n), EW_THREADS, 0, stream, n, d_r, d_q, d_dinv, d_rz, d_pq, d_out2, d_partials, d_counter, (PcgCtl *)nullptr));
+    PSFEM_CUDA_CHECK(launch_pdl(pcg_update_kernel, ew_grid(n), EW_THREADS, 0, stream, n, d_r, d_q, d_dinv, d_rz, d_pq, d_out2, d_partials, d_counter, (PcgCtl *)nullptr, 0));
     PSFEM_LAUNCH_CHECK();
     return PSFEM_OK;
 }
@@ -1380,8 +1387,9 @@ double *pcg_dinv_ptr(void *d_ws, int64_t n, int64_t n_blocks) { return carve_pcg
 // h_acc (optional): host accumulators of the multi-kernel path (sum of iterations, max relres, status).
 int pcg_solve(const psfem_csr *A, const double *d_b, double *d_x, double rtol, int64_t maxit, int64_t check_every,
               double *h_info, double *d_info, double *h_acc, void *d_ws, size_t ws_bytes, bool have_dinv,
-              cudaStream_t stream) {
+              cudaStream_t stream, bool masked) {
     const int64_t n = A->n_rows;
+    PSFEM_REQUIRE(!masked || n > SMALL_MAX_N, "pcg: the masked solve is for systems above %d rows (reduce smaller ones)", SMALL_MAX_N);
     PcgWs w = carve_pcg(d_ws, n, A->n_blocks);
     PSFEM_REQUIRE(ws_bytes >= w.total, "pcg: workspace too small (%zu < %zu)", ws_bytes, w.total);
     if (!have_dinv) {
@@ -1406,7 +1414,7 @@ int pcg_solve(const psfem_csr *A, const double *d_b, double *d_x, double rtol, i
     int rc = launch_spmv(A, nullptr, d_x, nullptr, -1.0, 0.0, 1.0, d_b, w.r, nullptr, nullptr, nullptr, nullptr, nullptr, stream);
     if (rc) return rc;
     const int g = ew_grid(n);
-    pcg_init_kernel<<<g, EW_THREADS, 0, stream>>>(n, w.r, w.dinv, d_b, w.p, nullptr, w.partials, w.counter, w.ctl, rtol);
+    pcg_init_kernel<<<g, EW_THREADS, 0, stream>>>(n, w.r, w.dinv, d_b, w.p, nullptr, w.partials, w.counter, w.ctl, rtol, masked ? 1 : 0);
     PSFEM_LAUNCH_CHECK();
     if (check_every < 1) check_every = 50;
     PcgCtl h{};
@@ -1421,7 +1429,7 @@ int pcg_solve(const psfem_csr *A, const double *d_b, double *d_x, double rtol, i
             rc = launch_spmv(A, nullptr, w.p, nullptr, 1.0, 0.0, 0.0, nullptr, w.q, w.p, &w.ctl->pq, w.partials, w.counter, &w.ctl->done, stream);
             if (rc) return rc;
             PSFEM_CUDA_CHECK(launch_pdl(pcg_update_kernel, (unsigned)g, EW_THREADS, 0, stream, n, w.r, (const double *)w.q, (const double *)w.dinv, (const double *)nullptr,
-                                        (const double *)nullptr, (double *)nullptr, w.partials, w.counter + 1, w.ctl));
+                                        (const double *)nullptr, (double *)nullptr, w.partials, w.counter + 1, w.ctl, masked ? 1 : 0));
             PSFEM_CUDA_CHECK(launch_pdl(pcg_pupdate_kernel, (unsigned)g, EW_THREADS, 0, stream, n, w.p, d_x, (const double *)w.r, (const double *)w.dinv, (const double *)nullptr,
                                         (const double *)nullptr, (const double *)nullptr, w.ctl, w.counter + 2));
         }
@@ -1448,7 +1456,27 @@ extern "C" int psfem_pcg_jacobi(const psfem_csr *A, const double *d_b, double *d
     PcgWs w = carve_pcg(d_ws, A->n_rows, A->n_blocks);
     PSFEM_REQUIRE(ws_bytes >= w.total, "pcg_jacobi: workspace too small (%zu < %zu)", ws_bytes, w.total);
     PSFEM_CUDA_CHECK(cudaMemsetAsync(w.scal, 0, 16 * sizeof(double), stream));
-    return psfem::pcg_solve(A, d_b, d_x, rtol, maxit, check_every, h_info, w.scal, nullptr, d_ws, ws_bytes, false, stream);
+    return psfem::pcg_solve(A, d_b, d_x, rtol, maxit, check_every, h_info, w.scal, nullptr, d_ws, ws_bytes, false, stream, false);
+}
+
+__global__ void mask_dinv_kernel(int64_t n, const int32_t *__restrict__ new_id, double *__restrict__ dinv) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n && new_id[i] < 0) dinv[i] = 0.0;
+}
+
+extern "C" int psfem_pcg_jacobi_masked(const psfem_csr *A, const double *d_b, double *d_x, const int32_t *d_new_id, double rtol,
+                                       int64_t maxit, int64_t check_every, double *h_info, void *d_ws, size_t ws_bytes, void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    PSFEM_REQUIRE(A && d_b && d_x && d_new_id && h_info, "pcg_jacobi_masked: null argument");
+    const int64_t n = A->n_rows;
+    PcgWs w = carve_pcg(d_ws, n, A->n_blocks);
+    PSFEM_REQUIRE(ws_bytes >= w.total, "pcg_jacobi_masked: workspace too small (%zu < %zu)", ws_bytes, w.total);
+    PSFEM_CUDA_CHECK(cudaMemsetAsync(w.scal, 0, 16 * sizeof(double), stream));
+    int rc = psfem_extract_diag(A, 0, 1, w.dinv, stream);
+    if (rc) return rc;
+    mask_dinv_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, stream>>>(n, d_new_id, w.dinv);
+    PSFEM_LAUNCH_CHECK();
+    return psfem::pcg_solve(A, d_b, d_x, rtol, maxit, check_every, h_info, w.scal, nullptr, d_ws, ws_bytes, true, stream, true);
 }
 
 extern "C" int psfem_axpby(int64_t n, double a, const double *d_x, double b, const double *d_y, double *d_out, void *stream_) {

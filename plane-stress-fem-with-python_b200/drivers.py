@@ -37,6 +37,28 @@ def _to_dev(v):
 # ---------------------------------------------------------------------------------------------
 # static
 # ---------------------------------------------------------------------------------------------
+MASKED_MIN_ROWS = 16384      # below: the single-CTA solver on the reduced system
+
+
+def _pcg_masked(Kd: DeviceCSR, fm: FreeMap, F_dev, rtol, maxit, check_every):
+    torch = _capi.torch_cuda()
+    _capi.bind_device()
+    n = Kd.n_rows
+    x = torch.zeros(n, dtype=torch.float64, device="cuda")
+    if maxit is None:
+        maxit = 10 * n + 100
+    s = Kd.struct()
+    sz = C.c_size_t(0)
+    call("psfem_pcg_workspace", n, s.n_blocks, C.byref(sz))
+    ws = workspace(sz.value)
+    info = (C.c_double * 4)()
+    rc = lib.psfem_pcg_jacobi_masked(C.byref(s), ptr(F_dev), ptr(x), ptr(fm.new_id), float(rtol), int(maxit), int(check_every),
+                                     info, ptr(ws), sz.value, stream_ptr())
+    out = dict(iterations=int(info[0]), relres=float(info[1]), bnorm=float(info[2]), converged=(rc == _capi.OK), masked=True)
+    check(rc)
+    return x, out
+
+
 def static_solve(K, F, bc, rtol=1e-8, maxit=None, check_every=50, return_device=False):
     """Solve K U = F with the DOFs of `bc` fixed to zero.
 
@@ -48,10 +70,17 @@ def static_solve(K, F, bc, rtol=1e-8, maxit=None, check_every=50, return_device=
     constrained = constrained_dofs_of(bc)
     Kd = device_copy(K)
     fm = FreeMap(Kd.n_rows, constrained)
-    K_red = fm.reduce_csr(Kd)
-    F_red = fm.reduce_vec(_to_dev(F))
-    U_red, info = pcg_jacobi(K_red, F_red, rtol=rtol, maxit=maxit, check_every=check_every)
-    U = fm.expand(U_red)
+    if Kd.n_rows > MASKED_MIN_ROWS and Kd.plan()[3] is not None:
+        # large system whose matrix has the 2x2 node-block structure: solve on the UNREDUCED matrix with the
+        # constrained DOFs masked out (psfem_pcg_jacobi_masked) -- same iterates on the free DOFs as the reduced
+        # system of Polygones.py:1003, the 9-byte SpMV for any boundary conditions, no reduced copy of K
+        U, info = _pcg_masked(Kd, fm, _to_dev(F), rtol, maxit, check_every)
+        U_red = fm.reduce_vec(U)
+    else:
+        K_red = fm.reduce_csr(Kd)
+        F_red = fm.reduce_vec(_to_dev(F))
+        U_red, info = pcg_jacobi(K_red, F_red, rtol=rtol, maxit=maxit, check_every=check_every)
+        U = fm.expand(U_red)
     if return_device:
         return U, U_red, constrained, info
     Uh, Urh = to_host(U), to_host(U_red)          # page-locked landing buffers: DMA instead of the pageable path
