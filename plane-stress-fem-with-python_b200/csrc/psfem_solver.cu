@@ -1,11 +1,19 @@
-// psfem_solver.cu -- HBM-bound sparse kernels: shared-memory-staged CSR SpMV, the three fused
-// kernels of a Jacobi-PCG iteration, a single-CTA PCG for small systems, BLAS-1 helpers.
+// psfem_solver.cu -- HBM-bound sparse kernels of the static / Newmark / modal drivers.
 //
-// SpMV ("CSR stream"): a CTA owns a block of consecutive rows holding ~SPMV_T non-zeros.  All
-// threads stream vals/col_idx of the block with perfectly coalesced loads, multiply by the
-// gathered x entries (L1/L2 hits: FEM rows touch a narrow window of x) and park the products in
-// shared memory; then one thread per row reduces its products in column order (deterministic,
-// same order as scipy's CSR mat-vec).  12 B/nnz of HBM traffic is read exactly once.
+//   spmv_nb_kernel   SpMV (+ fused dot) on the 2x2 node-block structure of FEM matrices: persistent, one producer warp
+//                    streams 8 B values + one 4-byte node id per block through a TMA-fed shared ring, one DOF row per
+//                    consumer thread, x gathered as double2 -- 9 B per non-zero, the kernel PCG runs on
+//   spmv2_kernel     the same pipeline on plain CSR (12 B per non-zero) for matrices without that structure
+//   spmv_kernel      v1: one CTA per row block (small matrices, two-matrix right-hand side of Newmark without node blocks)
+//   pcg_*_kernel     the vector kernels of a Jacobi-PCG iteration (r -= alpha q with the reductions; x += alpha p,
+//                    p = D^-1 r + beta p), scalars on the device, deterministic last-block sums, masked variant for
+//                    solves on the unreduced matrix
+//   dist_*_kernel    the same iteration on a strip of a multi-GPU partition with the scalar all-reduces and the halo
+//                    exchange fused in (peer boards over CUDA-IPC memory, see PeerBoard)
+//   pcg_small_kernel whole solve in one single-CTA launch for n <= 16384
+//   BLAS-1 helpers for the Lanczos driver.
+// Every row is summed in column order (scipy's CSR order): the SpMV variants give bit-identical results.
+// The PCG kernels are chained with programmatic dependent launch (pdl_enter / launch_pdl).
 //
 // Replaces: np.linalg.solve / scipy.linalg.solve / lu_factor+lu_solve (Statictest.py:69,
 // StaticTest2.py:71, Beamexemple.py:63, main.py:286,295,314) and the dense mat-vecs of
