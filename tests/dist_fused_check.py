@@ -73,6 +73,27 @@ def main():
     assert np.array_equal(cols + off, one.K_red.col_idx[a:b_].cpu().numpy().astype(np.int64))
     assert np.abs(xp - x1[off:off + len(xp)]).max() <= 1e-8 * np.abs(x1).max()
     assert abs(rp - r1) <= 1e-5 * r1 and abs(bp - b1) <= 1e-12 * b1
+    # 3b. the other element types (T3, and the quadratic T6 / Q9 of mesh_type='fine', whose strips carry a two-column
+    #     left halo): owned matrix rows bit-identical to the single-GPU rows, same iterates
+    for et, mt, n_, m_ in (("tri", "coarse", 40 * world, 60), ("quad", "fine", 24 * world, 20), ("tri", "fine", 24 * world, 20)):
+        kw2 = dict(L=n_ * 1e-2, l=m_ * 1e-2, N=n_, M=m_, E=210e9, nu=0.3, t=0.1, element_type=et, mesh_type=mt)
+        pr = StripProblem(rank=rank, world=world, transport="peer", **kw2).setup()
+        rpo = pr.K_red.row_ptr.cpu().numpy().astype(np.int64)
+        vals_own = pr.K_red.vals[int(rpo[0]):int(rpo[-1])].cpu().numpy().copy()
+        pr.cg_iterations(25)
+        x_own = pr.st["x"].cpu().numpy().copy()
+        pr.release()
+        o1 = StripProblem(rank=0, world=1, **kw2).setup()
+        o1.cg_iterations(25)
+        sizes2 = [None] * world
+        dist.all_gather_object(sizes2, len(x_own))
+        off2 = sum(sizes2[:rank])
+        rp1 = o1.K_red.row_ptr.cpu().numpy().astype(np.int64)
+        assert np.array_equal(rpo - rpo[0], rp1[off2:off2 + len(x_own) + 1] - rp1[off2]), (et, mt)
+        assert np.array_equal(vals_own, o1.K_red.vals[int(rp1[off2]):int(rp1[off2 + len(x_own)])].cpu().numpy()), (et, mt)
+        x1_ = o1.st["x"].cpu().numpy()
+        assert np.abs(x_own - x1_[off2:off2 + len(x_own)]).max() <= 1e-9 * np.abs(x1_).max(), (et, mt)
+        o1.release()
     # 4. general boundary conditions and loads: rollers along the bottom edge (single DOFs constrained: the reduced
     #    matrix loses its node-block structure, CSR kernels), one pinned node, load on the top edge; the gathered
     #    solution against the single-GPU static_solve of the same problem
