@@ -239,6 +239,33 @@ def element_mass(nodes, conn, rho, t, element_type="tri", mesh_type="coarse"):
     return Me
 
 
+def body_forces(nodes, conn, force_vector, body_force, t, element_type="tri", mesh_type="coarse"):
+    """Polygones.py:1151-1200: fe[2i+p] = sum_gp w * N_i * f_p * t * |detJ| with the rule of get_gauss_points
+    (triangle weights sum to 1, so T3/T6 carry twice the area), added to force_vector in ascending element order
+    (mutated and returned, like the reference).  The T3 branch goes through the same Gauss loop (:1165-1193), not
+    through the closed form."""
+    conn = np.asarray(conn)
+    xy = nodes[conn]
+    nel, npe = conn.shape
+    pts, ws = gauss_points(element_type)
+    fe = np.zeros((nel, npe, 2))
+    for (xi, eta), w in zip(pts, ws):
+        Nv, dxi, det = shape_eval(element_type, mesh_type, xi, eta)
+        J00 = xy[:, :, 0] @ dxi
+        J01 = xy[:, :, 1] @ dxi
+        J10 = xy[:, :, 0] @ det
+        J11 = xy[:, :, 1] @ det
+        detJ = J00 * J11 - J01 * J10
+        bad = np.nonzero(np.abs(detJ) < 1e-10)[0]
+        if bad.size:
+            raise JacobianError(f"Jacobian determinant near zero for element {int(bad[0])}")
+        for p in (0, 1):
+            fe[:, :, p] += (w * Nv[None, :] * body_force[p] * t) * np.abs(detJ)[:, None]
+    np.add.at(force_vector, 2 * conn.ravel(), fe[:, :, 0].ravel())        # sequential, ascending element id
+    np.add.at(force_vector, 2 * conn.ravel() + 1, fe[:, :, 1].ravel())
+    return force_vector
+
+
 # --------------------------------------------------------------------------------------
 # global assembly  (Polygones.py:710-728, :1344-1364) as structural CSR (SURVEY A.6)
 # --------------------------------------------------------------------------------------

@@ -28,7 +28,7 @@ from .device import (Assembler, DeviceCSR, ElementTable, FreeMap, as_element_tab
 __all__ = ["mesh", "global_stiffness_matrix", "global_mass_matrix", "element_stiffness_matrix",
            "element_mass_matrix", "apply_boundary_conditions", "reduce", "reconstruct_full_vector",
            "reconstruct_full_vectors", "reconstruct_full_matrix", "boundary", "merge_boudary_conditions",
-           "edgeForces", "displacement", "get_deformed_nodes_list", "globalEnergy", "ElementTable"]
+           "edgeForces", "body_forces", "displacement", "get_deformed_nodes_list", "globalEnergy", "ElementTable"]
 
 
 def _etype(element_type, mesh_type):
@@ -279,6 +279,28 @@ def edgeForces(F, force, dir, l, N, M=0, element_type='tri', mesh_type='coarse')
     F[2 * ids] += force_per_node[0]
     F[2 * ids + 1] += force_per_node[1]
     return F
+
+
+def body_forces(nodes, elements, force_vector, body_force, t, element_type='tri', mesh_type='coarse'):
+    """Adds the consistent nodal forces of a uniform body force (fx, fy) to force_vector and returns it, like
+    Polygones.py:1151-1200 (fe[2i+p] = sum_gp w N_i f_p t |detJ|, elements in ascending order; no density).
+
+    On the device this is one mass assembly and one SpMV: sum_gp w N_i |detJ| t is the i-th row sum of the element
+    mass matrix with rho = 1 (the shape functions sum to one), so the added vector is M(rho=1) @ [fx, fy, fx, fy, ...].
+    The reference's 'tri'/'coarse' branch integrates with its triangle rule whose weights sum to 1 instead of 1/2
+    (Polygones.py:543-546) while its T3 mass is the closed form: its T3 body force is exactly twice M @ g, reproduced
+    here (tests: golden vectors of the reference for all four element types)."""
+    et = _etype(element_type, mesh_type)
+    torch = _capi.torch_cuda()
+    nodes = np.ascontiguousarray(nodes, dtype=np.float64)
+    plan, _ = _assembler(elements, len(nodes), et)
+    _, M_vals = plan.assemble(torch.from_numpy(nodes).cuda(), rho=1.0, t=t, what=2)
+    g = torch.tensor([float(body_force[0]), float(body_force[1])], dtype=torch.float64, device="cuda").repeat(len(nodes))
+    c = 2.0 if et == _capi.T3 else 1.0
+    add = plan.pattern_csr(M_vals).matvec(g, alpha=c)
+    torch.cuda.current_stream().synchronize()
+    force_vector += add.cpu().numpy()
+    return force_vector
 
 
 # ---------------------------------------------------------------------------------------------

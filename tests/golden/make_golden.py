@@ -265,9 +265,31 @@ def modal_cases(P):
     np.savez_compressed(f"{OUT}/ref_modal.npz", **out)
 
 
+def body_force_cases(P):
+    """Polygones.body_forces (Polygones.py:1151-1200; no caller in the reference) on the small meshes."""
+    t = 0.1
+    rng = np.random.default_rng(1)
+    out = {}
+    cases = {
+        "t3": dict(L=3, l=2.0, N=4, M=3, offsetX=0.5, offsetY=1, element_type="tri", mesh_type="coarse"),
+        "q4": dict(L=5.0, l=3, N=5, M=3, offsetX=0, offsetY=1.5, element_type="quad", mesh_type="coarse"),
+        "t6": dict(L=3, l=2, N=3, M=2, offsetX=0, offsetY=1, element_type="tri", mesh_type="fine"),
+        "q9": dict(L=2.0, l=1.5, N=2, M=2, offsetX=0.25, offsetY=0, element_type="quad", mesh_type="fine"),
+    }
+    for name, kw in cases.items():
+        nodes, elements = P.mesh(**kw)
+        n_, m_ = (kw["N"] + 1, kw["M"] + 1) if kw["mesh_type"] == "coarse" else (2 * kw["N"] + 1, 2 * kw["M"] + 1)
+        nodes = nodes + rng.uniform(-0.1, 0.1, nodes.shape) * np.array([kw["L"] / (n_ - 1), kw["l"] / (m_ - 1)])
+        F0 = rng.standard_normal(2 * len(nodes))
+        F = P.body_forces(nodes, elements, F0.copy(), (1.5, -9.81), t, kw["element_type"], kw["mesh_type"])
+        out[f"{name}_nodes"], out[f"{name}_conn"], out[f"{name}_F0"], out[f"{name}_F"] = nodes, conn_of(elements), F0, F
+        print("body_forces", name, np.abs(F - F0).max())
+    np.savez_compressed(f"{OUT}/ref_body_forces.npz", **out)
+
+
 if __name__ == "__main__":
     P = import_reference()
-    what = sys.argv[1:] or ["files", "small", "bc", "static", "newmark", "modal"]
+    what = sys.argv[1:] or ["files", "small", "bc", "static", "newmark", "modal", "body"]
     if "files" in what:
         golden_files()
     if "small" in what:
@@ -280,3 +302,5 @@ if __name__ == "__main__":
         newmark_cases(P)
     if "modal" in what:
         modal_cases(P)
+    if "body" in what:
+        body_force_cases(P)
