@@ -28,7 +28,9 @@ from .device import (Assembler, DeviceCSR, ElementTable, FreeMap, as_element_tab
 __all__ = ["mesh", "global_stiffness_matrix", "global_mass_matrix", "element_stiffness_matrix",
            "element_mass_matrix", "apply_boundary_conditions", "reduce", "reconstruct_full_vector",
            "reconstruct_full_vectors", "reconstruct_full_matrix", "boundary", "merge_boudary_conditions",
-           "edgeForces", "body_forces", "displacement", "get_deformed_nodes_list", "globalEnergy", "ElementTable"]
+           "edgeForces", "body_forces", "convert_to_banded", "convert_to_banded_optimized", "calculate_bandwidth",
+           "calculate_bandwidth_optimized", "normalize_matrix", "shapeFunctionCoeff", "shapeFunction", "strainDisplacement",
+           "local_stiffness_matrix", "localMassMtrix", "displacement", "get_deformed_nodes_list", "globalEnergy", "ElementTable"]
 
 
 def _etype(element_type, mesh_type):
@@ -301,6 +303,106 @@ def body_forces(nodes, elements, force_vector, body_force, t, element_type='tri'
     torch.cuda.current_stream().synchronize()
     force_vector += add.cpu().numpy()
     return force_vector
+
+
+# ---------------------------------------------------------------------------------------------
+# banded helpers of the reference's scripts (Polygones.py:959-987, :1205-1216), CSR-aware, O(nnz) on the host
+# ---------------------------------------------------------------------------------------------
+def _coo_parts(K):
+    if sparse.issparse(K):
+        C = sparse.coo_matrix(K)
+        return C.row.astype(np.int64), C.col.astype(np.int64), C.data
+    K = np.asarray(K)
+    r, c = np.nonzero(K)
+    return r.astype(np.int64), c.astype(np.int64), K[r, c]
+
+
+def convert_to_banded(K, lower_bandwidth, upper_bandwidth):
+    """LAPACK band storage ab[u + i - j, j] = K[i, j] of the entries with -lower <= j - i <= upper, what
+    scipy.linalg.solve_banded takes (Polygones.py:959-965; 2Dexemple.py:33-36).  Accepts the CSR matrices this
+    package returns as well as dense arrays."""
+    n = K.shape[0]
+    ab = np.zeros((lower_bandwidth + upper_bandwidth + 1, n))
+    r, c, v = _coo_parts(K)
+    keep = (c - r <= upper_bandwidth) & (r - c <= lower_bandwidth)
+    np.add.at(ab, (upper_bandwidth + r[keep] - c[keep], c[keep]), v[keep])     # duplicates of an unsummed sparse matrix add up
+    return ab
+
+
+convert_to_banded_optimized = convert_to_banded      # same result (Polygones.py:967-974)
+
+
+def calculate_bandwidth(K):
+    """(lower, upper) bandwidth over the NON-ZERO VALUES of K (Polygones.py:976-987): explicit zeros of the
+    structural CSR pattern do not count, like the reference's `K[i, j] != 0` test on its dense matrix."""
+    r, c, v = _coo_parts(K)
+    nz = v != 0
+    d = c[nz] - r[nz]
+    lower = int(max(0, -d.min())) if d.size else 0
+    upper = int(max(0, d.max())) if d.size else 0
+    return lower, upper
+
+
+def calculate_bandwidth_optimized(K):
+    """Polygones.py:1205-1216: the largest super-diagonal offset holding a non-zero value, returned twice.
+    (An all-zero upper triangle makes the reference loop forever; here it gives (0, 0).)"""
+    r, c, v = _coo_parts(K)
+    up = (v != 0) & (c >= r)
+    b = int((c[up] - r[up]).max()) if up.any() else 0
+    return b, b
+
+
+def normalize_matrix(matrix):
+    """Polygones.py:1368-1371."""
+    max_value = abs(matrix).max() if sparse.issparse(matrix) else np.max(np.abs(matrix))
+    if max_value == 0:
+        return matrix, max_value
+    return matrix / max_value, max_value
+
+
+# ---------------------------------------------------------------------------------------------
+# T3 element helpers of the reference (Polygones.py:840-883, :1228-1235): small host-side closed forms
+# ---------------------------------------------------------------------------------------------
+def shapeFunctionCoeff(nodes, elements, nbElement):
+    """[[a_i, b_i, c_i]] / (signed 2*area): N_i(x, y) = a_i + b_i x + c_i y  (Polygones.py:840-851)."""
+    p = np.asarray(nodes, dtype=np.float64)[list(elements[nbElement])]
+    x, y = p[:, 0], p[:, 1]
+    delta = x[0] * (y[1] - y[2]) + x[1] * (y[2] - y[0]) + x[2] * (y[0] - y[1])
+    L = []
+    for i in range(3):
+        j, k = (i + 1) % 3, (i + 2) % 3
+        L.append([(x[j] * y[k] - x[k] * y[j]) / delta, (y[j] - y[k]) / delta, (x[k] - x[j]) / delta])
+    return L
+
+
+def shapeFunction(nodes, elements, nbElement):
+    """Callable N(x, y) -> [N_0, N_1, N_2] of a T3 element (Polygones.py:853-860; 2Dexemple.py:40)."""
+    L = shapeFunctionCoeff(nodes, elements, nbElement)
+
+    def N(x, y):
+        return [a + b * x + c * y for a, b, c in L]
+    return N
+
+
+def strainDisplacement(nodes, elements, nbElement):
+    """Constant (3, 6) B matrix of a T3 element (Polygones.py:862-873)."""
+    L = shapeFunctionCoeff(nodes, elements, nbElement)
+    B = np.zeros((3, 6))
+    for i, (_, b, c) in enumerate(L):
+        B[0, 2 * i] = b
+        B[1, 2 * i + 1] = c
+        B[2, 2 * i], B[2, 2 * i + 1] = c, b
+    return B
+
+
+def local_stiffness_matrix(nodes, element, nbElement, E, nu, t):
+    """T3 element stiffness (Polygones.py:875-883) -- the device closed form of element_stiffness_matrix."""
+    return element_stiffness_matrix(nodes, element, nbElement, E, nu, t, 'tri', 'coarse')
+
+
+def localMassMtrix(nodes, elements, nbElement, rho, t):
+    """T3 element mass (Polygones.py:1228-1235; the reference's spelling)."""
+    return element_mass_matrix(nodes, elements, nbElement, rho, t, 'tri', 'coarse')
 
 
 # ---------------------------------------------------------------------------------------------

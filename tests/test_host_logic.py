@@ -66,3 +66,56 @@ def test_ramp_load_matches_main_py(psfem, golden):
     assert scale[0] == 0.0 and scale[-1] == -1e6 * 20 / 63
     T0 = 10001 // 3
     assert scale[T0] == -(3 * 1e6 * times[T0] / 10.0) * 20 / 63
+
+
+def test_banded_helpers_on_csr_and_dense(psfem):
+    """convert_to_banded / calculate_bandwidth (Polygones.py:959-987, :1205-1216) on the structural CSR this package
+    returns and on dense input, against the reference's own double loops restated here."""
+    import scipy.linalg
+    import scipy.sparse as sparse
+    import psfem_oracle as O
+    P = psfem.Polygones
+    nodes, conn = O.mesh(4.0, 1.0, 6, 2)
+    K = O.global_stiffness_matrix(nodes, conn, 210e9, 0.3, 0.1)              # structural CSR with explicit zeros
+    Kd = K.toarray()
+    n = Kd.shape[0]
+    lo = up = 0
+    for i in range(n):
+        for j in range(n):
+            if Kd[i, j] != 0:
+                if j < i:
+                    lo = max(lo, i - j)
+                else:
+                    up = max(up, j - i)
+    for M in (K, Kd):
+        assert P.calculate_bandwidth(M) == (lo, up)
+        assert P.calculate_bandwidth_optimized(M) == (up, up)
+        ab = P.convert_to_banded(M, lo, up)
+        ref = np.zeros((lo + up + 1, n))
+        for i in range(n):
+            for j in range(max(0, i - lo), min(n, i + up + 1)):
+                ref[up + i - j, j] = Kd[i, j]
+        assert np.array_equal(ab, ref) and np.array_equal(P.convert_to_banded_optimized(M, lo, up), ref)
+    # the flow of 2Dexemple.py:29-37: reduce, band, solve_banded
+    free = np.arange(6, n)
+    Kr = sparse.csr_matrix(K)[free][:, free]
+    lo, up = P.calculate_bandwidth(Kr)
+    F = np.linspace(1.0, 2.0, len(free))
+    U = scipy.linalg.solve_banded((lo, up), P.convert_to_banded(Kr, lo, up), F)
+    assert np.abs(Kr @ U - F).max() < 1e-9 * np.abs(F).max()
+    Mn, mx = P.normalize_matrix(K)
+    assert mx == abs(K).max() and abs(abs(Mn).max() - 1) < 1e-15
+
+
+def test_t3_host_helpers(psfem):
+    P = psfem.Polygones
+    nodes = np.array([[0, 0], [1, 0], [2, 0], [2, 1], [1, 1], [0, 1]], dtype=float)
+    elements = {0: [0, 1, 4], 1: [4, 1, 2], 2: [2, 3, 4], 3: [4, 5, 0]}                # 2Dexemple.py:11-17
+    N = P.shapeFunction(nodes, elements, 1)
+    assert np.allclose(N(1, 0), [0, 1, 0]) and np.allclose(N(1, 1), [1, 0, 0]) and np.allclose(N(2, 0), [0, 0, 1])
+    assert abs(sum(N(1.3, 0.2)) - 1) < 1e-15                                           # partition of unity
+    B = P.strainDisplacement(nodes, elements, 1)
+    L = P.shapeFunctionCoeff(nodes, elements, 1)
+    assert B.shape == (3, 6) and B[0, 0] == L[0][1] and B[1, 1] == L[0][2] and B[2, 0] == L[0][2] and B[2, 1] == L[0][1]
+    assert np.abs(B @ np.array([1, 0, 1, 0, 1, 0.0])).max() < 1e-15                     # a rigid translation has no strain
+
