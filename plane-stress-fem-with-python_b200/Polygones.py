@@ -25,7 +25,7 @@ from ._capi import ETYPE, NPE
 from .device import (Assembler, DeviceCSR, ElementTable, FreeMap, as_element_table, constrained_dofs_of,
                      device_mesh)
 
-__all__ = ["mesh", "global_stiffness_matrix", "global_mass_matrix", "element_stiffness_matrix",
+__all__ = ["mesh", "global_stiffness_matrix", "global_stiffness_matrix_linear", "get_gauss_points", "global_mass_matrix", "element_stiffness_matrix",
            "element_mass_matrix", "apply_boundary_conditions", "reduce", "reconstruct_full_vector",
            "reconstruct_full_vectors", "reconstruct_full_matrix", "boundary", "merge_boudary_conditions",
            "edgeForces", "body_forces", "convert_to_banded", "convert_to_banded_optimized", "calculate_bandwidth",
@@ -110,6 +110,23 @@ def global_stiffness_matrix(nodes, elements, E, nu, t, element_type='tri', mesh_
     plan, _ = _assembler(elements, len(nodes), et)
     K_vals, _ = plan.assemble(torch.from_numpy(nodes).cuda(), E=E, nu=nu, t=t, what=1)
     return _to_host_csr(plan.pattern_csr(K_vals))
+
+
+def global_stiffness_matrix_linear(nodes, element, E, nu, t):
+    """The reference's T3-only assembly variant (Polygones.py:885-896, no caller): same matrix as
+    global_stiffness_matrix(..., 'tri', 'coarse')."""
+    return global_stiffness_matrix(nodes, element, E, nu, t, 'tri', 'coarse')
+
+
+def get_gauss_points(element_type='tri'):
+    """Quadrature rule of the reference (Polygones.py:534-564): (points, weights); the triangle weights sum to 1,
+    not 1/2, exactly as there; 3x3 Gauss-Legendre for quadrilaterals (eta outer, xi inner)."""
+    if element_type == 'tri':
+        return [(1 / 6, 1 / 6), (2 / 3, 1 / 6), (1 / 6, 2 / 3)], [1 / 3, 1 / 3, 1 / 3]
+    a = np.sqrt(0.6)                       # every other element_type is a quadrilateral there (`else:`, :547)
+    w = [5 / 9, 8 / 9, 5 / 9]
+    g = [-a, 0, a]
+    return [(g[c], g[r]) for r in range(3) for c in range(3)], [w[r] * w[c] for r in range(3) for c in range(3)]
 
 
 def global_mass_matrix(nodes, elements, rho, t, element_type='tri', mesh_type='coarse', integration='gauss'):
