@@ -276,7 +276,10 @@ spmv_kernel(const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col
 // ---------------------------------------------------------------------------------------------
 constexpr int SPMV2_CONSUMERS = 256;
 constexpr int SPMV2_THREADS = SPMV2_CONSUMERS + 32;
-constexpr int SPMV2_STAGES = 2;
+#ifndef PSFEM_SPMV_STAGES
+#define PSFEM_SPMV_STAGES 2
+#endif
+constexpr int SPMV2_STAGES = PSFEM_SPMV_STAGES;
 constexpr int SPMV2_ROWCAP = 1024;  // row_ptr entries staged per block (blocks with more rows read row_ptr from global)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -448,7 +451,10 @@ spmv2_kernel(const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ co
 // gathered as double2 {x[2b], x[2b+1]}.  psfem_spmv_nb_plan detects the structure and builds node_ptr / pcol /
 // node blocks; operands without it keep using the CSR kernels.
 // ---------------------------------------------------------------------------------------------
-constexpr int NB_PAIRS = 1024;      // target 2x2 blocks per node block (4096 non-zeros)
+#ifndef PSFEM_NB_PAIRS
+#define PSFEM_NB_PAIRS 1024
+#endif
+constexpr int NB_PAIRS = PSFEM_NB_PAIRS;      // target 2x2 blocks per node block (4096 non-zeros at 1024)
 constexpr int NB_NODECAP = 1024;    // node_ptr entries staged per block
 #ifndef PSFEM_NB_U
 #define PSFEM_NB_U 5
