@@ -259,6 +259,10 @@ def main():
     idx_bytes = 2 if (node_block and nbp[5] is not None) else 4
     # node-block SpMV: 8 B value + one node id (16-bit offset or 32-bit) per 2x2 block, node_ptr, x, y
     spmv_bytes = (8 * nnz + idx_bytes * (nnz // 4) + 4 * (n // 2 + 1) + 16 * n) if node_block else csr_bytes
+    sym_lat = bool(getattr(prob, "sym_lattice", False)) and not os.environ.get("PSFEM_NO_SYMLATTICE")
+    if sym_lat:
+        # symmetric-lattice storage: 19 doubles of matrix per node (diagonal + 4 forward 2x2 blocks), x, y
+        spmv_bytes = (19 * 8 + 16 + 16) * (n // 2)
     spmv_t = t_spmv / (K_ * args.cg_iters)
     spmv_gbs = spmv_bytes / spmv_t / 1e9
     iter_bytes = spmv_bytes + (4 + 6) * 8 * n                            # update: q, r, dinv, r' ; p-update: p, x, r, dinv, p', x'
@@ -283,7 +287,9 @@ def main():
                      "roofline": {"bound": "hbm", "achieved": asm_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": asm_gbs / hbm_peak,
                                   "bytes_per_element": 320, "kernel": "lattice_q4_kernel<true> (marching warps, TMA bulk stores)",
                                   "traffic": asm_traffic}},
-        "roofline": {"kernel": (f"spmv_nb_kernel<true> (PCG SpMV + dot on the 2x2 node-block structure, TMA-staged, {8 + idx_bytes / 4:g} B/non-zero)" if node_block
+        "roofline": {"kernel": ("spmv_sl_kernel<true> (PCG SpMV + dot on symmetric-lattice storage: marching warps, 152 B of matrix per node, "
+                                "bit-identical to the CSR kernels)" if sym_lat else
+                                f"spmv_nb_kernel<true> (PCG SpMV + dot on the 2x2 node-block structure, TMA-staged, {8 + idx_bytes / 4:g} B/non-zero)" if node_block
                                 else "spmv2_kernel<true> (PCG SpMV + dot, CSR, TMA-staged, 12 B/non-zero)"),
                      "bound": "hbm", "achieved": spmv_gbs, "peak": hbm_peak,
                      "unit": "GB/s", "frac": spmv_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
@@ -298,7 +304,8 @@ def main():
     if os.path.exists(traffic_file):
         try:
             tj = json.load(open(traffic_file))
-            line["roofline"]["traffic"] = (tj.get("node_block") if node_block else tj.get("csr") or tj).get("dram_bytes_per_launch")
+            key = "sym_lattice" if sym_lat else ("node_block" if node_block else "csr")
+            line["roofline"]["traffic"] = (tj.get(key) or {}).get("dram_bytes_per_launch")
         except Exception:
             pass
 

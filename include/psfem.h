@@ -70,6 +70,16 @@ typedef struct psfem_csr {
     const int32_t *nb_nodeblk;  /* nb_n_blocks + 3 ints */
     int64_t nb_n_blocks;
     int64_t nb_max_pairs;
+    /* optional symmetric-lattice storage of exactly `vals` (psfem_spmv_sl_build; NULL / 0 otherwise): for symmetric
+     * matrices whose nodes couple with their 3x3 lattice neighbours only (node id = column*sl_m + row, the numbering of
+     * Polygones.mesh, Polygones.py:77), the diagonal and the four forward 2x2 blocks per node (19 doubles) stored as a
+     * structure of arrays.  The SpMV streams 184 instead of 360 bytes per node and returns the same bits as the CSR
+     * kernels.  Used only while sl_src_vals == vals. */
+    const double *sl_vals;
+    const double *sl_src_vals;  /* the value array sl_vals was built from */
+    int64_t sl_m;               /* nodes per lattice column */
+    int64_t sl_roff;            /* x node of row node 0 (0, or the halo nodes before the owned rows of a strip) */
+    int64_t sl_x_nodes;         /* nodes in the x vector (multiple of sl_m) */
 } psfem_csr;
 
 /* ---- mesh: Polygones.mesh, Polygones.py:62-108 ------------------------------------------
@@ -221,6 +231,21 @@ int psfem_spmv_nb_plan(int64_t n, const int32_t *d_row_ptr, const int32_t *d_col
 int psfem_spmv_nb_compress(int64_t n, const int32_t *d_node_ptr, const int32_t *d_pcol, int64_t nnz,
                            int16_t *d_pcol16, void *stream);
 /* y = alpha*A*x + gamma*z   (z may be NULL; y may alias z) */
+/* Symmetric-lattice storage for the SpMV of PCG (replaces the same dense products as psfem_spmv: main.py:310,383-384
+ * and the solves of Statictest.py:69, main.py:286,314 through PCG).
+ *   psfem_spmv_sl_candidates: proposals for the lattice column height m of a node-block operand (h_m[8], *h_count of them;
+ *                             0 when the operand cannot be a lattice); synchronises
+ *   psfem_spmv_sl_size:       bytes of the storage for (row nodes, row_node_offset, m); allocate 256 bytes more
+ *   psfem_spmv_sl_build:      checks that A is a 3x3-lattice matrix with column height m whose 2x2 blocks (a,b) and (b,a)
+ *                             are transposes (tol = 0: bit for bit, which makes the SpMV bit-identical to the CSR kernels;
+ *                             tol > 0: within tol * the node's diagonal) and writes the storage; *h_ok = 1 on success.
+ * row_node_offset = x node of the first row node (rows of a strip start after its left halo column), x_nodes = nodes
+ * in the operand vector.  The caller then sets sl_vals / sl_src_vals / sl_m / sl_roff / sl_x_nodes in psfem_csr. */
+int psfem_spmv_sl_candidates(const psfem_csr *A, int64_t row_node_offset, int64_t x_nodes, int64_t *h_m, int64_t *h_count,
+                             void *stream);
+int psfem_spmv_sl_size(int64_t n_row_nodes, int64_t row_node_offset, int64_t m, size_t *bytes);
+int psfem_spmv_sl_build(const psfem_csr *A, int64_t row_node_offset, int64_t x_nodes, int64_t m, double tol,
+                        double *d_sl_vals, size_t bytes, int64_t *h_ok, void *stream);
 int psfem_spmv(const psfem_csr *A, const double *d_x, double alpha, double gamma, const double *d_z,
                double *d_y, void *stream);
 /* y = alpha*A1*x1 + beta*A2*x2 + gamma*z, A2 = (pattern of A, d_vals2): Newmark RHS main.py:310 */

@@ -26,7 +26,9 @@ class psfem_csr(C.Structure):
     _fields_ = [("n_rows", C.c_int64), ("nnz", C.c_int64), ("row_ptr", C.c_void_p), ("col_idx", C.c_void_p),
                 ("vals", C.c_void_p), ("rowblk", C.c_void_p), ("n_blocks", C.c_int64), ("max_row_nnz", C.c_int64),
                 ("nb_node_ptr", C.c_void_p), ("nb_pcol", C.c_void_p), ("nb_pcol16", C.c_void_p), ("nb_nodeblk", C.c_void_p),
-                ("nb_n_blocks", C.c_int64), ("nb_max_pairs", C.c_int64)]
+                ("nb_n_blocks", C.c_int64), ("nb_max_pairs", C.c_int64),
+                ("sl_vals", C.c_void_p), ("sl_src_vals", C.c_void_p), ("sl_m", C.c_int64), ("sl_roff", C.c_int64),
+                ("sl_x_nodes", C.c_int64)]
 
 
 MAX_RANKS = 8
@@ -89,6 +91,9 @@ SIGNATURES = {
     "psfem_spmv_nb_plan_size": [_i64, _i64, _pi64],
     "psfem_spmv_nb_plan": [_i64, _ptr, _ptr, _i64, _ptr, _ptr, _ptr, _i64, _pi64, _ptr],
     "psfem_spmv_nb_compress": [_i64, _ptr, _ptr, _i64, _ptr, _ptr],
+    "psfem_spmv_sl_candidates": [_pcsr, _i64, _i64, _pi64, _pi64, _ptr],
+    "psfem_spmv_sl_size": [_i64, _i64, _i64, _psz],
+    "psfem_spmv_sl_build": [_pcsr, _i64, _i64, _i64, _dbl, _ptr, _sz, _pi64, _ptr],
     "psfem_spmv": [_pcsr, _ptr, _dbl, _dbl, _ptr, _ptr, _ptr],
     "psfem_spmv2": [_pcsr, _ptr, _ptr, _ptr, _dbl, _dbl, _dbl, _ptr, _ptr, _ptr],
     "psfem_extract_diag": [_pcsr, _i64, _i32, _ptr, _ptr],

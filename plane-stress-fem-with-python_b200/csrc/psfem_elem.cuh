@@ -220,11 +220,15 @@ template <bool DO_K, bool DO_M> struct ElemQ4 {
         }
         return ok;
     }
-    // {K(2i,2j), K(2i,2j+1), K(2i+1,2j), K(2i+1,2j+1)}
+    // {K(2i,2j), K(2i,2j+1), K(2i+1,2j), K(2i+1,2j+1)}.  The roundings are spelled out (one rounded product, one fused
+    // multiply-add) so that every instance of the expression rounds the same way: Ke(2i+p, 2j+q) and Ke(2j+q, 2i+p) are
+    // then the same bits, and so are K(r, c) and K(c, r) after the assembly (same contributions, same order) -- the
+    // symmetric-lattice SpMV (psfem_spmv_sl.cuh) relies on it.  Left to the compiler, the contraction of a*b + c*d
+    // differed between inlined instances (7 % of the entries of K differed from their mirror image by one ulp).
     __device__ __forceinline__ double4 kblock(int i, int j, const Mat &mat) const {
         const int b = i <= j ? tri_index<4>(i, j) : tri_index<4>(j, i);
-        return make_double4(mat.d00 * gxx[b] + mat.d22 * gyy[b], mat.d01 * gxy[i * 4 + j] + mat.d22 * gxy[j * 4 + i],
-                            mat.d01 * gxy[j * 4 + i] + mat.d22 * gxy[i * 4 + j], mat.d00 * gyy[b] + mat.d22 * gxx[b]);
+        return make_double4(fma(mat.d00, gxx[b], __dmul_rn(mat.d22, gyy[b])), fma(mat.d01, gxy[i * 4 + j], __dmul_rn(mat.d22, gxy[j * 4 + i])),
+                            fma(mat.d01, gxy[j * 4 + i], __dmul_rn(mat.d22, gxy[i * 4 + j])), fma(mat.d00, gyy[b], __dmul_rn(mat.d22, gxx[b])));
     }
     __device__ __forceinline__ double mval(int i, int j) const { return mm[i <= j ? tri_index<4>(i, j) : tri_index<4>(j, i)]; }
 };

@@ -635,6 +635,26 @@ spmv_nb_kernel(const int32_t *__restrict__ node_ptr, const void *__restrict__ pc
     }
 }
 
+#include "psfem_spmv_sl.cuh"
+
+// geometry of the symmetric-lattice operand attached to A (psfem_spmv_sl_build)
+bool sl_geometry(const psfem_csr *A, SlGeom *g, int sms) {
+    const int64_t m = A->sl_m, nodes = A->n_rows / 2;
+    if (m < 2 || nodes % m || A->sl_roff % m || A->sl_x_nodes % m) return false;
+    const int64_t owned_cols = nodes / m, c0x = A->sl_roff / m;
+    g->m = (int)m; g->mpad = (int)((m + 3) & ~3ll);
+    g->pre = c0x > 0 ? 1 : 0;
+    g->S = (int)owned_cols + g->pre;
+    g->xcol0 = (int)c0x - g->pre;
+    g->xcols = (int)(A->sl_x_nodes / m);
+    g->n_strips = (int)ceil_div(m, SL_ROWS);
+    int64_t G = (int64_t)sms * PSFEM_SL_CTAS * SL_WARPS / g->n_strips;   // one resident wave of warps
+    if (G > owned_cols / 4) G = owned_cols / 4;                           // segments of at least 4 columns
+    if (G < 1) G = 1;
+    g->G = (int)G;
+    return true;
+}
+
 int launch_spmv(const psfem_csr *A, const double *v2, const double *x1, const double *x2, double alpha, double beta,
                 double gamma, const double *z, double *y, const double *xdot, double *dot_out, double *partials,
                 unsigned int *counter, const int *done, cudaStream_t stream, const PeerSync *peer = nullptr) {
@@ -646,6 +666,24 @@ int launch_spmv(const psfem_csr *A, const double *v2, const double *x1, const do
     PSFEM_REQUIRE(smem <= 200 * 1024, "spmv: a row with %lld non-zeros does not fit the shared-memory stage", (long long)A->max_row_nnz);
     const bool dual = v2 != nullptr, dot = dot_out != nullptr;
     static const bool nb_off = getenv("PSFEM_NO_NODEBLOCK") != nullptr;   // A/B switch for measurements
+    static const bool sl_off = getenv("PSFEM_NO_SYMLATTICE") != nullptr;
+    // symmetric-lattice storage of exactly these values (psfem_spmv_sl_build): half the HBM traffic, same result
+    if (!dual && !sl_off && A->sl_vals && A->sl_src_vals == A->vals && (!dot || xdot == x1 + 2 * A->sl_roff) && y != x1 &&
+        ((reinterpret_cast<uintptr_t>(x1) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(z)) & 15) == 0) {
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        SlGeom g;
+        if (sl_geometry(A, &g, sms)) {
+            const unsigned grid = (unsigned)ceil_div((int64_t)g.n_strips * g.G, SL_WARPS);
+            if (dot)
+                PSFEM_CUDA_CHECK(launch_pdl(spmv_sl_kernel<true>, grid, SL_THREADS, 0, stream, A->sl_vals, g, x1, alpha, gamma, z, y, dot_out, partials, counter, done, ps));
+            else
+                PSFEM_CUDA_CHECK(launch_pdl(spmv_sl_kernel<false>, grid, SL_THREADS, 0, stream, A->sl_vals, g, x1, alpha, gamma, z, y, dot_out, partials, counter, done, ps));
+            PSFEM_LAUNCH_CHECK();
+            return PSFEM_OK;
+        }
+    }
     if (!dual && !nb_off && A->nb_node_ptr && (A->nb_pcol || A->nb_pcol16) && A->nb_n_blocks >= 8 && ((reinterpret_cast<uintptr_t>(A->vals) | reinterpret_cast<uintptr_t>(x1)) & 15) == 0) {
         const int cap = (int)((NB_PAIRS + A->nb_max_pairs + 8 + 3) & ~3ll);
         const size_t stage_bytes = (size_t)cap * 32 + (size_t)(cap + 16) * 4 + (NB_NODECAP + 8) * 4;
@@ -1185,6 +1223,71 @@ extern "C" int psfem_spmv_nb_compress(int64_t n, const int32_t *d_node_ptr, cons
     PSFEM_CUDA_CHECK(cudaMemsetAsync(d_pcol16 + nnz / 4, 0, 16 * sizeof(int16_t), stream));
     nb_compress_kernel<<<(unsigned)ceil_div(n / 2, 256), 256, 0, stream>>>(n / 2, d_node_ptr, d_pcol, d_pcol16);
     PSFEM_LAUNCH_CHECK();
+    return PSFEM_OK;
+}
+
+// ---- symmetric-lattice storage ----------------------------------------------------------------
+extern "C" int psfem_spmv_sl_candidates(const psfem_csr *A, int64_t row_node_offset, int64_t x_nodes, int64_t *h_m, int64_t *h_count,
+                                        void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    PSFEM_REQUIRE(A && h_m && h_count, "spmv_sl_candidates: null argument");
+    *h_count = 0;
+    if (!A->nb_node_ptr || !A->nb_pcol || A->n_rows < 4 || (A->n_rows & 1)) return PSFEM_OK;   // needs the 32-bit node-block view
+    int32_t np[2] = {0, 0};
+    PSFEM_CUDA_CHECK(cudaMemcpyAsync(np, A->nb_node_ptr, sizeof(np), cudaMemcpyDeviceToHost, stream));
+    PSFEM_CUDA_CHECK(cudaStreamSynchronize(stream));
+    const int deg = np[1] - np[0];
+    if (deg < 1 || deg > 9) return PSFEM_OK;
+    int32_t pc[9];
+    PSFEM_CUDA_CHECK(cudaMemcpyAsync(pc, A->nb_pcol, deg * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+    PSFEM_CUDA_CHECK(cudaStreamSynchronize(stream));
+    // the first row node sits at the bottom of a lattice column: its neighbours in the adjacent columns are m-1, m or
+    // m+1 ids away, so every |distance| > 1 proposes m in {d-1, d, d+1}; psfem_spmv_sl_build verifies a proposal
+    const int64_t nodes = A->n_rows / 2;
+    int64_t cnt = 0;
+    for (int k = 0; k < deg; ++k) {
+        const int64_t d = pc[k] > row_node_offset ? pc[k] - row_node_offset : row_node_offset - pc[k];
+        if (d <= 1) continue;
+        for (int64_t mm = d - 1; mm <= d + 1; ++mm) {
+            if (mm < 2 || nodes % mm || row_node_offset % mm || x_nodes % mm) continue;
+            bool seen = false;
+            for (int64_t q = 0; q < cnt; ++q) seen = seen || h_m[q] == mm;
+            if (!seen && cnt < 8) h_m[cnt++] = mm;
+        }
+    }
+    *h_count = cnt;
+    return PSFEM_OK;
+}
+
+extern "C" int psfem_spmv_sl_size(int64_t n_row_nodes, int64_t row_node_offset, int64_t m, size_t *bytes) {
+    PSFEM_REQUIRE(bytes && m >= 2 && n_row_nodes > 0 && n_row_nodes % m == 0 && row_node_offset >= 0 && row_node_offset % m == 0,
+                  "spmv_sl_size: bad arguments");
+    const int64_t S = n_row_nodes / m + (row_node_offset > 0 ? 1 : 0), mpad = (m + 3) & ~3ll;
+    *bytes = (size_t)S * SL_NC * (size_t)mpad * sizeof(double);
+    return PSFEM_OK;
+}
+
+extern "C" int psfem_spmv_sl_build(const psfem_csr *A, int64_t row_node_offset, int64_t x_nodes, int64_t m, double tol,
+                                   double *d_sl_vals, size_t bytes, int64_t *h_ok, void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    PSFEM_REQUIRE(A && d_sl_vals && h_ok && A->nb_node_ptr && A->nb_pcol && A->vals, "spmv_sl_build: needs a matrix with its 32-bit node-block view");
+    const int64_t nodes = A->n_rows / 2;
+    size_t want = 0;
+    if (int rc = psfem_spmv_sl_size(nodes, row_node_offset, m, &want)) return rc;
+    PSFEM_REQUIRE(bytes >= want + 256 && x_nodes % m == 0 && x_nodes >= row_node_offset + nodes && m < (1ll << 30) && x_nodes < (1ll << 31),
+                  "spmv_sl_build: bad sizes (buffer must hold psfem_spmv_sl_size bytes + 256)");
+    *h_ok = 0;
+    int *bad = reinterpret_cast<int *>(reinterpret_cast<char *>(d_sl_vals) + want);   // flag parked after the storage
+    PSFEM_CUDA_CHECK(cudaMemsetAsync(d_sl_vals, 0, want + 256, stream));
+    const int pre = row_node_offset > 0 ? 1 : 0;
+    sl_build_kernel<<<(unsigned)ceil_div(nodes, 128), 128, 0, stream>>>(nodes, row_node_offset, x_nodes, (int)m, (int)((m + 3) & ~3ll), pre,
+                                                                      (int)(row_node_offset / m), A->nb_node_ptr, A->nb_pcol, A->vals, tol,
+                                                                      d_sl_vals, bad);
+    PSFEM_LAUNCH_CHECK();
+    int h = 1;
+    PSFEM_CUDA_CHECK(cudaMemcpyAsync(&h, bad, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    PSFEM_CUDA_CHECK(cudaStreamSynchronize(stream));
+    *h_ok = h == 0 ? 1 : 0;
     return PSFEM_OK;
 }
 

@@ -101,6 +101,7 @@ class DeviceCSR:
         self.row_ptr, self.col_idx, self.vals = row_ptr, col_idx, vals
         self.nnz = int(col_idx.numel()) if nnz is None else int(nnz)
         self._plan = None
+        self._sl = None           # symmetric-lattice storage of self.vals (sym_lattice)
 
     @property
     def shape(self):
@@ -148,6 +149,46 @@ class DeviceCSR:
             pcol = None
         return (node_ptr, pcol, nodeblk, nb.value, int(info[1]), pcol16)
 
+    SL_ROUNDING_TOL = 1e-14   # |K(r,c) - K(c,r)| <= tol * |diagonal|: asymmetry from rounding only
+
+    def sym_lattice(self, row_node_offset=0, tol=None):
+        """Symmetric-lattice storage for the SpMV (psfem_spmv_sl_build): for a symmetric matrix whose nodes couple
+        with their 3x3 lattice neighbours only -- every K / M / K + a M of a Polygones.mesh mesh, its reductions by whole
+        node columns and the strips of the multi-GPU partition -- the SpMV then streams half the bytes and returns
+        the same bits.  Built once per value array; returns False (and changes nothing) for any other matrix.
+        row_node_offset: x node of the first row node (owned rows of a strip start after the left halo column).
+        tol: 0.0 accepts bitwise symmetric matrices only (the Q4 matrices assembled here; SpMV bit-identical to the CSR
+        kernels); a positive value accepts |K(r,c) - K(c,r)| <= tol * |diagonal| and applies the upper triangle for both
+        (T3 matrices: the reference's own B^T D B is symmetric up to rounding only, Polygones.py:877-882); None tries
+        0.0, then SL_ROUNDING_TOL."""
+        if os.environ.get("PSFEM_NO_SYMLATTICE") or self.vals is None:
+            return False
+        if self._sl is not None and self._sl["src"] == self.vals.data_ptr() and self._sl["roff"] == row_node_offset:
+            return True
+        self._sl = None
+        nbp = self.plan()[3]
+        if nbp is None or nbp[1] is None or self.n_cols % 2 or self.n_rows < 64:
+            return False
+        torch = _capi.torch_cuda()
+        s = self.struct()
+        x_nodes = self.n_cols // 2
+        cand, cnt = (C.c_int64 * 8)(), C.c_int64(0)
+        call("psfem_spmv_sl_candidates", C.byref(s), int(row_node_offset), x_nodes, cand, C.byref(cnt), stream_ptr())
+        tols = (0.0, self.SL_ROUNDING_TOL) if tol is None else (float(tol),)
+        for m, tol in [(m_, t_) for t_ in tols for m_ in list(cand[: cnt.value])]:
+            sz = C.c_size_t(0)
+            call("psfem_spmv_sl_size", self.n_rows // 2, int(row_node_offset), m, C.byref(sz))
+            nbytes = sz.value + 256
+            buf = torch.empty((nbytes + 7) // 8, dtype=torch.float64, device="cuda")
+            ok = C.c_int64(0)
+            call("psfem_spmv_sl_build", C.byref(s), int(row_node_offset), x_nodes, m, float(tol), ptr(buf), nbytes, C.byref(ok),
+                 stream_ptr())
+            if ok.value == 1:
+                self._sl = dict(vals=buf, src=self.vals.data_ptr(), m=int(m), roff=int(row_node_offset), x_nodes=x_nodes, tol=tol)
+                return True
+            del buf
+        return False
+
     def struct(self, vals=None):
         rowblk, nb, mx, nbp = self.plan()
         s = _capi.psfem_csr()
@@ -160,6 +201,10 @@ class DeviceCSR:
             s.nb_pcol = nbp[1].data_ptr() if nbp[1] is not None else None
             s.nb_pcol16 = nbp[5].data_ptr() if nbp[5] is not None else None
             s.nb_n_blocks, s.nb_max_pairs = nbp[3], nbp[4]
+        sl = self._sl
+        if sl is not None and sl["src"] == s.vals:
+            s.sl_vals, s.sl_src_vals = sl["vals"].data_ptr(), sl["src"]
+            s.sl_m, s.sl_roff, s.sl_x_nodes = sl["m"], sl["roff"], sl["x_nodes"]
         return s
 
     def to_scipy(self):
@@ -497,6 +542,9 @@ class FreeMap:
 # --------------------------------------------------------------------------------------------
 # solvers
 # --------------------------------------------------------------------------------------------
+SL_MIN_ROWS = 16384       # systems up to this size run in the single-CTA solver
+
+
 def pcg_jacobi(A: DeviceCSR, b, x0=None, rtol=1e-8, maxit=None, check_every=50, raise_on_fail=True):
     """Jacobi-PCG on the device.  Returns (x, info) with info = dict(iterations, relres, bnorm)."""
     torch = _capi.torch_cuda()
@@ -505,6 +553,8 @@ def pcg_jacobi(A: DeviceCSR, b, x0=None, rtol=1e-8, maxit=None, check_every=50, 
     x = torch.zeros(n, dtype=torch.float64, device="cuda") if x0 is None else x0.clone()
     if maxit is None:
         maxit = 10 * n + 100
+    if n > SL_MIN_ROWS:
+        A.sym_lattice()           # half the SpMV traffic when A is a symmetric lattice matrix (same SpMV results bit for bit)
     s = A.struct()
     sz = C.c_size_t(0)
     call("psfem_pcg_workspace", n, s.n_blocks, C.byref(sz))

@@ -344,6 +344,8 @@ class StripProblem:
         rp = self.K_ext_red.row_ptr[lo:hi + 1]
         self.K_red = DeviceCSR(hi - lo, self.n_ext_free, rp, self.K_ext_red.col_idx, self.K_ext_red.vals, nnz=None)
         self.K_red.nnz = int((rp[-1] - rp[0]).item())
+        # symmetric-lattice storage of the owned rows (+ the column before them): half the SpMV traffic, same bits
+        self.sym_lattice = (lo % 2 == 0) and self.K_red.sym_lattice(row_node_offset=lo // 2)
         self.A = self.K_red.struct()
         nb = self.K_red.plan()[1]
         # load: edgeForces(F,[0,-1e6],'right',l,N,M): f*l/(m-1) on every node of the right edge (global column n-1)

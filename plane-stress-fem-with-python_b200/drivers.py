@@ -47,6 +47,7 @@ def _pcg_masked(Kd: DeviceCSR, fm: FreeMap, F_dev, rtol, maxit, check_every):
     x = torch.zeros(n, dtype=torch.float64, device="cuda")
     if maxit is None:
         maxit = 10 * n + 100
+    Kd.sym_lattice()              # the unreduced matrix of a Polygones.mesh mesh is a symmetric lattice matrix
     s = Kd.struct()
     sz = C.c_size_t(0)
     call("psfem_pcg_workspace", n, s.n_blocks, C.byref(sz))

@@ -32,6 +32,7 @@ def main():
         prob = StripProblem(rank=rank, world=world, transport=transport, **kw).setup()
         assert prob.transport == transport, f"transport {transport} not available: fell back to {prob.transport}"
         assert (prob.fabric is not None) == (transport == "peer")
+        assert prob.sym_lattice or os.environ.get("PSFEM_NO_SYMLATTICE")   # the strips run the symmetric-lattice SpMV
         if transport == "peer":                                    # assembled + reduced rows this rank owns
             rp = prob.K_red.row_ptr.cpu().numpy().astype(np.int64)
             res["K_rows"] = (rp - rp[0], prob.K_red.vals[int(rp[0]):int(rp[-1])].cpu().numpy().copy(),
