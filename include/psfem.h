@@ -342,14 +342,15 @@ int psfem_multi_dot(int64_t m, int64_t n, const double *d_V, const double *d_w, 
 int psfem_multi_axpy(int64_t m, int64_t n, const double *d_V, const double *d_c, double *d_w, void *stream);
 
 /* ---- Newmark-beta as implemented by main.py:264-332 (NOT the textbook scheme) -------------
- * Runs steps 1..n_steps-1 on the reduced system K (vals = K), d_M_vals, d_Keff_vals on one pattern.
+ * Runs steps 1..n_steps-1 on the reduced system: K, M and Keff = K + M/(beta dt^2) are three operands on ONE
+ * pattern (same row_ptr / col_idx / plans, their own vals and, optionally, their own symmetric-lattice storage).
  * Load of step i: d_fshape * h_fscale[i] (main.py:226-251 is a fixed nodal pattern times a ramp).
  * d_U, d_V, d_A: column c (n doubles each) holds step c*store_every; any may be NULL.
  * d_energy: n_steps x 3 (kinetic, potential, total; main.py:377-385) or NULL.
  * Solves: Jacobi-PCG to rtol, warm-started from the previous acceleration.
  * h_info: [0]=total PCG iterations, [1]=max relres, [2]=stabiliser triggers (main.py:324-332). */
 int psfem_newmark_workspace(int64_t n, int64_t n_blocks, size_t *bytes);
-int psfem_newmark_run(const psfem_csr *K, const double *d_M_vals, const double *d_Keff_vals,
+int psfem_newmark_run(const psfem_csr *K, const psfem_csr *M, const psfem_csr *Keff,
                       const double *d_fshape, const double *h_fscale, int64_t n_steps,
                       double dt, double gamma, double beta, double alpha_R, double beta_R,
                       const double *d_a0, int64_t store_every,

@@ -119,7 +119,7 @@ SIGNATURES = {
     "psfem_multi_dot": [_i64, _i64, _ptr, _ptr, _ptr, _ptr],
     "psfem_multi_axpy": [_i64, _i64, _ptr, _ptr, _ptr, _ptr],
     "psfem_newmark_workspace": [_i64, _i64, _psz],
-    "psfem_newmark_run": [_pcsr, _ptr, _ptr, _ptr, _pdbl, _i64, _dbl, _dbl, _dbl, _dbl, _dbl, _ptr, _i64,
+    "psfem_newmark_run": [_pcsr, _pcsr, _pcsr, _ptr, _pdbl, _i64, _dbl, _dbl, _dbl, _dbl, _dbl, _ptr, _i64,
                           _ptr, _ptr, _ptr, _ptr, _dbl, _i64, _pdbl, _ptr, _sz, _ptr],
 }
 

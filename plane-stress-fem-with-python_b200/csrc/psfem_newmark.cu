@@ -147,20 +147,25 @@ extern "C" int psfem_newmark_workspace(int64_t n, int64_t n_blocks, size_t *byte
     return PSFEM_OK;
 }
 
-extern "C" int psfem_newmark_run(const psfem_csr *K, const double *d_M_vals, const double *d_Keff_vals,
+extern "C" int psfem_newmark_run(const psfem_csr *K, const psfem_csr *M, const psfem_csr *Keff_,
                                  const double *d_fshape, const double *h_fscale, int64_t n_steps, double dt, double gamma,
                                  double beta, double alpha_R, double beta_R, const double *d_a0, int64_t store_every,
                                  double *d_U, double *d_V, double *d_A, double *d_energy, double rtol, int64_t maxit,
                                  double *h_info, void *d_ws, size_t ws_bytes, void *stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    PSFEM_REQUIRE(K && d_M_vals && d_Keff_vals && d_fshape && h_fscale && h_info, "newmark: null argument");
+    PSFEM_REQUIRE(K && M && Keff_ && M->vals && Keff_->vals && d_fshape && h_fscale && h_info, "newmark: null argument");
+    PSFEM_REQUIRE(M->n_rows == K->n_rows && Keff_->n_rows == K->n_rows && M->nnz == K->nnz && Keff_->nnz == K->nnz,
+                  "newmark: K, M and K_eff must share one sparsity pattern");
     PSFEM_REQUIRE(n_steps >= 1 && store_every >= 1, "newmark: bad step counts");
     const int64_t n = K->n_rows;
     NmWs w = carve_nm(d_ws, n, K->n_blocks);
     PSFEM_REQUIRE(ws_bytes >= w.total, "newmark: workspace too small (%zu < %zu)", ws_bytes, w.total);
-    psfem_csr Keff = *K, Mm = *K;
-    Keff.vals = d_Keff_vals;
-    Mm.vals = d_M_vals;
+    // M and K_eff arrive as operands of their own: same pattern as K, their own values and (optionally) their own
+    // symmetric-lattice storage (psfem_spmv_sl_build), which the SpMV uses when it matches the value array
+    const psfem_csr Keff = *Keff_, Mm = *M;
+    const double *d_M_vals = M->vals;
+    // right-hand side in two passes of the fast single-matrix kernels when both operands have them
+    const bool two_pass = K->sl_vals && K->sl_src_vals == K->vals && Mm.sl_vals && Mm.sl_src_vals == Mm.vals;
     const int g = nm_grid(n);
     PSFEM_CUDA_CHECK(cudaMemsetAsync(w.u, 0, n * sizeof(double), stream));   // main.py:282-283
     PSFEM_CUDA_CHECK(cudaMemsetAsync(w.v, 0, n * sizeof(double), stream));
@@ -185,7 +190,13 @@ extern "C" int psfem_newmark_run(const psfem_csr *K, const double *d_M_vals, con
     for (int64_t i = 1; i < n_steps; ++i) {
         predictor_kernel<<<g, NT, 0, stream>>>(n, w.u, w.v, w.a, dt, c_u_pred, c_v_pred, beta_R, w.up, w.vp, w.w1);
         PSFEM_LAUNCH_CHECK();
-        int rc = psfem_spmv2(K, d_M_vals, w.w1, w.vp, -1.0, -alpha_R, h_fscale[i], d_fshape, w.rhs, stream);  // :310
+        int rc;   // F_i - K (u_p + beta_R v_p) - alpha_R M v_p, main.py:310
+        if (two_pass) {
+            rc = psfem_spmv(K, w.w1, -1.0, h_fscale[i], d_fshape, w.rhs, stream);
+            if (!rc) rc = psfem_spmv(&Mm, w.vp, -alpha_R, 1.0, w.rhs, w.rhs, stream);
+        } else {
+            rc = psfem_spmv2(K, d_M_vals, w.w1, w.vp, -1.0, -alpha_R, h_fscale[i], d_fshape, w.rhs, stream);
+        }
         if (rc) return rc;
         rc = pcg_solve(&Keff, w.rhs, w.a, rtol, maxit, 50, nullptr, w.info, h_acc, w.pcg, w.pcg_bytes, true, stream, false);  // :314
         if (rc && rc != PSFEM_ENOCONV) return rc;

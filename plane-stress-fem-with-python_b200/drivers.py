@@ -14,7 +14,7 @@ import numpy as np
 
 from . import _capi
 from ._capi import call, check, lib, ptr, stream_ptr, workspace
-from .device import Blas, DeviceCSR, FreeMap, constrained_dofs_of, pcg_jacobi, to_host
+from .device import SL_MIN_ROWS, Blas, DeviceCSR, FreeMap, constrained_dofs_of, pcg_jacobi, to_host
 from .Polygones import device_copy
 
 
@@ -141,7 +141,11 @@ def newmark(K, M, bc, f_shape, f_scale, dt=1e-3, gamma=0.5, beta=0.25, alpha_R=0
     V = torch.empty((n_store, n), **f64)
     A = torch.empty((n_store, n), **f64)
     E = torch.empty((n_steps, 3), **f64) if energies else None
-    s = K_red.struct()
+    Keff = K_red.with_vals(Keff_vals)
+    if n > SL_MIN_ROWS:           # large lattice systems: symmetric-lattice storage for the PCG operand and the two of the right-hand side
+        for A_ in (K_red, M_red, Keff):
+            A_.sym_lattice()
+    s, sM, sKeff = K_red.struct(), M_red.struct(), Keff.struct()
     sz = C.c_size_t(0)
     call("psfem_newmark_workspace", n, s.n_blocks, C.byref(sz))
     ws = workspace(sz.value)
@@ -149,7 +153,7 @@ def newmark(K, M, bc, f_shape, f_scale, dt=1e-3, gamma=0.5, beta=0.25, alpha_R=0
     scale_c = f_scale.ctypes.data_as(C.POINTER(C.c_double))
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    rc = lib.psfem_newmark_run(C.byref(s), ptr(M_red.vals), ptr(Keff_vals), ptr(fshape_red), scale_c, n_steps,
+    rc = lib.psfem_newmark_run(C.byref(s), C.byref(sM), C.byref(sKeff), ptr(fshape_red), scale_c, n_steps,
                                float(dt), float(gamma), float(beta), float(alpha_R), float(beta_R), ptr(a0),
                                int(store_every), ptr(U), ptr(V), ptr(A), ptr(E), float(rtol),
                                int(maxit if maxit is not None else 10 * n + 100), info, ptr(ws), sz.value, stream_ptr())
