@@ -1060,9 +1060,12 @@ dist_update_kernel(int64_t n, double *__restrict__ r,
     const double alpha = ps.scal[5 + (int)((ps.seq - 1) & 1)] / ps.scal[4];   // global sums left by the previous kernels' last blocks
     double v[2] = {0, 0};
     for (int64_t i = blockIdx.x * (int64_t)EW_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * EW_THREADS) {
-        const double ri = r[i] - alpha * q[i];
+        // D^-1 = 0 marks a constrained DOF that stayed in the matrix (masked strips: boundary conditions that remove
+        // single DOFs of a node): its residual stays zero, (K p) at that row is not part of the system
+        const double di = dinv[i];
+        const double ri = di == 0.0 ? 0.0 : r[i] - alpha * q[i];
         r[i] = ri;
-        v[0] += ri * (dinv[i] * ri);
+        v[0] += ri * (di * ri);
         v[1] += ri * ri;
     }
     double tot[2];
@@ -1349,7 +1352,9 @@ extern "C" int psfem_pcg_update(int64_t n, double *d_r, const double *d_q,
                                 const double *d_dinv, const double *d_rz, const double *d_pq, double *d_out2,
                                 double *d_partials, uint32_t *d_counter, void *stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    PSFEM_CUDA_CHECK(launch_pdl(pcg_update_kernel, ew_grid(n), EW_THREADS, 0, stream, n, d_r, d_q, d_dinv, d_rz, d_pq, d_out2, d_partials, d_counter, (PcgCtl *)nullptr, 0));
+    // masked = 1: rows with D^-1 = 0 are constrained DOFs kept in the matrix (strip solver on the unreduced matrix);
+    // a free DOF never has D^-1 = 0
+    PSFEM_CUDA_CHECK(launch_pdl(pcg_update_kernel, ew_grid(n), EW_THREADS, 0, stream, n, d_r, d_q, d_dinv, d_rz, d_pq, d_out2, d_partials, d_counter, (PcgCtl *)nullptr, 1));
     PSFEM_LAUNCH_CHECK();
     return PSFEM_OK;
 }

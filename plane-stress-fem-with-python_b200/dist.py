@@ -327,20 +327,35 @@ class StripProblem:
             from .device import constrained_dofs_of
             cd_global = np.asarray(constrained_dofs_of(self.bc), dtype=np.int64)
         self.constrained_global = cd_global
-        self.fm = FreeMap(p.n_ext_dof, p.local_constrained(cd_global))
-        self.K_ext_red = self.fm.reduce_csr(K_ext)
-        free = self.fm.free_dofs                                   # sorted extended-local ids of free DOFs
-
-        def count_free(a, b):
-            lo_ = int(torch.searchsorted(free, torch.tensor([a], dtype=free.dtype, device="cuda")).item())
-            hi_ = int(torch.searchsorted(free, torch.tensor([b], dtype=free.dtype, device="cuda")).item())
-            return hi_ - lo_
-        self.plan = p.halo_plan(count_free=count_free)
-        lo, hi = self.plan["own"]
-        self.n_owned_free = hi - lo
-        self.n_ext_free = self.plan["n_ext_free"]
-        # owned rows of the reduced extended matrix: a row slice (pointer offset), columns stay extended
+        cd_local = p.local_constrained(cd_global)
+        # Boundary conditions that fix single DOFs of a node (rollers) would take the 2x2 node-block structure away
+        # from the reduced matrix (Polygones.py:1003) and with it the fast SpMV kernels: such problems are solved on the
+        # UNREDUCED strip matrix with the constrained DOFs masked (D^-1 = 0, zero load and residual there) -- the
+        # iterates on the free DOFs are those of the reduced system, like psfem_pcg_jacobi_masked on one GPU.
+        whole_nodes = np.array_equal(np.unique(cd_local >> 1).repeat(2) * 2 + np.tile([0, 1], len(np.unique(cd_local >> 1))),
+                                     np.unique(cd_local))
+        import os
+        self.masked = (not whole_nodes) and K_ext.plan()[3] is not None and not os.environ.get("PSFEM_DIST_NO_MASK")
         from .device import DeviceCSR
+        if self.masked:
+            self.fm = None
+            self.K_ext_red = K_ext
+            self.plan = p.halo_plan(count_free=lambda a, b: b - a)
+            self._cd_owned = torch.from_numpy(np.unique(cd_local[(cd_local >= p.own_lo) & (cd_local < p.own_hi)]) - p.own_lo).cuda()
+        else:
+            self.fm = FreeMap(p.n_ext_dof, cd_local)
+            self.K_ext_red = self.fm.reduce_csr(K_ext)
+            free = self.fm.free_dofs                                   # sorted extended-local ids of free DOFs
+
+            def count_free(a, b):
+                lo_ = int(torch.searchsorted(free, torch.tensor([a], dtype=free.dtype, device="cuda")).item())
+                hi_ = int(torch.searchsorted(free, torch.tensor([b], dtype=free.dtype, device="cuda")).item())
+                return hi_ - lo_
+            self.plan = p.halo_plan(count_free=count_free)
+        lo, hi = self.plan["own"]
+        self.n_owned_free = hi - lo                                  # rows of this rank's operand (masked: constrained rows included)
+        self.n_ext_free = self.plan["n_ext_free"]
+        # owned rows of the (reduced) extended matrix: a row slice (pointer offset), columns stay extended
         rp = self.K_ext_red.row_ptr[lo:hi + 1]
         self.K_red = DeviceCSR(hi - lo, self.n_ext_free, rp, self.K_ext_red.col_idx, self.K_ext_red.vals, nnz=None)
         self.K_red.nnz = int((rp[-1] - rp[0]).item())
@@ -359,7 +374,11 @@ class StripProblem:
             a, b = p.dof_shift, p.dof_shift + p.n_ext_dof
             Fh = self.F(a, b) if callable(self.F) else np.asarray(self.F)[a:b]
             F_ext = torch.from_numpy(np.ascontiguousarray(Fh, dtype=np.float64)).cuda()
-        self.b_own = self.fm.reduce_vec(F_ext)[lo:hi].contiguous()
+        if self.masked:
+            self.b_own = F_ext[lo:hi].clone()
+            self.b_own[self._cd_owned] = 0.0                        # a load on a constrained DOF is dropped (Polygones.py:1004)
+        else:
+            self.b_own = self.fm.reduce_vec(F_ext)[lo:hi].contiguous()
         # global sizes
         self.n_dof_global = 2 * p.n * p.m
         cdg = cd_global[(cd_global >= 0) & (cd_global < self.n_dof_global)]
@@ -385,6 +404,8 @@ class StripProblem:
                        rz=torch.zeros(2, **f64), pq=torch.zeros(1, **f64), out2=torch.zeros(2, **f64),
                        out3=torch.zeros(8, **f64), parity=0, iters=0)
         call("psfem_extract_diag", C.byref(self.A), lo, 1, ptr(self.st["dinv"]), stream_ptr())
+        if self.masked:
+            self.st["dinv"][self._cd_owned] = 0.0
         if self.fabric:
             fb, st = self.fabric, self.st
             c = self.ctx = _capi.psfem_dist_ctx()
@@ -463,7 +484,10 @@ class StripProblem:
         torch = _capi.torch_cuda()
         lo, hi = self.plan["own"]
         torch.cuda.synchronize()
-        ids = (self.fm.free_dofs[lo:hi].cpu().numpy().astype(np.int64) + self.part.dof_shift)
+        if self.masked:
+            ids = np.arange(lo, hi, dtype=np.int64) + self.part.dof_shift
+        else:
+            ids = (self.fm.free_dofs[lo:hi].cpu().numpy().astype(np.int64) + self.part.dof_shift)
         vals = self.st["x"].cpu().numpy()
         if self.world == 1:
             parts = [(ids, vals)]
@@ -522,6 +546,6 @@ class StripProblem:
             self.st["p_ext"] = None
             self.fabric.close()
             self.fabric = None
-        for k in ("asm", "K_vals", "K_ext_red", "K_red", "fm", "st", "ops", "A", "b_own", "nodes", "conn", "ctx"):
+        for k in ("asm", "K_vals", "K_ext_red", "K_red", "fm", "st", "ops", "A", "b_own", "nodes", "conn", "ctx", "_cd_owned"):
             if hasattr(self, k):
                 delattr(self, k)

@@ -5,7 +5,8 @@ test_gpu_parity.py::test_fused_strip_pcg_multi_gpu):
   2. both match the single-GPU solver on the owned rows, and the assembled, reduced matrix rows a rank owns are
      the single-GPU rows bit for bit;
   3. a restarted solve (sequence numbers keep growing) converges to the requested residual;
-  4. a problem with general boundary conditions (rollers, a pinned node) and loads gives the single-GPU solution.
+  4. a problem with general boundary conditions (rollers, a pinned node) and loads gives the single-GPU solution
+     (solved on the unreduced strip matrix with the constrained DOFs masked).
 """
 import os
 import sys
@@ -96,7 +97,7 @@ def main():
         assert np.abs(x_own - x1_[off2:off2 + len(x_own)]).max() <= 1e-9 * np.abs(x1_).max(), (et, mt)
         o1.release()
     # 4. general boundary conditions and loads: rollers along the bottom edge (single DOFs constrained: the reduced
-    #    matrix loses its node-block structure, CSR kernels), one pinned node, load on the top edge; the gathered
+    #    matrix would lose its node-block structure, so the strips keep them as masked rows), one pinned node, load on the top edge; the gathered
     #    solution against the single-GPU static_solve of the same problem
     from psfem_b200 import Polygones as P
     nodes, elements = P.mesh(kw["L"], kw["l"], N, M, element_type="quad")
@@ -104,6 +105,8 @@ def main():
     Fg = P.edgeForces(np.zeros(2 * len(nodes)), [2e5, -1e6], "top", kw["L"], N, M)
     prob = StripProblem(rank=rank, world=world, transport="peer", bc=bc, F=lambda a, b: Fg[a:b], **kw).setup()
     assert prob.fabric is not None
+    # single DOFs constrained: solved on the unreduced strip matrix with masked DOFs, on the symmetric-lattice SpMV
+    assert prob.masked and (prob.sym_lattice or os.environ.get("PSFEM_NO_SYMLATTICE"))
     info = prob.solve(rtol=1e-11, maxit=40000, check_every=200)
     assert info["relres"] <= 1e-11, info
     Ug = prob.gather_solution(dst=0)
