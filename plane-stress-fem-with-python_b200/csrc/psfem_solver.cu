@@ -1248,6 +1248,16 @@ extern "C" int psfem_spmv_sl_candidates(const psfem_csr *A, int64_t row_node_off
     // m+1 ids away, so every |distance| > 1 proposes m in {d-1, d, d+1}; psfem_spmv_sl_build verifies a proposal
     const int64_t nodes = A->n_rows / 2;
     int64_t cnt = 0;
+    // most likely first: the nearest neighbour of the next column is exactly m ids ahead; a last column only has
+    // the previous one, whose farthest neighbour is m ids back
+    int64_t fwd = 0, bwd = 0;
+    for (int k = 0; k < deg; ++k) {
+        const int64_t d = (int64_t)pc[k] - row_node_offset;
+        if (d > 1 && (fwd == 0 || d < fwd)) fwd = d;
+        if (d < -1 && -d > bwd) bwd = -d;
+    }
+    const int64_t first = fwd ? fwd : bwd;
+    if (first >= 2 && nodes % first == 0 && row_node_offset % first == 0 && x_nodes % first == 0) h_m[cnt++] = first;
     for (int k = 0; k < deg; ++k) {
         const int64_t d = pc[k] > row_node_offset ? pc[k] - row_node_offset : row_node_offset - pc[k];
         if (d <= 1) continue;
