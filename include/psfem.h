@@ -287,6 +287,10 @@ int psfem_pcg_spmv_dot(const psfem_csr *A, const double *d_p_ext, int64_t x_offs
 int psfem_pcg_update(int64_t n, double *d_r, const double *d_q,
                      const double *d_dinv, const double *d_rz, const double *d_pq, double *d_out2,
                      double *d_partials, uint32_t *d_counter, void *stream);
+/* psfem_pcg_update for systems that keep constrained DOFs as masked rows (d_dinv = 0 there): their residual stays 0 */
+int psfem_pcg_update_masked(int64_t n, double *d_r, const double *d_q,
+                            const double *d_dinv, const double *d_rz, const double *d_pq, double *d_out2,
+                            double *d_partials, uint32_t *d_counter, void *stream);
 int psfem_pcg_pupdate(int64_t n, double *d_p, double *d_x, const double *d_r, const double *d_dinv,
                       const double *d_rz_old, const double *d_rz_new, const double *d_pq, void *stream);
 
@@ -315,6 +319,7 @@ typedef struct psfem_dist_ctx {
     double *out3;                          /* 8 doubles of local device memory: global scalars of the recurrence      */
     double *partials;                      /* max(n_blocks, 1184)*3 doubles                                           */
     uint32_t *counter;                     /* 4 zero-initialised uint32                                               */
+    int32_t masked;                        /* 1: constrained DOFs stay in the strip matrix as masked rows (dinv = 0 there) */
 } psfem_dist_ctx;
 int psfem_peer_board_bytes(size_t *bytes);
 int psfem_peer_alloc(size_t bytes, void **d_ptr, unsigned char *handle64);   /* zero-filled */

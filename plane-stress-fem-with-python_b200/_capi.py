@@ -40,7 +40,7 @@ class psfem_dist_ctx(C.Structure):
                 ("own_lo", C.c_int64), ("n_own", C.c_int64), ("send_left_n", C.c_int64), ("left_dst_off", C.c_int64),
                 ("send_right_n", C.c_int64), ("right_dst_off", C.c_int64),
                 ("x", C.c_void_p), ("r", C.c_void_p), ("q", C.c_void_p), ("dinv", C.c_void_p), ("out3", C.c_void_p),
-                ("partials", C.c_void_p), ("counter", C.c_void_p)]
+                ("partials", C.c_void_p), ("counter", C.c_void_p), ("masked", C.c_int32)]
 
 
 if not os.path.exists(LIB_PATH):
@@ -103,6 +103,7 @@ SIGNATURES = {
     "psfem_pcg_init": [_i64, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr],
     "psfem_pcg_spmv_dot": [_pcsr, _ptr, _i64, _ptr, _ptr, _ptr, _ptr, _ptr],
     "psfem_pcg_update": [_i64, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr],
+    "psfem_pcg_update_masked": [_i64, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr],
     "psfem_pcg_pupdate": [_i64, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr],
     "psfem_peer_board_bytes": [_psz],
     "psfem_peer_alloc": [_sz, C.POINTER(C.c_void_p), _ptr],

@@ -143,16 +143,26 @@ struct PcgCtl {
 // every rank gets the bit-identical sum -- and leaves the result in local memory for the next kernel, so no
 // collective is launched and no consumer block ever polls.  The halo of p is stored straight into the
 // neighbours' extended p vectors by the kernel that computes p.  Sequence numbers only grow (one per PCG
-// iteration / solve start), values are double buffered by sequence parity.
+// iteration / solve start).
+// Scalars travel as 8-byte words {32 data bits | 32-bit sequence number} (two per double), the way NCCL's LL protocol
+// packs a flag with its data: an 8-byte store is single-copy atomic, so a word that carries the expected sequence
+// number also carries its data -- no system-scope fence between "data" and "flag", one NVLink store latency per
+// reduction instead of store + fence round trip + store.  A rank cannot publish sequence s+1 of a stage before every
+// rank has consumed s (it first needs everybody's partial of the stage in between), so one buffer per stage suffices.
 // ---------------------------------------------------------------------------------------------
+#ifndef PSFEM_PEER_LL
+#define PSFEM_PEER_LL 1     // 0: values, one system-scope fence, then sequence numbers (the protocol this replaced; A/B)
+#endif
 struct PeerBoard {
-    double val[2][2][PSFEM_MAX_RANKS][4];           // [0: p.q | 1: {r.z, r.r, b.b}][seq parity][source rank][slot]
-    unsigned long long flag[2][PSFEM_MAX_RANKS];    // seq of the value last published by a rank
+    unsigned long long ll[2][PSFEM_MAX_RANKS][8];   // [0: p.q | 1: {r.z, r.r, b.b}][source rank][2 words per double]
     unsigned long long halo_flag[2];                 // [0] left / [1] right neighbour's halo for iteration seq is in
+    double val[2][2][PSFEM_MAX_RANKS][4];           // PSFEM_PEER_LL=0: [stage][seq parity][source rank][slot]
+    unsigned long long flag[2][PSFEM_MAX_RANKS];    // PSFEM_PEER_LL=0: seq of the value last published by a rank
 };
 struct PeerSync {
     PeerBoard *board[PSFEM_MAX_RANKS];               // board[w] of rank w (peer mapped), board[rank] is local
     int world, rank, has_left, has_right;
+    int halo_in_spmv;                                // the SpMV waits for the halo itself (edge segments of spmv_sl_kernel only)
     unsigned long long seq;
     int *err;                                        // local flag: set when a wait gave up (a peer died), never hangs the GPU
     double *scal;                                    // local scalars: [0] r.z [1] r.r [2] b.b [3] scratch [4] p.q [5+parity] r.z by sequence parity
@@ -169,13 +179,15 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 __device__ __forceinline__ void st_relaxed_sys(unsigned long long *p, unsigned long long v) {
     asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-__device__ __forceinline__ double ld_relaxed_sys(const double *p) {
-    double v;
-    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-// one thread: store my partial(s) into every rank's board, then the sequence number
+// one thread: my partial(s), packed with the sequence number, into every rank's board (no fence: see PeerBoard)
 template <int NV> __device__ __forceinline__ void peer_publish(const PeerSync &ps, int stage, const double (&v)[NV]) {
+    static_assert(NV <= 4, "four doubles per stage");
+#if !PSFEM_PEER_LL
     const int par = (int)(ps.seq & 1);
     for (int w = 0; w < ps.world; ++w) {
 #pragma unroll
@@ -183,26 +195,60 @@ template <int NV> __device__ __forceinline__ void peer_publish(const PeerSync &p
     }
     __threadfence_system();
     for (int w = 0; w < ps.world; ++w) st_relaxed_sys(&ps.board[w]->flag[stage][ps.rank], ps.seq);
+    return;
+#endif
+    const unsigned long long tag = (ps.seq & 0xffffffffull) << 32;
+    for (int w = 0; w < ps.world; ++w) {
+        unsigned long long *dst = ps.board[w]->ll[stage][ps.rank];
+#pragma unroll
+        for (int q = 0; q < NV; ++q) {
+            const unsigned long long bits = (unsigned long long)__double_as_longlong(v[q]);
+            st_relaxed_sys(dst + 2 * q, tag | (bits & 0xffffffffull));
+            st_relaxed_sys(dst + 2 * q + 1, tag | (bits >> 32));
+        }
+    }
 }
 // one thread: wait until every rank's partial of sequence `seq` is on my board, add them in rank order
 template <int NV> __device__ __forceinline__ void peer_wait_sum(const PeerSync &ps, int stage, unsigned long long seq, double (&out)[NV]) {
     PeerBoard *me = ps.board[ps.rank];
     long long spins = 0;
+#if !PSFEM_PEER_LL
     for (int w = 0; w < ps.world; ++w)
         while (ld_acquire_sys(&me->flag[stage][w]) < seq)
             if (++spins > PEER_SPIN_LIMIT) { *ps.err = 1; break; }
 #pragma unroll
     for (int q = 0; q < NV; ++q) {
-        double s = 0.0;
-        for (int w = 0; w < ps.world; ++w) s += ld_relaxed_sys(&me->val[stage][(int)(seq & 1)][w][q]);
-        out[q] = s;
+        double t = 0.0;
+        for (int w = 0; w < ps.world; ++w) t += __longlong_as_double((long long)ld_relaxed_sys_u64(reinterpret_cast<const unsigned long long *>(&me->val[stage][(int)(seq & 1)][w][q])));
+        out[q] = t;
     }
+    return;
+#endif
+    const unsigned long long tag = seq & 0xffffffffull;
+    double s[NV];
+#pragma unroll
+    for (int q = 0; q < NV; ++q) s[q] = 0.0;
+    for (int w = 0; w < ps.world; ++w) {
+#pragma unroll
+        for (int q = 0; q < NV; ++q) {
+            unsigned long long a, b;
+            for (;;) {
+                a = ld_relaxed_sys_u64(&me->ll[stage][w][2 * q]);
+                b = ld_relaxed_sys_u64(&me->ll[stage][w][2 * q + 1]);
+                if ((a >> 32) == tag && (b >> 32) == tag) break;
+                if (++spins > PEER_SPIN_LIMIT) { *ps.err = 1; break; }
+            }
+            s[q] += __longlong_as_double((long long)((a & 0xffffffffull) | (b << 32)));
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < NV; ++q) out[q] = s[q];
 }
-__device__ __forceinline__ void peer_wait_halo(const PeerSync &ps) {   // one thread
+__device__ __forceinline__ void peer_wait_halo(const PeerSync &ps, bool left = true, bool right = true) {   // one thread
     PeerBoard *me = ps.board[ps.rank];
     long long spins = 0;
-    if (ps.has_left) while (ld_acquire_sys(&me->halo_flag[0]) < ps.seq) if (++spins > PEER_SPIN_LIMIT) { *ps.err = 1; break; }
-    if (ps.has_right) while (ld_acquire_sys(&me->halo_flag[1]) < ps.seq) if (++spins > PEER_SPIN_LIMIT) { *ps.err = 1; break; }
+    if (left && ps.has_left) while (ld_acquire_sys(&me->halo_flag[0]) < ps.seq) if (++spins > PEER_SPIN_LIMIT) { *ps.err = 1; break; }
+    if (right && ps.has_right) while (ld_acquire_sys(&me->halo_flag[1]) < ps.seq) if (++spins > PEER_SPIN_LIMIT) { *ps.err = 1; break; }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -655,6 +701,15 @@ bool sl_geometry(const psfem_csr *A, SlGeom *g, int sms) {
     return true;
 }
 
+// does launch_spmv run spmv_sl_kernel for this call?  (also decides where the strip solver waits for its halo)
+bool sl_usable(const psfem_csr *A, bool dual, const double *x1, const double *y, const double *z, const double *xdot, bool dot) {
+    static const bool sl_off = getenv("PSFEM_NO_SYMLATTICE") != nullptr;
+    SlGeom g;
+    return !dual && !sl_off && A->sl_vals && A->sl_src_vals == A->vals && (!dot || xdot == x1 + 2 * A->sl_roff) && y != x1 &&
+           ((reinterpret_cast<uintptr_t>(x1) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(z)) & 15) == 0 &&
+           sl_geometry(A, &g, 148);
+}
+
 int launch_spmv(const psfem_csr *A, const double *v2, const double *x1, const double *x2, double alpha, double beta,
                 double gamma, const double *z, double *y, const double *xdot, double *dot_out, double *partials,
                 unsigned int *counter, const int *done, cudaStream_t stream, const PeerSync *peer = nullptr) {
@@ -666,10 +721,9 @@ int launch_spmv(const psfem_csr *A, const double *v2, const double *x1, const do
     PSFEM_REQUIRE(smem <= 200 * 1024, "spmv: a row with %lld non-zeros does not fit the shared-memory stage", (long long)A->max_row_nnz);
     const bool dual = v2 != nullptr, dot = dot_out != nullptr;
     static const bool nb_off = getenv("PSFEM_NO_NODEBLOCK") != nullptr;   // A/B switch for measurements
-    static const bool sl_off = getenv("PSFEM_NO_SYMLATTICE") != nullptr;
     // symmetric-lattice storage of exactly these values (psfem_spmv_sl_build): half the HBM traffic, same result
-    if (!dual && !sl_off && A->sl_vals && A->sl_src_vals == A->vals && (!dot || xdot == x1 + 2 * A->sl_roff) && y != x1 &&
-        ((reinterpret_cast<uintptr_t>(x1) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(z)) & 15) == 0) {
+    PSFEM_REQUIRE(!ps.halo_in_spmv || sl_usable(A, dual, x1, y, z, xdot, dot), "spmv: the halo wait was delegated to a kernel that does not run");
+    if (sl_usable(A, dual, x1, y, z, xdot, dot)) {
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -802,11 +856,12 @@ pcg_init_kernel(int64_t n, double *__restrict__ r, const double *__restrict__ di
 // r -= alpha q; rz_new = r.(dinv r); rr = r.r      alpha = rz/pq
 // (x += alpha p is done by the p-update kernel, which streams p anyway: 8 B per DOF and iteration less than
 //  reading p here as well)
+template <bool MASKED>
 __global__ void __launch_bounds__(EW_THREADS)
 pcg_update_kernel(int64_t n, double *__restrict__ r,
                   const double *__restrict__ q, const double *__restrict__ dinv, const double *__restrict__ rz_in,
                   const double *__restrict__ pq_in, double *__restrict__ out2, double *__restrict__ partials,
-                  unsigned int *counter, PcgCtl *ctl, int masked) {
+                  unsigned int *counter, PcgCtl *ctl) {
     pdl_enter();
     __shared__ double red[EW_THREADS / 32];
     double rz, pq;
@@ -819,8 +874,11 @@ pcg_update_kernel(int64_t n, double *__restrict__ r,
     const double alpha = rz / pq;
     double v[2] = {0, 0};
     for (int64_t i = blockIdx.x * (int64_t)EW_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * EW_THREADS) {
+        // MASKED: (K p) at a constrained row (D^-1 = 0) is not part of the system.  The mask is applied as a factor (x 1.0
+        // is exact) so that the loads of r and q do not wait for D^-1: written as a select, ptxas predicated them on the
+        // loaded value (dependent loads, +30 % kernel time).  The unmasked instance is the plain recurrence.
         const double di = dinv[i];
-        const double ri = (masked && di == 0.0) ? 0.0 : r[i] - alpha * q[i];   // (K p) at a constrained row is not part of the system
+        const double ri = MASKED ? (r[i] - alpha * q[i]) * (di == 0.0 ? 0.0 : 1.0) : r[i] - alpha * q[i];
         r[i] = ri;
         v[0] += ri * (di * ri);
         v[1] += ri * ri;
@@ -1040,6 +1098,7 @@ dist_init_kernel(int64_t n, const double *__restrict__ b, const double *__restri
     double tot[3];
     if (grid_sum<EW_THREADS, 3, true>(v, partials, counter, red, tot)) {
         peer_publish<3>(ps, 1, tot);
+        __threadfence_system();   // the halo stores of every block (ordered before this thread by the ticket) precede the halo flags
         halo_signal(ps);
         double g[3];
         peer_wait_sum<3>(ps, 1, ps.seq, g);
@@ -1051,6 +1110,7 @@ dist_init_kernel(int64_t n, const double *__restrict__ b, const double *__restri
 }
 
 // alpha = (r.z)/(p.q) from the boards; r -= alpha q; publishes {r.z, r.r}  (x += alpha p: see dist_pupdate_kernel)
+template <bool MASKED>
 __global__ void __launch_bounds__(EW_THREADS)
 dist_update_kernel(int64_t n, double *__restrict__ r,
                    const double *__restrict__ q, const double *__restrict__ dinv, PeerSync ps, double *__restrict__ partials,
@@ -1063,7 +1123,7 @@ dist_update_kernel(int64_t n, double *__restrict__ r,
         // D^-1 = 0 marks a constrained DOF that stayed in the matrix (masked strips: boundary conditions that remove
         // single DOFs of a node): its residual stays zero, (K p) at that row is not part of the system
         const double di = dinv[i];
-        const double ri = di == 0.0 ? 0.0 : r[i] - alpha * q[i];
+        const double ri = MASKED ? (r[i] - alpha * q[i]) * (di == 0.0 ? 0.0 : 1.0) : r[i] - alpha * q[i];   // a factor, not a select: see pcg_update_kernel
         r[i] = ri;
         v[0] += ri * (di * ri);
         v[1] += ri * ri;
@@ -1104,15 +1164,18 @@ dist_pupdate_kernel(int64_t n, double *__restrict__ p, double *__restrict__ x, c
         *counter = 0;
         __threadfence_system();
         halo_signal(ps);
-        PeerSync nxt = ps;
-        nxt.seq = ps.seq + 1;
-        peer_wait_halo(nxt);   // my neighbours' columns for the next SpMV are in before this kernel ends
+        if (!ps.halo_in_spmv) {   // spmv_sl_kernel waits itself, in the two column segments that read the halo
+            PeerSync nxt = ps;
+            nxt.seq = ps.seq + 1;
+            peer_wait_halo(nxt);   // my neighbours' columns for the next SpMV are in before this kernel ends
+        }
     }
 }
 
-PeerSync make_peer(const psfem_dist_ctx *c, unsigned long long seq) {
+PeerSync make_peer(const psfem_dist_ctx *c, unsigned long long seq, bool halo_in_spmv = false) {
     PeerSync ps;
     memset(&ps, 0, sizeof(ps));
+    ps.halo_in_spmv = halo_in_spmv ? 1 : 0;
     for (int w = 0; w < c->world && w < PSFEM_MAX_RANKS; ++w) ps.board[w] = static_cast<PeerBoard *>(c->board[w]);
     ps.world = c->world; ps.rank = c->rank; ps.has_left = c->has_left; ps.has_right = c->has_right;
     ps.seq = seq;
@@ -1362,9 +1425,17 @@ extern "C" int psfem_pcg_update(int64_t n, double *d_r, const double *d_q,
                                 const double *d_dinv, const double *d_rz, const double *d_pq, double *d_out2,
                                 double *d_partials, uint32_t *d_counter, void *stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    // masked = 1: rows with D^-1 = 0 are constrained DOFs kept in the matrix (strip solver on the unreduced matrix);
-    // a free DOF never has D^-1 = 0
-    PSFEM_CUDA_CHECK(launch_pdl(pcg_update_kernel, ew_grid(n), EW_THREADS, 0, stream, n, d_r, d_q, d_dinv, d_rz, d_pq, d_out2, d_partials, d_counter, (PcgCtl *)nullptr, 1));
+    PSFEM_CUDA_CHECK(launch_pdl(pcg_update_kernel<false>, ew_grid(n), EW_THREADS, 0, stream, n, d_r, d_q, d_dinv, d_rz, d_pq, d_out2, d_partials, d_counter, (PcgCtl *)nullptr));
+    PSFEM_LAUNCH_CHECK();
+    return PSFEM_OK;
+}
+
+// the same step for systems that keep constrained DOFs as masked rows (D^-1 = 0 there): their residual stays zero
+extern "C" int psfem_pcg_update_masked(int64_t n, double *d_r, const double *d_q,
+                                       const double *d_dinv, const double *d_rz, const double *d_pq, double *d_out2,
+                                       double *d_partials, uint32_t *d_counter, void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    PSFEM_CUDA_CHECK(launch_pdl(pcg_update_kernel<true>, ew_grid(n), EW_THREADS, 0, stream, n, d_r, d_q, d_dinv, d_rz, d_pq, d_out2, d_partials, d_counter, (PcgCtl *)nullptr));
     PSFEM_LAUNCH_CHECK();
     return PSFEM_OK;
 }
@@ -1444,14 +1515,23 @@ extern "C" int psfem_dist_pcg_iterations(const psfem_csr *A, const psfem_dist_ct
     if (int rc = dist_check(c)) return rc;
     PSFEM_REQUIRE(A && A->n_rows == c->n_own && seq_first >= 2, "dist_pcg_iterations: bad arguments");
     double *p_own = c->p_ext + c->own_lo;
+    // with the symmetric-lattice SpMV only its first / last column segment read the halo columns: those warps wait for
+    // the neighbours' flags themselves and the p-update kernel ends without waiting (one cross-GPU wait less on the
+    // critical path of an iteration); the other SpMV kernels keep the wait at the end of the p-update
+    static const bool halo_late_off = getenv("PSFEM_DIST_HALO_EARLY") != nullptr;   // A/B switch
+    const bool halo_in_spmv = !halo_late_off && sl_usable(A, false, c->p_ext, c->q, nullptr, p_own, true);
     for (int64_t j = 0; j < k; ++j) {
-        const PeerSync ps = make_peer(c, seq_first + (uint64_t)j);
+        const PeerSync ps = make_peer(c, seq_first + (uint64_t)j, halo_in_spmv);
         // q = A p_ext (waits for the neighbours' halo), p.q partial -> all boards
         int rc = launch_spmv(A, nullptr, c->p_ext, nullptr, 1.0, 0.0, 0.0, nullptr, c->q, p_own, c->out3 + 3 /* local p.q, unused */, c->partials,
                              c->counter, nullptr, stream, &ps);
         if (rc) return rc;
-        PSFEM_CUDA_CHECK(launch_pdl(dist_update_kernel, ew_grid(c->n_own), EW_THREADS, 0, stream, c->n_own, c->r, (const double *)c->q, (const double *)c->dinv, ps, c->partials,
-                                    (unsigned int *)(c->counter + 1)));
+        if (c->masked)
+            PSFEM_CUDA_CHECK(launch_pdl(dist_update_kernel<true>, ew_grid(c->n_own), EW_THREADS, 0, stream, c->n_own, c->r, (const double *)c->q, (const double *)c->dinv, ps, c->partials,
+                                        (unsigned int *)(c->counter + 1)));
+        else
+            PSFEM_CUDA_CHECK(launch_pdl(dist_update_kernel<false>, ew_grid(c->n_own), EW_THREADS, 0, stream, c->n_own, c->r, (const double *)c->q, (const double *)c->dinv, ps, c->partials,
+                                        (unsigned int *)(c->counter + 1)));
         PSFEM_CUDA_CHECK(launch_pdl(dist_pupdate_kernel, ew_grid(c->n_own), EW_THREADS, 0, stream, c->n_own, p_own, c->x, (const double *)c->r, (const double *)c->dinv, make_halo(c), ps,
                                     (unsigned int *)(c->counter + 2)));
     }
@@ -1475,7 +1555,8 @@ extern "C" int psfem_dist_pcg_profile(const psfem_csr *A, const psfem_dist_ctx *
         int rc = launch_spmv(A, nullptr, c->p_ext, nullptr, 1.0, 0.0, 0.0, nullptr, c->q, p_own, c->out3 + 3, c->partials, c->counter, nullptr, stream, &ps);
         if (rc) return rc;
         cudaEventRecord(ev[3 * j + 1], stream);
-        dist_update_kernel<<<ew_grid(c->n_own), EW_THREADS, 0, stream>>>(c->n_own, c->r, c->q, c->dinv, ps, c->partials, c->counter + 1);
+        if (c->masked) dist_update_kernel<true><<<ew_grid(c->n_own), EW_THREADS, 0, stream>>>(c->n_own, c->r, c->q, c->dinv, ps, c->partials, c->counter + 1);
+        else dist_update_kernel<false><<<ew_grid(c->n_own), EW_THREADS, 0, stream>>>(c->n_own, c->r, c->q, c->dinv, ps, c->partials, c->counter + 1);
         cudaEventRecord(ev[3 * j + 2], stream);
         dist_pupdate_kernel<<<ew_grid(c->n_own), EW_THREADS, 0, stream>>>(c->n_own, p_own, c->x, c->r, c->dinv, make_halo(c), ps, c->counter + 2);
         cudaEventRecord(ev[3 * j + 3], stream);
@@ -1560,8 +1641,12 @@ int pcg_solve(const psfem_csr *A, const double *d_b, double *d_x, double rtol, i
         for (int64_t it = 0; it < batch; ++it) {
             rc = launch_spmv(A, nullptr, w.p, nullptr, 1.0, 0.0, 0.0, nullptr, w.q, w.p, &w.ctl->pq, w.partials, w.counter, &w.ctl->done, stream);
             if (rc) return rc;
-            PSFEM_CUDA_CHECK(launch_pdl(pcg_update_kernel, (unsigned)g, EW_THREADS, 0, stream, n, w.r, (const double *)w.q, (const double *)w.dinv, (const double *)nullptr,
-                                        (const double *)nullptr, (double *)nullptr, w.partials, w.counter + 1, w.ctl, masked ? 1 : 0));
+            if (masked)
+                PSFEM_CUDA_CHECK(launch_pdl(pcg_update_kernel<true>, (unsigned)g, EW_THREADS, 0, stream, n, w.r, (const double *)w.q, (const double *)w.dinv, (const double *)nullptr,
+                                            (const double *)nullptr, (double *)nullptr, w.partials, w.counter + 1, w.ctl));
+            else
+                PSFEM_CUDA_CHECK(launch_pdl(pcg_update_kernel<false>, (unsigned)g, EW_THREADS, 0, stream, n, w.r, (const double *)w.q, (const double *)w.dinv, (const double *)nullptr,
+                                            (const double *)nullptr, (double *)nullptr, w.partials, w.counter + 1, w.ctl));
             PSFEM_CUDA_CHECK(launch_pdl(pcg_pupdate_kernel, (unsigned)g, EW_THREADS, 0, stream, n, w.p, d_x, (const double *)w.r, (const double *)w.dinv, (const double *)nullptr,
                                         (const double *)nullptr, (const double *)nullptr, w.ctl, w.counter + 2));
         }

@@ -85,11 +85,22 @@ spmv_sl_kernel(const double *__restrict__ sv, const SlGeom g, const double *__re
         const int sb = g.pre + (int)((long long)(seg + 1) * owned_cols / g.G);
         const size_t mp = (size_t)g.mpad, cstride = (size_t)SL_NC * mp;
         const double2 *__restrict__ x2 = reinterpret_cast<const double2 *>(x);
+        // x through L2 (ld.global.cg): the halo columns of a strip are written by the neighbouring GPUs
         auto xload = [&](int s) -> double2 {   // x of storage column s at this lane's row, zero outside the vector
             const int xc = s + g.xcol0;
-            if (valid && xc < g.xcols) return __ldg(x2 + (size_t)xc * g.m + j);
+            if (valid && xc < g.xcols) return __ldcg(x2 + (size_t)xc * g.m + j);
             return make_double2(0.0, 0.0);
         };
+        if (ps.halo_in_spmv) {
+            // strip of a multi-GPU partition: only the first column segment reads the left halo column (its pre-step)
+            // and only the last one the right halo column; their warps wait for the neighbours' flags here, everybody
+            // else starts at once (dist_pupdate_kernel then ends without waiting)
+            const bool need_l = seg == 0, need_r = seg == g.G - 1;
+            if (need_l || need_r) {
+                if (lane == 0) peer_wait_halo(ps, need_l, need_r);
+                __syncwarp();
+            }
+        }
         auto load_col = [&](int s, double (&F)[SL_NC]) {
             const double *p = sv + (size_t)s * cstride + j;
 #pragma unroll

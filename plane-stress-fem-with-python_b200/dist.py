@@ -249,10 +249,11 @@ class PeerFabric:
 # CUDA backend
 # ------------------------------------------------------------------------------------------------
 class CudaOps:
-    def __init__(self, A_struct, n_own, n_blocks):
+    def __init__(self, A_struct, n_own, n_blocks, masked=False):
         torch = _capi.torch_cuda()
         self.A = A_struct
         self.n = n_own
+        self._update = "psfem_pcg_update_masked" if masked else "psfem_pcg_update"
         npart = max(n_blocks, 148 * 8) * 3
         self.partials = torch.empty(npart, dtype=torch.float64, device="cuda")
         self.counter = torch.zeros(4, dtype=torch.int32, device="cuda")
@@ -262,7 +263,7 @@ class CudaOps:
              ptr(self.counter), stream_ptr())
 
     def update(self, r, q, dinv, rz, pq, out2):
-        call("psfem_pcg_update", self.n, ptr(r), ptr(q), ptr(dinv), ptr(rz), ptr(pq), ptr(out2),
+        call(self._update, self.n, ptr(r), ptr(q), ptr(dinv), ptr(rz), ptr(pq), ptr(out2),
              ptr(self.partials), C.c_void_p(self.counter.data_ptr() + 4), stream_ptr())
 
     def pupdate(self, p_own, x, r, dinv, rz_old, rz_new, pq):
@@ -387,7 +388,7 @@ class StripProblem:
         self.nel_global = self.N * self.M * per_cell
         self.nel_owned = self.asm.nel
         # PCG state
-        self.ops = CudaOps(self.A, self.n_owned_free, nb)
+        self.ops = CudaOps(self.A, self.n_owned_free, nb, masked=self.masked)
         import torch.distributed as dist
         self.comm = Comm(p, self.plan, dist if self.world > 1 else None)
         n = self.n_owned_free
@@ -420,6 +421,7 @@ class StripProblem:
             c.x, c.r, c.q, c.dinv = st["x"].data_ptr(), st["r"].data_ptr(), st["q"].data_ptr(), st["dinv"].data_ptr()
             c.out3 = st["out3"].data_ptr()
             c.partials, c.counter = self.ops.partials.data_ptr(), self.ops.counter.data_ptr()
+            c.masked = int(self.masked)
         self.start()
         torch.cuda.synchronize()
         return self

@@ -17,6 +17,18 @@ for rep in range(3):
     call("psfem_dist_pcg_profile", C.byref(prob.A), C.byref(prob.ctx), 25, prob.seq + 1, h, stream_ptr())
     prob.seq += 25
     print(f"rank {rank} cells {cells}: spmv+dot {h[0]:.4f} update {h[1]:.4f} pupdate {h[2]:.4f} sum {sum(h):.4f} ms", flush=True)
+# the single-GPU vector kernels on the same buffers, in this multi-GPU process (no peer waits): what the kernels cost alone
+st = prob.st
+lo, hi = prob.plan["own"]
+rz = torch.ones(2, dtype=torch.float64, device="cuda"); pq = torch.ones(1, dtype=torch.float64, device="cuda"); out2 = torch.zeros(2, dtype=torch.float64, device="cuda")
+for name, fn in (("pcg_update (r,q,dinv -> r)", lambda: prob.ops.update(st["r"], st["q"], st["dinv"], rz[0:1], pq, out2)),
+                 ("pcg_pupdate (p,x,r,dinv -> p,x)", lambda: prob.ops.pupdate(st["p_ext"][lo:hi], st["x"], st["r"], st["dinv"], rz[0:1], rz[1:2], pq)),
+                 ("spmv+dot alone", lambda: prob.ops.spmv_dot(st["p_ext"], lo, st["q"], pq))):
+    ts = []
+    for rep in range(12):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
+    print(f"rank {rank} alone {name}: min {min(ts[2:]):.4f} median {sorted(ts[2:])[5]:.4f} ms", flush=True)
 # streaming bandwidth of the peer-visible allocation against ordinary device memory (same kernel, same size)
 from psfem_b200._capi import ptr
 n = prob.n_owned_free
