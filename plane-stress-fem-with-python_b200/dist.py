@@ -96,6 +96,15 @@ class StripPartition:
         return plan
 
 
+def constrains_whole_nodes(constrained_dofs) -> bool:
+    """True when every constrained node has BOTH of its DOFs fixed (clamped edges): the reduced matrix of
+    Polygones.py:1003 then keeps the 2x2 node-block structure.  Rollers and other single-DOF conditions return False:
+    the strip solver keeps those DOFs in the matrix as masked rows instead (StripProblem.setup)."""
+    cd = np.unique(np.asarray(list(constrained_dofs), dtype=np.int64))
+    nodes = np.unique(cd >> 1)
+    return cd.size == 2 * nodes.size
+
+
 # ------------------------------------------------------------------------------------------------
 # rank-local PCG iteration loop (backend-agnostic)
 # ------------------------------------------------------------------------------------------------
@@ -333,10 +342,8 @@ class StripProblem:
         # from the reduced matrix (Polygones.py:1003) and with it the fast SpMV kernels: such problems are solved on the
         # UNREDUCED strip matrix with the constrained DOFs masked (D^-1 = 0, zero load and residual there) -- the
         # iterates on the free DOFs are those of the reduced system, like psfem_pcg_jacobi_masked on one GPU.
-        whole_nodes = np.array_equal(np.unique(cd_local >> 1).repeat(2) * 2 + np.tile([0, 1], len(np.unique(cd_local >> 1))),
-                                     np.unique(cd_local))
         import os
-        self.masked = (not whole_nodes) and K_ext.plan()[3] is not None and not os.environ.get("PSFEM_DIST_NO_MASK")
+        self.masked = (not constrains_whole_nodes(cd_local)) and K_ext.plan()[3] is not None and not os.environ.get("PSFEM_DIST_NO_MASK")
         from .device import DeviceCSR
         if self.masked:
             self.fm = None

@@ -41,6 +41,21 @@ def test_bad_argument_reports_text(psfem):
     assert "bad sizes" in psfem._capi.last_error()
 
 
+def test_symmetric_lattice_storage_size(psfem):
+    """psfem_spmv_sl_size is host arithmetic: 19 doubles per node of every owned lattice column (+ the column before the
+    first owned one when the rows start inside the x vector), node rows padded to a multiple of 4."""
+    import ctypes as C
+    lib = psfem._capi.lib
+    sz = C.c_size_t(0)
+    assert lib.psfem_spmv_sl_size(4096 * 4097, 0, 4097, C.byref(sz)) == 0
+    assert sz.value == 4096 * 19 * 4100 * 8                                   # the 33.6 M-DOF plate, clamped: 2.55 GB
+    assert lib.psfem_spmv_sl_size(10 * 30, 30, 30, C.byref(sz)) == 0            # a strip behind a left halo column
+    assert sz.value == 11 * 19 * 32 * 8
+    for bad in ((10, 0, 3), (12, 2, 3), (12, 0, 1), (0, 0, 4)):                # rows / offset not whole columns, m < 2, empty
+        assert lib.psfem_spmv_sl_size(*bad, C.byref(sz)) == psfem._capi.EINVAL
+    assert "spmv_sl_size" in psfem._capi.last_error()
+
+
 def test_no_cpu_fallback(psfem):
     """Without a CUDA device every compute entry of the facade must raise, not fall back."""
     import pytest

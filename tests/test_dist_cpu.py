@@ -61,7 +61,7 @@ class NumpyOps:
     @staticmethod
     def update(r, q, dinv, rz, pq, out2):
         alpha = rz.numpy()[0] / pq.numpy()[0]
-        r.numpy()[:] -= alpha * q.numpy()
+        r.numpy()[:] = (r.numpy() - alpha * q.numpy()) * (dinv.numpy() != 0.0)   # masked rows (D^-1 = 0) keep a zero residual
         out2.numpy()[0] = r.numpy() @ (dinv.numpy() * r.numpy())
         out2.numpy()[1] = r.numpy() @ r.numpy()
 
@@ -82,7 +82,7 @@ class NumpyOps:
         dst.numpy()[:] = src.numpy()
 
 
-def _worker(rank, world, port, N, M, iters, out_dir):
+def _worker(rank, world, port, N, M, iters, out_dir, rollers=False):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import torch
@@ -101,25 +101,45 @@ def _worker(rank, world, port, N, M, iters, out_dir):
     nodes_s = nodes[part.e0 * m:part.e1 * m]
     conn_s = conn[part.cell0 * M:part.cell1 * M] - part.e0 * m
     K_ext = O.global_stiffness_matrix(nodes_s, conn_s, 210e9, 0.3, 0.1, "quad")
+    from psfem_b200.dist import constrains_whole_nodes
+    if rollers:   # one pinned node + rollers along the bottom edge (u_y = 0): single DOFs of nodes
+        bc = [(0, [0, 0])] + O.boundary("bottom", [None, 0], N, M)[1:]
+        cd_global = np.array(O.constrained_dofs_of(bc))
+        F = O.edge_forces(np.zeros(2 * len(nodes)), [2e5, -1e6], "top", L, N, M)
+    else:
+        cd_global = np.arange(2 * m)
+        F = O.edge_forces(np.zeros(2 * len(nodes)), [0, -1e6], "right", l, N, M)
+    cd_local = part.local_constrained(cd_global)
     mask = np.ones(part.n_ext_dof, bool)
-    mask[part.local_constrained(np.arange(2 * m))] = False
-    free = np.nonzero(mask)[0]
-    K_red = K_ext[free][:, free]
-    plan = part.halo_plan(free_mask_ext=mask)
-    lo, hi = plan["own"]
-    A_own = K_red[lo:hi]
-    F = O.edge_forces(np.zeros(2 * len(nodes)), [0, -1e6], "right", l, N, M)
-    b_own = F[part.dof_shift:part.dof_shift + part.n_ext_dof][free][lo:hi]
+    mask[cd_local] = False
+    masked = not constrains_whole_nodes(cd_local)
+    assert masked == rollers or len(cd_local) == 0
+    F_ext = F[part.dof_shift:part.dof_shift + part.n_ext_dof]
+    if masked:    # StripProblem.setup, masked branch: the unreduced strip matrix, D^-1 = 0 and zero load at constrained DOFs
+        plan = part.halo_plan(count_free=lambda a, b: b - a)
+        lo, hi = plan["own"]
+        assert (lo, hi) == (part.own_lo, part.own_hi)
+        A_own = K_ext[lo:hi]
+        b_own = np.where(mask[lo:hi], F_ext[lo:hi], 0.0)
+        dinv = np.where(mask[lo:hi], 1.0 / A_own[:, lo:hi].diagonal(), 0.0)
+    else:
+        free = np.nonzero(mask)[0]
+        K_red = K_ext[free][:, free]
+        plan = part.halo_plan(free_mask_ext=mask)
+        lo, hi = plan["own"]
+        A_own = K_red[lo:hi]
+        b_own = F_ext[free][lo:hi]
+        dinv = 1.0 / A_own[:, lo:hi].diagonal()
     f64 = torch.float64
     st = dict(x=torch.zeros(hi - lo, dtype=f64), r=torch.from_numpy(b_own.copy()), q=torch.zeros(hi - lo, dtype=f64),
-              dinv=torch.from_numpy(1.0 / A_own[:, lo:hi].diagonal()), p_ext=torch.zeros(plan["n_ext_free"], dtype=f64),
+              dinv=torch.from_numpy(dinv), p_ext=torch.zeros(plan["n_ext_free"], dtype=f64),
               rz=torch.zeros(2, dtype=f64), pq=torch.zeros(1, dtype=f64), out2=torch.zeros(2, dtype=f64),
               out3=torch.zeros(3, dtype=f64), parity=0, iters=0)
     ops = NumpyOps(A_own)
     comm = Comm(part, plan, dist)
     pcg_start(ops, comm, st, torch.from_numpy(b_own.copy()))
     pcg_iterations(ops, comm, st, iters)
-    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), x=st["x"].numpy(), rr=st["out2"].numpy()[1],
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), x=st["x"].numpy(), rr=st["out2"].numpy()[1], free=mask[part.own_lo:part.own_hi],
              rows=A_own.toarray() if A_own.shape[0] * A_own.shape[1] < 4e6 else np.zeros(1), lo=lo, hi=hi)
     dist.barrier()
     dist.destroy_process_group()
@@ -153,3 +173,29 @@ def test_strip_pcg_over_gloo_matches_single_process(tmp_path, psfem, world):
         col0 = row0 - int(d["lo"])
         assert np.array_equal(rows, Kd[row0:row0 + nr, col0:col0 + rows.shape[1]])
         row0 += nr
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_masked_strip_pcg_over_gloo_matches_reduced_system(tmp_path, psfem, world):
+    """Boundary conditions that fix single DOFs of a node (rollers): the strips keep those DOFs as masked rows of the
+    unreduced matrix (D^-1 = 0, zero load and residual).  The iterates on the free DOFs are those of the reduced system
+    of Polygones.py:1003 -- same recurrence, same number of iterations, zeros at the constrained DOFs."""
+    import torch.multiprocessing as mp
+    import psfem_oracle as O
+    from psfem_b200.dist import constrains_whole_nodes
+    assert constrains_whole_nodes([0, 1, 8, 9, 9, 8]) and constrains_whole_nodes([]) and not constrains_whole_nodes([0, 1, 9])
+    N, M, iters = 12, 5, 40
+    port = 31500 + os.getpid() % 2000 + world
+    mp.spawn(_worker, args=(world, port, N, M, iters, str(tmp_path), True), nprocs=world, join=True)
+    nodes, conn = O.mesh(0.001 * N, 0.001 * M, N, M, element_type="quad")
+    K = O.global_stiffness_matrix(nodes, conn, 210e9, 0.3, 0.1, "quad")
+    bc = [(0, [0, 0])] + O.boundary("bottom", [None, 0], N, M)[1:]
+    F = O.edge_forces(np.zeros(K.shape[0]), [2e5, -1e6], "top", 0.001 * N, N, M)
+    K_red, F_red, _ = O.apply_boundary_conditions(K, F, bc)
+    x_ref, it, rel = O.jacobi_pcg(K_red, F_red, rtol=0.0, maxit=iters)
+    xs = [np.load(tmp_path / f"rank{r}.npz") for r in range(world)]
+    x = np.concatenate([d["x"] for d in xs])
+    free = np.concatenate([d["free"] for d in xs])
+    assert x.shape[0] == K.shape[0] and free.sum() == x_ref.shape[0]
+    assert np.all(x[~free] == 0.0)
+    assert np.abs(x[free] - x_ref).max() <= 1e-7 * np.abs(x_ref).max()
