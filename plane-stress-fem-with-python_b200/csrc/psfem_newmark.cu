@@ -7,6 +7,7 @@
 //   F_i - K (u_p + beta_R v_p) - alpha_R M v_p,
 // a Jacobi-PCG solve warm-started from the previous acceleration (replaces lu_solve :314), corrector
 // kernel with the stabiliser's reductions, store kernel.  Energies (:377-385) are two SpMV+dot.
+#include <cstdlib>
 #include "psfem_common.cuh"
 
 namespace psfem {
@@ -112,8 +113,197 @@ __global__ void energy_finish_kernel(int64_t n_steps, double *__restrict__ e) {
     e[3 * i] = kin; e[3 * i + 1] = pot; e[3 * i + 2] = kin + pot;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Small systems (the reference's own Newmark cases: main.py runs 10 001 steps on a few hundred DOFs): the WHOLE time
+// loop in one persistent single-CTA kernel.  K_eff = K + M/(beta dt^2) is banded (node id = column*m + row); its
+// Cholesky factor L is computed once per launch in shared memory (band storage Lb[i][k] = L[i][i-k], k = 0..hb) and
+// every step solves K_eff x = rhs by a forward and a backward substitution of warp 0 -- the direct solve main.py itself
+// does with lu_factor / lu_solve (:295, :314), instead of a PCG solve to 1e-13 per step (1.4 ms per step for the 410
+// DOFs of BASELINE config 2; here about 0.1 ms).  Predictor, right-hand side, corrector, stabiliser, stores and the
+// two energy products of a step run in the same kernel between block barriers; no launch per step.
+// ---------------------------------------------------------------------------------------------
+constexpr int NB_T = 1024;          // threads of the single CTA
+constexpr int NB_MAX_HB = 32;       // sub-diagonals of the band (one warp lane per term of a substitution row)
+constexpr int NB_CHUNK = 2048;      // time steps per launch (their load factors travel through the work space)
+constexpr size_t NB_SMEM_MAX = 200 * 1024;
+
+struct NbArgs {
+    int n, hb;
+    const int32_t *row_ptr, *col_idx;
+    const double *K, *M, *Keff, *fshape, *fs;   // fs: load factors of this launch's steps
+    long long step0, nsteps, store_every;
+    double dt, c_u_pred, c_v_pred, c_v_corr, c_u_corr, alpha_R, beta_R;
+    double *u, *v, *a, *up, *vp, *w1;
+    NmCtl *ctl;
+    double *U, *V, *A, *energy;
+    double *info;                                // [4] = 1: factorisation failed (not positive definite), nothing was done
+};
+
+__global__ void band_width_kernel(int n, const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col_idx, int *__restrict__ out) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    int hb = 0;
+    for (int k = row_ptr[r]; k < row_ptr[r + 1]; ++k) hb = max(hb, abs(r - col_idx[k]));
+    atomicMax(out, hb);
+}
+
+__global__ void __launch_bounds__(NB_T)
+newmark_band_kernel(const NbArgs g) {
+    extern __shared__ double sm[];
+    __shared__ double red[NB_T / 32];
+    __shared__ double bcast[4];
+    __shared__ int fail;
+    const int n = g.n, hb = g.hb, w = hb + 1, t = threadIdx.x, lane = t & 31;
+    double *Lb = sm;                      // n * (hb+1)
+    double *invd = Lb + (size_t)n * w;    // n
+    double *ys = invd + n;                // n: right-hand side / solution of the current step
+    // ---- band of K_eff (lower triangle) ----
+    for (int i = t; i < n * w; i += NB_T) Lb[i] = 0.0;
+    if (t == 0) fail = 0;
+    __syncthreads();
+    for (int r = t; r < n; r += NB_T)
+        for (int k = g.row_ptr[r]; k < g.row_ptr[r + 1]; ++k) {
+            const int c = g.col_idx[k];
+            if (c <= r) Lb[(size_t)r * w + (r - c)] = g.Keff[k];
+        }
+    __syncthreads();
+    // ---- right-looking banded Cholesky: column j, scale, rank-1 update of the trailing (hb x hb) triangle ----
+    for (int j = 0; j < n; ++j) {
+        const double ajj = Lb[(size_t)j * w];
+        if (!(ajj > 0.0)) { if (t == 0) fail = 1; }
+        __syncthreads();
+        if (fail) break;
+        const double d = sqrt(ajj), id = 1.0 / d;
+        const int na = min(hb, n - 1 - j);           // rows below the diagonal in this column
+        if (t < na) Lb[(size_t)(j + 1 + t) * w + (t + 1)] *= id;
+        if (t == NB_T - 1) { Lb[(size_t)j * w] = d; invd[j] = id; }
+        __syncthreads();
+        // pairs (a, b), 1 <= b <= a <= na:  A[j+a][j+b] -= L[j+a][j] * L[j+b][j]
+        for (int q = t; q < na * (na + 1) / 2; q += NB_T) {
+            int a = (int)((sqrt(8.0 * q + 1.0) - 1.0) * 0.5);
+            while (a * (a + 1) / 2 > q) --a;
+            while ((a + 1) * (a + 2) / 2 <= q) ++a;
+            const int b = q - a * (a + 1) / 2;       // 0 <= b <= a
+            const int ra = j + 1 + a, rb = j + 1 + b;
+            Lb[(size_t)ra * w + (a - b)] -= Lb[(size_t)ra * w + (a + 1)] * Lb[(size_t)rb * w + (b + 1)];
+        }
+        __syncthreads();
+    }
+    if (fail) { if (t == 0) g.info[4] = 1.0; return; }
+    auto bsum = [&](double x) -> double {          // block sum, broadcast to every thread
+        const double s = block_sum<NB_T>(x, red);
+        if (t == 0) bcast[0] = s;
+        __syncthreads();
+        const double o = bcast[0];
+        __syncthreads();
+        return o;
+    };
+    for (long long sidx = 0; sidx < g.nsteps; ++sidx) {
+        const long long step = g.step0 + sidx;
+        const double fsc = g.fs[sidx];
+        // predictor (main.py:306-307)
+        for (int i = t; i < n; i += NB_T) {
+            const double ai = g.a[i], vi = g.v[i];
+            const double upi = g.u[i] + g.dt * vi + g.c_u_pred * ai;
+            const double vpi = vi + g.c_v_pred * ai;
+            g.up[i] = upi; g.vp[i] = vpi; g.w1[i] = upi + g.beta_R * vpi;
+        }
+        __syncthreads();
+        // right-hand side F_i - K (u_p + beta_R v_p) - alpha_R M v_p (main.py:310)
+        for (int r = t; r < n; r += NB_T) {
+            double s1 = 0.0, s2 = 0.0;
+            for (int k = g.row_ptr[r]; k < g.row_ptr[r + 1]; ++k) {
+                const int c = g.col_idx[k];
+                s1 += g.K[k] * g.w1[c];
+                s2 += g.M[k] * g.vp[c];
+            }
+            ys[r] = (fsc * g.fshape[r] - s1) - g.alpha_R * s2;
+        }
+        __syncthreads();
+        // K_eff a = rhs: L y = rhs, L^T a = y (warp 0; lane k carries term k of the row)
+        if (t < 32) {
+            for (int i = 0; i < n; ++i) {
+                double term = 0.0;
+                if (lane < hb && i - 1 - lane >= 0) term = Lb[(size_t)i * w + (lane + 1)] * ys[i - 1 - lane];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) term += __shfl_xor_sync(0xffffffffu, term, o);
+                if (lane == 0) ys[i] = (ys[i] - term) * invd[i];
+                __syncwarp();
+            }
+            for (int i = n - 1; i >= 0; --i) {
+                double term = 0.0;
+                if (lane < hb && i + 1 + lane < n) term = Lb[(size_t)(i + 1 + lane) * w + (lane + 1)] * ys[i + 1 + lane];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) term += __shfl_xor_sync(0xffffffffu, term, o);
+                if (lane == 0) ys[i] = (ys[i] - term) * invd[i];
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        // corrector (main.py:319-321) + the reductions of the stabiliser test (:324-331)
+        double mx = 0.0, sa = 0.0;
+        for (int i = t; i < n; i += NB_T) {
+            const double ai = ys[i];
+            g.a[i] = ai;
+            const double vi = g.vp[i] + g.c_v_corr * ai;
+            const double ui = g.up[i] + g.c_u_corr * ai;
+            g.v[i] = vi; g.u[i] = ui;
+            mx = fmax(mx, fabs(ui)); sa += fabs(ui);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        __syncthreads();
+        if (lane == 0) red[t >> 5] = mx;
+        __syncthreads();
+        if (t == 0) { for (int q = 1; q < NB_T / 32; ++q) mx = fmax(mx, red[q]); bcast[1] = mx; }
+        __syncthreads();
+        const double gmax = bcast[1];
+        const double gsum = bsum(sa);
+        if (t == 0) {
+            double scale = 1.0;
+            if (step > 10) {
+                double h = 0;
+                for (int k = 0; k < 10; ++k) h += g.ctl->hist[k];
+                const double mean = h / (10.0 * (double)n);  // np.mean(np.abs(U[:, i-10:i]))
+                if (gmax > 100.0 * mean) { scale = 10.0 * mean / gmax; g.ctl->triggers += 1.0; }
+            }
+            g.ctl->scale = scale;
+            g.ctl->hist[step % 10] = gsum * scale;           // column i is stored scaled (:329)
+            bcast[2] = scale;
+        }
+        __syncthreads();
+        const double scale = bcast[2];
+        const bool st = (step % g.store_every) == 0;
+        const long long col = step / g.store_every;
+        for (int i = t; i < n; i += NB_T) {
+            double ui = g.u[i], vi = g.v[i];
+            if (scale != 1.0) { ui *= scale; vi *= scale; g.u[i] = ui; g.v[i] = vi; }
+            if (st && g.U) g.U[col * n + i] = ui;
+            if (st && g.V) g.V[col * n + i] = vi;
+            if (st && g.A) g.A[col * n + i] = ys[i];
+        }
+        __syncthreads();
+        if (g.energy) {   // main.py:383-384: v.(M v), u.(K u); halved and summed by energy_finish_kernel
+            double ek = 0.0, ep = 0.0;
+            for (int r = t; r < n; r += NB_T) {
+                double s1 = 0.0, s2 = 0.0;
+                for (int k = g.row_ptr[r]; k < g.row_ptr[r + 1]; ++k) {
+                    const int c = g.col_idx[k];
+                    s1 += g.M[k] * g.v[c];
+                    s2 += g.K[k] * g.u[c];
+                }
+                ek += g.v[r] * s1; ep += g.u[r] * s2;
+            }
+            const double ekt = bsum(ek), ept = bsum(ep);
+            if (t == 0) { g.energy[3 * step] = ekt; g.energy[3 * step + 1] = ept; }
+        }
+        __syncthreads();
+    }
+}
+
 struct NmWs {
-    double *u, *v, *a, *up, *vp, *w1, *rhs, *tmp, *partials, *info;
+    double *u, *v, *a, *up, *vp, *w1, *rhs, *tmp, *partials, *info, *fs;
     NmCtl *ctl;
     unsigned int *counter;
     void *pcg;
@@ -129,6 +319,7 @@ NmWs carve_nm(void *ws, int64_t n, int64_t n_blocks) {
     int64_t np = n_blocks > 148 * 8 ? n_blocks : 148 * 8;
     w.partials = c.take<double>(2 * np);
     w.info = c.take<double>(8);
+    w.fs = c.take<double>(NB_CHUNK);
     w.ctl = c.take<NmCtl>(1);
     w.counter = c.take<unsigned int>(4);
     psfem_pcg_workspace(n, n_blocks, &w.pcg_bytes);
@@ -187,7 +378,45 @@ extern "C" int psfem_newmark_run(const psfem_csr *K, const psfem_csr *M, const p
     double h_acc[3] = {0, 0, 0};
     const double c_u_pred = (0.5 - beta) * dt * dt, c_v_pred = (1 - gamma) * dt;
     const double c_v_corr = gamma * dt, c_u_corr = beta * dt * dt;
-    for (int64_t i = 1; i < n_steps; ++i) {
+    int64_t first_step = 1;
+    static const bool band_off = getenv("PSFEM_NEWMARK_NO_BAND") != nullptr;   // A/B switch
+    if (n <= 16384 && n_steps > 1 && !band_off) {
+        // small banded system: the whole time loop in newmark_band_kernel (direct solves with the Cholesky factor of K_eff)
+        int *d_hb = reinterpret_cast<int *>(w.counter + 2);
+        band_width_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, stream>>>((int)n, K->row_ptr, K->col_idx, d_hb);
+        PSFEM_LAUNCH_CHECK();
+        int hb = 0;
+        PSFEM_CUDA_CHECK(cudaMemcpyAsync(&hb, d_hb, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        PSFEM_CUDA_CHECK(cudaStreamSynchronize(stream));
+        PSFEM_CUDA_CHECK(cudaMemsetAsync(d_hb, 0, sizeof(int), stream));
+        const size_t smem = ((size_t)n * (hb + 1) + 2 * (size_t)n) * sizeof(double);
+        if (hb <= NB_MAX_HB && smem <= NB_SMEM_MAX && K->row_ptr && Keff.row_ptr == K->row_ptr && Mm.row_ptr == K->row_ptr) {
+            PSFEM_CUDA_CHECK(cudaFuncSetAttribute(newmark_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            NbArgs g;
+            g.n = (int)n; g.hb = hb; g.row_ptr = K->row_ptr; g.col_idx = K->col_idx;
+            g.K = K->vals; g.M = Mm.vals; g.Keff = Keff.vals; g.fshape = d_fshape; g.fs = w.fs;
+            g.store_every = store_every; g.dt = dt; g.c_u_pred = c_u_pred; g.c_v_pred = c_v_pred; g.c_v_corr = c_v_corr;
+            g.c_u_corr = c_u_corr; g.alpha_R = alpha_R; g.beta_R = beta_R;
+            g.u = w.u; g.v = w.v; g.a = w.a; g.up = w.up; g.vp = w.vp; g.w1 = w.w1; g.ctl = w.ctl;
+            g.U = d_U; g.V = d_V; g.A = d_A; g.energy = d_energy; g.info = w.info;
+            bool ok = true;
+            for (int64_t s0 = 1; s0 < n_steps && ok; s0 += NB_CHUNK) {
+                const int64_t cnt = n_steps - s0 < NB_CHUNK ? n_steps - s0 : NB_CHUNK;
+                PSFEM_CUDA_CHECK(cudaMemcpyAsync(w.fs, h_fscale + s0, cnt * sizeof(double), cudaMemcpyHostToDevice, stream));
+                g.step0 = s0; g.nsteps = cnt;
+                newmark_band_kernel<<<1, NB_T, smem, stream>>>(g);
+                PSFEM_LAUNCH_CHECK();
+                if (s0 == 1) {   // the factorisation of the first launch decides: not positive definite -> PCG path below
+                    double flag = 0.0;
+                    PSFEM_CUDA_CHECK(cudaMemcpyAsync(&flag, w.info + 4, sizeof(double), cudaMemcpyDeviceToHost, stream));
+                    PSFEM_CUDA_CHECK(cudaStreamSynchronize(stream));
+                    if (flag != 0.0) { ok = false; PSFEM_CUDA_CHECK(cudaMemsetAsync(w.info + 4, 0, sizeof(double), stream)); }
+                }
+            }
+            if (ok) first_step = n_steps;   // every step done
+        }
+    }
+    for (int64_t i = first_step; i < n_steps; ++i) {
         predictor_kernel<<<g, NT, 0, stream>>>(n, w.u, w.v, w.a, dt, c_u_pred, c_v_pred, beta_R, w.up, w.vp, w.w1);
         PSFEM_LAUNCH_CHECK();
         int rc;   // F_i - K (u_p + beta_R v_p) - alpha_R M v_p, main.py:310
