@@ -18,5 +18,7 @@ from ._capi import ConvergenceError  # noqa: F401
 from .device import (Assembler, DeviceCSR, ElementTable, FreeMap, device_mesh, pcg_jacobi)  # noqa: F401
 from .drivers import modal, newmark, ramp_load, static_solve  # noqa: F401
 from .matio import load_matrix, save_matrix  # noqa: F401
+from .diagnostics import (check_matrix_properties, critical_time_step, estimate_max_eigenvalue,  # noqa: F401
+                          extreme_eigenvalues)
 
 __version__ = "0.1.0"

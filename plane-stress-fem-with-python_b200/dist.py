@@ -450,8 +450,22 @@ class StripProblem:
     # -- timed pieces -----------------------------------------------------------------------------
     def assemble(self):
         self.asm.assemble(self.nodes, E=self.E, nu=self.nu, t=self.t, what=1, K_out=self.K_vals)
+        # masked strips solve on K_vals itself (no reduced copy): a re-assembly changes the operand under its
+        # symmetric-lattice storage, which is rebuilt before the next iteration
+        if getattr(self, "masked", False) and getattr(self, "sym_lattice", False):
+            self._sl_stale = True
+
+    def _refresh_operand(self):
+        if getattr(self, "_sl_stale", False):
+            lo, _ = self.plan["own"]
+            self.K_red._sl = None
+            self.sym_lattice = self.K_red.sym_lattice(row_node_offset=lo // 2)
+            self.A = self.K_red.struct()
+            self.ops.A = self.A
+            self._sl_stale = False
 
     def cg_iterations(self, k):
+        self._refresh_operand()
         if self.fabric:   # three kernels per iteration, no collective launches: scalars and halo go through peer memory
             call("psfem_dist_pcg_iterations", C.byref(self.A), C.byref(self.ctx), int(k), self.seq + 1, stream_ptr())
             self.seq += int(k)
@@ -460,6 +474,7 @@ class StripProblem:
             pcg_iterations(self.ops, self.comm, self.st, k)
 
     def spmv_only(self, k):
+        self._refresh_operand()
         lo, _ = self.plan["own"]
         for _ in range(k):
             self.ops.spmv_dot(self.st["p_ext"], lo, self.st["q"], self.st["pq"])

@@ -119,3 +119,19 @@ def test_t3_host_helpers(psfem):
     assert B.shape == (3, 6) and B[0, 0] == L[0][1] and B[1, 1] == L[0][2] and B[2, 0] == L[0][2] and B[2, 1] == L[0][1]
     assert np.abs(B @ np.array([1, 0, 1, 0, 1, 0.0])).max() < 1e-15                     # a rigid translation has no strain
 
+
+
+def test_sparse_symmetry_check_has_allclose_semantics(psfem):
+    """diagnostics._is_symmetric == np.allclose(A, A.T, rtol=1e-5, atol=1e-8) (main.py:65-66) without densifying."""
+    import scipy.sparse as sparse
+    from psfem_b200.diagnostics import _is_symmetric
+    A = sparse.random(60, 60, 0.1, random_state=1, format="csr")
+    S = (A + A.T).tocsr()
+    cases = [S]
+    for (i, j, d) in ((3, 7, 1e-7), (3, 7, 1e-9), (2, 9, 5.0), (11, 12, -3e-6)):
+        B = S.tolil()
+        B[i, j] = B[i, j] + d
+        cases.append(B.tocsr())
+    for B in cases:
+        D = B.toarray()
+        assert _is_symmetric(B) == np.allclose(D, D.T, rtol=1e-5, atol=1e-8)
