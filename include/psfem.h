@@ -363,6 +363,16 @@ int psfem_newmark_run(const psfem_csr *K, const psfem_csr *M, const psfem_csr *K
                       double rtol, int64_t maxit, double *h_info,
                       void *d_ws, size_t ws_bytes, void *stream);
 
+/* ---- modified explicit Euler as implemented by main.py:334-372 (the `use_newmark = False` branch) ----
+ * u_i = u_{i-1} + dt v_{i-1};  a_i = M^-1 (F_i - K u_i);  v_i = v_{i-1} + dt/2 (a_{i-1} + a_i);  stabiliser with
+ * threshold 10 (main.py:365-370).  Same buffers, outputs and h_info as psfem_newmark_run; the solves are with the mass
+ * matrix (Jacobi-PCG, or the banded Cholesky factor of M for small banded systems).  The reference steps with
+ * times[i] - times[i-1] of a linspace; this entry uses the constant dt. */
+int psfem_explicit_run(const psfem_csr *K, const psfem_csr *M, const double *d_fshape, const double *h_fscale,
+                       int64_t n_steps, double dt, const double *d_a0, int64_t store_every,
+                       double *d_U, double *d_V, double *d_A, double *d_energy,
+                       double rtol, int64_t maxit, double *h_info, void *d_ws, size_t ws_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -551,6 +551,30 @@ def newmark(K_red, M_red, F_red_of_step, n_steps, dt=1e-3, gamma=0.5, beta=0.25,
     return U, V, A
 
 
+def explicit_euler(K_red, M_red, F_red_of_step, n_steps, dt=1e-3):
+    """The modified explicit Euler branch of main.py:334-372 (`use_newmark = False`): a0 = M^-1 (F0 - K u0) (:344);
+    per step u_i = u_{i-1} + dt v_{i-1} (:352), a_i = M^-1 (F_i - K u_i) (:355-359), v_i = v_{i-1} + dt/2 (a_{i-1} + a_i)
+    (:362) and the stabiliser with threshold 10 (:365-370).  Dense solves like the reference; constant dt (the
+    reference takes times[i] - times[i-1] of a linspace)."""
+    Kd = K_red.toarray() if sparse.issparse(K_red) else np.asarray(K_red)
+    Md = M_red.toarray() if sparse.issparse(M_red) else np.asarray(M_red)
+    n = Kd.shape[0]
+    U = np.zeros((n, n_steps))
+    V = np.zeros((n, n_steps))
+    A = np.zeros((n, n_steps))
+    lu = scipy.linalg.lu_factor(Md)
+    A[:, 0] = scipy.linalg.lu_solve(lu, F_red_of_step(0) - Kd @ U[:, 0])
+    for i in range(1, n_steps):
+        U[:, i] = U[:, i - 1] + dt * V[:, i - 1]
+        A[:, i] = scipy.linalg.lu_solve(lu, F_red_of_step(i) - Kd @ U[:, i])
+        V[:, i] = V[:, i - 1] + 0.5 * dt * (A[:, i - 1] + A[:, i])
+        if i > 10 and np.max(np.abs(U[:, i])) > 10 * np.mean(np.abs(U[:, i - 10:i])):
+            s = 10 * np.mean(np.abs(U[:, i - 10:i])) / np.max(np.abs(U[:, i]))
+            U[:, i] *= s
+            V[:, i] *= s
+    return U, V, A
+
+
 def energies(K_red, M_red, U, V):
     """main.py:377-385."""
     kin = 0.5 * np.einsum("it,it->t", V, M_red @ V)

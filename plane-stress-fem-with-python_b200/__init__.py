@@ -16,7 +16,7 @@ from . import _capi  # noqa: F401  (loads the shared library)
 from . import Polygones  # noqa: F401
 from ._capi import ConvergenceError  # noqa: F401
 from .device import (Assembler, DeviceCSR, ElementTable, FreeMap, device_mesh, pcg_jacobi)  # noqa: F401
-from .drivers import modal, newmark, ramp_load, static_solve  # noqa: F401
+from .drivers import explicit_euler, modal, newmark, ramp_load, static_solve  # noqa: F401
 from .matio import load_matrix, save_matrix  # noqa: F401
 from .diagnostics import (check_matrix_properties, critical_time_step, estimate_max_eigenvalue,  # noqa: F401
                           extreme_eigenvalues)

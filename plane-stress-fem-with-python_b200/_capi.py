@@ -122,6 +122,8 @@ SIGNATURES = {
     "psfem_newmark_workspace": [_i64, _i64, _psz],
     "psfem_newmark_run": [_pcsr, _pcsr, _pcsr, _ptr, _pdbl, _i64, _dbl, _dbl, _dbl, _dbl, _dbl, _ptr, _i64,
                           _ptr, _ptr, _ptr, _ptr, _dbl, _i64, _pdbl, _ptr, _sz, _ptr],
+    "psfem_explicit_run": [_pcsr, _pcsr, _ptr, _pdbl, _i64, _dbl, _ptr, _i64, _ptr, _ptr, _ptr, _ptr, _dbl, _i64, _pdbl,
+                           _ptr, _sz, _ptr],
 }
 
 for _name, _args in SIGNATURES.items():

@@ -49,7 +49,7 @@ __global__ void predictor_kernel(int64_t n, const double *__restrict__ u, const 
 __global__ void __launch_bounds__(NT)
 corrector_kernel(int64_t n, const double *__restrict__ up, const double *__restrict__ vp, const double *__restrict__ a,
                  double c_v, double c_u, double *__restrict__ u, double *__restrict__ v, double *__restrict__ partials,
-                 unsigned int *counter, NmCtl *ctl, int64_t step) {
+                 unsigned int *counter, NmCtl *ctl, int64_t step, double thresh) {
     __shared__ double red[NT / 32];
     __shared__ bool is_last;
     double mx = 0, sm = 0;
@@ -85,7 +85,7 @@ corrector_kernel(int64_t n, const double *__restrict__ up, const double *__restr
             double h = 0;
             for (int k = 0; k < 10; ++k) h += ctl->hist[k];
             const double mean = h / (10.0 * (double)n);  // np.mean(np.abs(U[:, i-10:i]))
-            if (gmax > 100.0 * mean) { scale = 10.0 * mean / gmax; ctl->triggers += 1.0; }
+            if (gmax > thresh * mean) { scale = 10.0 * mean / gmax; ctl->triggers += 1.0; }   // 100 in the Newmark loop (:325), 10 in the explicit one (:365)
         }
         ctl->scale = scale;
         ctl->hist[step % 10] = gsum * scale;  // column i is stored scaled (:329)
@@ -133,7 +133,7 @@ struct NbArgs {
     const int32_t *row_ptr, *col_idx;
     const double *K, *M, *Keff, *fshape, *fs;   // fs: load factors of this launch's steps
     long long step0, nsteps, store_every;
-    double dt, c_u_pred, c_v_pred, c_v_corr, c_u_corr, alpha_R, beta_R;
+    double dt, c_u_pred, c_v_pred, c_v_corr, c_u_corr, alpha_R, beta_R, thresh;
     double *u, *v, *a, *up, *vp, *w1;
     NmCtl *ctl;
     double *U, *V, *A, *energy;
@@ -266,7 +266,7 @@ newmark_band_kernel(const NbArgs g) {
                 double h = 0;
                 for (int k = 0; k < 10; ++k) h += g.ctl->hist[k];
                 const double mean = h / (10.0 * (double)n);  // np.mean(np.abs(U[:, i-10:i]))
-                if (gmax > 100.0 * mean) { scale = 10.0 * mean / gmax; g.ctl->triggers += 1.0; }
+                if (gmax > g.thresh * mean) { scale = 10.0 * mean / gmax; g.ctl->triggers += 1.0; }
             }
             g.ctl->scale = scale;
             g.ctl->hist[step % 10] = gsum * scale;           // column i is stored scaled (:329)
@@ -338,12 +338,21 @@ extern "C" int psfem_newmark_workspace(int64_t n, int64_t n_blocks, size_t *byte
     return PSFEM_OK;
 }
 
-extern "C" int psfem_newmark_run(const psfem_csr *K, const psfem_csr *M, const psfem_csr *Keff_,
-                                 const double *d_fshape, const double *h_fscale, int64_t n_steps, double dt, double gamma,
-                                 double beta, double alpha_R, double beta_R, const double *d_a0, int64_t store_every,
-                                 double *d_U, double *d_V, double *d_A, double *d_energy, double rtol, int64_t maxit,
-                                 double *h_info, void *d_ws, size_t ws_bytes, void *stream_) {
+// The time loop shared by the two integrators of main.py.  Per step:
+//   u_p = u + dt v + c_u_pred a,  v_p = v + c_v_pred a,  rhs = F_i - K (u_p + beta_R v_p) - alpha_R M v_p,
+//   a = S^-1 rhs,  v = v_p + c_v_corr a,  u = u_p + c_u_corr a,  stabiliser with threshold `thresh`, stores, energies.
+// Newmark-beta (:304-332): S = K_eff, c_u_pred = (1/2 - beta) dt^2, c_v_pred = (1 - gamma) dt, c_v_corr = gamma dt,
+// c_u_corr = beta dt^2, thresh = 100.  Modified explicit Euler (:346-372): S = M, u_p = u + dt v is the new
+// displacement itself (c_u_pred = c_u_corr = 0), v = v + dt/2 (a_old + a_new) (c_v_pred = c_v_corr = dt/2), no damping,
+// thresh = 10.
+struct LoopConsts { double c_u_pred, c_v_pred, c_v_corr, c_u_corr, alpha_R, beta_R, thresh; };
+
+static int time_loop(const psfem_csr *K, const psfem_csr *M, const psfem_csr *Keff_, const LoopConsts lc,
+                     const double *d_fshape, const double *h_fscale, int64_t n_steps, double dt, const double *d_a0, int64_t store_every,
+                     double *d_U, double *d_V, double *d_A, double *d_energy, double rtol, int64_t maxit,
+                     double *h_info, void *d_ws, size_t ws_bytes, void *stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const double alpha_R = lc.alpha_R, beta_R = lc.beta_R;
     PSFEM_REQUIRE(K && M && Keff_ && M->vals && Keff_->vals && d_fshape && h_fscale && h_info, "newmark: null argument");
     PSFEM_REQUIRE(M->n_rows == K->n_rows && Keff_->n_rows == K->n_rows && M->nnz == K->nnz && Keff_->nnz == K->nnz,
                   "newmark: K, M and K_eff must share one sparsity pattern");
@@ -376,8 +385,7 @@ extern "C" int psfem_newmark_run(const psfem_csr *K, const psfem_csr *M, const p
         if (rc) return rc;
     }
     double h_acc[3] = {0, 0, 0};
-    const double c_u_pred = (0.5 - beta) * dt * dt, c_v_pred = (1 - gamma) * dt;
-    const double c_v_corr = gamma * dt, c_u_corr = beta * dt * dt;
+    const double c_u_pred = lc.c_u_pred, c_v_pred = lc.c_v_pred, c_v_corr = lc.c_v_corr, c_u_corr = lc.c_u_corr;
     int64_t first_step = 1;
     static const bool band_off = getenv("PSFEM_NEWMARK_NO_BAND") != nullptr;   // A/B switch
     if (n <= 16384 && n_steps > 1 && !band_off) {
@@ -396,7 +404,7 @@ extern "C" int psfem_newmark_run(const psfem_csr *K, const psfem_csr *M, const p
             g.n = (int)n; g.hb = hb; g.row_ptr = K->row_ptr; g.col_idx = K->col_idx;
             g.K = K->vals; g.M = Mm.vals; g.Keff = Keff.vals; g.fshape = d_fshape; g.fs = w.fs;
             g.store_every = store_every; g.dt = dt; g.c_u_pred = c_u_pred; g.c_v_pred = c_v_pred; g.c_v_corr = c_v_corr;
-            g.c_u_corr = c_u_corr; g.alpha_R = alpha_R; g.beta_R = beta_R;
+            g.c_u_corr = c_u_corr; g.alpha_R = alpha_R; g.beta_R = beta_R; g.thresh = lc.thresh;
             g.u = w.u; g.v = w.v; g.a = w.a; g.up = w.up; g.vp = w.vp; g.w1 = w.w1; g.ctl = w.ctl;
             g.U = d_U; g.V = d_V; g.A = d_A; g.energy = d_energy; g.info = w.info;
             bool ok = true;
@@ -420,7 +428,9 @@ extern "C" int psfem_newmark_run(const psfem_csr *K, const psfem_csr *M, const p
         predictor_kernel<<<g, NT, 0, stream>>>(n, w.u, w.v, w.a, dt, c_u_pred, c_v_pred, beta_R, w.up, w.vp, w.w1);
         PSFEM_LAUNCH_CHECK();
         int rc;   // F_i - K (u_p + beta_R v_p) - alpha_R M v_p, main.py:310
-        if (two_pass) {
+        if (alpha_R == 0.0) {
+            rc = psfem_spmv(K, w.w1, -1.0, h_fscale[i], d_fshape, w.rhs, stream);
+        } else if (two_pass) {
             rc = psfem_spmv(K, w.w1, -1.0, h_fscale[i], d_fshape, w.rhs, stream);
             if (!rc) rc = psfem_spmv(&Mm, w.vp, -alpha_R, 1.0, w.rhs, w.rhs, stream);
         } else {
@@ -429,7 +439,7 @@ extern "C" int psfem_newmark_run(const psfem_csr *K, const psfem_csr *M, const p
         if (rc) return rc;
         rc = pcg_solve(&Keff, w.rhs, w.a, rtol, maxit, 50, nullptr, w.info, h_acc, w.pcg, w.pcg_bytes, true, stream, false);  // :314
         if (rc && rc != PSFEM_ENOCONV) return rc;
-        corrector_kernel<<<g, NT, 0, stream>>>(n, w.up, w.vp, w.a, c_v_corr, c_u_corr, w.u, w.v, w.partials, w.counter, w.ctl, i);
+        corrector_kernel<<<g, NT, 0, stream>>>(n, w.up, w.vp, w.a, c_v_corr, c_u_corr, w.u, w.v, w.partials, w.counter, w.ctl, i, lc.thresh);
         PSFEM_LAUNCH_CHECK();
         const bool st = (i % store_every) == 0;
         const int64_t col = i / store_every;
@@ -455,4 +465,28 @@ extern "C" int psfem_newmark_run(const psfem_csr *K, const psfem_csr *M, const p
     h_info[0] = hi[0] + h_acc[0]; h_info[1] = hi[1] > h_acc[1] ? hi[1] : h_acc[1]; h_info[2] = hc.triggers;
     if (hi[3] != 0.0 || h_acc[2] != 0.0) { set_error("newmark: a PCG solve did not converge (max relres %.3e)", hi[1]); return PSFEM_ENOCONV; }
     return PSFEM_OK;
+}
+
+extern "C" int psfem_newmark_run(const psfem_csr *K, const psfem_csr *M, const psfem_csr *Keff,
+                                 const double *d_fshape, const double *h_fscale, int64_t n_steps, double dt, double gamma,
+                                 double beta, double alpha_R, double beta_R, const double *d_a0, int64_t store_every,
+                                 double *d_U, double *d_V, double *d_A, double *d_energy, double rtol, int64_t maxit,
+                                 double *h_info, void *d_ws, size_t ws_bytes, void *stream) {
+    LoopConsts lc;
+    lc.c_u_pred = (0.5 - beta) * dt * dt; lc.c_v_pred = (1 - gamma) * dt;
+    lc.c_v_corr = gamma * dt; lc.c_u_corr = beta * dt * dt;
+    lc.alpha_R = alpha_R; lc.beta_R = beta_R; lc.thresh = 100.0;
+    return time_loop(K, M, Keff, lc, d_fshape, h_fscale, n_steps, dt, d_a0, store_every, d_U, d_V, d_A, d_energy, rtol, maxit, h_info,
+                     d_ws, ws_bytes, stream);
+}
+
+extern "C" int psfem_explicit_run(const psfem_csr *K, const psfem_csr *M, const double *d_fshape, const double *h_fscale,
+                                  int64_t n_steps, double dt, const double *d_a0, int64_t store_every, double *d_U, double *d_V,
+                                  double *d_A, double *d_energy, double rtol, int64_t maxit, double *h_info, void *d_ws,
+                                  size_t ws_bytes, void *stream) {
+    LoopConsts lc;
+    lc.c_u_pred = 0.0; lc.c_v_pred = 0.5 * dt; lc.c_v_corr = 0.5 * dt; lc.c_u_corr = 0.0;
+    lc.alpha_R = 0.0; lc.beta_R = 0.0; lc.thresh = 10.0;
+    return time_loop(K, M, M, lc, d_fshape, h_fscale, n_steps, dt, d_a0, store_every, d_U, d_V, d_A, d_energy, rtol, maxit, h_info,
+                     d_ws, ws_bytes, stream);
 }

@@ -169,6 +169,56 @@ def newmark(K, M, bc, f_shape, f_scale, dt=1e-3, gamma=0.5, beta=0.25, alpha_R=0
     return out
 
 
+def explicit_euler(K, M, bc, f_shape, f_scale, dt=1e-3, store_every=1, energies=True, rtol=1e-13, maxit=None):
+    """The modified explicit Euler scheme of main.py:334-372 (its `use_newmark = False` branch), on the device:
+    u_i = u_{i-1} + dt v_{i-1}; a_i = M^-1 (F_i - K u_i); v_i = v_{i-1} + dt/2 (a_{i-1} + a_i); the stabiliser of
+    :365-370 (threshold 10).  Arguments and the returned dict are those of `newmark`; the dense `np.linalg.solve` with M
+    per step (:359) is a Jacobi-PCG solve warm-started from the previous acceleration (small banded systems: the
+    banded Cholesky factor of M inside one persistent kernel).  Constant dt (the reference takes times[i] - times[i-1]
+    of a linspace, equal to dt up to rounding)."""
+    torch = _capi.torch_cuda()
+    _capi.bind_device()
+    constrained = constrained_dofs_of(bc)
+    Kd, Md = device_copy(K), device_copy(M)
+    fm = FreeMap(Kd.n_rows, constrained)
+    K_red = fm.reduce_csr(Kd)
+    M_red = fm.reduce_csr(Md)
+    if M_red.nnz != K_red.nnz:
+        raise ValueError("K and M must share one sparsity pattern (assemble both with this package)")
+    n = K_red.n_rows
+    f_scale = np.ascontiguousarray(f_scale, dtype=np.float64)
+    n_steps = int(f_scale.size)
+    fshape_red = fm.reduce_vec(_to_dev(f_shape))
+    f64 = dict(dtype=torch.float64, device="cuda")
+    f0 = torch.empty(n, **f64)
+    call("psfem_axpby", n, float(f_scale[0]), ptr(fshape_red), 0.0, ptr(None), ptr(f0), stream_ptr())
+    a0, _ = pcg_jacobi(M_red, f0, rtol=rtol, maxit=maxit)            # main.py:344 (u0 = 0)
+    n_store = (n_steps - 1) // store_every + 1
+    U = torch.empty((n_store, n), **f64)
+    V = torch.empty((n_store, n), **f64)
+    A = torch.empty((n_store, n), **f64)
+    En = torch.empty((n_steps, 3), **f64) if energies else None
+    if n > SL_MIN_ROWS:
+        for A_ in (K_red, M_red):
+            A_.sym_lattice()
+    s, sM = K_red.struct(), M_red.struct()
+    sz = C.c_size_t(0)
+    call("psfem_newmark_workspace", n, s.n_blocks, C.byref(sz))
+    ws = workspace(sz.value)
+    info = (C.c_double * 4)()
+    rc = lib.psfem_explicit_run(C.byref(s), C.byref(sM), ptr(fshape_red), f_scale.ctypes.data_as(C.POINTER(C.c_double)), n_steps,
+                                float(dt), ptr(a0), int(store_every), ptr(U), ptr(V), ptr(A), ptr(En), float(rtol),
+                                int(maxit if maxit is not None else 10 * n + 100), info, ptr(ws), sz.value, stream_ptr())
+    check(rc)
+    torch.cuda.current_stream().synchronize()
+    out = dict(U=U.cpu().numpy().T, V=V.cpu().numpy().T, A=A.cpu().numpy().T, constrained_dofs=constrained,
+               info=dict(pcg_iterations=int(info[0]), max_relres=float(info[1]), stabiliser_triggers=int(info[2])))
+    if energies:
+        e = En.cpu().numpy()
+        out.update(kinetic_energy=e[:, 0].copy(), potential_energy=e[:, 1].copy(), total_energy=e[:, 2].copy())
+    return out
+
+
 # ---------------------------------------------------------------------------------------------
 # modal (freeModes.py)
 # ---------------------------------------------------------------------------------------------

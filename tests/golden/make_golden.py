@@ -246,6 +246,22 @@ def newmark_cases(P):
     np.savez_compressed(f"{OUT}/ref_newmark.npz", **out)
 
 
+def explicit_case(P):
+    """main.py with `use_newmark = False` (the modified explicit Euler branch, :334-372; dead in the shipped script).
+    dt = 1e-3 is far above its stability limit: the series explodes by a factor ~370 per step until the stabiliser
+    (:365-370) takes over at step 11, and rounding differences take over the digits after ~45 steps; the first 41
+    columns pin the recurrence and the stabiliser (an independent restatement reproduces them to 1e-14)."""
+    base = dict(L=20, l=2, E=210e9, nu=0.3, pho=7850)
+    cp = dict(base, N=20, G=2, t=0.1, elt="tri", met="coarse")
+    g, K, M = _run_script(P, "main.py", dict(elt="tri", met="coarse", use_newmark=False), cp)
+    n = 41
+    out = dict(ex_U=g["U_reduced"][:, :n], ex_V=g["V_reduced"][:, :n], ex_A=g["A_reduced"][:, :n],
+               ex_constrained=np.array(g["constrained_dofs"]), ex_dt=g["dt"], ex_F=g["ForcesVectors_reduced"][:, :n],
+               ex_kin=g["kinetic_energy"][:n], ex_pot=g["potential_energy"][:n])
+    print("explicit", g["U_reduced"].shape, "max|U[:, :41]|", np.max(np.abs(out["ex_U"])))
+    np.savez_compressed(f"{OUT}/ref_explicit.npz", **out)
+
+
 def modal_cases(P):
     out = {}
     base = dict(L=20, l=2, E=210e9, nu=0.3, pho=7850, t=0.01)
@@ -289,7 +305,7 @@ def body_force_cases(P):
 
 if __name__ == "__main__":
     P = import_reference()
-    what = sys.argv[1:] or ["files", "small", "bc", "static", "newmark", "modal", "body"]
+    what = sys.argv[1:] or ["files", "small", "bc", "static", "newmark", "explicit", "modal", "body"]
     if "files" in what:
         golden_files()
     if "small" in what:
@@ -300,6 +316,8 @@ if __name__ == "__main__":
         static_cases(P)
     if "newmark" in what:
         newmark_cases(P)
+    if "explicit" in what:
+        explicit_case(P)
     if "modal" in what:
         modal_cases(P)
     if "body" in what:
