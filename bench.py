@@ -152,7 +152,10 @@ def reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
-def workload_name(n_gpus, cells, scaling="weak"):
+def workload_name(n_gpus, cells, scaling="weak", total_cols=0):
+    if total_cols:
+        return (f"synthetic {total_cols}x{cells} Q4 strip, left edge clamped, right edge loaded: numeric assembly of K + "
+                f"Jacobi-PCG iterations; split into {n_gpus} strips of ~{total_cols // n_gpus} cell columns")
     if scaling == "strong":
         return (f"synthetic {cells}x{cells} Q4 plate, left edge clamped, right edge loaded: numeric assembly of K + "
                 f"Jacobi-PCG iterations; the plate is split into {n_gpus} strips of ~{cells // n_gpus} cell columns")
@@ -172,6 +175,9 @@ def main():
     ap.add_argument("--cells", type=int, default=4096, help="cells per side of the per-GPU plate")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: `--cells` cell columns PER GPU (default, the driver's contract); strong: the cells x cells plate split over all GPUs")
+    ap.add_argument("--total-cols", type=int, default=0,
+                    help="cell columns of the WHOLE plate, split over all GPUs (rows = --cells): --total-cols 16384 is BASELINE's "
+                         "16384x4096 strip (configs[4]) on any number of GPUs; reported as strong scaling")
     ap.add_argument("--cg-iters", type=int, default=25, help="PCG iterations per step")
     ap.add_argument("--e2e-iters", type=int, default=200, help="PCG iterations of one end-to-end static_solve call")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
@@ -199,7 +205,9 @@ def main():
     hbm_peak, peak_src = peaks()
 
     cells = args.cells
-    cols_total = cells * world if args.scaling == "weak" else cells
+    if args.total_cols:
+        args.scaling = "strong"
+    cols_total = args.total_cols or (cells * world if args.scaling == "weak" else cells)
     prob = StripProblem(L=cols_total * 1e-3, l=cells * 1e-3, N=cols_total, M=cells, rank=rank, world=world,
                         E=E, nu=NU, t=T)
     prob.setup()                       # mesh strip, symbolic pattern, first assembly, BC reduction, load vector
@@ -281,7 +289,7 @@ def main():
         "metric": METRIC, "value": cg_rate, "unit": UNIT, "n_gpus": world, "steps": K_, "warmup": args.warmup,
         "ms_per_step": 1e3 * (t_asm + t_cg) / K_, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(world, cells, args.scaling), "dof": int(prob.n_dof_global), "free_dof": int(n_free_global),
+        "config": {"workload": workload_name(world, cells, args.scaling, args.total_cols), "dof": int(prob.n_dof_global), "free_dof": int(n_free_global),
                    "elements": int(prob.nel_global), "nnz_per_gpu": int(nnz), "cg_iters_per_step": args.cg_iters,
                    "l2": "inputs (>7 GB CSR per GPU) exceed the 126 MB L2; no flush",
                    "parallelism": f"strip{world}", "transport": prob.transport if world > 1 else "single GPU"},
