@@ -1,5 +1,8 @@
 // psfem_solver.cu -- HBM-bound sparse kernels of the static / Newmark / modal drivers.
 //
+//   spmv_sl_kernel   (psfem_spmv_sl.cuh) SpMV (+ fused dot) on symmetric-lattice storage: the matrices of Polygones.mesh
+//                    meshes as 19 doubles per node, marching warps, transposed products as shuffle chains -- half the
+//                    bytes of the node-block kernel, the same bits; the kernel PCG runs on whenever the operand allows
 //   spmv_nb_kernel   SpMV (+ fused dot) on the 2x2 node-block structure of FEM matrices: persistent, one producer warp
 //                    streams 8 B values + one 4-byte node id per block through a TMA-fed shared ring, one DOF row per
 //                    consumer thread, x gathered as double2 -- 9 B per non-zero, the kernel PCG runs on
@@ -12,7 +15,8 @@
 //                    exchange fused in (peer boards over CUDA-IPC memory, see PeerBoard)
 //   pcg_small_kernel whole solve in one single-CTA launch for n <= 16384
 //   BLAS-1 helpers for the Lanczos driver.
-// Every row is summed in column order (scipy's CSR order): the SpMV variants give bit-identical results.
+// Every row is summed in column order (scipy's CSR order): spmv_sl_kernel, spmv_nb_kernel and spmv2_kernel give
+// bit-identical results (fused multiply-adds in that order; the one-CTA-per-block spmv_kernel rounds its products first).
 // The PCG kernels are chained with programmatic dependent launch (pdl_enter / launch_pdl).
 //
 // Replaces: np.linalg.solve / scipy.linalg.solve / lu_factor+lu_solve (Statictest.py:69,
