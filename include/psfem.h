@@ -302,7 +302,9 @@ int psfem_pcg_pupdate(int64_t n, double *d_p, double *d_x, const double *d_r, co
  *   - the SpMV kernel publishes its p.q partial to every board, the update kernel spins on its OWN board, adds the
  *     partials in rank order (bit-identical on every rank) and publishes {r.z, r.r}; the p-update kernel reads them,
  *     computes p and stores the first / last owned node column straight into the neighbours' extended vectors,
- *     then raises their halo flag, which the next SpMV waits for.
+ *     then raises their halo flag, which the next SpMV waits for (inside the two edge column segments of the
+ *     symmetric-lattice kernel; at the end of the p-update kernel for the other SpMV kernels).
+ *   Scalars travel as 8-byte words {32 data bits | 32-bit sequence number}: no fence between data and flag.
  * Sequence numbers only grow: psfem_dist_pcg_start takes seq >= 1, the following iterations seq+1, seq+2, ...
  * (the host keeps the counter; it is never reset while the boards live).  Same recurrence and the same per-rank
  * kernels as psfem_pcg_spmv_dot / _update / _pupdate. */
