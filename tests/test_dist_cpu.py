@@ -82,7 +82,7 @@ class NumpyOps:
         dst.numpy()[:] = src.numpy()
 
 
-def _worker(rank, world, port, N, M, iters, out_dir, rollers=False):
+def _worker(rank, world, port, N, M, iters, out_dir, rollers=False, et="quad"):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import torch
@@ -95,12 +95,13 @@ def _worker(rank, world, port, N, M, iters, out_dir, rollers=False):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     part = StripPartition(N, M, world, rank)
     L, l = 0.001 * N, 0.001 * M
-    nodes, conn = O.mesh(L, l, N, M, element_type="quad")
+    nodes, conn = O.mesh(L, l, N, M, element_type=et)
     m = part.m
+    per_cell = 2 if et == "tri" else 1
     # the strip: nodes of columns [e0,e1), elements of cell columns [cell0,cell1), ids made local
     nodes_s = nodes[part.e0 * m:part.e1 * m]
-    conn_s = conn[part.cell0 * M:part.cell1 * M] - part.e0 * m
-    K_ext = O.global_stiffness_matrix(nodes_s, conn_s, 210e9, 0.3, 0.1, "quad")
+    conn_s = conn[part.cell0 * M * per_cell:part.cell1 * M * per_cell] - part.e0 * m
+    K_ext = O.global_stiffness_matrix(nodes_s, conn_s, 210e9, 0.3, 0.1, et)
     from psfem_b200.dist import constrains_whole_nodes
     if rollers:   # one pinned node + rollers along the bottom edge (u_y = 0): single DOFs of nodes
         bc = [(0, [0, 0])] + O.boundary("bottom", [None, 0], N, M)[1:]
@@ -145,16 +146,16 @@ def _worker(rank, world, port, N, M, iters, out_dir, rollers=False):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_strip_pcg_over_gloo_matches_single_process(tmp_path, psfem, world):
+@pytest.mark.parametrize("world,et", [(2, "quad"), (3, "quad"), (2, "tri")])
+def test_strip_pcg_over_gloo_matches_single_process(tmp_path, psfem, world, et):
     import torch.multiprocessing as mp
     import psfem_oracle as O
     N, M, iters = 12, 5, 40
-    port = 29500 + os.getpid() % 2000 + world
-    mp.spawn(_worker, args=(world, port, N, M, iters, str(tmp_path)), nprocs=world, join=True)
+    port = 29500 + os.getpid() % 2000 + world + (10 if et == "tri" else 0)
+    mp.spawn(_worker, args=(world, port, N, M, iters, str(tmp_path), False, et), nprocs=world, join=True)
     # single-process reference: same recurrence, same number of iterations
-    nodes, conn = O.mesh(0.001 * N, 0.001 * M, N, M, element_type="quad")
-    K = O.global_stiffness_matrix(nodes, conn, 210e9, 0.3, 0.1, "quad")
+    nodes, conn = O.mesh(0.001 * N, 0.001 * M, N, M, element_type=et)
+    K = O.global_stiffness_matrix(nodes, conn, 210e9, 0.3, 0.1, et)
     F = O.edge_forces(np.zeros(K.shape[0]), [0, -1e6], "right", 0.001 * M, N, M)
     K_red, F_red, _ = O.apply_boundary_conditions(K, F, O.boundary("left", [0, 0], N, M))
     x_ref, it, rel = O.jacobi_pcg(K_red, F_red, rtol=0.0, maxit=iters)
