@@ -188,6 +188,13 @@ int psfem_element_matrices(const double *d_nodes, const int32_t *d_conn, int64_t
                            double E, double nu, double rho, double t, int what, double *d_Ke, double *d_Me,
                            void *d_ws, size_t ws_bytes, int64_t *h_bad_element, void *stream);
 
+/* compute_B_matrix_at_point, Polygones.py:657-708: strain-displacement matrix B (3 x 2npe, rows eps_x, eps_y, gamma_xy),
+ * Jacobian J and det J of ONE element (d_conn1: its npe node ids) at the reference point (xi, eta); shape functions of
+ * Polygones.py:441-518 for all four element kinds.  d_out / h_out: 6*npe + 6 doubles = B row-major, J00 J01 J10 J11,
+ * detJ, flag.  Returns PSFEM_EJACOBIAN when |detJ| < 1e-10 (:686-687).  Synchronises. */
+int psfem_b_matrix_at_point(const double *d_nodes, const int32_t *d_conn1, int etype, double xi, double eta,
+                            double *d_out, double *h_out, void *stream);
+
 /* ---- boundary conditions: Polygones.apply_boundary_conditions :989-1006, reduce :898-911 ----
  * psfem_free_map: d_constrained (nc DOF ids, duplicates and out-of-range ids allowed, as the list
  * membership test of :1000 allows them) -> d_new_id[n] (reduced index or -1) and d_free_dofs
@@ -271,6 +278,33 @@ int psfem_pcg_jacobi(const psfem_csr *A, const double *d_b, double *d_x, double 
  * (zeros at constrained DOFs).  For systems above 16384 rows. */
 int psfem_pcg_jacobi_masked(const psfem_csr *A, const double *d_b, double *d_x, const int32_t *d_new_id, double rtol,
                             int64_t maxit, int64_t check_every, double *h_info, void *d_ws, size_t ws_bytes, void *stream);
+
+/* ---- direct static solve of SMALL banded systems + iterative refinement on a compensated residual --------------
+ * The reference's static solves are dense LAPACK LU (np.linalg.solve: TestBeam/Statictest.py:69, StaticTest2.py:71;
+ * scipy.linalg.solve: Beamexemple.py:63; solve_banded: 2Dexemple.py:36).  For systems of up to
+ * psfem_direct_limits() rows / half bandwidth this entry does the same kind of solve on the device: banded Cholesky
+ * (node id = column*m + row makes K banded), then `refine_rounds` rounds of  r = b - K x  (accumulated in
+ * double-double),  K d = r,  x += d.  x ends within a few ulp of the exact solution of the fp64 system, so its distance
+ * to the reference's answer is the reference's own LU rounding error (4.7e-11 on the README cantilever, kappa = 7e7).
+ *   psfem_band_width:   max |row - col| over the pattern (d_ws >= 16 bytes; synchronises)
+ *   psfem_direct_solve: h_info[0] = refinement rounds done, [1] = ||b - K x|| / ||b|| (compensated), [2] = ||b||,
+ *                       [3] = status, [4] = ||last correction|| / ||x||.  Returns PSFEM_ENOCONV when a Cholesky pivot
+ *                       is not positive.  Synchronises.
+ *   psfem_residual_dd:  r = b - A x with the same compensated accumulation for ANY CSR operand: the residual of the
+ *                       PCG-based refinement of systems beyond the band solver's limits. */
+int psfem_band_width(const psfem_csr *A, int64_t *h_half_bandwidth, void *d_ws, size_t ws_bytes, void *stream);
+int psfem_direct_limits(int64_t *max_rows, int64_t *max_half_bandwidth);
+int psfem_direct_workspace(int64_t n, int64_t half_bandwidth, size_t *bytes);
+int psfem_direct_solve(const psfem_csr *A, const double *d_b, double *d_x, int64_t half_bandwidth, int refine_rounds,
+                       double *h_info /* [5] */, void *d_ws, size_t ws_bytes, void *stream);
+int psfem_residual_dd(const psfem_csr *A, const double *d_x, const double *d_b, double *d_r, void *stream);
+
+/* np.allclose(A, A.T, rtol, atol) on CSR -- the symmetry test of main.py:65-66, Beamexemple.py:48, SparseTest.py:37 without
+ * a dense transpose: every stored entry is compared with its mirror entry (0 when not stored).  *h_violations = entries
+ * with |A[r,c] - A[c,r]| > atol + rtol |A[c,r]|, *h_max_abs_diff = largest |A[r,c] - A[c,r]|.  d_ws >= 16 bytes.
+ * Needs sorted column indices.  Synchronises. */
+int psfem_csr_symmetry(const psfem_csr *A, double rtol, double atol, int64_t *h_violations, double *h_max_abs_diff,
+                       void *d_ws, size_t ws_bytes, void *stream);
 
 /* The kernels of one PCG iteration, exposed so the strip-partitioned multi-GPU driver can put its
  * halo exchange and all-reduces between them (scalars stay on the device):

@@ -25,7 +25,8 @@ from ._capi import ETYPE, NPE
 from .device import (Assembler, DeviceCSR, ElementTable, FreeMap, as_element_table, constrained_dofs_of,
                      device_mesh)
 
-__all__ = ["mesh", "global_stiffness_matrix", "global_stiffness_matrix_linear", "get_gauss_points", "global_mass_matrix", "element_stiffness_matrix",
+__all__ = ["shape_functions", "get_shape_derivatives", "create_shape_functions", "compute_B_matrix_at_point",
+           "mesh", "global_stiffness_matrix", "global_stiffness_matrix_linear", "get_gauss_points", "global_mass_matrix", "element_stiffness_matrix",
            "element_mass_matrix", "apply_boundary_conditions", "reduce", "reconstruct_full_vector",
            "reconstruct_full_vectors", "reconstruct_full_matrix", "boundary", "merge_boudary_conditions",
            "edgeForces", "body_forces", "convert_to_banded", "convert_to_banded_optimized", "calculate_bandwidth",
@@ -77,27 +78,68 @@ def _assembler(elements, n_nodes, et) -> tuple[Assembler, ElementTable]:
     return plan, tab
 
 
+class DeviceBackedCSR(sparse.csr_matrix):
+    """The `scipy.sparse.csr_matrix` the assembly functions return: an ordinary CSR matrix for the caller that also
+    remembers its device-resident copy, so that the drivers do not upload 7 GB again.
+
+    The cached copy must never go stale (a penalty boundary condition `K[i, i] = 1e20` after assembly has to reach the
+    solver), so the value array is handed out READ-ONLY and every mutating method of this class (`K[i, j] = v`,
+    `setdiag`, `K *= a`, `K /= a`, `eliminate_zeros`, `sum_duplicates`, `sort_indices`, `prune`, `resize`) first drops
+    the device copy and makes the values writeable again.  A direct write `K.data[k] = v` raises numpy's
+    "assignment destination is read-only" instead of being lost; `K.data.flags.writeable = True` (or assigning a new
+    `K.data`) is seen by `device_copy`, which then uploads the host values."""
+
+    _psfem_dev = None
+    _psfem_key = None
+
+    def _psfem_attach(self, dev):
+        self.data.flags.writeable = False
+        self._psfem_dev = dev
+        self._psfem_key = (self.data.ctypes.data, self.data.size, self.indices.ctypes.data, self.indptr.ctypes.data)
+        return self
+
+    def _psfem_valid(self):
+        return (self._psfem_dev is not None and not self.data.flags.writeable and self._psfem_key ==
+                (self.data.ctypes.data, self.data.size, self.indices.ctypes.data, self.indptr.ctypes.data))
+
+    def _psfem_touch(self):
+        self._psfem_dev = None
+        self._psfem_key = None
+        try:
+            self.data.flags.writeable = True
+        except ValueError:                      # a view of a buffer that is itself read-only: take a private copy
+            self.data = self.data.copy()
+
+
+def _mutator(name):
+    base = getattr(sparse.csr_matrix, name)
+
+    def method(self, *args, **kwargs):
+        self._psfem_touch()
+        return base(self, *args, **kwargs)
+    method.__name__ = name
+    method.__doc__ = base.__doc__
+    return method
+
+
+for _name in ("__setitem__", "setdiag", "__imul__", "__itruediv__", "__iadd__", "__isub__", "eliminate_zeros", "sum_duplicates",
+              "sort_indices", "prune", "resize"):
+    if hasattr(sparse.csr_matrix, _name):
+        setattr(DeviceBackedCSR, _name, _mutator(_name))
+
+
 def _to_host_csr(dev: DeviceCSR):
-    A = dev.to_scipy()
-    A._psfem_dev = dev
-    A._psfem_fingerprint = _fingerprint(A)
-    return A
-
-
-def _fingerprint(A):
-    """Cheap staleness check of the cached device copy: buffer address + 64 sampled values."""
-    d = A.data
-    idx = np.linspace(0, max(d.size - 1, 0), num=min(64, d.size), dtype=np.int64)
-    return (d.ctypes.data, d.size, float(d[idx].sum()) if d.size else 0.0)
+    A = dev.to_scipy(cls=DeviceBackedCSR)
+    return A._psfem_attach(dev)
 
 
 def device_copy(A) -> DeviceCSR:
-    """Device CSR of a matrix: the cached copy made at assembly if still valid, else an upload."""
+    """Device CSR of a matrix: the copy cached at assembly while the host matrix is provably untouched (see
+    DeviceBackedCSR), else an upload of the host arrays."""
     if isinstance(A, DeviceCSR):
         return A
-    dev = getattr(A, "_psfem_dev", None)
-    if dev is not None and getattr(A, "_psfem_fingerprint", None) == _fingerprint(A):
-        return dev
+    if isinstance(A, DeviceBackedCSR) and A._psfem_valid():
+        return A._psfem_dev
     return DeviceCSR.from_scipy(sparse.csr_matrix(A))
 
 
@@ -127,6 +169,98 @@ def get_gauss_points(element_type='tri'):
     w = [5 / 9, 8 / 9, 5 / 9]
     g = [-a, 0, a]
     return [(g[c], g[r]) for r in range(3) for c in range(3)], [w[r] * w[c] for r in range(3) for c in range(3)]
+
+
+# ---------------------------------------------------------------------------------------------
+# shape functions (Polygones.py:441-532) and the single-point B matrix (:657-708)
+# ---------------------------------------------------------------------------------------------
+def _shape_tables(element_type, mesh_type):
+    """Numeric (N, dN/dxi, dN/deta)(xi, eta) of the four element kinds: the closed forms the device kernels
+    integrate (csrc/psfem_assemble.cu shape_eval_host), node order as Polygones.py:457-497."""
+    et = _etype(element_type, mesh_type)
+    if et == _capi.T3:
+        def f(xi, eta):
+            z = 0 * (xi + eta)
+            return ([1 - xi - eta, xi + z, eta + z], [z - 1, z + 1, z], [z - 1, z, z + 1])
+    elif et == _capi.Q4:
+        sx, sy = (-1, 1, 1, -1), (-1, -1, 1, 1)
+
+        def f(xi, eta):
+            return ([(1 + a * xi) * (1 + b * eta) / 4 for a, b in zip(sx, sy)],
+                    [a * (1 + b * eta) / 4 + 0 * xi for a, b in zip(sx, sy)],
+                    [b * (1 + a * xi) / 4 + 0 * eta for a, b in zip(sx, sy)])
+    elif et == _capi.T6:
+        def f(xi, eta):
+            s = 1 - xi - eta
+            z = 0 * (xi + eta)
+            return ([s * (2 * s - 1), xi * (2 * xi - 1) + z, eta * (2 * eta - 1) + z, 4 * xi * s, 4 * xi * eta, 4 * eta * s],
+                    [4 * xi + 4 * eta - 3, 4 * xi - 1 + z, z, 4 - 8 * xi - 4 * eta, 4 * eta + z, -4 * eta + z],
+                    [4 * xi + 4 * eta - 3, z, 4 * eta - 1 + z, -4 * xi + z, 4 * xi + z, 4 - 4 * xi - 8 * eta])
+    else:
+        ab = ((0, 0), (2, 0), (2, 2), (0, 2), (1, 0), (2, 1), (1, 2), (0, 1), (1, 1))   # corners, mid-sides, centre (:487-497)
+
+        def f(xi, eta):
+            fx = (xi * (xi - 1) / 2, 1 - xi * xi, xi * (xi + 1) / 2)
+            fy = (eta * (eta - 1) / 2, 1 - eta * eta, eta * (eta + 1) / 2)
+            gx = (xi - 0.5, -2 * xi, xi + 0.5)
+            gy = (eta - 0.5, -2 * eta, eta + 0.5)
+            return ([fx[a] * fy[b] for a, b in ab], [gx[a] * fy[b] for a, b in ab], [fx[a] * gy[b] for a, b in ab])
+    return f
+
+
+def shape_functions(element_type='tri', mesh_type='coarse'):
+    """(N, xi, eta): the shape functions as sympy expressions in the symbols xi, eta, like Polygones.py:441-502 (so
+    `expr.subs({'xi': .., 'eta': ..})` keeps working).  Built by evaluating the closed forms on the symbols; sympy is
+    imported here only -- the assembly never touches it (the reference spends 97 % of its Q4 time in sympy.simplify)."""
+    import sympy as sp
+    xi, eta = sp.symbols('xi eta')
+    N, _, _ = _shape_tables(element_type, mesh_type)(xi, eta)
+    return [sp.expand(sp.nsimplify(n)) for n in N], xi, eta
+
+
+def get_shape_derivatives(element_type='tri', mesh_type='coarse'):
+    """(dN_dxi, dN_deta) as sympy expressions (Polygones.py:504-518)."""
+    import sympy as sp
+    N, xi, eta = shape_functions(element_type, mesh_type)
+    return [sp.diff(n, xi) for n in N], [sp.diff(n, eta) for n in N]
+
+
+def create_shape_functions(element_type='tri', mesh_type='coarse'):
+    """(N_funcs, dN_dxi_funcs, dN_deta_funcs): lists of NumPy callables f(xi, eta) (Polygones.py:520-532), here plain
+    closed forms instead of lambdified sympy expressions."""
+    f = _shape_tables(element_type, mesh_type)
+    n = NPE[_etype(element_type, mesh_type)]
+
+    def pick(part, i):
+        return lambda xi, eta: f(np.asarray(xi, dtype=np.float64), np.asarray(eta, dtype=np.float64))[part][i] + 0.0
+    return [pick(0, i) for i in range(n)], [pick(1, i) for i in range(n)], [pick(2, i) for i in range(n)]
+
+
+def compute_B_matrix_at_point(nodes, elements, element_number, xi, eta, element_type='tri', mesh_type='coarse'):
+    """(B, J, detJ) of one element at the reference point (xi, eta), Polygones.py:657-708: B is (3, 2*npe) with rows
+    eps_x, eps_y, gamma_xy, J the 2x2 Jacobian [[dx/dxi, dy/dxi], [dx/deta, dy/deta]].  Evaluated on the device
+    (psfem_b_matrix_at_point); raises the reference's ValueError when |detJ| < 1e-10 (:686-687)."""
+    import ctypes as C
+    torch = _capi.torch_cuda()
+    _capi.bind_device()
+    et = _etype(element_type, mesh_type)
+    npe = NPE[et]
+    conn = np.asarray(elements[element_number], dtype=np.int32).reshape(-1)
+    if conn.size != npe:
+        raise ValueError(f"element {element_number} has {conn.size} nodes, expected {npe}")
+    nodes = np.ascontiguousarray(nodes, dtype=np.float64)
+    if conn.min() < 0 or conn.max() >= len(nodes):
+        raise IndexError(f"element {element_number} refers to a node outside the node array")
+    # only the element's own nodes travel to the device
+    pts = torch.from_numpy(np.ascontiguousarray(nodes[conn])).cuda()
+    local = torch.arange(npe, dtype=torch.int32, device="cuda")
+    out = torch.empty(6 * npe + 6, dtype=torch.float64, device="cuda")
+    h = (C.c_double * (6 * npe + 6))()
+    rc = _capi.lib.psfem_b_matrix_at_point(_capi.ptr(pts), _capi.ptr(local), et, float(xi), float(eta), _capi.ptr(out), h,
+                                           _capi.stream_ptr())
+    _capi.check(rc, element_number)
+    v = np.frombuffer(h, dtype=np.float64).copy()
+    return v[:6 * npe].reshape(3, 2 * npe), v[6 * npe:6 * npe + 4].reshape(2, 2), float(v[6 * npe + 4])
 
 
 def global_mass_matrix(nodes, elements, rho, t, element_type='tri', mesh_type='coarse', integration='gauss'):

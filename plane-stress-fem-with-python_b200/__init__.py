@@ -19,6 +19,6 @@ from .device import (Assembler, DeviceCSR, ElementTable, FreeMap, device_mesh, p
 from .drivers import explicit_euler, modal, newmark, ramp_load, static_solve  # noqa: F401
 from .matio import load_matrix, save_matrix  # noqa: F401
 from .diagnostics import (check_matrix_properties, critical_time_step, estimate_max_eigenvalue,  # noqa: F401
-                          extreme_eigenvalues)
+                          extreme_eigenvalues, rigid_body_check, symmetry_defect)
 
 __version__ = "0.1.0"

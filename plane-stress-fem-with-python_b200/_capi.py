@@ -79,6 +79,7 @@ SIGNATURES = {
     "psfem_lattice_pattern": [_i64, _i64, _i32, _ptr, _ptr, _ptr, _pi64, _ptr],
     "psfem_assemble_lattice": [_ptr, _i64, _i64, _i32, _dbl, _dbl, _dbl, _dbl, _i32, _ptr, _ptr, _ptr, _sz, _pi64, _ptr],
     "psfem_element_matrices": [_ptr, _ptr, _i64, _i32, _dbl, _dbl, _dbl, _dbl, _i32, _ptr, _ptr, _ptr, _sz, _pi64, _ptr],
+    "psfem_b_matrix_at_point": [_ptr, _ptr, _i32, _dbl, _dbl, _ptr, _pdbl, _ptr],
     "psfem_scan_workspace": [_i64, _psz],
     "psfem_free_map": [_i64, _ptr, _i64, _ptr, _ptr, _pi64, _ptr, _sz, _ptr],
     "psfem_reduce_count": [_i64, _ptr, _ptr, _ptr, _i64, _ptr, _pi64, _ptr, _sz, _ptr],
@@ -100,6 +101,12 @@ SIGNATURES = {
     "psfem_pcg_workspace": [_i64, _i64, _psz],
     "psfem_pcg_jacobi": [_pcsr, _ptr, _ptr, _dbl, _i64, _i64, _pdbl, _ptr, _sz, _ptr],
     "psfem_pcg_jacobi_masked": [_pcsr, _ptr, _ptr, _ptr, _dbl, _i64, _i64, _pdbl, _ptr, _sz, _ptr],
+    "psfem_band_width": [_pcsr, _pi64, _ptr, _sz, _ptr],
+    "psfem_direct_limits": [_pi64, _pi64],
+    "psfem_direct_workspace": [_i64, _i64, _psz],
+    "psfem_direct_solve": [_pcsr, _ptr, _ptr, _i64, _i32, _pdbl, _ptr, _sz, _ptr],
+    "psfem_residual_dd": [_pcsr, _ptr, _ptr, _ptr, _ptr],
+    "psfem_csr_symmetry": [_pcsr, _dbl, _dbl, _pi64, _pdbl, _ptr, _sz, _ptr],
     "psfem_pcg_init": [_i64, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr],
     "psfem_pcg_spmv_dot": [_pcsr, _ptr, _i64, _ptr, _ptr, _ptr, _ptr, _ptr],
     "psfem_pcg_update": [_i64, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr],

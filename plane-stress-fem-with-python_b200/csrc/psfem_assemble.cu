@@ -24,8 +24,12 @@ struct ShapeTab {
 
 __constant__ ShapeTab c_tab[4];  // indexed by element kind (T3 unused)
 
-void shape_eval_host(int etype, double xi, double eta, double *N, double *dxi, double *det) {
-    if (etype == PSFEM_Q4) {  // Polygones.py:479-484
+__host__ __device__ void shape_eval_host(int etype, double xi, double eta, double *N, double *dxi, double *det) {
+    if (etype == PSFEM_T3) {  // Polygones.py:460-464 (used by compute_B_matrix_at_point only; Ke/Me of T3 are closed forms)
+        N[0] = 1 - xi - eta; N[1] = xi; N[2] = eta;
+        dxi[0] = -1; dxi[1] = 1; dxi[2] = 0;
+        det[0] = -1; det[1] = 0; det[2] = 1;
+    } else if (etype == PSFEM_Q4) {  // Polygones.py:479-484
         const double sx[4] = {-1, 1, 1, -1}, sy[4] = {-1, -1, 1, 1};
         for (int i = 0; i < 4; ++i) {
             N[i] = (1 + sx[i] * xi) * (1 + sy[i] * eta) / 4;
@@ -208,6 +212,34 @@ gauss_kernel(const double2 *__restrict__ nodes, const int32_t *__restrict__ conn
     if (DO_M) {
 #pragma unroll
         for (int j = 0; j < NPE; ++j) mblk[base + j] = macc[j];
+    }
+}
+
+// ---- compute_B_matrix_at_point (Polygones.py:657-708): B (3 x 2npe), J (2 x 2), detJ of ONE element at (xi, eta) ----
+// out: B row-major [3][2npe], then J00 J01 J10 J11, then detJ, then a flag (1.0: |detJ| < 1e-10, B not written)
+__global__ void b_matrix_kernel(const double2 *__restrict__ nodes, const int32_t *__restrict__ conn1, int etype, int npe,
+                                double xi, double eta, double *__restrict__ out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double N[9], dxi[9], det[9];
+    shape_eval_host(etype, xi, eta, N, dxi, det);
+    double j00 = 0, j01 = 0, j10 = 0, j11 = 0;
+    for (int i = 0; i < npe; ++i) {   // :675-682
+        const double2 p = nodes[conn1[i]];
+        j00 += dxi[i] * p.x; j01 += dxi[i] * p.y;
+        j10 += det[i] * p.x; j11 += det[i] * p.y;
+    }
+    const double detJ = j00 * j11 - j01 * j10;
+    double *B = out, *J = out + 6 * npe;
+    J[0] = j00; J[1] = j01; J[2] = j10; J[3] = j11; J[4] = detJ;
+    if (fabs(detJ) < 1e-10) { J[5] = 1.0; return; }   // :686-687
+    J[5] = 0.0;
+    const double inv = 1.0 / detJ;
+    const double i00 = j11 * inv, i01 = -j01 * inv, i10 = -j10 * inv, i11 = j00 * inv;
+    for (int i = 0; i < npe; ++i) {   // :692-706
+        const double dx = i00 * dxi[i] + i01 * det[i], dy = i10 * dxi[i] + i11 * det[i];
+        B[2 * i] = dx; B[2 * i + 1] = 0.0;
+        B[2 * npe + 2 * i] = 0.0; B[2 * npe + 2 * i + 1] = dy;
+        B[4 * npe + 2 * i] = dy; B[4 * npe + 2 * i + 1] = dx;
     }
 }
 
@@ -399,4 +431,20 @@ extern "C" int psfem_element_matrices(const double *d_nodes, const int32_t *d_co
                                                                          (what & 1) ? d_Ke : nullptr, (what & 2) ? d_Me : nullptr);
     PSFEM_LAUNCH_CHECK();
     return finish_bad(w.bad, h_bad_element, stream);
+}
+
+extern "C" int psfem_b_matrix_at_point(const double *d_nodes, const int32_t *d_conn1, int etype, double xi, double eta,
+                                       double *d_out, double *h_out, void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const int npe = psfem_nodes_per_element(etype);
+    PSFEM_REQUIRE(npe > 0 && d_nodes && d_conn1 && d_out && h_out, "b_matrix_at_point: bad arguments");
+    b_matrix_kernel<<<1, 32, 0, stream>>>(reinterpret_cast<const double2 *>(d_nodes), d_conn1, etype, npe, xi, eta, d_out);
+    PSFEM_LAUNCH_CHECK();
+    PSFEM_CUDA_CHECK(cudaMemcpyAsync(h_out, d_out, (size_t)(6 * npe + 6) * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    PSFEM_CUDA_CHECK(cudaStreamSynchronize(stream));
+    if (h_out[6 * npe + 5] != 0.0) {
+        set_error("Jacobian determinant near zero");
+        return PSFEM_EJACOBIAN;
+    }
+    return PSFEM_OK;
 }

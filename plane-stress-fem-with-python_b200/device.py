@@ -85,9 +85,13 @@ def to_host(t):
 
 def to_device(a, dtype=None):
     """Host ndarray -> device tensor; page-locked sources (e.g. arrays this package returned) go by DMA."""
+    import warnings
     torch = _capi.torch_cuda()
     a = np.ascontiguousarray(a, dtype=dtype)
-    return torch.from_numpy(a).to("cuda", non_blocking=False)
+    with warnings.catch_warnings():          # the read-only value arrays of DeviceBackedCSR are only read here
+        warnings.filterwarnings("ignore", message="The given NumPy array is not writable")
+        t = torch.from_numpy(a)
+    return t.to("cuda", non_blocking=False)
 
 
 # --------------------------------------------------------------------------------------------
@@ -207,14 +211,17 @@ class DeviceCSR:
             s.sl_m, s.sl_roff, s.sl_x_nodes = sl["m"], sl["roff"], sl["x_nodes"]
         return s
 
-    def to_scipy(self):
+    def to_scipy(self, cls=None):
         """Host scipy CSR.  Large arrays land in page-locked host memory (torch's caching host allocator), so the
         7 GB of a 33.6 M-DOF matrix cross PCIe at DMA speed instead of through the pageable staging path; the
         arrays are ordinary NumPy arrays for the caller (and upload at DMA speed when handed back to a driver)."""
         torch = _capi.torch_cuda()
         parts = [to_host(t) for t in (self.vals, self.col_idx, self.row_ptr)]
         torch.cuda.current_stream().synchronize()
-        return sparse.csr_matrix(tuple(h.numpy() for h in parts), shape=self.shape)
+        A = (cls or sparse.csr_matrix)(tuple(h.numpy() for h in parts), shape=self.shape)
+        # device-built patterns are sorted and duplicate-free: tell scipy, so that it never scans (or rewrites) the arrays
+        A.has_canonical_format = True
+        return A
 
     @classmethod
     def from_scipy(cls, A):
@@ -567,6 +574,57 @@ def pcg_jacobi(A: DeviceCSR, b, x0=None, rtol=1e-8, maxit=None, check_every=50, 
         return x, out
     check(rc)
     return x, out
+
+
+def direct_limits():
+    """(max rows, max half bandwidth) of the banded direct solver (psfem_direct_limits)."""
+    a, b = C.c_int64(0), C.c_int64(0)
+    call("psfem_direct_limits", C.byref(a), C.byref(b))
+    return a.value, b.value
+
+
+def half_bandwidth(A: DeviceCSR) -> int:
+    """max |row - col| over the pattern (psfem_band_width)."""
+    _capi.bind_device()
+    hb = C.c_int64(0)
+    ws = workspace(256)
+    s = A.struct()
+    call("psfem_band_width", C.byref(s), C.byref(hb), ptr(ws), 256, stream_ptr())
+    return int(hb.value)
+
+
+def direct_solve(A: DeviceCSR, b, refine=2, hb=None):
+    """Banded Cholesky + `refine` rounds of iterative refinement on a double-double residual (psfem_direct_solve): the
+    device counterpart of the dense LU the reference's static scripts call (Statictest.py:69, Beamexemple.py:63).
+    Returns (x, info)."""
+    torch = _capi.torch_cuda()
+    _capi.bind_device()
+    n = A.n_rows
+    if hb is None:
+        hb = half_bandwidth(A)
+    x = torch.empty(n, dtype=torch.float64, device="cuda")
+    sz = C.c_size_t(0)
+    call("psfem_direct_workspace", n, hb, C.byref(sz))
+    ws = workspace(sz.value)
+    info = (C.c_double * 5)()
+    s = A.struct()
+    rc = lib.psfem_direct_solve(C.byref(s), ptr(b), ptr(x), hb, int(refine), info, ptr(ws), sz.value, stream_ptr())
+    if rc == _capi.ENOCONV:
+        raise np.linalg.LinAlgError(_capi.last_error())        # what np.linalg.solve / cholesky raise on such a matrix
+    check(rc)
+    return x, dict(method="direct", iterations=0, refinement_rounds=int(info[0]), relres=float(info[1]), bnorm=float(info[2]),
+                   last_correction=float(info[4]), half_bandwidth=int(hb), converged=True)
+
+
+def residual_dd(A: DeviceCSR, x, b, out=None):
+    """r = b - A x accumulated in double-double (psfem_residual_dd)."""
+    torch = _capi.torch_cuda()
+    _capi.bind_device()
+    if out is None:
+        out = torch.empty(A.n_rows, dtype=torch.float64, device="cuda")
+    s = A.struct()
+    call("psfem_residual_dd", C.byref(s), ptr(x), ptr(b), ptr(out), stream_ptr())
+    return out
 
 
 class Blas:

@@ -20,15 +20,51 @@ def _identity_like(A):
     return sparse.identity(A.shape[0], dtype=np.float64, format="csr")
 
 
+def symmetry_defect(A, rtol=1e-5, atol=1e-8):
+    """(violations, max |A[r,c] - A[c,r]|) with np.allclose semantics |a - b| <= atol + rtol |b| per stored entry, on the
+    device (psfem_csr_symmetry): no transposed copy, no dense matrix."""
+    import ctypes as C
+    from ._capi import call, ptr, stream_ptr, workspace
+    dev = device_copy(A)
+    if dev.n_rows != dev.n_cols:
+        return dev.nnz, float("inf")
+    s = dev.struct()
+    bad, worst = C.c_int64(0), C.c_double(0.0)
+    ws = workspace(256)
+    call("psfem_csr_symmetry", C.byref(s), float(rtol), float(atol), C.byref(bad), C.byref(worst), ptr(ws), 256, stream_ptr())
+    return int(bad.value), float(worst.value)
+
+
 def _is_symmetric(A, rtol=1e-5, atol=1e-8):
-    """np.allclose(A, A.T, rtol, atol) (main.py:65-66) on the union of the two patterns: |a - b| <= atol + rtol |b|."""
-    A = sparse.csr_matrix(A)
-    At = A.T.tocsr()
-    D = (A - At).tocoo()
-    if D.nnz == 0:
-        return True
-    ref = np.abs(np.asarray(At[D.row, D.col]).ravel())
-    return bool(np.all(np.abs(D.data) <= atol + rtol * ref))
+    """np.allclose(A, A.T, rtol, atol) (main.py:65-66) for a CSR matrix."""
+    return symmetry_defect(A, rtol, atol)[0] == 0
+
+
+def rigid_body_check(K, nodes, rtol=1e-9):
+    """The rigid-body test of an UNCONSTRAINED stiffness matrix (the idea of SparseTest.py:29-36, which applies
+    u = ones and expects K u = 0): K must annihilate the two translations and the in-plane rotation
+    u = (-(y - yc), x - xc) of the mesh.  Three device SpMVs.  Returns a dict: `residuals` = ||K r|| / (||K||_max ||r||)
+    for [translation x, translation y, rotation], `passed` = all below rtol, `patch_test` = np.allclose(K @ ones, 0)
+    with the reference's absolute tolerance (1e-8, meaningless for E ~ 1e11 but reported as the script prints it)."""
+    torch = _capi.torch_cuda()
+    dev = device_copy(K)
+    nodes = np.asarray(nodes, dtype=np.float64)
+    n2 = 2 * len(nodes)
+    if dev.n_rows != n2:
+        raise ValueError("rigid_body_check needs the full (unconstrained) matrix of these nodes")
+    c = nodes.mean(axis=0)
+    modes = np.zeros((3, n2))
+    modes[0, 0::2] = 1.0
+    modes[1, 1::2] = 1.0
+    modes[2, 0::2] = -(nodes[:, 1] - c[1])
+    modes[2, 1::2] = nodes[:, 0] - c[0]
+    kmax = float(torch.max(torch.abs(dev.vals)).item()) if dev.nnz else 0.0
+    res = []
+    for r in modes:
+        f = dev.matvec(torch.from_numpy(r).cuda())
+        res.append(float(torch.linalg.vector_norm(f).item()) / max(kmax * np.linalg.norm(r), 1e-300))
+    ones = dev.matvec(torch.ones(n2, dtype=torch.float64, device="cuda"))
+    return dict(residuals=res, passed=bool(max(res) <= rtol), patch_test=bool(torch.all(torch.abs(ones) <= 1e-8).item()))
 
 
 def extreme_eigenvalues(A, tol=1e-10):

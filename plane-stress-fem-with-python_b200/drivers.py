@@ -14,7 +14,8 @@ import numpy as np
 
 from . import _capi
 from ._capi import call, check, lib, ptr, stream_ptr, workspace
-from .device import SL_MIN_ROWS, Blas, DeviceCSR, FreeMap, constrained_dofs_of, pcg_jacobi, to_host
+from .device import (SL_MIN_ROWS, Blas, DeviceCSR, FreeMap, constrained_dofs_of, direct_limits, direct_solve, half_bandwidth,
+                     pcg_jacobi, residual_dd, to_host)
 from .Polygones import device_copy
 
 
@@ -40,7 +41,7 @@ def _to_dev(v):
 MASKED_MIN_ROWS = 16384      # below: the single-CTA solver on the reduced system
 
 
-def _pcg_masked(Kd: DeviceCSR, fm: FreeMap, F_dev, rtol, maxit, check_every):
+def _pcg_masked(Kd: DeviceCSR, fm: FreeMap, F_dev, rtol, maxit, check_every, raise_on_fail=True):
     torch = _capi.torch_cuda()
     _capi.bind_device()
     n = Kd.n_rows
@@ -55,32 +56,102 @@ def _pcg_masked(Kd: DeviceCSR, fm: FreeMap, F_dev, rtol, maxit, check_every):
     info = (C.c_double * 4)()
     rc = lib.psfem_pcg_jacobi_masked(C.byref(s), ptr(F_dev), ptr(x), ptr(fm.new_id), float(rtol), int(maxit), int(check_every),
                                      info, ptr(ws), sz.value, stream_ptr())
-    out = dict(iterations=int(info[0]), relres=float(info[1]), bnorm=float(info[2]), converged=(rc == _capi.OK), masked=True)
+    out = dict(method="pcg", iterations=int(info[0]), relres=float(info[1]), bnorm=float(info[2]), converged=(rc == _capi.OK), masked=True)
+    if rc == _capi.ENOCONV and not raise_on_fail:
+        return x, out
     check(rc)
     return x, out
 
 
-def static_solve(K, F, bc, rtol=1e-8, maxit=None, check_every=50, return_device=False):
+def _norm(blas: Blas, v):
+    return float(np.sqrt(max(blas.dot(v, v), 0.0)))
+
+
+def _refine(solve, residual, x, bnorm, rounds, info):
+    """Iterative refinement with a compensated residual: r = b - K x in double-double (psfem_residual_dd), K d = r by
+    the inner solver, x += d.  Stops early once the true relative residual is at the rounding level."""
+    blas = Blas()
+    done = 0
+    for _ in range(int(rounds)):
+        r = residual(x)
+        rel = _norm(blas, r) / bnorm if bnorm > 0 else 0.0
+        info["relres_true"] = rel
+        if rel <= 4 * np.finfo(float).eps:
+            break
+        d, inner = solve(r)
+        info["iterations"] += inner["iterations"]
+        Blas.axpby(1.0, x, 1.0, d, x)
+        done += 1
+    info["refinement_rounds"] = done
+    r = residual(x)
+    info["relres_true"] = _norm(blas, r) / bnorm if bnorm > 0 else 0.0
+    return x
+
+
+def static_solve(K, F, bc, rtol=1e-8, maxit=None, check_every=50, return_device=False, method="auto", refine=None,
+                 raise_on_fail=True):
     """Solve K U = F with the DOFs of `bc` fixed to zero.
 
-    Same steps as Statictest.py:66-75: apply_boundary_conditions -> solve -> scatter back with zeros
-    at constrained DOFs; the dense LU (`np.linalg.solve`, :69) is replaced by Jacobi-PCG on the
-    device (x0 = 0, stop at ||r|| <= rtol ||b||).
+    Same steps as Statictest.py:66-75: apply_boundary_conditions -> solve -> scatter back with zeros at constrained DOFs.
+    The dense LU of the reference (`np.linalg.solve`, :69) is replaced on the device by
+      method="direct": banded Cholesky + iterative refinement on a double-double residual (psfem_direct_solve) -- small
+                       systems (<= 16 384 free DOFs, half bandwidth <= 320), accurate to rounding like the LU it replaces;
+      method="pcg":    Jacobi-PCG (x0 = 0, stop at ||r|| <= rtol ||b||), the path of the large plates; `refine` > 0 adds
+                       that many rounds of refinement with the compensated residual around it (each an inner PCG solve);
+      method="auto":   direct when the reduced system fits the band solver, else pcg.
     Returns (U, U_reduced, constrained_dofs, info)."""
     torch = _capi.torch_cuda()
+    if method not in ("auto", "direct", "pcg"):
+        raise ValueError("method must be 'auto', 'direct' or 'pcg'")
     constrained = constrained_dofs_of(bc)
     Kd = device_copy(K)
     fm = FreeMap(Kd.n_rows, constrained)
-    if Kd.n_rows > MASKED_MIN_ROWS and Kd.plan()[3] is not None:
+    max_rows, max_hb = direct_limits()
+    K_red = None
+    hb = None
+    if method != "pcg" and 0 < fm.n_free <= max_rows:
+        K_red = fm.reduce_csr(Kd)
+        hb = half_bandwidth(K_red)
+        if hb > max_hb:
+            if method == "direct":
+                raise ValueError(f"method='direct': half bandwidth {hb} exceeds the band solver's limit {max_hb}")
+            method = "pcg"
+        else:
+            method = "direct"
+    elif method == "direct":
+        raise ValueError(f"method='direct': {fm.n_free} free DOFs exceed the band solver's limit {max_rows}")
+    else:
+        method = "pcg"
+    if method == "direct":
+        F_red = fm.reduce_vec(_to_dev(F))
+        U_red, info = direct_solve(K_red, F_red, refine=2 if refine is None else refine, hb=hb)
+        U = fm.expand(U_red)
+    elif Kd.n_rows > MASKED_MIN_ROWS and Kd.plan()[3] is not None:
         # large system whose matrix has the 2x2 node-block structure: solve on the UNREDUCED matrix with the
         # constrained DOFs masked out (psfem_pcg_jacobi_masked) -- same iterates on the free DOFs as the reduced
         # system of Polygones.py:1003, the 9-byte SpMV for any boundary conditions, no reduced copy of K
-        U, info = _pcg_masked(Kd, fm, _to_dev(F), rtol, maxit, check_every)
+        F_dev = _to_dev(F)
+        U, info = _pcg_masked(Kd, fm, F_dev, rtol, maxit, check_every, raise_on_fail)
+        if refine:
+            cd_idx = fm.constrained_dev.long() if fm.constrained_dev is not None else None
+
+            def masked_residual(x):
+                r = residual_dd(Kd, x, F_dev)
+                if cd_idx is not None:
+                    r.index_fill_(0, cd_idx, 0.0)          # rows of constrained DOFs are not part of the system (reactions)
+                return r
+            _refine(lambda r: _pcg_masked(Kd, fm, r, rtol, maxit, check_every, raise_on_fail), masked_residual, U,
+                    info["bnorm"], refine, info)
         U_red = fm.reduce_vec(U)
     else:
-        K_red = fm.reduce_csr(Kd)
+        if K_red is None:
+            K_red = fm.reduce_csr(Kd)
         F_red = fm.reduce_vec(_to_dev(F))
-        U_red, info = pcg_jacobi(K_red, F_red, rtol=rtol, maxit=maxit, check_every=check_every)
+        U_red, info = pcg_jacobi(K_red, F_red, rtol=rtol, maxit=maxit, check_every=check_every, raise_on_fail=raise_on_fail)
+        info["method"] = "pcg"
+        if refine:
+            _refine(lambda r: pcg_jacobi(K_red, r, rtol=rtol, maxit=maxit, check_every=check_every, raise_on_fail=raise_on_fail),
+                    lambda x: residual_dd(K_red, x, F_red), U_red, info["bnorm"], refine, info)
         U = fm.expand(U_red)
     if return_device:
         return U, U_red, constrained, info

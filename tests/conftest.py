@@ -33,3 +33,23 @@ def psfem():
     """The product package (fails loudly if libpsfem.so is missing)."""
     import psfem_b200
     return psfem_b200
+
+
+@pytest.fixture(scope="session")
+def measured():
+    """measured(name, value, bar): print a measured parity error next to its bar and append it to
+    gpurun_out/parity_measured.jsonl (the table in DESIGN.md section 1 is made from that file)."""
+    import json
+    path = os.environ.get("PSFEM_MEASURED_FILE", os.path.join(ROOT, "gpurun_out", "parity_measured.jsonl"))
+
+    def rec(name, value, bar=None):
+        value = float(value)
+        print(f"[measured] {name}: {value:.3e}" + (f" (bar {bar:.1e})" if bar is not None else ""))
+        try:
+            os.makedirs(os.path.dirname(path), exist_ok=True)
+            with open(path, "a") as f:
+                f.write(json.dumps({"name": name, "value": value, "bar": bar}) + "\n")
+        except OSError:
+            pass
+        return value
+    return rec

@@ -303,9 +303,45 @@ def body_force_cases(P):
     np.savez_compressed(f"{OUT}/ref_body_forces.npz", **out)
 
 
+def b_matrix_cases(P):
+    """Polygones.compute_B_matrix_at_point (Polygones.py:657-708) on jittered small meshes of all four element kinds:
+    (B, J, detJ) of two elements at three reference points each, plus the shape functions / derivatives evaluated at
+    those points (shape_functions :441, get_shape_derivatives :504, create_shape_functions :520)."""
+    rng = np.random.default_rng(2)
+    out = {}
+    cases = {
+        "t3": dict(L=3, l=2.0, N=4, M=3, offsetX=0.5, offsetY=1, element_type="tri", mesh_type="coarse"),
+        "q4": dict(L=5.0, l=3, N=5, M=3, offsetX=0, offsetY=1.5, element_type="quad", mesh_type="coarse"),
+        "t6": dict(L=3, l=2, N=3, M=2, offsetX=0, offsetY=1, element_type="tri", mesh_type="fine"),
+        "q9": dict(L=2.0, l=1.5, N=2, M=2, offsetX=0.25, offsetY=0, element_type="quad", mesh_type="fine"),
+    }
+    pts = [(0.2, 0.3), (-0.55, 0.1), (1 / 6, 2 / 3)]
+    for name, kw in cases.items():
+        nodes, elements = P.mesh(**kw)
+        n_, m_ = (kw["N"] + 1, kw["M"] + 1) if kw["mesh_type"] == "coarse" else (2 * kw["N"] + 1, 2 * kw["M"] + 1)
+        nodes = nodes + rng.uniform(-0.1, 0.1, nodes.shape) * np.array([kw["L"] / (n_ - 1), kw["l"] / (m_ - 1)])
+        et, mt = kw["element_type"], kw["mesh_type"]
+        Bs, Js, ds = [], [], []
+        for e in (0, len(elements) - 1):
+            for xi, eta in pts:
+                B, J, detJ = P.compute_B_matrix_at_point(nodes, elements, e, xi, eta, et, mt)
+                Bs.append(B); Js.append(J); ds.append(detJ)
+        N, sx, se = P.shape_functions(et, mt)
+        d1, d2 = P.get_shape_derivatives(et, mt)
+        vals = np.array([[[float(f.subs({sx: xi, se: eta})) for f in grp] for grp in (N, d1, d2)] for xi, eta in pts])
+        out[f"{name}_nodes"], out[f"{name}_conn"] = nodes, conn_of(elements)
+        out[f"{name}_B"], out[f"{name}_J"], out[f"{name}_detJ"] = np.array(Bs), np.array(Js), np.array(ds)
+        out[f"{name}_shape_vals"] = vals                     # (points, [N, dN/dxi, dN/deta], npe)
+        print("b_matrix", name, np.array(Bs).shape, ds[:2])
+    out["points"] = np.array(pts)
+    np.savez_compressed(f"{OUT}/ref_b_matrix.npz", **out)
+
+
 if __name__ == "__main__":
     P = import_reference()
-    what = sys.argv[1:] or ["files", "small", "bc", "static", "newmark", "explicit", "modal", "body"]
+    what = sys.argv[1:] or ["files", "small", "bc", "static", "newmark", "explicit", "modal", "body", "bmat"]
+    if "bmat" in what:
+        b_matrix_cases(P)
     if "files" in what:
         golden_files()
     if "small" in what:

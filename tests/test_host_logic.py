@@ -1,5 +1,6 @@
 """Host-side (index / load) logic of the facade against the reference fixtures -- runs on CPU."""
 import numpy as np
+import pytest
 
 BC = [(1, [0, 0]), (13, [None, 0]), (7, [5.0, None]), (1, [0, None]), (4, [None, None])]
 
@@ -121,8 +122,10 @@ def test_t3_host_helpers(psfem):
 
 
 
+@pytest.mark.gpu
 def test_sparse_symmetry_check_has_allclose_semantics(psfem):
-    """diagnostics._is_symmetric == np.allclose(A, A.T, rtol=1e-5, atol=1e-8) (main.py:65-66) without densifying."""
+    """diagnostics._is_symmetric == np.allclose(A, A.T, rtol=1e-5, atol=1e-8) (main.py:65-66) without densifying
+    (device kernel psfem_csr_symmetry)."""
     import scipy.sparse as sparse
     from psfem_b200.diagnostics import _is_symmetric
     A = sparse.random(60, 60, 0.1, random_state=1, format="csr")
@@ -135,3 +138,62 @@ def test_sparse_symmetry_check_has_allclose_semantics(psfem):
     for B in cases:
         D = B.toarray()
         assert _is_symmetric(B) == np.allclose(D, D.T, rtol=1e-5, atol=1e-8)
+
+
+def test_shape_function_api_vs_reference(psfem, golden):
+    """shape_functions / get_shape_derivatives / create_shape_functions (Polygones.py:441-532) against values of the
+    unmodified reference's sympy expressions at three reference points (tests/golden/make_golden.py b_matrix_cases)."""
+    P = psfem.Polygones
+    d = golden("ref_b_matrix.npz")
+    pts = d["points"]
+    for name, (et, mt) in {"t3": ("tri", "coarse"), "q4": ("quad", "coarse"), "t6": ("tri", "fine"), "q9": ("quad", "fine")}.items():
+        ref = d[f"{name}_shape_vals"]                               # (points, [N, dN/dxi, dN/deta], npe)
+        groups = P.create_shape_functions(et, mt)
+        for k, (xi, eta) in enumerate(pts):
+            got = np.array([[float(f(xi, eta)) for f in grp] for grp in groups])
+            assert np.abs(got - ref[k]).max() <= 1e-14
+        # vectorised evaluation, like the lambdified functions of the reference
+        assert np.allclose(groups[0][0](pts[:, 0], pts[:, 1]), ref[:, 0, 0], rtol=0, atol=1e-14)
+        N, xi_s, eta_s = P.shape_functions(et, mt)                  # sympy expressions in the symbols xi, eta
+        dxi, deta = P.get_shape_derivatives(et, mt)
+        assert len(N) == ref.shape[2] and str(xi_s) == "xi" and str(eta_s) == "eta"
+        for k, (xi, eta) in enumerate(pts):
+            sub = {"xi": xi, "eta": eta}                            # the reference substitutes by NAME (Polygones.py:676)
+            got = np.array([[float(f.subs(sub)) for f in grp] for grp in (N, dxi, deta)])
+            assert np.abs(got - ref[k]).max() <= 1e-14
+        assert abs(sum(float(n.subs({"xi": 0.3, "eta": 0.2})) for n in N) - 1.0) < 1e-14     # partition of unity
+
+
+def test_device_backed_csr_never_goes_stale(psfem):
+    """The matrices the assembly returns remember their device copy; any host-side edit must invalidate it
+    (a penalty `K[i, i] = 1e20` used to be ignored by the drivers).  Pure host logic."""
+    import pytest
+    import scipy.sparse as sparse
+    from psfem_b200.Polygones import DeviceBackedCSR
+
+    def fresh():
+        A = DeviceBackedCSR((np.arange(1.0, 8.0), np.array([0, 1, 0, 1, 2, 1, 2]), np.array([0, 2, 5, 7])), shape=(3, 3))
+        A.has_canonical_format = True
+        return A._psfem_attach("device copy")
+    A = fresh()
+    assert A._psfem_valid() and isinstance(A, sparse.csr_matrix) and sparse.issparse(A)
+    assert np.array_equal(A @ np.ones(3), [3.0, 12.0, 13.0]) and A._psfem_valid()        # reading keeps the cache
+    assert A[np.ix_([0, 2], [0, 2])].shape == (2, 2) and (A * 2)._psfem_dev is None and A._psfem_valid()
+    with pytest.raises(ValueError, match="read-only"):
+        A.data[0] = 5.0                                                                   # direct writes fail loudly
+    A[0, 0] = 1e20                                                                        # the penalty idiom
+    assert not A._psfem_valid() and A._psfem_dev is None and A[0, 0] == 1e20
+    for edit in (lambda M: M.setdiag(3.0), lambda M: M.__imul__(2.0), lambda M: M.__itruediv__(2.0),
+                 lambda M: M.eliminate_zeros(), lambda M: M.sort_indices(), lambda M: M.sum_duplicates()):
+        A = fresh()
+        edit(A)
+        assert not A._psfem_valid() and A.data.flags.writeable
+    A = fresh()
+    A.data.flags.writeable = True                                                         # the caller unlocks the values
+    A.data[1] = 7.0
+    assert not A._psfem_valid()
+    A = fresh()
+    A.data = A.data.copy()                                                                # or swaps the array
+    assert not A._psfem_valid()
+    A = fresh()
+    assert A.copy()._psfem_dev is None and A.copy().data.flags.writeable and A._psfem_valid()
