@@ -2,22 +2,28 @@
 """bench.py -- headline benchmark of the plane-stress FEM hot path on B200.
 
 Metric (BASELINE.json): "Q4 elements assembled/s + CG DOF*iter/s, 33.6M-DOF plate, 1/2/4/8 B200".
-Workload (configs[3] at N=1): synthetic 4096x4096 Q4 plate (16 785 409 nodes, 33 570 818 DOF),
-left edge clamped, right edge loaded -- mesh(4.096, 4.096, 4096, 4096, element_type='quad').
-For N>1 every rank owns a strip of 4096 cell columns of a (4096*N)x4096 plate (weak scaling;
-N=4 is BASELINE's configs[4], the 16384x4096 strip), halo columns exchanged over NCCL each SpMV,
-CG dot products all-reduced.
+Workload (configs[3] at N=1): synthetic 4096x4096 Q4 plate (16 785 409 nodes, 33 570 818 DOF), left edge clamped,
+right edge loaded -- mesh(4.096, 4.096, 4096, 4096, element_type='quad').  For N>1 every rank owns a strip of 4096
+cell columns of a (4096*N)x4096 plate (weak scaling; N=4 is BASELINE's configs[4], the 16384x4096 strip); the halo
+columns and the CG dot products travel over NVLink peer memory inside the PCG kernels (PSFEM_DIST_TRANSPORT=nccl
+selects NCCL between the kernels instead).
 
-One STEP = one numeric assembly of K over all elements of the rank (one launch of the lattice kernel) +
-`--cg-iters` Jacobi-PCG iterations on the clamped system (three kernels each; for N>1 the reductions and the
-halo exchange are fused into those kernels over peer memory, PSFEM_DIST_TRANSPORT=nccl selects NCCL instead).  `value` = CG DOF*iterations/s (whole job); the assembly rate is
-in the `assembly` object.  Device timing with CUDA events on the launching stream, max over ranks.
-All inputs (> 7 GB of CSR per rank) are far larger than the 126 MB L2, so no explicit L2 flush.
+One STEP = one numeric assembly of K over all elements of the rank + `--cg-iters` Jacobi-PCG iterations on the clamped
+system.  `value` = CG DOF*iterations/s (whole job); the assembly rate is in the `assembly` object.  Device timing with
+CUDA events on the launching stream, max over ranks.  All inputs (> 2.5 GB of matrix per rank) are far larger than the
+126 MB L2, so no explicit L2 flush.
+
+Besides the contract keys the line carries
+  roofline / assembly.roofline   dominant kernels against the measured HBM peak (algorithmic bytes)
+  e2e                            the same metric through the public API with HOST buffers (copies inside the timed region)
+  cpu_baseline                   the oracle port on the host cores, SAME plate (bounded sample), BLAS pinned to one thread
+  full_solve                     (N=1) the north-star solve of the plate to 1e-8
+  extras                         (N=1) mass / K+M / T3 assembly, symbolic phase, Newmark step at C4, configs 2 and 3
+  dist_check / strong            (N>1) multi-GPU correctness checks run before timing; strong scaling of C4 and C5
 
     python bench.py [--gpus N --steps K --warmup W] [--impl reference] [--cells 4096]
 """
 import argparse
-import ctypes as C
 import json
 import os
 import subprocess
@@ -33,6 +39,16 @@ sys.path.insert(0, ROOT)
 METRIC = "Q4 elements assembled/s + CG DOF*iter/s, 33.6M-DOF plate, 1/2/4/8 B200"
 UNIT = "DOF*iter/s"
 E, NU, T, RHO = 210e9, 0.3, 0.1, 7850.0
+ASM_BYTES_PER_Q4 = 304        # 16 B coordinates + 288 B CSR values; the lattice kernel reads no connectivity (SURVEY 8d counts 320 with it)
+
+# the UNMODIFIED reference, timed in the build container (8 cores; /root/reference does not exist on the GPU box):
+# BASELINE.md section 2 / section 3 (iii), "for the record"
+REFERENCE_RECORDED = {
+    "where": "build container, 8 host cores, reference imported unmodified (matplotlib stubbed)",
+    "c1_T3_global_stiffness_matrix_s": 0.19, "c1_T3_elements_per_s": 16800.0,
+    "q4_16x16_global_stiffness_matrix_elements_per_s": 2.1,
+    "main_py_T3_10001_steps_s": 4.0, "freeModes_py_T3_80x8_s": 3.0,
+}
 
 
 def peaks():
@@ -41,6 +57,34 @@ def peaks():
         return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def plate_counts(cols, rows):
+    """(nodes, dof, free dof with the left edge clamped, elements, structural nnz) of a cols x rows Q4 plate."""
+    n, m = cols + 1, rows + 1
+    return n * m, 2 * n * m, 2 * (n - 1) * m, cols * rows, 4 * (3 * n - 2) * (3 * m - 2)
+
+
+def workload_name(n_gpus, cells, scaling="weak", total_cols=0):
+    if total_cols:
+        return (f"synthetic {total_cols}x{cells} Q4 strip, left edge clamped, right edge loaded: numeric assembly of K + "
+                f"Jacobi-PCG iterations; split into {n_gpus} strips of ~{total_cols // n_gpus} cell columns")
+    if scaling == "strong":
+        return (f"synthetic {cells}x{cells} Q4 plate, left edge clamped, right edge loaded: numeric assembly of K + "
+                f"Jacobi-PCG iterations; the plate is split into {n_gpus} strips of ~{cells // n_gpus} cell columns")
+    return (f"synthetic {cells * n_gpus}x{cells} Q4 plate, left edge clamped, right edge loaded: numeric assembly of K + "
+            f"Jacobi-PCG iterations; {cells} cell columns per GPU (strip partition)")
+
+
+def config_of(args, world):
+    """The `config` object of BOTH arms (pure arithmetic, no GPU): the reference arm runs on this arm's config."""
+    cols = args.total_cols or (args.cells * world if args.scaling == "weak" else args.cells)
+    _, dof, free, nel, _ = plate_counts(cols, args.cells)
+    return {"workload": workload_name(world, args.cells, args.scaling, args.total_cols), "dof": int(dof), "free_dof": int(free),
+            "elements": int(nel), "cg_iters_per_step": args.cg_iters,
+            "l2": "inputs (> 2.5 GB of matrix per GPU) exceed the 126 MB L2; no flush",
+            "parallelism": f"strip{world}",
+            "transport": (os.environ.get("PSFEM_DIST_TRANSPORT", "peer") if world > 1 else "single GPU")}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -93,74 +137,88 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-# reference arm / cpu baseline: the oracle (NumPy/SciPy restatement of the reference) on host cores
+# reference arm / cpu baseline: the oracle (NumPy/SciPy restatement of the reference) on the host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_run(steps, warmup, asm_cells=512, cg_cells=1024, cg_iters=20):
-    """Bounded sample of the same workload on the host: Q4 assembly (Ke + coo->csr, structural
-    pattern) of an asm_cells^2 plate and cg_iters Jacobi-PCG iterations on a clamped cg_cells^2 plate."""
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import psfem_oracle as O
-    cores = os.cpu_count() or 1
-    h = 1e-3
-    nodes, conn = O.mesh(asm_cells * h, asm_cells * h, asm_cells, asm_cells, element_type="quad")
-    n2, c2 = O.mesh(cg_cells * h, cg_cells * h, cg_cells, cg_cells, element_type="quad")
-    K2 = O.global_stiffness_matrix(n2, c2, E, NU, T, "quad")
-    F = O.edge_forces(np.zeros(K2.shape[0]), [0, -1e6], "right", cg_cells * h, cg_cells)
-    K_red, F_red, _ = O.apply_boundary_conditions(K2, F, O.boundary("left", [0, 0], cg_cells))
-    n_free = K_red.shape[0]
-    t_asm, t_cg, used = [], [], 1
-    for s in range(warmup + steps):
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+class CpuPlate:
+    """The SAME plate as the GPU arm on the host (one GPU's share: cells x cells Q4 cells, left edge clamped, right edge
+    loaded), built once with the oracle in threaded slabs (untimed set-up; the one-shot COO of 16.7 M elements would
+    need 17 GB).  A step = a bounded sample of the workload with every host thread busy and BLAS / OpenMP pinned to ONE
+    thread per pool thread (threadpoolctl), so that the same code prints the same rate under `python` and under
+    `torchrun` (which exports OMP_NUM_THREADS=1): round 1's N=1 leg lost 5x to oversubscription.
+      assembly  NumPy Ke + scipy coo->csr of `asm_cols` cell columns (x cells rows) of that plate, threaded slabs
+      CG        `cg_iters` Jacobi-PCG iterations (SciPy CSR mat-vec over row blocks on all threads) on the whole plate"""
+
+    def __init__(self, cells, asm_cols=128, cg_iters=5):
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import psfem_oracle as O
+        from threadpoolctl import threadpool_limits
+        self.O, self.limits = O, threadpool_limits
+        self.cells, self.cores = cells, host_threads()
+        self.asm_cols, self.cg_iters = min(asm_cols, cells), cg_iters
+        h = 1e-3
         t0 = time.perf_counter()
-        Ke = O.element_stiffness_threads(nodes, conn, E, NU, T, "quad", "coarse", cores)
-        O.assemble(Ke, conn, len(nodes))
-        ta = time.perf_counter() - t0
-        best = None
-        for nt in sorted({1, cores}):
-            _, _, sec = O.jacobi_pcg_threads(K_red, F_red, cg_iters, nt)
-            if best is None or sec < best[0]:
-                best = (sec, nt)
-        if s >= warmup:
-            t_asm.append(ta)
-            t_cg.append(best[0])
-            used = best[1]
-    asm_rate = asm_cells * asm_cells * len(t_asm) / sum(t_asm)
-    cg_rate = n_free * cg_iters * len(t_cg) / sum(t_cg)
-    sample = (f"per step: Q4 assembly (NumPy Ke on {cores} threads + scipy coo->csr) of a {asm_cells}x{asm_cells} plate "
-              f"and {cg_iters} Jacobi-PCG iterations (SciPy CSR mat-vec, best of 1/{cores} threads) on a clamped "
-              f"{cg_cells}x{cg_cells} plate ({n_free} DOF)")
-    return dict(cg_rate=cg_rate, asm_rate=asm_rate, cores=max(used, cores), cg_threads=used, sample=sample,
-                ms_per_step=1e3 * (sum(t_asm) + sum(t_cg)) / len(t_cg))
+        with threadpool_limits(1):
+            self.nodes, self.conn = O.mesh(cells * h, cells * h, cells, cells, element_type="quad")
+            self.K_red = O.assemble_chunked(self.nodes, self.conn, cells, cells, E, NU, T, self.cores, drop_first_node_column=True)
+            F = O.edge_forces(np.zeros(2 * len(self.nodes)), [0, -1e6], "right", cells * h, cells, cells)
+            self.F_red = F[2 * (cells + 1):]
+        self.n_free = self.K_red.shape[0]
+        self.setup_s = time.perf_counter() - t0
+
+    def step(self):
+        O = self.O
+        with self.limits(1):
+            t0 = time.perf_counter()
+            O.assemble_chunked(self.nodes, self.conn, self.cells, self.cells, E, NU, T, self.cores, col0=0, col1=self.asm_cols)
+            t_asm = time.perf_counter() - t0
+            _, _, t_cg = O.jacobi_pcg_threads(self.K_red, self.F_red, self.cg_iters, self.cores)
+        return t_asm, t_cg
+
+    def run(self, steps, warmup):
+        ta, tc = [], []
+        for s in range(warmup + steps):
+            a, c = self.step()
+            if s >= warmup:
+                ta.append(a)
+                tc.append(c)
+        # rows of asm_cols node columns are produced from (asm_cols) cell columns (+ nothing before column 0)
+        asm_rate = self.asm_cols * self.cells * len(ta) / sum(ta)
+        cg_rate = self.n_free * self.cg_iters * len(tc) / sum(tc)
+        sample = (f"per step, on {self.cores} threads (BLAS/OpenMP pinned to 1 per thread): Q4 assembly (NumPy Ke + scipy coo->csr, "
+                  f"threaded slabs) of {self.asm_cols} cell columns of the {self.cells}x{self.cells} plate and {self.cg_iters} Jacobi-PCG "
+                  f"iterations (SciPy CSR mat-vec over row blocks) on the whole clamped plate ({self.n_free} DOF)")
+        return dict(cg_rate=cg_rate, asm_rate=asm_rate, cores=self.cores, sample=sample,
+                    ms_per_step=1e3 * (sum(ta) + sum(tc)) / len(tc), setup_s=self.setup_s)
 
 
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    r = cpu_run(args.steps, args.warmup)
+    world = args.gpus
+    r = CpuPlate(args.cells).run(args.steps, args.warmup)
+    base = {"value": r["cg_rate"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"],
+            "assembly_elements_per_s": r["asm_rate"], "setup_s": r["setup_s"], "reference_unmodified": REFERENCE_RECORDED}
     line = {
-        "impl": "reference", "metric": METRIC, "value": r["cg_rate"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": METRIC, "value": r["cg_rate"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args.gpus, args.cells), "sample": r["sample"]},
+        "config": config_of(args, world),
         "assembly": {"value": r["asm_rate"], "unit": "elements/s"},
-        "cpu_baseline": {"value": r["cg_rate"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"],
-                         "assembly_elements_per_s": r["asm_rate"]},
+        "cpu_baseline": base,
         "e2e": {"value": r["cg_rate"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "the unmodified reference (pure Python, dense (2n)^2 storage, ~2 Q4 elements/s) cannot run this workload; "
-                "this arm times oracle/psfem_oracle.py, the NumPy/SciPy restatement pinned to the reference's goldens",
+        "note": "the unmodified reference (pure Python, dense (2n)^2 storage, ~2 Q4 elements/s) cannot run this workload; this arm "
+                "times oracle/psfem_oracle.py, the NumPy/SciPy restatement pinned to the reference's goldens, on one GPU's share of "
+                "the plate (the per-DOF rate does not depend on the number of strips)",
     }
     print(json.dumps(line), flush=True)
-
-
-def workload_name(n_gpus, cells, scaling="weak", total_cols=0):
-    if total_cols:
-        return (f"synthetic {total_cols}x{cells} Q4 strip, left edge clamped, right edge loaded: numeric assembly of K + "
-                f"Jacobi-PCG iterations; split into {n_gpus} strips of ~{total_cols // n_gpus} cell columns")
-    if scaling == "strong":
-        return (f"synthetic {cells}x{cells} Q4 plate, left edge clamped, right edge loaded: numeric assembly of K + "
-                f"Jacobi-PCG iterations; the plate is split into {n_gpus} strips of ~{cells // n_gpus} cell columns")
-    return (f"synthetic {cells * n_gpus}x{cells} Q4 plate, left edge clamped, right edge loaded: numeric assembly of K + "
-            f"Jacobi-PCG iterations; {cells} cell columns per GPU (strip partition)")
 
 
 # ------------------------------------------------------------------------------------------------
@@ -182,10 +240,14 @@ def main():
     ap.add_argument("--e2e-iters", type=int, default=200, help="PCG iterations of one end-to-end static_solve call")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the N=1 side records (M / K+M / T3 assembly, Newmark step, configs 2-3)")
+    ap.add_argument("--no-strong", action="store_true", help="N>1: skip the dist check and the strong-scaling records")
     ap.add_argument("--full-solve", action="store_true", help="also solve the plate to 1e-8 and report iterations/seconds "
                     "(on by default for the plain single-GPU run: 24 500 iterations, about 22 s)")
     ap.add_argument("--no-full-solve", action="store_true")
     args = ap.parse_args()
+    if args.total_cols:
+        args.scaling = "strong"
     if args.impl == "reference":
         return reference_arm(args)
     args.warmup = max(args.warmup, 3)
@@ -193,7 +255,6 @@ def main():
     import torch
     import torch.distributed as dist
     import psfem_b200
-    from psfem_b200 import _capi
     from psfem_b200.dist import StripProblem
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -203,27 +264,46 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     hbm_peak, peak_src = peaks()
-
     cells = args.cells
-    if args.total_cols:
-        args.scaling = "strong"
-    cols_total = args.total_cols or (cells * world if args.scaling == "weak" else cells)
-    prob = StripProblem(L=cols_total * 1e-3, l=cells * 1e-3, N=cols_total, M=cells, rank=rank, world=world,
-                        E=E, nu=NU, t=T)
-    prob.setup()                       # mesh strip, symbolic pattern, first assembly, BC reduction, load vector
-    n_free_global = prob.n_free_global
-    nel_local = prob.nel_owned
-    ev = lambda: torch.cuda.Event(enable_timing=True)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def maxr(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    line_extra = {}
+    # ---- N>1: correctness of the strip solver on THIS box before anything is timed ----------------------------
+    if world > 1 and not args.no_strong:
+        try:
+            from psfem_b200.dist_check import run_checks
+            chk = run_checks(world, rank)
+            line_extra["dist_check"] = "ok"
+            line_extra["dist_check_detail"] = {"what": "peer == NCCL iterates, owned rows bit-identical to the single-GPU matrix (Q4, T3, T6, Q9), "
+                                                       "restart converges, rollers + pinned node through dist.static_solve == single-GPU static_solve",
+                                               **{k: (float(v) if isinstance(v, float) else v) for k, v in chk.items()}}
+        except Exception as e:                                  # noqa: BLE001 -- report, never hide
+            line_extra["dist_check"] = f"FAILED: {type(e).__name__}: {e}"[:400]
+
+    cols_total = args.total_cols or (cells * world if args.scaling == "weak" else cells)
+    prob = StripProblem(L=cols_total * 1e-3, l=cells * 1e-3, N=cols_total, M=cells, rank=rank, world=world, E=E, nu=NU, t=T)
+    t0 = time.perf_counter()
+    prob.setup()                       # mesh strip, symbolic pattern, first assembly, BC reduction, load vector
+    setup_s = time.perf_counter() - t0
+    n_free_global = prob.n_free_global
+    nel_local = prob.nel_owned
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+
     sampler = ClockSampler(local)
     sampler.start()                                        # nvidia-smi is up before the first warm-up step
     asm_ms, cg_ms, spmv_ms = [], [], []
     launches = 0
+    kpi = prob.kernels_per_iteration
     barrier()
     sampler.mark_load()
     for s in range(args.warmup + args.steps):
@@ -234,7 +314,7 @@ def main():
         e0.record()
         prob.assemble()                                    # numeric assembly of K (one marching-warp lattice kernel)
         e1.record()
-        prob.cg_iterations(args.cg_iters)                  # 3 kernels per iteration (+ halo / all-reduce when world > 1)
+        prob.cg_iterations(args.cg_iters)                  # the PCG kernels (+ halo / reductions fused in when world > 1)
         e2.record()
         prob.spmv_only(args.cg_iters)                      # the dominant kernel alone, for its roofline line
         e3.record()
@@ -243,16 +323,10 @@ def main():
             asm_ms.append(e0.elapsed_time(e1))
             cg_ms.append(e1.elapsed_time(e2))
             spmv_ms.append(e2.elapsed_time(e3))
-            launches += 1 + 3 * args.cg_iters + args.cg_iters   # assembly + PCG kernels + the SpMV-only leg
+            launches += 1 + kpi * args.cg_iters + args.cg_iters   # assembly + PCG kernels + the SpMV-only leg
     barrier()
     wall = time.perf_counter() - t_wall0
     clocks = sampler.stop()
-
-    def maxr(x):
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
 
     t_asm = maxr(sum(asm_ms)) / 1e3
     t_cg = maxr(sum(cg_ms)) / 1e3
@@ -261,63 +335,58 @@ def main():
     cg_rate = n_free_global * args.cg_iters * K_ / t_cg
     asm_rate = prob.nel_global * K_ / t_asm
 
-    # roofline of the dominant kernel (SpMV+dot of the PCG iteration), per rank
+    # roofline of the dominant kernel (SpMV + dot of the PCG iteration), per rank
     nnz, n = prob.K_red.nnz, prob.n_owned_free
     csr_bytes = 12 * nnz + 4 * (n + 1) + 16 * n                          # CSR SpMV
     nbp = prob.K_red.plan()[3]
     node_block = nbp is not None and not os.environ.get("PSFEM_NO_NODEBLOCK")
     idx_bytes = 2 if (node_block and nbp[5] is not None) else 4
-    # node-block SpMV: 8 B value + one node id (16-bit offset or 32-bit) per 2x2 block, node_ptr, x, y
     spmv_bytes = (8 * nnz + idx_bytes * (nnz // 4) + 4 * (n // 2 + 1) + 16 * n) if node_block else csr_bytes
     sym_lat = bool(getattr(prob, "sym_lattice", False)) and not os.environ.get("PSFEM_NO_SYMLATTICE")
     if sym_lat:
-        # symmetric-lattice storage: 19 doubles of matrix per node (diagonal + 4 forward 2x2 blocks), x, y
-        spmv_bytes = (19 * 8 + 16 + 16) * (n // 2)
+        spmv_bytes = (19 * 8 + 16 + 16) * (n // 2)                        # 19 doubles of matrix per node + x + y
     spmv_t = t_spmv / (K_ * args.cg_iters)
     spmv_gbs = spmv_bytes / spmv_t / 1e9
-    iter_bytes = spmv_bytes + (4 + 6) * 8 * n                            # update: q, r, dinv, r' ; p-update: p, x, r, dinv, p', x'
+    iter_bytes = prob.iteration_bytes(spmv_bytes)
     iter_gbs = iter_bytes / (t_cg / (K_ * args.cg_iters)) / 1e9
-    asm_bytes = 320 * nel_local                                           # 16 conn + 16 coords + 288 CSR values
+    asm_bytes = ASM_BYTES_PER_Q4 * nel_local
     asm_gbs = asm_bytes / (t_asm / K_) / 1e9
-    asm_traffic = None
-    try:
-        asm_traffic = json.load(open(os.path.join(ROOT, "profiles", "asm_traffic.json"))).get("dram_bytes_per_launch")
-    except Exception:
-        pass
+    same_workload = cells == 4096 and world == 1                          # committed ncu traffic figures are for this configuration only
 
+    def traffic(name, key=None):
+        if not same_workload:
+            return None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", name)))
+            return (tj.get(key) or {}).get("dram_bytes_per_launch") if key else tj.get("dram_bytes_per_launch")
+        except Exception:
+            return None
+
+    cfg = config_of(args, world)
+    cfg["nnz_per_gpu"] = int(nnz)
+    cfg["pcg"] = prob.pcg_variant
     line = {
         "metric": METRIC, "value": cg_rate, "unit": UNIT, "n_gpus": world, "steps": K_, "warmup": args.warmup,
         "ms_per_step": 1e3 * (t_asm + t_cg) / K_, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(world, cells, args.scaling, args.total_cols), "dof": int(prob.n_dof_global), "free_dof": int(n_free_global),
-                   "elements": int(prob.nel_global), "nnz_per_gpu": int(nnz), "cg_iters_per_step": args.cg_iters,
-                   "l2": "inputs (>7 GB CSR per GPU) exceed the 126 MB L2; no flush",
-                   "parallelism": f"strip{world}", "transport": prob.transport if world > 1 else "single GPU"},
+        "dtype": "f64", "data": "synthetic", "config": cfg,
         "assembly": {"value": asm_rate, "unit": "elements/s", "ms": 1e3 * t_asm / K_,
                      "roofline": {"bound": "hbm", "achieved": asm_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": asm_gbs / hbm_peak,
-                                  "bytes_per_element": 320, "kernel": "lattice_q4_kernel<true> (marching warps, TMA bulk stores)",
-                                  "traffic": asm_traffic}},
-        "roofline": {"kernel": ("spmv_sl_kernel<true> (PCG SpMV + dot on symmetric-lattice storage: marching warps, 152 B of matrix per node, "
-                                "bit-identical to the CSR kernels)" if sym_lat else
-                                f"spmv_nb_kernel<true> (PCG SpMV + dot on the 2x2 node-block structure, TMA-staged, {8 + idx_bytes / 4:g} B/non-zero)" if node_block
-                                else "spmv2_kernel<true> (PCG SpMV + dot, CSR, TMA-staged, 12 B/non-zero)"),
+                                  "bytes_per_element": ASM_BYTES_PER_Q4,
+                                  "bytes_note": "16 B coordinates + 288 B CSR values; connectivity is not read (SURVEY 8d's 320 B counts it)",
+                                  "kernel": "lattice_q4_kernel<true> (marching warps, TMA bulk stores)",
+                                  "traffic": traffic("asm_traffic.json")}},
+        "roofline": {"kernel": prob.dominant_kernel(sym_lat, node_block, idx_bytes),
                      "bound": "hbm", "achieved": spmv_gbs, "peak": hbm_peak,
-                     "unit": "GB/s", "frac": spmv_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
-                     "bytes_per_launch": spmv_bytes, "ms_per_launch": 1e3 * spmv_t,
+                     "unit": "GB/s", "frac": spmv_gbs / hbm_peak,
+                     "traffic": traffic("spmv_traffic.json", "sym_lattice" if sym_lat else ("node_block" if node_block else "csr")),
+                     "peak_source": peak_src, "bytes_per_launch": spmv_bytes, "ms_per_launch": 1e3 * spmv_t,
                      "csr_equivalent": {"bytes_per_launch": csr_bytes, "gbs": csr_bytes / spmv_t / 1e9,
                                         "note": "SURVEY 8d counts the CSR formulation, 12 B per non-zero"}},
         "pcg_iteration": {"achieved": iter_gbs, "unit": "GB/s", "frac": iter_gbs / hbm_peak, "bytes_per_dof_iter": iter_bytes / n,
-                          "ms": 1e3 * t_cg / (K_ * args.cg_iters)},
-        "gpu_launches": launches, "clocks": clocks, "timed_region_wall_s": wall,
+                          "ms": 1e3 * t_cg / (K_ * args.cg_iters), "kernels": kpi},
+        "gpu_launches": launches, "clocks": clocks, "timed_region_wall_s": wall, "setup_s": setup_s,
     }
-    traffic_file = os.path.join(ROOT, "profiles", "spmv_traffic.json")
-    if os.path.exists(traffic_file):
-        try:
-            tj = json.load(open(traffic_file))
-            key = "sym_lattice" if sym_lat else ("node_block" if node_block else "csr")
-            line["roofline"]["traffic"] = (tj.get(key) or {}).get("dram_bytes_per_launch")
-        except Exception:
-            pass
+    line.update(line_extra)
 
     # anti-shortcut variant: interior nodes jittered by U(-0.2h, 0.2h), every element distinct -- same kernel
     try:
@@ -337,25 +406,181 @@ def main():
         prob.nodes = nodes0
         prob.assemble()                                    # restore K of the regular plate
         line["assembly"]["jittered_mesh_ms"] = maxr(min(ts[1:]))
+        del jit, ii, interior
     except Exception as e:                                 # never lose the bench line over the side measurement
         line["assembly"]["jittered_mesh_ms"] = f"skipped: {e}"
     if world == 1 and not (args.no_cpu or args.no_e2e or args.no_full_solve):
         args.full_solve = True                             # the default run also carries the north-star solve to 1e-8
     if args.full_solve:                                    # before the e2e legs, which release the device-resident state
         line["full_solve"] = prob.full_solve(1e-8)
+    if world == 1 and not args.no_extras:
+        try:
+            line["extras"] = extras_leg(psfem_b200, prob, cells, hbm_peak)
+        except Exception as e:                             # noqa: BLE001
+            line["extras"] = f"skipped: {type(e).__name__}: {e}"[:300]
+    # ---- N>1: strong scaling of C4 and C5, each against the single-GPU iteration measured in this same run ----
+    if world > 1 and not args.no_strong:
+        prob.release()
+        torch.cuda.empty_cache()
+        try:
+            line["strong"] = strong_leg(StripProblem, world, rank, cells, args.cg_iters, barrier, maxr)
+        except Exception as e:                             # noqa: BLE001
+            line["strong"] = f"FAILED: {type(e).__name__}: {e}"[:400]
     # ---- end to end through the public API with HOST buffers ------------------------------------
-    if not args.no_e2e and world == 1:
-        line["e2e"] = e2e_leg(psfem_b200, prob, args, cells)
-    elif world > 1:
-        line["e2e"] = prob.e2e_distributed(args.e2e_iters, min(K_, 2))
+    if not args.no_e2e:
+        if world == 1:
+            line["e2e"] = e2e_leg(psfem_b200, prob, args, cells)
+        else:
+            line["e2e"] = e2e_distributed(psfem_b200, prob, args, cols_total, cells, world, rank, barrier, maxr)
     if rank == 0 and not args.no_cpu and world == 1:
-        r = cpu_run(1, 0)
+        r = CpuPlate(cells).run(1, 0)
         line["cpu_baseline"] = {"value": r["cg_rate"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"],
-                                "assembly_elements_per_s": r["asm_rate"]}
+                                "assembly_elements_per_s": r["asm_rate"], "setup_s": r["setup_s"],
+                                "reference_unmodified": REFERENCE_RECORDED}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def strong_leg(StripProblem, world, rank, cells, cg_iters, barrier, maxr):
+    """Strong scaling inside the driver's weak run: the C4 plate (cells x cells) and BASELINE's C5 strip (4*cells x cells)
+    split over all ranks, PCG iteration time against ONE GPU running the whole C4 plate, measured here on every rank
+    (independent replicas, max over ranks).  C5 does not fit one GPU's int32 indices (2.4e9 non-zeros), its reference
+    is 4 x the single-GPU C4 iteration (the same per-DOF rate)."""
+    import torch
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+
+    def time_iters(prob, reps=4, iters=50):
+        ts = []
+        for _ in range(reps):
+            barrier()
+            a, b = ev(), ev()
+            a.record(); prob.cg_iterations(iters); b.record(); torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b) / iters)
+        return maxr(min(ts[1:]))
+
+    out = {}
+    one = StripProblem(L=cells * 1e-3, l=cells * 1e-3, N=cells, M=cells, rank=0, world=1, E=E, nu=NU, t=T).setup()
+    t1 = time_iters(one)
+    n_free_c4 = one.n_free_global
+    one.release()
+    torch.cuda.empty_cache()
+    out["single_gpu_c4_ms_per_iter"] = t1
+    for name, cols in (("c4", cells), ("c5", 4 * cells)):
+        if cols // world < 2:
+            continue
+        p = StripProblem(L=cols * 1e-3, l=cells * 1e-3, N=cols, M=cells, rank=rank, world=world, E=E, nu=NU, t=T).setup()
+        tn = time_iters(p)
+        ref = t1 * (cols // cells)
+        out[name] = {"plate": f"{cols}x{cells}", "free_dof": int(p.n_free_global), "ms_per_iter": tn,
+                     "dof_iter_per_s": p.n_free_global / (tn * 1e-3), "speedup_vs_one_gpu": ref / tn,
+                     "one_gpu_reference_ms": ref, "transport": p.transport, "pcg": p.pcg_variant,
+                     "cols_per_gpu": cols // world}
+        p.release()
+        torch.cuda.empty_cache()
+    out["note"] = ("speedup = (single-GPU C4 iteration measured in this run x plate size / C4 size) / N-GPU iteration; device-timed, "
+                   "max over ranks, best of 3 batches of 50 iterations")
+    return out
+
+
+def extras_leg(psfem_b200, prob, cells, hbm_peak):
+    """Driver-visible numbers for the rest of the path at C4 (VERDICT r1 missing #5): mass assembly, K+M in one pass,
+    T3 assembly, symbolic phase, a Newmark-beta step (main.py:304-332 recurrence) -- and BASELINE configs 2 and 3 as wall
+    time next to the unmodified reference's recorded run."""
+    import torch
+    from psfem_b200 import Polygones as P
+    from psfem_b200.device import Assembler, device_mesh
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    f64 = dict(dtype=torch.float64, device="cuda")
+
+    def best(fn, reps=4):
+        ts = []
+        for _ in range(reps):
+            a, b = ev(), ev()
+            a.record(); fn(); b.record(); torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return min(ts[1:])
+
+    out = {}
+    nel = prob.nel_owned
+    asm = prob.asm
+    M_vals = torch.empty(asm.nnz, **f64)
+    K2 = torch.empty(asm.nnz, **f64)
+    ms = best(lambda: asm.assemble(prob.nodes, rho=RHO, t=T, what=2, M_out=M_vals))
+    out["assembly_M"] = {"ms": ms, "elements_per_s": nel / ms * 1e3, "bytes_per_element": ASM_BYTES_PER_Q4,
+                         "hbm_frac": ASM_BYTES_PER_Q4 * nel / (ms * 1e-3) / 1e9 / hbm_peak}
+    ms = best(lambda: asm.assemble(prob.nodes, E=E, nu=NU, rho=RHO, t=T, what=3, K_out=K2, M_out=M_vals))
+    bkm = 16 + 2 * 288
+    out["assembly_KM"] = {"ms": ms, "elements_per_s": nel / ms * 1e3, "bytes_per_element": bkm,
+                          "hbm_frac": bkm * nel / (ms * 1e-3) / 1e9 / hbm_peak}
+    del K2
+    # symbolic phase of the lattice (topology check + closed-form pattern), once per mesh
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    a2 = Assembler(prob.conn, prob.part.n_ext_nodes, asm.etype)
+    torch.cuda.synchronize()
+    out["symbolic_ms"] = 1e3 * (time.perf_counter() - t0)
+    out["symbolic_note"] = "lattice detection on the connectivity + row_ptr / col_idx / node_ptr written in closed form (2.5 GB), host-timed"
+    del a2
+    # T3 on the same nodes (33.5 M triangles)
+    _, conn3 = device_mesh(cells * 1e-3, cells * 1e-3, cells, cells, 0, 0, "tri", "coarse")
+    a3 = Assembler(conn3, prob.part.n_ext_nodes, psfem_b200._capi.T3)
+    K3 = torch.empty(a3.nnz, **f64)
+    ms = best(lambda: a3.assemble(prob.nodes, E=E, nu=NU, t=T, what=1, K_out=K3))
+    b3 = 8 + 14 * 8
+    out["assembly_T3"] = {"ms": ms, "elements_per_s": a3.nel / ms * 1e3, "bytes_per_element": b3,
+                          "hbm_frac": b3 * a3.nel / (ms * 1e-3) / 1e9 / hbm_peak}
+    del a3, K3, conn3
+    torch.cuda.empty_cache()
+    # Newmark-beta step at C4: dt ~ h / wave speed (K_eff = K + M/(beta dt^2) well conditioned), warm-started PCG to 1e-8
+    try:
+        K_ext = asm.pattern_csr(prob.K_vals)
+        Md = K_ext.with_vals(M_vals)
+        dt, steps = 2e-7, 9
+        bc = P.boundary("left", [0, 0], cells, cells)
+        n_nodes = prob.part.n_ext_nodes
+        shape, scale, _ = psfem_b200.ramp_load(n_nodes, cells * 1e-3, P=1e6, T=10000 * dt, dt=dt)
+        nm = psfem_b200.newmark(K_ext, Md, bc, shape, scale[:steps], dt=dt, store_every=steps, energies=True, rtol=1e-8, maxit=300)
+        its = nm["info"]["pcg_iterations"]
+        out["newmark_step"] = {"ms_per_step": nm["info"]["run_ms"] / (steps - 1), "pcg_iterations_per_step": its / (steps - 1),
+                               "dt": dt, "steps": steps - 1, "energies": True, "max_relres": nm["info"]["max_relres"],
+                               "what": "predictor, RHS F - K(u_p + beta_R v_p) - alpha_R M v_p (2 SpMV), PCG solve with K_eff, corrector, "
+                                       "stabiliser, 2 energy SpMV+dot (main.py:304-332, :377-385) on the clamped 4096x4096 plate"}
+        del nm, Md, K_ext
+    except Exception as e:                                 # noqa: BLE001
+        out["newmark_step"] = f"skipped: {type(e).__name__}: {e}"[:300]
+    del M_vals
+    torch.cuda.empty_cache()
+    # BASELINE configs 2 and 3 end to end (mesh -> K, M -> driver), wall clock, second of two runs
+    try:
+        L, l, N, G = 20, 2, 20, 2
+        for rep in range(2):
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            nodes, elements = P.mesh(L, l, N, G, element_type="quad", mesh_type="fine", offsetY=l / 2)
+            K = P.global_stiffness_matrix(nodes, elements, E, NU, 0.1, "quad", "fine")
+            M = P.global_mass_matrix(nodes, elements, RHO, 0.1, "quad", "fine")
+            bc = [(int(G / 2), [0, 0]), (int((len(nodes) - 1) - G / 2), [None, 0])]
+            shape, scale, _ = psfem_b200.ramp_load(len(nodes), L)
+            o = psfem_b200.newmark(K, M, bc, shape, scale, dt=1e-3)
+            torch.cuda.synchronize(); t2 = time.perf_counter() - t0
+        out["config2_newmark_q9_10001_steps"] = {"wall_s": t2, "kernel_ms": o["info"]["run_ms"], "free_dof": int(o["U"].shape[0]),
+                                                 "reference_main_py_T3_123dof_s": REFERENCE_RECORDED["main_py_T3_10001_steps_s"],
+                                                 "note": "the reference needs ~2.6 s per Q9 ELEMENT to assemble this mesh (sympy); its 4.0 s is main.py as shipped (T3, 123 DOF)"}
+        for rep in range(2):
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            nodes, elements = P.mesh(20, 2, 80, 8, element_type="tri", mesh_type="fine", offsetY=1)
+            K = P.global_stiffness_matrix(nodes, elements, E, NU, 0.01, "tri", "fine")
+            M = P.global_mass_matrix(nodes, elements, RHO, 0.01, "tri", "fine")
+            bc = [(4, [0, 0]), (int((len(nodes) - 1) - 4), [None, 0])]
+            f, modes, cd, inf = psfem_b200.modal(K, M, bc, k=20)
+            torch.cuda.synchronize(); t3 = time.perf_counter() - t0
+        out["config3_modal_t6_80x8_20_modes"] = {"wall_s": t3, "free_dof": int(K.shape[0] - len(cd)), "lanczos_steps": inf["lanczos_steps"],
+                                                 "f1_hz": float(f[0]), "converged": bool(inf["converged"]),
+                                                 "reference_freeModes_py_T3_1455dof_s": REFERENCE_RECORDED["freeModes_py_T3_80x8_s"]}
+    except Exception as e:                                 # noqa: BLE001
+        out["configs_2_3"] = f"skipped: {type(e).__name__}: {e}"[:300]
+    return out
 
 
 def e2e_leg(psfem_b200, prob, args, cells):
@@ -374,8 +599,8 @@ def e2e_leg(psfem_b200, prob, args, cells):
     steps = min(args.steps, 2)
     t_asm, t_cg = 0.0, 0.0
     h2d = d2h = 0
+    its_done = 0
     for s in range(steps + 1):
-        elements._plan_keep = elements._plan                   # symbolic plan is reused like in the device loop
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         K = P.global_stiffness_matrix(nodes, elements, E, NU, T, "quad")
@@ -384,26 +609,90 @@ def e2e_leg(psfem_b200, prob, args, cells):
         Kh = sparse.csr_matrix((K.data, K.indices, K.indptr), shape=K.shape, copy=False)   # plain host CSR: no cached device copy
         del K
         t2 = time.perf_counter()
-        try:
-            U, U_red, cd, info = psfem_b200.static_solve(Kh, F, bc, rtol=1e-8, maxit=args.e2e_iters)
-            its = info["iterations"]
-        except psfem_b200.ConvergenceError:
-            its = args.e2e_iters
+        U, U_red, cd, info = psfem_b200.static_solve(Kh, F, bc, rtol=1e-8, maxit=args.e2e_iters, method="pcg", raise_on_fail=False)
         torch.cuda.synchronize()
         t3 = time.perf_counter()
         if s >= 1:
             t_asm += t1 - t0
             t_cg += t3 - t2
+            its_done += info["iterations"]
             h2d = nodes.nbytes + Kh.data.nbytes + Kh.indices.nbytes + Kh.indptr.nbytes + F.nbytes
-            d2h = Kh.data.nbytes + Kh.indices.nbytes + Kh.indptr.nbytes + F.nbytes
-        n_free = Kh.shape[0] - len(set(2 * k for k, _ in bc)) * 2
-        del Kh
-    return {"value": n_free * args.e2e_iters * steps / t_cg, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-            "d2h_bytes_per_step": int(d2h), "steps": steps, "pcg_iters_per_call": args.e2e_iters,
+            d2h = Kh.data.nbytes + Kh.indices.nbytes + Kh.indptr.nbytes + U.nbytes + U_red.nbytes
+        n_free = U_red.shape[0]
+        del Kh, U, U_red
+    return {"value": n_free * its_done / t_cg, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+            "d2h_bytes_per_step": int(d2h), "steps": steps, "pcg_iters_per_call": its_done // steps,
             "assembly_elements_per_s": cells * cells * steps / t_asm,
             "calls": "Polygones.global_stiffness_matrix(host nodes, elements) -> host scipy CSR; "
-                     "static_solve(host CSR, host F, bc, maxit) -> host U (nodes, F: the caller's pageable arrays; the CSR arrays are the "
-                     "page-locked buffers global_stiffness_matrix returned)"}
+                     "static_solve(host CSR, host F, bc, maxit, raise_on_fail=False) -> host U and U_reduced (nodes, F: the caller's "
+                     "pageable arrays; the CSR arrays are the page-locked buffers global_stiffness_matrix returned)"}
+
+
+def e2e_distributed(psfem_b200, prob, args, cols_total, cells, world, rank, barrier, maxr):
+    """End to end at N>1 through the public multi-GPU call `psfem_b200.dist.static_solve`: host coordinates and host
+    load in (each rank uploads the rows of its strip from pinned memory), device mesh connectivity, assembly, boundary
+    conditions, `e2e_iters` PCG iterations, and the displacement vector gathered to the host of rank 0 -- all inside the
+    timed region."""
+    import torch
+    from psfem_b200 import dist as pdist
+    from psfem_b200.device import device_mesh
+    if hasattr(prob, "asm"):
+        prob.release()
+    torch.cuda.empty_cache()
+    p = prob.part
+    h = 1e-3
+    # host inputs of THIS rank's strip, page-locked (a user holds the global arrays; each rank touches only its rows)
+    nd, _ = device_mesh(cols_total * h, cells * h, cols_total, cells, 0, 0, "quad", "coarse", col0=p.e0, ncols=p.e1 - p.e0,
+                        cell0=p.cell0, ncells=p.cell1 - p.cell0)
+    nodes_strip = nd.cpu().pin_memory().numpy()
+    del nd
+
+    def load(a, b):                                       # Polygones.edgeForces(zeros, [0, -1e6], 'right', ...) restricted to [a, b)
+        Fh = np.zeros(b - a)
+        m = p.m
+        k0 = 2 * (p.n - 1) * m
+        lo_, hi_ = max(a, k0), min(b, k0 + 2 * m)
+        if hi_ > lo_:
+            idx = np.arange(lo_, hi_)
+            Fh[idx[idx % 2 == 1] - a] = -1e6 * (cells * h) / (m - 1)
+        return Fh
+
+    steps = min(args.steps, 2)
+    times, infos = [], []
+    for s in range(steps + 1):
+        barrier()
+        t0 = time.perf_counter()
+        U, info = pdist.static_solve(cols_total * h, cells * h, cols_total, cells, F=load, E=E, nu=NU, t=T, nodes=_StripNodes(nodes_strip, p),
+                                     rtol=1e-8, maxit=args.e2e_iters, check_every=args.e2e_iters, raise_on_fail=False)
+        barrier()
+        times.append(time.perf_counter() - t0)
+        infos.append(info)
+        del U
+    t = maxr(sum(times[1:]))
+    its = infos[-1]["iterations"]
+    return {"value": prob.n_free_global * its * steps / t, "unit": UNIT, "h2d_bytes_per_step": int(infos[-1]["h2d_bytes"]),
+            "d2h_bytes_per_step": int(infos[-1]["d2h_bytes"]), "steps": steps, "pcg_iters_per_call": int(its),
+            "calls": "per rank: psfem_b200.dist.static_solve(L, l, N, M, F=host load, nodes=host coordinates, maxit) -> strip upload from "
+                     "pinned host memory, device connectivity, pattern + assembly + BC, PCG iterations, D2H of the owned displacements, "
+                     "gather of the global U on rank 0"}
+
+
+class _StripNodes:
+    """Stands for the global (n*m, 2) host coordinate array inside a rank that holds only the rows of its strip."""
+
+    def __init__(self, strip, part):
+        self._strip, self._part = strip, part
+        self.shape = (part.n * part.m, 2)
+        self.dtype = strip.dtype
+
+    def __getitem__(self, sl):
+        p = self._part
+        if not (isinstance(sl, slice) and sl.start == p.e0 * p.m and sl.stop == p.e1 * p.m):
+            raise IndexError("this rank holds the rows of its own strip only")
+        return self._strip
+
+    def __array__(self, *a, **k):
+        raise TypeError("a strip window cannot be materialised as the global array")
 
 
 if __name__ == "__main__":

@@ -508,6 +508,43 @@ def element_stiffness_threads(nodes, conn, E, nu, t, element_type, mesh_type, nt
     return np.concatenate(parts, axis=0)
 
 
+def assemble_chunked(nodes, conn, n_cols, m_cells, E, nu, t, nthreads, col0=0, col1=None, drop_first_node_column=False):
+    """global_stiffness_matrix of a Q4 plate mesh (n_cols x m_cells cells, element id = i*m_cells + j, Polygones.py:96-100)
+    assembled in slabs of cell columns on `nthreads` threads -- the CPU path with every host core busy, and the only
+    way to build the 7.3 GB matrix of the 4096 x 4096 plate without a 17 GB COO intermediate.  A slab assembles every
+    element touching its node columns (its own cells + the cell column before them) with `assemble` and keeps the rows
+    of its node columns, so every row is complete and identical to the one-shot assembly (tests/test_oracle_golden.py).
+    col0/col1: node-column range of the rows to produce (default all).  drop_first_node_column: return
+    K[np.ix_(free, free)] for a clamped left edge (Polygones.boundary('left', [0, 0], ...) + apply_boundary_conditions,
+    Polygones.py:989-1006) without ever forming K."""
+    from concurrent.futures import ThreadPoolExecutor
+    m = m_cells + 1
+    n_node_cols = n_cols + 1
+    col1 = n_node_cols if col1 is None else col1
+    first = max(col0, 1 if drop_first_node_column else 0)
+    bounds = np.unique(np.linspace(first, col1, max(min(4 * nthreads, col1 - first), 1) + 1).astype(np.int64))
+    ndof = 2 * len(nodes)
+    shift = 2 * m if drop_first_node_column else 0
+
+    def slab(k):
+        c0, c1 = int(bounds[k]), int(bounds[k + 1])                     # node columns whose rows this slab produces
+        e0, e1 = max(c0 - 1, 0) * m_cells, min(c1, n_cols) * m_cells     # cells touching them
+        Ke = element_stiffness(nodes, conn[e0:e1], E, nu, t, "quad", "coarse")
+        A = assemble(Ke, conn[e0:e1], len(nodes))[2 * m * c0:2 * m * c1]
+        if shift:
+            if c0 <= 1:
+                A = A[:, shift:]                                         # rows of node column 1 couple with the clamped column
+            else:
+                A = sparse.csr_matrix((A.data, A.indices - shift, A.indptr), shape=(A.shape[0], ndof - shift))
+        return A
+
+    with ThreadPoolExecutor(nthreads) as pool:
+        parts = list(pool.map(slab, range(len(bounds) - 1)))
+    K = sparse.vstack(parts, format="csr")
+    K.sort_indices()
+    return K
+
+
 def newmark_forces(n_nodes, L, P=1e6, T=10.0, dt=1e-3, accel_ratio=3):
     """Ramp load of main.py:201,208-209,226-236.  Returns times, nbPoints, T0, F_y(t) per node (scalar series)."""
     nb = int(T / dt) + 1

@@ -105,10 +105,12 @@ class DeviceBackedCSR(sparse.csr_matrix):
     def _psfem_touch(self):
         self._psfem_dev = None
         self._psfem_key = None
-        try:
-            self.data.flags.writeable = True
-        except ValueError:                      # a view of a buffer that is itself read-only: take a private copy
-            self.data = self.data.copy()
+        data = self.__dict__.get("data")        # (scipy's constructor calls prune() before / while the arrays are set)
+        if data is not None and not data.flags.writeable:
+            try:
+                data.flags.writeable = True
+            except ValueError:                  # a view of a buffer that is itself read-only: take a private copy
+                self.data = data.copy()
 
 
 def _mutator(name):

@@ -83,6 +83,19 @@ def to_host(t):
     return h
 
 
+def host_array(h):
+    """NumPy view of a host tensor whose WRITEABLE flag can be cleared AND set again.  `tensor.numpy()` arrays cannot be
+    made writeable once locked (their base is not a buffer exporter), so DeviceBackedCSR -- which hands its values out
+    read-only and unlocks them on the first in-place edit -- would have to copy 4.8 GB; a ctypes view of the same
+    (page-locked) memory can be toggled.  The tensor stays alive as long as the array does."""
+    n = h.numel() * h.element_size()
+    if n == 0:
+        return h.numpy()
+    buf = (C.c_ubyte * n).from_address(h.data_ptr())
+    buf._psfem_keep = h
+    return np.frombuffer(buf, dtype=h.numpy().dtype).reshape(tuple(h.shape))
+
+
 def to_device(a, dtype=None):
     """Host ndarray -> device tensor; page-locked sources (e.g. arrays this package returned) go by DMA."""
     import warnings
@@ -218,7 +231,7 @@ class DeviceCSR:
         torch = _capi.torch_cuda()
         parts = [to_host(t) for t in (self.vals, self.col_idx, self.row_ptr)]
         torch.cuda.current_stream().synchronize()
-        A = (cls or sparse.csr_matrix)(tuple(h.numpy() for h in parts), shape=self.shape)
+        A = (cls or sparse.csr_matrix)(tuple(host_array(h) for h in parts), shape=self.shape)
         # device-built patterns are sorted and duplicate-free: tell scipy, so that it never scans (or rewrites) the arrays
         A.has_canonical_format = True
         return A

@@ -186,45 +186,88 @@ class PeerFabric:
     handles and the halo sizes once, through torch.distributed."""
 
     def __init__(self, part: StripPartition, plan: dict, dist_module):
+        """Collective: every rank must call it.  Whether the peer transport is usable is decided TOGETHER -- a failure of
+        cudaIpcGetMemHandle / cudaIpcOpenMemHandle on any rank (no P2P between one pair of GPUs) is all-reduced, every
+        rank then releases what it had allocated or mapped and raises, so that all ranks fall back to NCCL in step
+        (a rank that skipped the collectives below on its own would leave the others hanging in them)."""
         torch = _capi.torch_cuda()
         self.part, self.plan, self.dist = part, plan, dist_module
         self.opened = []
         self.own = []
+        self.p_ext = None
         world, rank = part.world, part.rank
         if world > _capi.MAX_RANKS:
             raise RuntimeError(f"fused strip solver supports up to {_capi.MAX_RANKS} ranks")
-        sz = C.c_size_t(0)
-        call("psfem_peer_board_bytes", C.byref(sz))
-        self.board_ptr, hb = self._alloc(sz.value)
         self.n_ext_free = plan["n_ext_free"]
-        self.p_ptr, hp = self._alloc(max(self.n_ext_free, 1) * 8)
         lo, hi = plan["own"]
+
+        def agree(err):
+            """all-reduce(MIN) of 'my step worked'; on any failure release everything on every rank and raise"""
+            ok = torch.tensor([0 if err else 1], dtype=torch.int32, device="cuda")
+            dist_module.all_reduce(ok, op=dist_module.ReduceOp.MIN)
+            if int(ok.item()) == 0:
+                self._release_local()
+                raise RuntimeError(f"peer-memory transport unavailable on at least one rank ({err or 'a peer rank failed'})")
+
+        # stage 1 (local): my board and my extended p vector
+        err, hb, hp = None, None, None
+        try:
+            sz = C.c_size_t(0)
+            call("psfem_peer_board_bytes", C.byref(sz))
+            self.board_ptr, hb = self._alloc(sz.value)
+            self.p_ptr, hp = self._alloc(max(self.n_ext_free, 1) * 8)
+        except Exception as e:                                # noqa: BLE001 -- any failure means "no peer transport"
+            err = str(e)
+        agree(err)
+        # stage 2 (collective): swap the IPC handles and the halo sizes
         mine = dict(board=hb, p=hp, lo=lo, hi=hi, n_ext_free=self.n_ext_free,
                     send_left=plan["send_left"], send_right=plan["send_right"])
         everyone = [None] * world
         dist_module.all_gather_object(everyone, mine)
-        self.boards = [None] * world
-        for w in range(world):
-            self.boards[w] = self.board_ptr if w == rank else self._open(everyone[w]["board"])
-        self.left_p = self.right_p = None
-        self.left_dst_off = self.right_dst_off = 0
-        self.send_left_n = self.send_right_n = 0
-        if part.left is not None:
-            nb = everyone[part.left]
-            self.left_p = self._open(nb["p"])
-            self.left_dst_off = nb["hi"]                                   # its recv_right region [hi, n_ext_free)
-            self.send_left_n = plan["send_left"][1] - plan["send_left"][0]
-            if self.send_left_n != nb["n_ext_free"] - nb["hi"] or plan["send_left"][0] != lo:
-                raise RuntimeError("halo plan mismatch with the left neighbour")
-        if part.right is not None:
-            nb = everyone[part.right]
-            self.right_p = self._open(nb["p"])
-            self.right_dst_off = 0                                           # its recv_left region [0, lo)
-            self.send_right_n = plan["send_right"][1] - plan["send_right"][0]
-            if self.send_right_n != nb["lo"] or plan["send_right"][1] != hi:
-                raise RuntimeError("halo plan mismatch with the right neighbour")
+        # stage 3 (local): map the other ranks' boards and my neighbours' vectors
+        err = None
+        try:
+            self.boards = [None] * world
+            for w in range(world):
+                self.boards[w] = self.board_ptr if w == rank else self._open(everyone[w]["board"])
+            self.left_p = self.right_p = None
+            self.left_dst_off = self.right_dst_off = 0
+            self.send_left_n = self.send_right_n = 0
+            if part.left is not None:
+                nb = everyone[part.left]
+                self.left_p = self._open(nb["p"])
+                self.left_dst_off = nb["hi"]                                   # its recv_right region [hi, n_ext_free)
+                self.send_left_n = plan["send_left"][1] - plan["send_left"][0]
+                if self.send_left_n != nb["n_ext_free"] - nb["hi"] or plan["send_left"][0] != lo:
+                    raise RuntimeError("halo plan mismatch with the left neighbour")
+            if part.right is not None:
+                nb = everyone[part.right]
+                self.right_p = self._open(nb["p"])
+                self.right_dst_off = 0                                           # its recv_left region [0, lo)
+                self.send_right_n = plan["send_right"][1] - plan["send_right"][0]
+                if self.send_right_n != nb["lo"] or plan["send_right"][1] != hi:
+                    raise RuntimeError("halo plan mismatch with the right neighbour")
+        except Exception as e:                                # noqa: BLE001
+            err = str(e)
+        agree(err)
         self.p_ext = torch.as_tensor(_RawDeviceArray(self.p_ptr, self.n_ext_free), device="cuda")
         dist_module.barrier()
+
+    def _release_local(self):
+        """Unmap and free without any collective (the failure path of __init__: every rank runs it after the all-reduce)."""
+        self.p_ext = None
+        for q in self.opened:
+            try:
+                call("psfem_peer_close", C.c_void_p(q))
+            except Exception:                                  # noqa: BLE001
+                pass
+        self.opened = []
+        for q in self.own:
+            try:
+                call("psfem_peer_free", C.c_void_p(q))
+            except Exception:                                  # noqa: BLE001
+                pass
+        self.own = []
 
     def _alloc(self, nbytes):
         p = C.c_void_p(0)
@@ -402,9 +445,9 @@ class StripProblem:
         if self.world > 1 and self.transport == "peer":
             try:
                 self.fabric = PeerFabric(p, self.plan, dist)
-            except Exception as e:                      # no P2P / IPC on this box: keep the NCCL transport
-                import warnings
-                warnings.warn(f"peer-memory transport unavailable ({e}); using NCCL")
+            except RuntimeError as e:                   # no P2P / IPC on this box: PeerFabric decided that COLLECTIVELY and
+                import warnings                         # released its memory on every rank, so all ranks switch together
+                warnings.warn(f"{e}; using NCCL")
                 self.fabric, self.transport = None, "nccl"
         p_ext = self.fabric.p_ext if self.fabric else torch.zeros(self.n_ext_free, **f64)
         self.st = dict(x=torch.zeros(n, **f64), r=self.b_own.clone(), q=torch.empty(n, **f64),
@@ -436,6 +479,13 @@ class StripProblem:
     def start(self):
         """x = 0, r = b, p = D^-1 r with its halo, r.z / r.r / b.b."""
         if self.fabric:
+            if self.seq > 0:
+                # restart on live boards: every rank must have consumed the previous sequence numbers of stage 1 before
+                # a fast rank publishes the start step into the same slots
+                torch = _capi.torch_cuda()
+                import torch.distributed as dist
+                torch.cuda.synchronize()
+                dist.barrier()
             self.seq += 1
             call("psfem_dist_pcg_start", C.byref(self.ctx), ptr(self.b_own), self.seq, stream_ptr())
             self.st["iters"] = 0
@@ -446,6 +496,24 @@ class StripProblem:
             self.st["x"].zero_()
             self.st["r"].copy_(self.b_own)
             pcg_start(self.ops, self.comm, self.st, self.b_own)
+
+    # -- what the benchmark reports about the iteration ------------------------------------------------
+    pcg_variant = "classic Jacobi-PCG: SpMV+dot | r-update+dots | x,p-update (3 kernels, 2 reductions per iteration)"
+    kernels_per_iteration = 3
+
+    def iteration_bytes(self, spmv_bytes):
+        """algorithmic HBM bytes of one PCG iteration on this rank: the SpMV + update (q, r, dinv read, r written) +
+        p-update (p, x, r, dinv read, p, x written) = spmv + 80 B per DOF"""
+        return spmv_bytes + (4 + 6) * 8 * self.n_owned_free
+
+    @staticmethod
+    def dominant_kernel(sym_lat, node_block, idx_bytes):
+        if sym_lat:
+            return ("spmv_sl_kernel<true> (PCG SpMV + dot on symmetric-lattice storage: marching warps, 152 B of matrix per node, "
+                    "bit-identical to the CSR kernels)")
+        if node_block:
+            return f"spmv_nb_kernel<true> (PCG SpMV + dot on the 2x2 node-block structure, TMA-staged, {8 + idx_bytes / 4:g} B/non-zero)"
+        return "spmv2_kernel<true> (PCG SpMV + dot, CSR, TMA-staged, 12 B/non-zero)"
 
     # -- timed pieces -----------------------------------------------------------------------------
     def assemble(self):
@@ -573,3 +641,58 @@ class StripProblem:
         for k in ("asm", "K_vals", "K_ext_red", "K_red", "fm", "st", "ops", "A", "b_own", "nodes", "conn", "ctx", "_cd_owned"):
             if hasattr(self, k):
                 delattr(self, k)
+
+
+# ------------------------------------------------------------------------------------------------
+# public multi-GPU entry point
+# ------------------------------------------------------------------------------------------------
+def static_solve(L, l, N, M=0, bc=None, F=None, E=210e9, nu=0.3, t=0.1, element_type="quad", mesh_type="coarse",
+                 nodes=None, rtol=1e-8, maxit=200000, check_every=100, dst=0, raise_on_fail=True, transport=None):
+    """Static solve of a `Polygones.mesh(L, l, N, M, element_type=..., mesh_type=...)` plate on ALL ranks of the default
+    torch.distributed process group (one process per GPU): the multi-GPU counterpart of `drivers.static_solve`, i.e. of
+    mesh -> global_stiffness_matrix -> apply_boundary_conditions -> solve -> reconstruct (Statictest.py:49-75).
+
+    Every rank calls it with the same arguments, all HOST data:
+      bc     boundary conditions like the reference's lists [(node, [ux, uy]), ...] (default: left edge clamped),
+      F      global load vector (2 * nodes), or a callable (dof_lo, dof_hi) -> slice (default: edgeForces on the right edge),
+      nodes  optional (n*m, 2) coordinates replacing the regular ones (a deformed / jittered structured mesh); each rank
+             uploads only the rows of its strip.
+    The strip of each rank is meshed, assembled and reduced on its GPU without communication; the PCG runs with the
+    collectives fused into its kernels over peer memory (NCCL when peer access is unavailable).
+    Returns (U, info): U = the global displacement vector with zeros at constrained DOFs (reconstruct_full_vector,
+    Polygones.py:913-921) on rank `dst`, None elsewhere; info = dict(iterations, relres, converged, seconds, transport,
+    h2d_bytes, d2h_bytes of this rank)."""
+    import torch.distributed as dist
+    torch = _capi.torch_cuda()
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    M = M or N
+    prob = StripProblem(L=L, l=l, N=N, M=M, rank=rank, world=world, E=E, nu=nu, t=t, element_type=element_type,
+                        mesh_type=mesh_type, bc=bc, F=F, transport=transport)
+    h2d = 0
+    nodes_conn = None
+    if nodes is not None:
+        from .device import device_mesh
+        p = prob.part
+        if tuple(nodes.shape) != (p.n * p.m, 2):
+            raise ValueError(f"nodes must have shape ({p.n * p.m}, 2) for this mesh")
+        _, conn = device_mesh(L, l, N, M, 0, 0, element_type, mesh_type, col0=p.e0, ncols=p.e1 - p.e0, cell0=p.cell0,
+                              ncells=p.cell1 - p.cell0)
+        part = nodes[p.e0 * p.m:p.e1 * p.m]
+        part = part if isinstance(part, np.ndarray) and part.dtype == np.float64 else np.ascontiguousarray(part, dtype=np.float64)
+        nd = torch.from_numpy(part).to("cuda", non_blocking=True)
+        h2d += part.nbytes
+        nodes_conn = (nd, conn)
+    prob.setup(nodes_conn)
+    if F is not None:
+        h2d += 8 * prob.part.n_ext_dof
+    info = prob.solve(rtol=rtol, maxit=maxit, check_every=check_every)
+    info["converged"] = bool(info["relres"] <= rtol)
+    info["transport"] = prob.transport if world > 1 else "single GPU"
+    U = prob.gather_solution(dst=dst)
+    info["h2d_bytes"] = int(h2d)
+    info["d2h_bytes"] = int(8 * prob.n_owned_free)
+    prob.release()
+    if raise_on_fail and not info["converged"]:
+        raise _capi.ConvergenceError(f"strip PCG: relres {info['relres']:.3e} after {info['iterations']} iterations")
+    return U, info

@@ -1,0 +1,108 @@
+"""Multi-GPU self-check of the strip-partitioned PCG (every rank of an initialised NCCL process group calls
+`run_checks`; `tests/dist_fused_check.py` runs it under torchrun, `bench.py --gpus N` before it times anything):
+  1. the peer-memory transport (collectives fused into the PCG kernels) and the NCCL transport give the same
+     iterates (bit-identical for 2 ranks: the scalar sums have two addends);
+  2. both match the single-GPU solver on the owned rows, and the assembled, reduced matrix rows a rank owns are
+     the single-GPU rows bit for bit;
+  3. a restarted solve (sequence numbers keep growing) converges to the requested residual;
+  3b. the same for T3 and the quadratic T6 / Q9 strips (two-column left halo);
+  4. a problem with general boundary conditions (rollers, a pinned node) and loads gives the single-GPU solution
+     (solved on the unreduced strip matrix with the constrained DOFs masked), through the public `dist.static_solve`.
+Everything is compared with the PRODUCT's single-GPU path (itself pinned to the oracle by tests/test_gpu_parity.py).
+"""
+import os
+
+import numpy as np
+
+
+def run_checks(world, rank):
+    import torch.distributed as dist
+    import psfem_b200
+    from psfem_b200.dist import StripProblem, static_solve
+    N, M, iters = 96 * world, 80, 40
+    kw = dict(L=N * 1e-2, l=M * 1e-2, N=N, M=M, E=210e9, nu=0.3, t=0.1)
+    res = {}
+    for transport in ("peer", "nccl"):
+        prob = StripProblem(rank=rank, world=world, transport=transport, **kw).setup()
+        assert prob.transport == transport, f"transport {transport} not available: fell back to {prob.transport}"
+        assert (prob.fabric is not None) == (transport == "peer")
+        assert prob.sym_lattice or os.environ.get("PSFEM_NO_SYMLATTICE")   # the strips run the symmetric-lattice SpMV
+        if transport == "peer":                                    # assembled + reduced rows this rank owns
+            rp = prob.K_red.row_ptr.cpu().numpy().astype(np.int64)
+            res["K_rows"] = (rp - rp[0], prob.K_red.vals[int(rp[0]):int(rp[-1])].cpu().numpy().copy(),
+                             prob.K_red.col_idx[int(rp[0]):int(rp[-1])].cpu().numpy().astype(np.int64) - prob.plan["own"][0])
+        prob.cg_iterations(iters)
+        r, b = prob.residual()
+        res[transport] = (prob.st["x"].cpu().numpy().copy(), r, b)
+        if transport == "peer":                                    # restart on the same boards, solve to 1e-9
+            info = prob.full_solve(1e-9)
+            assert info["relres"] <= 1e-9, info
+            res["solve_iters"] = info["iterations"]
+        lo_hi = (prob.part.dof_shift, prob.plan["own"])
+        prob.release()
+    xp, rp, bp = res["peer"]
+    xn, rn, bn = res["nccl"]
+    scale = np.abs(xn).max()
+    if world == 2:
+        assert np.array_equal(xp, xn), np.abs(xp - xn).max() / scale
+        assert rp == rn and bp == bn
+    else:
+        assert np.abs(xp - xn).max() <= 1e-9 * scale
+        assert abs(rp - rn) <= 1e-6 * rn
+    # single-GPU solver on the whole plate (every rank repeats it; small)
+    one = StripProblem(rank=0, world=1, **kw).setup()
+    one.cg_iterations(iters)
+    x1 = one.st["x"].cpu().numpy()
+    r1, b1 = one.residual()
+    # owned free DOFs of this rank inside the global free vector: rank 0 starts at 0, sizes are gathered
+    sizes = [None] * world
+    dist.all_gather_object(sizes, len(xp))
+    off = sum(sizes[:rank])
+    assert sum(sizes) == len(x1)
+    # the strip's owned rows of K are the single-GPU rows BIT FOR BIT (pattern, values; columns up to the strip offset)
+    rp1 = one.K_red.row_ptr.cpu().numpy().astype(np.int64)
+    a, b_ = int(rp1[off]), int(rp1[off + len(xp)])
+    rel_ptr, vals, cols = res["K_rows"]
+    assert np.array_equal(rel_ptr, rp1[off:off + len(xp) + 1] - a)
+    assert np.array_equal(vals, one.K_red.vals[a:b_].cpu().numpy())
+    assert np.array_equal(cols + off, one.K_red.col_idx[a:b_].cpu().numpy().astype(np.int64))
+    assert np.abs(xp - x1[off:off + len(xp)]).max() <= 1e-8 * np.abs(x1).max()
+    assert abs(rp - r1) <= 1e-5 * r1 and abs(bp - b1) <= 1e-12 * b1
+    # 3b. the other element types (T3, and the quadratic T6 / Q9 of mesh_type='fine', whose strips carry a two-column
+    #     left halo): owned matrix rows bit-identical to the single-GPU rows, same iterates
+    for et, mt, n_, m_ in (("tri", "coarse", 40 * world, 60), ("quad", "fine", 24 * world, 20), ("tri", "fine", 24 * world, 20)):
+        kw2 = dict(L=n_ * 1e-2, l=m_ * 1e-2, N=n_, M=m_, E=210e9, nu=0.3, t=0.1, element_type=et, mesh_type=mt)
+        pr = StripProblem(rank=rank, world=world, transport="peer", **kw2).setup()
+        rpo = pr.K_red.row_ptr.cpu().numpy().astype(np.int64)
+        vals_own = pr.K_red.vals[int(rpo[0]):int(rpo[-1])].cpu().numpy().copy()
+        pr.cg_iterations(25)
+        x_own = pr.st["x"].cpu().numpy().copy()
+        pr.release()
+        o1 = StripProblem(rank=0, world=1, **kw2).setup()
+        o1.cg_iterations(25)
+        sizes2 = [None] * world
+        dist.all_gather_object(sizes2, len(x_own))
+        off2 = sum(sizes2[:rank])
+        rp1 = o1.K_red.row_ptr.cpu().numpy().astype(np.int64)
+        assert np.array_equal(rpo - rpo[0], rp1[off2:off2 + len(x_own) + 1] - rp1[off2]), (et, mt)
+        assert np.array_equal(vals_own, o1.K_red.vals[int(rp1[off2]):int(rp1[off2 + len(x_own)])].cpu().numpy()), (et, mt)
+        x1_ = o1.st["x"].cpu().numpy()
+        assert np.abs(x_own - x1_[off2:off2 + len(x_own)]).max() <= 1e-9 * np.abs(x1_).max(), (et, mt)
+        o1.release()
+    # 4. general boundary conditions and loads: rollers along the bottom edge (single DOFs constrained: the reduced
+    #    matrix would lose its node-block structure, so the strips keep them as masked rows), one pinned node, load on the top edge; the gathered
+    #    solution against the single-GPU static_solve of the same problem
+    from psfem_b200 import Polygones as P
+    nodes, elements = P.mesh(kw["L"], kw["l"], N, M, element_type="quad")
+    bc = [(0, [0, 0])] + P.boundary("bottom", [None, 0], N, M)[1:]
+    Fg = P.edgeForces(np.zeros(2 * len(nodes)), [2e5, -1e6], "top", kw["L"], N, M)
+    Ug, info = static_solve(kw["L"], kw["l"], N, M, bc=bc, F=Fg, E=kw["E"], nu=kw["nu"], t=kw["t"], rtol=1e-11, maxit=40000,
+                            check_every=200, transport="peer")
+    assert info["relres"] <= 1e-11 and info["transport"] == "peer", info
+    if rank == 0:
+        K = P.global_stiffness_matrix(nodes, elements, kw["E"], kw["nu"], kw["t"], "quad")
+        U1, _, cd, _ = psfem_b200.static_solve(K, Fg, bc, rtol=1e-11, check_every=200)
+        assert np.all(Ug[cd] == 0)
+        assert np.abs(Ug - U1).max() <= 1e-8 * np.abs(U1).max(), np.abs(Ug - U1).max() / np.abs(U1).max()
+    dist.barrier()
+    return dict(world=world, iters=iters, relres=rp / bp, full_solve_iterations=res["solve_iters"])
