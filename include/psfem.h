@@ -306,6 +306,28 @@ int psfem_residual_dd(const psfem_csr *A, const double *d_x, const double *d_b, 
 int psfem_csr_symmetry(const psfem_csr *A, double rtol, double atol, int64_t *h_violations, double *h_max_abs_diff,
                        void *d_ws, size_t ws_bytes, void *stream);
 
+/* ---- Jacobi-PCG with ONE KERNEL PER ITERATION on symmetric-lattice operands ------------------------------------------
+ * Same solves as psfem_pcg_jacobi / psfem_pcg_jacobi_masked (Statictest.py:69, main.py:286,314) for operands that carry
+ * their symmetric-lattice storage (psfem_spmv_sl_build: the matrices of Polygones.mesh meshes), in the Chronopoulos-Gear
+ * form of the recurrence (one reduction per iteration; same Krylov iterates in exact arithmetic):
+ *     p = u + beta p;  s = w + beta s;  x += alpha p;  r -= alpha s;  u = D^-1 r;  w = A u;  {r.u, w.u, r.r} -> alpha', beta'
+ * The pointwise part rides on the marching warps of the SpMV: 312 B of HBM traffic per node and iteration instead of
+ * 344 B in three kernels, D^-1 taken from the streamed diagonal.  d_new_id != NULL: constrained DOFs stay as masked rows.
+ *   psfem_cg_sl_usable     *h_usable = 1 when A can take this path (symmetric-lattice storage of A->vals, rows = columns)
+ *   psfem_cg_sl_start      x0 = d_x on entry; r0, u0, w0, alpha0 (uses the SpMV kernel twice)
+ *   psfem_cg_sl_iterations k launches; iters_done = iterations launched since the start (selects the buffer parity)
+ *   psfem_cg_sl_state      h_info = {iterations, relative residual, ||b||, done, status}; synchronises
+ *   psfem_cg_sl_solve      start + batches of check_every iterations until ||r|| <= rtol ||b|| (decided on the device) */
+int psfem_cg_sl_usable(const psfem_csr *A, int *h_usable);
+int psfem_cg_sl_workspace(int64_t n, size_t *bytes);
+int psfem_cg_sl_start(const psfem_csr *A, const double *d_b, double *d_x, const int32_t *d_new_id, double rtol,
+                      void *d_ws, size_t ws_bytes, void *stream);
+int psfem_cg_sl_iterations(const psfem_csr *A, double *d_x, int masked, int64_t k, int64_t iters_done, void *d_ws,
+                           size_t ws_bytes, void *stream);
+int psfem_cg_sl_state(void *d_ws, int64_t n, double *h_info /* [5] */, void *stream);
+int psfem_cg_sl_solve(const psfem_csr *A, const double *d_b, double *d_x, const int32_t *d_new_id, double rtol, int64_t maxit,
+                      int64_t check_every, double *h_info, void *d_ws, size_t ws_bytes, void *stream);
+
 /* The kernels of one PCG iteration, exposed so the strip-partitioned multi-GPU driver can put its
  * halo exchange and all-reduces between them (scalars stay on the device):
  *   init    : p = dinv*r ; out3 = {r.dinv r, r.r, b.b}  (local sums)

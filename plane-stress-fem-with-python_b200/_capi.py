@@ -107,6 +107,12 @@ SIGNATURES = {
     "psfem_direct_solve": [_pcsr, _ptr, _ptr, _i64, _i32, _pdbl, _ptr, _sz, _ptr],
     "psfem_residual_dd": [_pcsr, _ptr, _ptr, _ptr, _ptr],
     "psfem_csr_symmetry": [_pcsr, _dbl, _dbl, _pi64, _pdbl, _ptr, _sz, _ptr],
+    "psfem_cg_sl_usable": [_pcsr, C.POINTER(C.c_int)],
+    "psfem_cg_sl_workspace": [_i64, _psz],
+    "psfem_cg_sl_start": [_pcsr, _ptr, _ptr, _ptr, _dbl, _ptr, _sz, _ptr],
+    "psfem_cg_sl_iterations": [_pcsr, _ptr, _i32, _i64, _i64, _ptr, _sz, _ptr],
+    "psfem_cg_sl_state": [_ptr, _i64, _pdbl, _ptr],
+    "psfem_cg_sl_solve": [_pcsr, _ptr, _ptr, _ptr, _dbl, _i64, _i64, _pdbl, _ptr, _sz, _ptr],
     "psfem_pcg_init": [_i64, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr],
     "psfem_pcg_spmv_dot": [_pcsr, _ptr, _i64, _ptr, _ptr, _ptr, _ptr, _ptr],
     "psfem_pcg_update": [_i64, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr],

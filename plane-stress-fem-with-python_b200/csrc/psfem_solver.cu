@@ -688,7 +688,7 @@ spmv_nb_kernel(const int32_t *__restrict__ node_ptr, const void *__restrict__ pc
 #include "psfem_spmv_sl.cuh"
 
 // geometry of the symmetric-lattice operand attached to A (psfem_spmv_sl_build)
-bool sl_geometry(const psfem_csr *A, SlGeom *g, int sms) {
+bool sl_geometry(const psfem_csr *A, SlGeom *g, int sms, int ctas_per_sm = PSFEM_SL_CTAS) {
     const int64_t m = A->sl_m, nodes = A->n_rows / 2;
     if (m < 2 || nodes % m || A->sl_roff % m || A->sl_x_nodes % m) return false;
     const int64_t owned_cols = nodes / m, c0x = A->sl_roff / m;
@@ -698,7 +698,7 @@ bool sl_geometry(const psfem_csr *A, SlGeom *g, int sms) {
     g->xcol0 = (int)c0x - g->pre;
     g->xcols = (int)(A->sl_x_nodes / m);
     g->n_strips = (int)ceil_div(m, SL_ROWS);
-    int64_t G = (int64_t)sms * PSFEM_SL_CTAS * SL_WARPS / g->n_strips;   // one resident wave of warps
+    int64_t G = (int64_t)sms * ctas_per_sm * SL_WARPS / g->n_strips;     // one resident wave of warps
     if (G > owned_cols / 4) G = owned_cols / 4;                           // segments of at least 4 columns
     if (G < 1) G = 1;
     g->G = (int)G;
@@ -1193,6 +1193,28 @@ HaloPush make_halo(const psfem_dist_ctx *c) {
     h.right = c->has_right ? c->right_p_ext + c->right_dst_off : nullptr;
     h.left_n = c->send_left_n; h.right_n = c->send_right_n; h.n = c->n_own;
     return h;
+}
+
+#include "psfem_cg_sl.cuh"
+
+struct CgWs {
+    double *r[2], *s[2], *w[2], *p, *dinv, *partials, *scal;
+    CgCtl *ctl;
+    unsigned int *counter;
+    size_t total;
+};
+CgWs carve_cg(void *ws, int64_t n) {
+    CgWs w;
+    Carver c(ws);
+    for (int q = 0; q < 2; ++q) { w.r[q] = c.take<double>(n); w.s[q] = c.take<double>(n); w.w[q] = c.take<double>(n); }
+    w.p = c.take<double>(n);
+    w.dinv = c.take<double>(n);
+    w.partials = c.take<double>(3 * 148 * 8);
+    w.scal = c.take<double>(16);
+    w.ctl = c.take<CgCtl>(1);
+    w.counter = c.take<unsigned int>(4);
+    w.total = c.used();
+    return w;
 }
 
 struct PcgWs {
@@ -1743,5 +1765,142 @@ extern "C" int psfem_multi_axpy(int64_t m, int64_t n, const double *d_V, const d
     if (m == 0 || n == 0) return PSFEM_OK;
     multi_axpy_kernel<<<ew_grid(n), EW_THREADS, 0, stream>>>(m, n, d_V, d_c, d_w);
     PSFEM_LAUNCH_CHECK();
+    return PSFEM_OK;
+}
+
+// =============================================================================================
+// fused single-kernel PCG iteration on symmetric-lattice operands (psfem_cg_sl.cuh)
+// =============================================================================================
+namespace {
+bool cg_sl_ok(const psfem_csr *A, bool strip) {
+    static const bool off = getenv("PSFEM_NO_SYMLATTICE") != nullptr;
+    SlGeom g;
+    return !off && A && A->sl_vals && A->sl_src_vals == A->vals && sl_geometry(A, &g, 148, PSFEM_CG_CTAS) && (strip || A->sl_roff == 0) &&
+           (!strip || A->sl_roff == 0 || A->sl_roff == A->sl_m);
+}
+int cg_sl_launch(const psfem_csr *A, double *d_x, const CgWs &w, bool masked, int64_t it, const PeerSync *peer, const CgVec *halo, cudaStream_t stream) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    SlGeom g;
+    PSFEM_REQUIRE(sl_geometry(A, &g, sms, PSFEM_CG_CTAS), "cg_sl: operand has no symmetric-lattice geometry");
+    const int cur = (int)(it & 1);
+    CgVec v;
+    memset(&v, 0, sizeof(v));
+    if (halo) v = *halo;
+    v.x = d_x; v.p = w.p;
+    v.r_in = w.r[cur]; v.s_in = w.s[cur]; v.w_in = w.w[cur];
+    v.r_out = w.r[cur ^ 1]; v.s_out = w.s[cur ^ 1]; v.w_out = w.w[cur ^ 1];
+    v.dinv = w.dinv;
+    PeerSync ps;
+    memset(&ps, 0, sizeof(ps));
+    if (peer) ps = *peer;
+    const unsigned grid = (unsigned)ceil_div((int64_t)g.n_strips * g.G, SL_WARPS);
+    PSFEM_REQUIRE(grid <= 148 * 8, "cg_sl: grid larger than the partial-sum buffer");
+    if (peer) {
+        if (masked) PSFEM_CUDA_CHECK(launch_pdl(cg_sl_kernel<true, true>, grid, SL_THREADS, 0, stream, A->sl_vals, g, v, w.ctl, w.partials, w.counter, ps));
+        else PSFEM_CUDA_CHECK(launch_pdl(cg_sl_kernel<false, true>, grid, SL_THREADS, 0, stream, A->sl_vals, g, v, w.ctl, w.partials, w.counter, ps));
+    } else {
+        if (masked) PSFEM_CUDA_CHECK(launch_pdl(cg_sl_kernel<true, false>, grid, SL_THREADS, 0, stream, A->sl_vals, g, v, w.ctl, w.partials, w.counter, ps));
+        else PSFEM_CUDA_CHECK(launch_pdl(cg_sl_kernel<false, false>, grid, SL_THREADS, 0, stream, A->sl_vals, g, v, w.ctl, w.partials, w.counter, ps));
+    }
+    return PSFEM_OK;
+}
+}  // namespace
+
+extern "C" int psfem_cg_sl_usable(const psfem_csr *A, int *h_usable) {
+    PSFEM_REQUIRE(A && h_usable, "cg_sl_usable: null argument");
+    *h_usable = cg_sl_ok(A, false) ? 1 : 0;
+    return PSFEM_OK;
+}
+
+extern "C" int psfem_cg_sl_workspace(int64_t n, size_t *bytes) {
+    PSFEM_REQUIRE(bytes && n >= 0, "cg_sl_workspace: bad arguments");
+    *bytes = carve_cg(nullptr, n).total;
+    return PSFEM_OK;
+}
+
+extern "C" int psfem_cg_sl_start(const psfem_csr *A, const double *d_b, double *d_x, const int32_t *d_new_id, double rtol,
+                                 void *d_ws, size_t ws_bytes, void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    PSFEM_REQUIRE(A && d_b && d_x && d_ws, "cg_sl_start: null argument");
+    PSFEM_REQUIRE(cg_sl_ok(A, false), "cg_sl_start: the operand needs its symmetric-lattice storage (psfem_spmv_sl_build, rows = columns)");
+    const int64_t n = A->n_rows;
+    CgWs w = carve_cg(d_ws, n);
+    PSFEM_REQUIRE(ws_bytes >= w.total, "cg_sl_start: workspace too small (%zu < %zu)", ws_bytes, w.total);
+    PSFEM_CUDA_CHECK(cudaMemsetAsync(w.counter, 0, 4 * sizeof(unsigned int), stream));
+    PSFEM_CUDA_CHECK(cudaMemsetAsync(w.scal, 0, 16 * sizeof(double), stream));
+    PSFEM_CUDA_CHECK(cudaMemsetAsync(w.ctl, 0, sizeof(CgCtl), stream));
+    int rc = psfem_extract_diag(A, 0, 1, w.dinv, stream);
+    if (rc) return rc;
+    const bool masked = d_new_id != nullptr;
+    if (masked) {
+        mask_dinv_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, stream>>>(n, d_new_id, w.dinv);
+        PSFEM_LAUNCH_CHECK();
+    }
+    // r_0 = b - A x_0 ; u_0 = D^-1 r_0 (parked in p) ; w_0 = A u_0 ; gamma_0 = r.u, delta_0 = u.w ; s = 0
+    rc = launch_spmv(A, nullptr, d_x, nullptr, -1.0, 0.0, 1.0, d_b, w.r[0], nullptr, nullptr, nullptr, nullptr, nullptr, stream);
+    if (rc) return rc;
+    pcg_init_kernel<<<ew_grid(n), EW_THREADS, 0, stream>>>(n, w.r[0], w.dinv, d_b, w.p, w.scal, w.partials, w.counter, nullptr, rtol, masked ? 1 : 0);
+    PSFEM_LAUNCH_CHECK();
+    rc = launch_spmv(A, nullptr, w.p, nullptr, 1.0, 0.0, 0.0, nullptr, w.w[0], w.p, w.scal + 4, w.partials, w.counter + 1, nullptr, stream);
+    if (rc) return rc;
+    PSFEM_CUDA_CHECK(cudaMemsetAsync(w.s[0], 0, (size_t)n * sizeof(double), stream));
+    cg_start_ctl_kernel<<<1, 32, 0, stream>>>(w.ctl, w.scal, w.scal + 4, rtol);
+    PSFEM_LAUNCH_CHECK();
+    return PSFEM_OK;
+}
+
+extern "C" int psfem_cg_sl_iterations(const psfem_csr *A, double *d_x, int masked, int64_t k, int64_t iters_done, void *d_ws,
+                                      size_t ws_bytes, void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    PSFEM_REQUIRE(A && d_x && d_ws && k >= 0 && iters_done >= 0, "cg_sl_iterations: bad arguments");
+    PSFEM_REQUIRE(cg_sl_ok(A, false), "cg_sl_iterations: the operand needs its symmetric-lattice storage");
+    CgWs w = carve_cg(d_ws, A->n_rows);
+    PSFEM_REQUIRE(ws_bytes >= w.total, "cg_sl_iterations: workspace too small");
+    for (int64_t j = 0; j < k; ++j) {
+        int rc = cg_sl_launch(A, d_x, w, masked != 0, iters_done + j, nullptr, nullptr, stream);
+        if (rc) return rc;
+    }
+    PSFEM_LAUNCH_CHECK();
+    return PSFEM_OK;
+}
+
+extern "C" int psfem_cg_sl_state(void *d_ws, int64_t n, double *h_info, void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    PSFEM_REQUIRE(d_ws && h_info, "cg_sl_state: null argument");
+    CgWs w = carve_cg(d_ws, n);
+    CgCtl h;
+    PSFEM_CUDA_CHECK(cudaMemcpyAsync(&h, w.ctl, sizeof(h), cudaMemcpyDeviceToHost, stream));
+    PSFEM_CUDA_CHECK(cudaStreamSynchronize(stream));
+    h_info[0] = (double)h.iters;
+    h_info[1] = h.bb > 0 ? sqrt(h.rr / h.bb) : 0.0;
+    h_info[2] = sqrt(h.bb);
+    h_info[3] = (double)h.done;
+    h_info[4] = (double)h.status;
+    return PSFEM_OK;
+}
+
+extern "C" int psfem_cg_sl_solve(const psfem_csr *A, const double *d_b, double *d_x, const int32_t *d_new_id, double rtol, int64_t maxit,
+                                 int64_t check_every, double *h_info, void *d_ws, size_t ws_bytes, void *stream_) {
+    PSFEM_REQUIRE(h_info, "cg_sl_solve: null argument");
+    int rc = psfem_cg_sl_start(A, d_b, d_x, d_new_id, rtol, d_ws, ws_bytes, stream_);
+    if (rc) return rc;
+    if (check_every < 1) check_every = 50;
+    int64_t launched = 0;
+    double st[5];
+    while (true) {
+        rc = psfem_cg_sl_state(d_ws, A->n_rows, st, stream_);
+        if (rc) return rc;
+        if (st[3] != 0.0 || launched >= maxit) break;
+        int64_t batch = check_every;
+        if (launched + batch > maxit) batch = maxit - launched;
+        rc = psfem_cg_sl_iterations(A, d_x, d_new_id != nullptr, batch, launched, d_ws, ws_bytes, stream_);
+        if (rc) return rc;
+        launched += batch;
+    }
+    h_info[0] = st[0]; h_info[1] = st[1]; h_info[2] = st[2];
+    if (st[4] != 0.0) { set_error("cg_sl: breakdown (matrix not positive definite?) after %.0f iterations, relres %.3e", st[0], st[1]); return PSFEM_ENOCONV; }
+    if (!(st[1] <= rtol) && st[2] > 0) { set_error("pcg: not converged (relres %.3e after %.0f iterations)", st[1], st[0]); return PSFEM_ENOCONV; }
     return PSFEM_OK;
 }

@@ -565,6 +565,60 @@ class FreeMap:
 SL_MIN_ROWS = 16384       # systems up to this size run in the single-CTA solver
 
 
+def fused_cg_enabled():
+    """PSFEM_PCG=classic selects the three-kernel recurrence everywhere (A/B measurements, bit-comparison with the oracle's PCG)."""
+    return os.environ.get("PSFEM_PCG", "fused") != "classic"
+
+
+class FusedCG:
+    """Jacobi-PCG with one kernel per iteration on an operand that carries its symmetric-lattice storage
+    (psfem_cg_sl_*: Chronopoulos-Gear recurrence fused into the marching-warp SpMV).  `new_id` (FreeMap.new_id) keeps
+    constrained DOFs in the matrix as masked rows."""
+
+    def __init__(self, A: "DeviceCSR", new_id=None):
+        _capi.bind_device()
+        self.A, self.new_id = A, new_id
+        self.n = A.n_rows
+        sz = C.c_size_t(0)
+        call("psfem_cg_sl_workspace", self.n, C.byref(sz))
+        self.ws, self.ws_bytes = workspace(sz.value), sz.value
+        self.launched = 0
+        self.x = None
+
+    @staticmethod
+    def usable(A: "DeviceCSR") -> bool:
+        if not fused_cg_enabled() or A._sl is None:
+            return False
+        ok = C.c_int(0)
+        s = A.struct()
+        call("psfem_cg_sl_usable", C.byref(s), C.byref(ok))
+        return bool(ok.value)
+
+    def start(self, b, x, rtol=1e-8):
+        """x: start vector on entry (updated in place by the iterations)."""
+        self.x, self.launched = x, 0
+        s = self.A.struct()
+        call("psfem_cg_sl_start", C.byref(s), ptr(b), ptr(x), ptr(self.new_id), float(rtol), ptr(self.ws), self.ws_bytes, stream_ptr())
+
+    def iterations(self, k):
+        s = self.A.struct()
+        call("psfem_cg_sl_iterations", C.byref(s), ptr(self.x), 1 if self.new_id is not None else 0, int(k), self.launched,
+             ptr(self.ws), self.ws_bytes, stream_ptr())
+        self.launched += int(k)
+
+    def state(self):
+        h = (C.c_double * 5)()
+        call("psfem_cg_sl_state", ptr(self.ws), self.n, h, stream_ptr())
+        return dict(iterations=int(h[0]), relres=float(h[1]), bnorm=float(h[2]), done=bool(h[3]), status=int(h[4]))
+
+    def solve(self, b, x, rtol, maxit, check_every):
+        s = self.A.struct()
+        info = (C.c_double * 4)()
+        rc = lib.psfem_cg_sl_solve(C.byref(s), ptr(b), ptr(x), ptr(self.new_id), float(rtol), int(maxit), int(check_every), info,
+                                   ptr(self.ws), self.ws_bytes, stream_ptr())
+        return rc, dict(iterations=int(info[0]), relres=float(info[1]), bnorm=float(info[2]), converged=(rc == _capi.OK), pcg="fused")
+
+
 def pcg_jacobi(A: DeviceCSR, b, x0=None, rtol=1e-8, maxit=None, check_every=50, raise_on_fail=True):
     """Jacobi-PCG on the device.  Returns (x, info) with info = dict(iterations, relres, bnorm)."""
     torch = _capi.torch_cuda()
@@ -575,6 +629,12 @@ def pcg_jacobi(A: DeviceCSR, b, x0=None, rtol=1e-8, maxit=None, check_every=50, 
         maxit = 10 * n + 100
     if n > SL_MIN_ROWS:
         A.sym_lattice()           # half the SpMV traffic when A is a symmetric lattice matrix (same SpMV results bit for bit)
+        if FusedCG.usable(A):     # ... and then the whole iteration is ONE kernel
+            rc, out = FusedCG(A).solve(b, x, rtol, maxit, check_every)
+            if rc == _capi.ENOCONV and not raise_on_fail:
+                return x, out
+            check(rc)
+            return x, out
     s = A.struct()
     sz = C.c_size_t(0)
     call("psfem_pcg_workspace", n, s.n_blocks, C.byref(sz))
@@ -582,7 +642,7 @@ def pcg_jacobi(A: DeviceCSR, b, x0=None, rtol=1e-8, maxit=None, check_every=50, 
     info = (C.c_double * 4)()
     rc = lib.psfem_pcg_jacobi(C.byref(s), ptr(b), ptr(x), float(rtol), int(maxit), int(check_every), info, ptr(ws), sz.value,
                               stream_ptr())
-    out = dict(iterations=int(info[0]), relres=float(info[1]), bnorm=float(info[2]), converged=(rc == _capi.OK))
+    out = dict(iterations=int(info[0]), relres=float(info[1]), bnorm=float(info[2]), converged=(rc == _capi.OK), pcg="classic")
     if rc == _capi.ENOCONV and not raise_on_fail:
         return x, out
     check(rc)

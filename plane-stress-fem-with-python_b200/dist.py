@@ -472,12 +472,27 @@ class StripProblem:
             c.out3 = st["out3"].data_ptr()
             c.partials, c.counter = self.ops.partials.data_ptr(), self.ops.counter.data_ptr()
             c.masked = int(self.masked)
+        # one GPU, symmetric-lattice operand: the whole iteration is one kernel (psfem_cg_sl.cuh)
+        self.fused = None
+        if self.world == 1 and self.sym_lattice:
+            from .device import FusedCG
+            if FusedCG.usable(self.K_red):
+                new_id = None
+                if self.masked:
+                    new_id = torch.zeros(n, dtype=torch.int32, device="cuda")
+                    new_id[self._cd_owned] = -1
+                self.fused = FusedCG(self.K_red, new_id=new_id)
         self.start()
         torch.cuda.synchronize()
         return self
 
     def start(self):
         """x = 0, r = b, p = D^-1 r with its halo, r.z / r.r / b.b."""
+        if self.fused is not None:
+            self.st["x"].zero_()
+            self.fused.start(self.b_own, self.st["x"], rtol=0.0)
+            self.st["iters"] = 0
+            return
         if self.fabric:
             if self.seq > 0:
                 # restart on live boards: every rank must have consumed the previous sequence numbers of stage 1 before
@@ -498,12 +513,23 @@ class StripProblem:
             pcg_start(self.ops, self.comm, self.st, self.b_own)
 
     # -- what the benchmark reports about the iteration ------------------------------------------------
-    pcg_variant = "classic Jacobi-PCG: SpMV+dot | r-update+dots | x,p-update (3 kernels, 2 reductions per iteration)"
-    kernels_per_iteration = 3
+    @property
+    def pcg_variant(self):
+        if getattr(self, "fused", None) is not None or getattr(self, "fused_dist", False):
+            return ("fused Chronopoulos-Gear Jacobi-PCG: pointwise updates inside the marching-warp symmetric-lattice SpMV "
+                    "(1 kernel, 1 reduction per iteration)")
+        return "classic Jacobi-PCG: SpMV+dot | r-update+dots | x,p-update (3 kernels, 2 reductions per iteration)"
+
+    @property
+    def kernels_per_iteration(self):
+        return 1 if (getattr(self, "fused", None) is not None or getattr(self, "fused_dist", False)) else 3
 
     def iteration_bytes(self, spmv_bytes):
-        """algorithmic HBM bytes of one PCG iteration on this rank: the SpMV + update (q, r, dinv read, r written) +
-        p-update (p, x, r, dinv read, p, x written) = spmv + 80 B per DOF"""
+        """algorithmic HBM bytes of one PCG iteration on this rank.  Classic: the SpMV + update (q, r, dinv read, r
+        written) + p-update (p, x, r, dinv read, p, x written) = spmv + 80 B per DOF.  Fused: 152 B of matrix per node +
+        r, w, s, p, x read and r, s, w, p, x written = 152 + 160 B per node (D^-1 comes from the streamed diagonal)."""
+        if self.kernels_per_iteration == 1:
+            return (152 + 160) * (self.n_owned_free // 2)
         return spmv_bytes + (4 + 6) * 8 * self.n_owned_free
 
     @staticmethod
@@ -534,6 +560,10 @@ class StripProblem:
 
     def cg_iterations(self, k):
         self._refresh_operand()
+        if self.fused is not None:
+            self.fused.iterations(k)
+            self.st["iters"] += int(k)
+            return
         if self.fabric:   # three kernels per iteration, no collective launches: scalars and halo go through peer memory
             call("psfem_dist_pcg_iterations", C.byref(self.A), C.byref(self.ctx), int(k), self.seq + 1, stream_ptr())
             self.seq += int(k)
@@ -549,6 +579,9 @@ class StripProblem:
 
     def residual(self):
         """(||r||, ||b||) from the recurrence (global)."""
+        if self.fused is not None:
+            st = self.fused.state()
+            return st["relres"] * st["bnorm"], st["bnorm"]
         if self.fabric:
             h = (C.c_double * 3)()
             call("psfem_dist_pcg_residual", C.byref(self.ctx), self.seq, h, stream_ptr())
@@ -638,7 +671,7 @@ class StripProblem:
             self.st["p_ext"] = None
             self.fabric.close()
             self.fabric = None
-        for k in ("asm", "K_vals", "K_ext_red", "K_red", "fm", "st", "ops", "A", "b_own", "nodes", "conn", "ctx", "_cd_owned"):
+        for k in ("asm", "K_vals", "K_ext_red", "K_red", "fm", "st", "ops", "A", "b_own", "nodes", "conn", "ctx", "_cd_owned", "fused"):
             if hasattr(self, k):
                 delattr(self, k)
 

@@ -14,7 +14,7 @@ import numpy as np
 
 from . import _capi
 from ._capi import call, check, lib, ptr, stream_ptr, workspace
-from .device import (SL_MIN_ROWS, Blas, DeviceCSR, FreeMap, constrained_dofs_of, direct_limits, direct_solve, half_bandwidth,
+from .device import (SL_MIN_ROWS, Blas, DeviceCSR, FreeMap, FusedCG, constrained_dofs_of, direct_limits, direct_solve, half_bandwidth,
                      pcg_jacobi, residual_dd, to_host)
 from .Polygones import device_copy
 
@@ -49,6 +49,13 @@ def _pcg_masked(Kd: DeviceCSR, fm: FreeMap, F_dev, rtol, maxit, check_every, rai
     if maxit is None:
         maxit = 10 * n + 100
     Kd.sym_lattice()              # the unreduced matrix of a Polygones.mesh mesh is a symmetric lattice matrix
+    if FusedCG.usable(Kd):        # one kernel per iteration (constrained DOFs as masked rows)
+        rc, out = FusedCG(Kd, new_id=fm.new_id).solve(F_dev, x, rtol, maxit, check_every)
+        out.update(method="pcg", masked=True)
+        if rc == _capi.ENOCONV and not raise_on_fail:
+            return x, out
+        check(rc)
+        return x, out
     s = Kd.struct()
     sz = C.c_size_t(0)
     call("psfem_pcg_workspace", n, s.n_blocks, C.byref(sz))
@@ -56,7 +63,8 @@ def _pcg_masked(Kd: DeviceCSR, fm: FreeMap, F_dev, rtol, maxit, check_every, rai
     info = (C.c_double * 4)()
     rc = lib.psfem_pcg_jacobi_masked(C.byref(s), ptr(F_dev), ptr(x), ptr(fm.new_id), float(rtol), int(maxit), int(check_every),
                                      info, ptr(ws), sz.value, stream_ptr())
-    out = dict(method="pcg", iterations=int(info[0]), relres=float(info[1]), bnorm=float(info[2]), converged=(rc == _capi.OK), masked=True)
+    out = dict(method="pcg", iterations=int(info[0]), relres=float(info[1]), bnorm=float(info[2]), converged=(rc == _capi.OK), masked=True,
+               pcg="classic")
     if rc == _capi.ENOCONV and not raise_on_fail:
         return x, out
     check(rc)
