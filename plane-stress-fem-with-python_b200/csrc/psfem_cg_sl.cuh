@@ -270,6 +270,244 @@ cg_sl_kernel(const double *__restrict__ sv, const SlGeom g, const CgVec v, CgCtl
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// The same iteration with the operands staged through shared memory by bulk async copies (TMA) + mbarriers.
+//
+// The register-prefetch version above is latency bound (ncu, gpurun_out/r2d: 8 warps per SM at 182 registers, 7 long-
+// scoreboard stalls per issue, 4.2 TB/s).  Here a CTA = one producer warp + four consumer warps that own four adjacent
+// 28-row strips of one column segment.  Per lattice column the producer issues 24 bulk copies (cp.async.bulk, completion
+// on an mbarrier) of the CTA's 116-row window: the 17 off-diagonal components of column c, the two diagonal components of
+// column c+1, and r, w, s, p of column c+1 -- into a 3-stage ring, two columns ahead of the consumers.  Nothing is
+// prefetched in registers (98 registers instead of 182), the loads in flight no longer depend on occupancy.
+// Consumer step for stage {M(c), D(c+1), V(c+1)}:  u(c+1) from V and 1/D  ->  r, s, p, x of column c+1 written;  row sums of
+// column c from M(c), D(c) (carried in registers), u(c), u(c+1)  ->  w of column c written;  chain heads for column c+1.
+// ---------------------------------------------------------------------------------------------
+constexpr int CGT_CONSUMERS = 4;                       // consumer warps = strips per CTA
+constexpr int CGT_THREADS = 32 * (CGT_CONSUMERS + 1);
+constexpr int CGT_RW = SL_ROWS * CGT_CONSUMERS + 4;    // rows of the CTA window: 2 pad/halo rows on either side (116)
+#ifndef PSFEM_CG_STAGES
+#define PSFEM_CG_STAGES 3
+#endif
+constexpr int CGT_STAGES = PSFEM_CG_STAGES;
+static_assert((CGT_RW * 8) % 16 == 0, "bulk copies move multiples of 16 bytes");
+
+struct CgStage {
+    double M[SL_NC][CGT_RW];      // components 1, 3..18 of column c; slots 0 and 2 hold D00 / D11 of column c+1
+    double2 R[CGT_RW], W[CGT_RW], S[CGT_RW], P[CGT_RW], DI[CGT_RW];   // column c+1 (DI: DINV_VEC only)
+};
+
+template <bool DINV_VEC, bool DIST>
+__global__ void __launch_bounds__(CGT_THREADS, 2)
+cg_sl_tma_kernel(const double *__restrict__ sv, const SlGeom g, const CgVec v, CgCtl *__restrict__ ctl, double *__restrict__ partials,
+                 unsigned int *counter, const PeerSync ps, const int n_groups) {
+    extern __shared__ __align__(128) unsigned char cg_smem[];
+    __shared__ double red[CGT_THREADS / 32];
+    __shared__ uint64_t full_bar[CGT_STAGES], empty_bar[CGT_STAGES];
+    CgStage *stages = reinterpret_cast<CgStage *>(cg_smem);
+    pdl_enter();
+    if (ctl->done) return;
+    const double alpha = ctl->alpha, beta = ctl->beta;
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
+    const int gidx = blockIdx.x % n_groups, seg = blockIdx.x / n_groups;
+    const int own0 = g.pre, own1 = g.S, owned_cols = own1 - own0;
+    const int sa = own0 + (int)((long long)seg * owned_cols / g.G);
+    const int sb = own0 + (int)((long long)(seg + 1) * owned_cols / g.G);
+    const int nsteps = (sb - sa) + 2;
+    const size_t mp = (size_t)g.mpad, cstride = (size_t)SL_NC * mp;
+    const long long row0 = (long long)SL_ROWS * CGT_CONSUMERS * gidx - 2;   // first row of the CTA window (may be -2)
+    if (threadIdx.x == 0) {
+        for (int q = 0; q < CGT_STAGES; ++q) { mbar_init(&full_bar[q], 1); mbar_init(&empty_bar[q], CGT_CONSUMERS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    double dots[3] = {0.0, 0.0, 0.0};
+    if (wq == CGT_CONSUMERS) {
+        // ---------------- producer warp ----------------
+        for (int q = 0; q < nsteps; ++q) {
+            const int st = q % CGT_STAGES;
+            if (q >= CGT_STAGES) mbar_wait(&empty_bar[st], ((q / CGT_STAGES) - 1) & 1);
+            CgStage &S = stages[st];
+            const int cM = sa + q - 2, cV = sa + q - 1;
+            const bool haveM = q >= 1 && cM >= 0 && cM < g.S;
+            const bool haveV = cV >= own0 && cV < own1;
+            const uint32_t bM = (uint32_t)(CGT_RW * sizeof(double)), bV = (uint32_t)(CGT_RW * sizeof(double2));
+            uint32_t bytes = 0;
+            if (haveM) bytes += 17u * bM;
+            if (haveV) bytes += 2u * bM + (DINV_VEC ? 5u : 4u) * bV;
+            if (lane == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the consumers' reads of this stage precede the async writes
+                if (bytes) mbar_expect_tx(&full_bar[st], bytes); else mbar_arrive(&full_bar[st]);
+            }
+            __syncwarp();
+            if (haveM && lane < SL_NC && lane != 0 && lane != 2)
+                bulk_g2s(&S.M[lane][0], sv + (size_t)cM * cstride + (size_t)lane * mp + row0, bM, &full_bar[st]);
+            if (haveV) {
+                const long long a0 = (long long)(cV - own0) * g.m + row0;          // first node of the window in the owned-row vectors
+                if (lane == 0 || lane == 2)
+                    bulk_g2s(&S.M[lane][0], sv + (size_t)cV * cstride + (size_t)lane * mp + row0, bM, &full_bar[st]);
+                if (lane == 19) bulk_g2s(&S.R[0], reinterpret_cast<const double2 *>(v.r_in) + a0, bV, &full_bar[st]);
+                if (lane == 20) bulk_g2s(&S.W[0], reinterpret_cast<const double2 *>(v.w_in) + a0, bV, &full_bar[st]);
+                if (lane == 21) bulk_g2s(&S.S[0], reinterpret_cast<const double2 *>(v.s_in) + a0, bV, &full_bar[st]);
+                if (lane == 22) bulk_g2s(&S.P[0], reinterpret_cast<const double2 *>(v.p) + a0, bV, &full_bar[st]);
+                if (DINV_VEC && lane == 23) bulk_g2s(&S.DI[0], reinterpret_cast<const double2 *>(v.dinv) + a0, bV, &full_bar[st]);
+            }
+        }
+    } else {
+        // ---------------- consumer warps ----------------
+        const int sidx = gidx * CGT_CONSUMERS + wq;
+        const int j = sidx * SL_ROWS - 2 + lane;                  // lanes 2..29 own rows, lanes 1 and 30 are the halo rows
+        const int wrow = wq * SL_ROWS + lane;                     // row inside the CTA window
+        const bool active = sidx < g.n_strips;
+        const bool valid = active && j >= 0 && j < g.m && lane >= 1 && lane <= SL_ROWS + 2;
+        const bool owned = valid && lane >= 2 && lane <= SL_ROWS + 1;
+        const bool lo = valid && lane <= SL_ROWS + 1;             // lanes 1..29 hold F1, F4 (blocks towards the row above)
+        const bool hi = valid && lane >= 2;                       // lanes 2..30 hold F2 (block towards the row below)
+        const bool left_halo = DIST && ps.has_left && g.pre == 1;
+        const bool right_halo = DIST && ps.has_right;
+        int *err = ps.err;
+        auto in_seg = [&](int c) { return c >= sa && c < sb; };
+        auto xaddr = [&](int c) { return reinterpret_cast<double2 *>(v.x) + ((size_t)(c - own0) * g.m + j); };
+        if (DIST) {
+            // the last owned column reaches the right neighbour first (its first segment waits for it): computed here from
+            // global memory once more, without the stores
+            if (seg == g.G - 1 && ps.has_right && owned_cols > 0 && owned) {
+                const int c = own1 - 1;
+                const size_t a = (size_t)(c - own0) * g.m + j;
+                const double2 r_ = __ldg(reinterpret_cast<const double2 *>(v.r_in) + a), w_ = __ldg(reinterpret_cast<const double2 *>(v.w_in) + a);
+                const double2 s_ = __ldg(reinterpret_cast<const double2 *>(v.s_in) + a);
+                double2 di;
+                if (DINV_VEC) di = __ldg(reinterpret_cast<const double2 *>(v.dinv) + a);
+                else { const double *pd = sv + (size_t)c * cstride + j; di = make_double2(1.0 / __ldg(pd), 1.0 / __ldg(pd + 2 * mp)); }
+                double2 sn, rn;
+                sn.x = w_.x + beta * s_.x; sn.y = w_.y + beta * s_.y;
+                rn.x = r_.x - alpha * sn.x; rn.y = r_.y - alpha * sn.y;
+                if (DINV_VEC) { rn.x *= (di.x == 0.0 ? 0.0 : 1.0); rn.y *= (di.y == 0.0 ? 0.0 : 1.0); }
+                cg_ll_store(v.ll_to_right + 4 * (size_t)j, make_double2(di.x * rn.x, di.y * rn.y), ps.seq);
+            }
+        }
+        double2 u_prev = make_double2(0.0, 0.0);      // u of column cM
+        double d0 = 0.0, d2 = 0.0;                    // D00, D11 of column cM (arrived one stage earlier)
+        double p0 = 0.0, p1 = 0.0;                    // chain heads for column cM
+        double2 xpre = make_double2(0.0, 0.0);        // x of the vector column of this step, loaded one step ahead
+        for (int q = 0; q < nsteps; ++q) {
+            const int st = q % CGT_STAGES;
+            const int cM = sa + q - 2, cV = sa + q - 1;
+            const bool mineV = in_seg(cV);
+            // x of the NEXT vector column (plain load: x is the caller's buffer, not padded for window copies)
+            double2 xnext = make_double2(0.0, 0.0);
+            if (owned && in_seg(cV + 1)) xnext = *xaddr(cV + 1);
+            mbar_wait(&full_bar[st], (q / CGT_STAGES) & 1);
+            const CgStage &S = stages[st];
+            // ---- u of column cV (+ the pointwise updates of the nodes this lane owns) ----
+            double2 un = make_double2(0.0, 0.0);
+            double dn0 = 0.0, dn2 = 0.0;
+            if (cV >= own0 && cV < own1) {
+                if (valid) {
+                    const double2 r_ = S.R[wrow], w_ = S.W[wrow], s_ = S.S[wrow];
+                    dn0 = S.M[0][wrow]; dn2 = S.M[2][wrow];
+                    double2 di;
+                    if (DINV_VEC) di = S.DI[wrow];
+                    else di = make_double2(1.0 / dn0, 1.0 / dn2);
+                    double2 sn, rn;
+                    sn.x = w_.x + beta * s_.x; sn.y = w_.y + beta * s_.y;
+                    rn.x = r_.x - alpha * sn.x; rn.y = r_.y - alpha * sn.y;
+                    if (DINV_VEC) { rn.x *= (di.x == 0.0 ? 0.0 : 1.0); rn.y *= (di.y == 0.0 ? 0.0 : 1.0); }
+                    un.x = di.x * rn.x; un.y = di.y * rn.y;
+                    if (mineV && owned) {
+                        const size_t a = (size_t)(cV - own0) * g.m + j;
+                        const double2 p_ = S.P[wrow];
+                        double2 pn, xn_;
+                        pn.x = di.x * r_.x + beta * p_.x; pn.y = di.y * r_.y + beta * p_.y;      // p_i = u_i + beta_i p_{i-1}
+                        xn_.x = xpre.x + alpha * pn.x; xn_.y = xpre.y + alpha * pn.y;
+                        reinterpret_cast<double2 *>(v.p)[a] = pn;
+                        reinterpret_cast<double2 *>(v.x)[a] = xn_;
+                        reinterpret_cast<double2 *>(v.r_out)[a] = rn;
+                        reinterpret_cast<double2 *>(v.s_out)[a] = sn;
+                        dots[0] += rn.x * un.x; dots[0] += rn.y * un.y;
+                        dots[2] += rn.x * rn.x; dots[2] += rn.y * rn.y;
+                        if (DIST && cV == own0 && ps.has_left) cg_ll_store(v.ll_to_left + 4 * (size_t)j, un, ps.seq);
+                    }
+                }
+            } else if (DIST && valid) {
+                if (cV == own0 - 1 && left_halo) un = cg_ll_load(v.ll_from_left + 4 * (size_t)j, ps.seq, err);
+                else if (cV == own1 && right_halo) un = cg_ll_load(v.ll_from_right + 4 * (size_t)j, ps.seq, err);
+            }
+            // ---- column cM: row sums (q >= 2) and chain heads for the next column (q >= 1) ----
+            if (q >= 1 && cM >= 0 && cM < g.S) {
+                auto F = [&](int k, bool on) -> double { return on ? S.M[k][wrow] : 0.0; };
+                const double2 xc = u_prev, xn = un;
+                if (q >= 2) {
+                    const double f3 = F(3, lo), f4 = F(4, lo), f5 = F(5, lo), f6 = F(6, lo);
+                    double s0 = p0, s1 = p1;
+                    s0 += f3 * xc.x; s0 += f5 * xc.y;
+                    s1 += f4 * xc.x; s1 += f6 * xc.y;
+                    s0 = __shfl_up_sync(FULL, s0, 1); s1 = __shfl_up_sync(FULL, s1, 1);
+                    double2 xr, xnl, xnr;
+                    xr.x = __shfl_down_sync(FULL, xc.x, 1); xr.y = __shfl_down_sync(FULL, xc.y, 1);
+                    xnl.x = __shfl_up_sync(FULL, xn.x, 1); xnl.y = __shfl_up_sync(FULL, xn.y, 1);
+                    xnr.x = __shfl_down_sync(FULL, xn.x, 1); xnr.y = __shfl_down_sync(FULL, xn.y, 1);
+                    const double f0 = owned ? d0 : 0.0, f1 = F(1, owned), f2 = owned ? d2 : 0.0;
+                    s0 += f0 * xc.x; s0 += f1 * xc.y;
+                    s1 += f1 * xc.x; s1 += f2 * xc.y;
+                    s0 += f3 * xr.x; s0 += f4 * xr.y;
+                    s1 += f5 * xr.x; s1 += f6 * xr.y;
+                    s0 += F(7, hi) * xnl.x; s0 += F(8, hi) * xnl.y;
+                    s1 += F(9, hi) * xnl.x; s1 += F(10, hi) * xnl.y;
+                    s0 += F(11, owned) * xn.x; s0 += F(12, owned) * xn.y;
+                    s1 += F(13, owned) * xn.x; s1 += F(14, owned) * xn.y;
+                    s0 += F(15, lo) * xnr.x; s0 += F(16, lo) * xnr.y;
+                    s1 += F(17, lo) * xnr.x; s1 += F(18, lo) * xnr.y;
+                    if (owned) {
+                        const size_t a = (size_t)(cM - own0) * g.m + j;
+                        reinterpret_cast<double2 *>(v.w_out)[a] = make_double2(s0, s1);
+                        dots[1] += xc.x * s0; dots[1] += xc.y * s1;
+                    }
+                }
+                if (q + 1 < nsteps) {   // chain heads of column cM + 1 (phaseP)
+                    double c0 = 0.0, c1 = 0.0;
+                    c0 += F(15, lo) * xc.x; c0 += F(17, lo) * xc.y;
+                    c1 += F(16, lo) * xc.x; c1 += F(18, lo) * xc.y;
+                    c0 = __shfl_up_sync(FULL, c0, 1); c1 = __shfl_up_sync(FULL, c1, 1);
+                    c0 += F(11, owned) * xc.x; c0 += F(13, owned) * xc.y;
+                    c1 += F(12, owned) * xc.x; c1 += F(14, owned) * xc.y;
+                    c0 = __shfl_up_sync(FULL, c0, 1); c1 = __shfl_up_sync(FULL, c1, 1);
+                    c0 += F(7, hi) * xc.x; c0 += F(9, hi) * xc.y;
+                    c1 += F(8, hi) * xc.x; c1 += F(10, hi) * xc.y;
+                    p0 = __shfl_down_sync(FULL, c0, 2); p1 = __shfl_down_sync(FULL, c1, 2);
+                }
+            } else {
+                p0 = 0.0; p1 = 0.0;
+            }
+            u_prev = un; d0 = dn0; d2 = dn2; xpre = xnext;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[st]);
+        }
+    }
+    double total[3];
+    if (grid_sum<CGT_THREADS, 3>(dots, partials, counter, red, total)) {
+        if (DIST) {
+            peer_publish<3>(ps, 1, total);
+            double gsum[3];
+            peer_wait_sum<3>(ps, 1, ps.seq, gsum);
+            total[0] = gsum[0]; total[1] = gsum[1]; total[2] = gsum[2];
+        }
+        const double gamma_new = total[0], delta = total[1];
+        const double beta_new = gamma_new / ctl->gamma;
+        const double den = delta - beta_new * gamma_new / alpha;
+        ctl->gamma = gamma_new;
+        ctl->delta = delta;
+        ctl->rr = total[2];
+        ctl->iters += 1;
+        ctl->beta = beta_new;
+        ctl->alpha = gamma_new / den;
+        if (total[2] <= ctl->tol2) ctl->done = 1;
+        else if (!(den > 0.0) || !(gamma_new > 0.0)) { ctl->done = 1; ctl->status = 2; }
+        __threadfence();
+    }
+}
+
 // start of a solve: gamma_0, delta_0 are in place (pcg_init_kernel: p = u_0 = D^-1 r_0, {r.u, r.r, b.b}; the SpMV: w_0 = A u_0,
 // delta_0 = u_0 . w_0); alpha_0 = gamma_0 / delta_0, beta_0 = 0
 __global__ void cg_start_ctl_kernel(CgCtl *ctl, const double *init3 /* r.u, r.r, b.b */, const double *delta, double rtol) {

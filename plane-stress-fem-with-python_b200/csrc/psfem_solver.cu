@@ -1206,9 +1206,12 @@ struct CgWs {
 CgWs carve_cg(void *ws, int64_t n) {
     CgWs w;
     Carver c(ws);
-    for (int q = 0; q < 2; ++q) { w.r[q] = c.take<double>(n); w.s[q] = c.take<double>(n); w.w[q] = c.take<double>(n); }
-    w.p = c.take<double>(n);
-    w.dinv = c.take<double>(n);
+    // every vector is read through 116-row window copies (cg_sl_tma_kernel) that start two rows before a strip group and
+    // may run past the last column: 256 bytes in front, 2 KB behind
+    auto vec = [&]() { c.take<char>(256); double *p = c.take<double>(n); c.take<char>(2048); return p; };
+    for (int q = 0; q < 2; ++q) { w.r[q] = vec(); w.s[q] = vec(); w.w[q] = vec(); }
+    w.p = vec();
+    w.dinv = vec();
     w.partials = c.take<double>(3 * 148 * 8);
     w.scal = c.take<double>(16);
     w.ctl = c.take<CgCtl>(1);
@@ -1795,6 +1798,28 @@ int cg_sl_launch(const psfem_csr *A, double *d_x, const CgWs &w, bool masked, in
     PeerSync ps;
     memset(&ps, 0, sizeof(ps));
     if (peer) ps = *peer;
+    static const bool no_tma = getenv("PSFEM_CG_NO_TMA") != nullptr;   // A/B switch: the register-prefetch kernel
+    if (!no_tma) {
+        // TMA-staged kernel: CTAs of four strips; one resident wave of 2 CTAs per SM
+        const int n_groups = (int)ceil_div(g.n_strips, CGT_CONSUMERS);
+        int64_t G = (int64_t)sms * 2 / n_groups;
+        const int64_t owned_cols = g.S - g.pre;
+        if (G > owned_cols / 4) G = owned_cols / 4;
+        if (G < 1) G = 1;
+        g.G = (int)G;
+        const unsigned grid = (unsigned)(n_groups * g.G);
+        PSFEM_REQUIRE(grid <= 148 * 8, "cg_sl: grid larger than the partial-sum buffer");
+        const size_t smem = sizeof(CgStage) * CGT_STAGES + 128;
+#define PSFEM_CG_LAUNCH(D, P_)                                                                                                         \
+    do {                                                                                                                              \
+        PSFEM_CUDA_CHECK(cudaFuncSetAttribute(cg_sl_tma_kernel<D, P_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
+        PSFEM_CUDA_CHECK(launch_pdl(cg_sl_tma_kernel<D, P_>, grid, CGT_THREADS, smem, stream, A->sl_vals, g, v, w.ctl, w.partials, w.counter, ps, n_groups)); \
+    } while (0)
+        if (peer) { if (masked) PSFEM_CG_LAUNCH(true, true); else PSFEM_CG_LAUNCH(false, true); }
+        else { if (masked) PSFEM_CG_LAUNCH(true, false); else PSFEM_CG_LAUNCH(false, false); }
+#undef PSFEM_CG_LAUNCH
+        return PSFEM_OK;
+    }
     const unsigned grid = (unsigned)ceil_div((int64_t)g.n_strips * g.G, SL_WARPS);
     PSFEM_REQUIRE(grid <= 148 * 8, "cg_sl: grid larger than the partial-sum buffer");
     if (peer) {

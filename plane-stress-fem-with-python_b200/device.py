@@ -195,8 +195,11 @@ class DeviceCSR:
         for m, tol in [(m_, t_) for t_ in tols for m_ in list(cand[: cnt.value])]:
             sz = C.c_size_t(0)
             call("psfem_spmv_sl_size", self.n_rows // 2, int(row_node_offset), m, C.byref(sz))
+            # the fused PCG kernel reads the storage through 116-row window copies that start two rows before a strip group
+            # and end after the last one: 256 bytes of slack in front, 2 KB behind (psfem_cg_sl.cuh)
             nbytes = sz.value + 256
-            buf = torch.empty((nbytes + 7) // 8, dtype=torch.float64, device="cuda")
+            whole = torch.empty((nbytes + 7) // 8 + 32 + 256, dtype=torch.float64, device="cuda")
+            buf = whole[32:]
             ok = C.c_int64(0)
             call("psfem_spmv_sl_build", C.byref(s), int(row_node_offset), x_nodes, m, float(tol), ptr(buf), nbytes, C.byref(ok),
                  stream_ptr())
