@@ -311,12 +311,14 @@ int psfem_csr_symmetry(const psfem_csr *A, double rtol, double atol, int64_t *h_
  * their symmetric-lattice storage (psfem_spmv_sl_build: the matrices of Polygones.mesh meshes), in the Chronopoulos-Gear
  * form of the recurrence (one reduction per iteration; same Krylov iterates in exact arithmetic):
  *     p = u + beta p;  s = w + beta s;  x += alpha p;  r -= alpha s;  u = D^-1 r;  w = A u;  {r.u, w.u, r.r} -> alpha', beta'
- * The pointwise part rides on the marching warps of the SpMV: 312 B of HBM traffic per node and iteration instead of
- * 344 B in three kernels, D^-1 taken from the streamed diagonal.  d_new_id != NULL: constrained DOFs stay as masked rows.
+ * The pointwise part rides on the marching warps of the SpMV, operands staged through a TMA + mbarrier shared-memory ring:
+ * 296 B of HBM traffic per node and iteration instead of 344 B in three kernels, D^-1 taken from the streamed diagonal.  d_new_id != NULL: constrained DOFs stay as masked rows.
  *   psfem_cg_sl_usable     *h_usable = 1 when A can take this path (symmetric-lattice storage of A->vals, rows = columns)
  *   psfem_cg_sl_start      x0 = d_x on entry; r0, u0, w0, alpha0 (uses the SpMV kernel twice)
  *   psfem_cg_sl_iterations k launches; iters_done = iterations launched since the start (selects the buffer parity)
  *   psfem_cg_sl_state      h_info = {iterations, relative residual, ||b||, done, status}; synchronises
+ *   psfem_cg_sl_finish     x is written every other iteration only (x += alpha_{i-1} p_{i-1} + alpha_i p_i): this adds the
+ *                          pending half, if any; call it before reading d_x after psfem_cg_sl_iterations
  *   psfem_cg_sl_solve      start + batches of check_every iterations until ||r|| <= rtol ||b|| (decided on the device) */
 int psfem_cg_sl_usable(const psfem_csr *A, int *h_usable);
 int psfem_cg_sl_workspace(int64_t n, size_t *bytes);
@@ -325,6 +327,7 @@ int psfem_cg_sl_start(const psfem_csr *A, const double *d_b, double *d_x, const 
 int psfem_cg_sl_iterations(const psfem_csr *A, double *d_x, int masked, int64_t k, int64_t iters_done, void *d_ws,
                            size_t ws_bytes, void *stream);
 int psfem_cg_sl_state(void *d_ws, int64_t n, double *h_info /* [5] */, void *stream);
+int psfem_cg_sl_finish(double *d_x, int64_t n, void *d_ws, void *stream);
 int psfem_cg_sl_solve(const psfem_csr *A, const double *d_b, double *d_x, const int32_t *d_new_id, double rtol, int64_t maxit,
                       int64_t check_every, double *h_info, void *d_ws, size_t ws_bytes, void *stream);
 

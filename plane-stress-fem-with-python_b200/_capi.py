@@ -112,6 +112,7 @@ SIGNATURES = {
     "psfem_cg_sl_start": [_pcsr, _ptr, _ptr, _ptr, _dbl, _ptr, _sz, _ptr],
     "psfem_cg_sl_iterations": [_pcsr, _ptr, _i32, _i64, _i64, _ptr, _sz, _ptr],
     "psfem_cg_sl_state": [_ptr, _i64, _pdbl, _ptr],
+    "psfem_cg_sl_finish": [_ptr, _i64, _ptr, _ptr],
     "psfem_cg_sl_solve": [_pcsr, _ptr, _ptr, _ptr, _dbl, _i64, _i64, _pdbl, _ptr, _sz, _ptr],
     "psfem_pcg_init": [_i64, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr],
     "psfem_pcg_spmv_dot": [_pcsr, _ptr, _i64, _ptr, _ptr, _ptr, _ptr, _ptr],

@@ -11,7 +11,9 @@
 // Everything before `w = A u` is pointwise, so it rides on the marching warps of the symmetric-lattice SpMV: a warp computes
 // u of a lattice column from r, w, s (and the diagonal it streams anyway: D^-1 is NOT read as a vector) when it pulls the
 // column in as SpMV input, writes r, s, p, x for the nodes it owns on the way, and writes w when the row sums are done.
-// Per node and iteration: 152 B matrix + reads r, w, s, p, x (80) + writes r, s, w, p, x (80) = 312 B instead of 344, in
+// x is touched every OTHER iteration only: p_{i-1} is in hand anyway when p_i = u_i + beta_i p_{i-1} is formed, so
+// x += alpha_{i-1} p_{i-1} + alpha_i p_i costs one read-modify-write of x per two iterations (CgCtl::alpha_pend).
+// Per node and iteration: 152 B matrix + reads r, w, s, p (64) + writes r, s, w, p (64) + x 32/2 = 296 B instead of 344, in
 // one launch instead of three, with one cross-GPU scalar exchange instead of two.
 // r, s, w are double buffered (a warp reads the OLD values of the halo rows / columns that other warps update).
 //
@@ -21,12 +23,9 @@
 // boards like the classic strip solver and leaves alpha', beta' in the control block for the next launch.
 #pragma once
 
-#ifndef PSFEM_CG_CTAS
-#define PSFEM_CG_CTAS 2       // CTAs of 4 warps per SM (register cap 255)
-#endif
-
 struct CgCtl {
     double gamma, alpha, beta, rr, bb, tol2, delta;
+    double alpha_pend;        // x lags by alpha_pend * p (the x update of every other iteration is folded into the next one)
     long long iters;
     int done, status;         // status 2: breakdown (delta - beta gamma / alpha <= 0)
 };
@@ -63,220 +62,13 @@ __device__ __forceinline__ double2 cg_ll_load(const unsigned long long *src, uns
                         __longlong_as_double((long long)((q[2] & 0xffffffffull) | (q[3] << 32))));
 }
 
-template <bool DINV_VEC, bool DIST>
-__global__ void __launch_bounds__(SL_THREADS, PSFEM_CG_CTAS)
-cg_sl_kernel(const double *__restrict__ sv, const SlGeom g, const CgVec v, CgCtl *__restrict__ ctl, double *__restrict__ partials,
-             unsigned int *counter, const PeerSync ps) {
-    __shared__ double red[SL_THREADS / 32];
-    pdl_enter();
-    if (ctl->done) return;
-    const double alpha = ctl->alpha, beta = ctl->beta;
-    constexpr unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const int w = blockIdx.x * SL_WARPS + (threadIdx.x >> 5);
-    double dots[3] = {0.0, 0.0, 0.0};   // gamma' = r.u, delta = w.u, rr = r.r of the rows this thread owns
-    if (w < g.n_strips * g.G) {
-        const int sidx = w % g.n_strips, seg = w / g.n_strips;
-        const int j = sidx * SL_ROWS - 1 + lane;
-        const bool valid = j >= 0 && j < g.m && lane <= SL_ROWS + 1;
-        const bool owned = valid && lane >= 1 && lane <= SL_ROWS;
-        const bool lo = valid && lane <= SL_ROWS;
-        const bool hi = valid && lane >= 1;
-        const int own0 = g.pre, own1 = g.S;           // owned storage columns [own0, own1)
-        const int owned_cols = own1 - own0;
-        const int sa = own0 + (int)((long long)seg * owned_cols / g.G);
-        const int sb = own0 + (int)((long long)(seg + 1) * owned_cols / g.G);
-        const size_t mp = (size_t)g.mpad, cstride = (size_t)SL_NC * mp;
-        const bool left_halo = DIST && ps.has_left && g.pre == 1;        // storage column 0 = the left neighbour's last column
-        const bool right_halo = DIST && ps.has_right;                   // column own1 = the right neighbour's first column
-        int *err = ps.err;
-
-        // ---- the pointwise part of the iteration at node (c, j): returns u_{i+1}; writes r, s, p, x when `mine` ----
-        struct Raw { double2 r, w, s, d, p, x; };
-        auto load_raw = [&](int c, bool mine, Raw &q) {
-            q.r = q.w = q.s = q.d = q.p = q.x = make_double2(0.0, 0.0);
-            if (!valid || c < own0 || c >= own1) return;
-            const size_t a = (size_t)(c - own0) * g.m + j;
-            q.r = __ldg(reinterpret_cast<const double2 *>(v.r_in) + a);
-            q.w = __ldg(reinterpret_cast<const double2 *>(v.w_in) + a);
-            q.s = __ldg(reinterpret_cast<const double2 *>(v.s_in) + a);
-            if (DINV_VEC) {
-                q.d = __ldg(reinterpret_cast<const double2 *>(v.dinv) + a);
-            } else {
-                const double *pd = sv + (size_t)c * cstride + j;
-                q.d = make_double2(__ldg(pd), __ldg(pd + 2 * mp));
-            }
-            if (mine && owned) {
-                q.p = reinterpret_cast<const double2 *>(v.p)[a];
-                q.x = reinterpret_cast<const double2 *>(v.x)[a];
-            }
-        };
-        auto finish_raw = [&](int c, bool mine, const Raw &q) -> double2 {
-            if (!valid) return make_double2(0.0, 0.0);
-            if (c < own0 || c >= own1) {
-                if (DIST) {
-                    if (c == own0 - 1 && left_halo) return cg_ll_load(v.ll_from_left + 4 * (size_t)j, ps.seq, err);
-                    if (c == own1 && right_halo) return cg_ll_load(v.ll_from_right + 4 * (size_t)j, ps.seq, err);
-                }
-                return make_double2(0.0, 0.0);
-            }
-            double2 di = q.d;
-            if (!DINV_VEC) { di.x = 1.0 / di.x; di.y = 1.0 / di.y; }
-            double2 sn, rn, un;
-            sn.x = q.w.x + beta * q.s.x; sn.y = q.w.y + beta * q.s.y;
-            rn.x = q.r.x - alpha * sn.x; rn.y = q.r.y - alpha * sn.y;
-            if (DINV_VEC) {   // masked rows (D^-1 = 0: constrained DOFs kept in the matrix) keep a zero residual
-                rn.x *= (di.x == 0.0 ? 0.0 : 1.0); rn.y *= (di.y == 0.0 ? 0.0 : 1.0);
-            }
-            un.x = di.x * rn.x; un.y = di.y * rn.y;
-            if (mine && owned) {
-                const size_t a = (size_t)(c - own0) * g.m + j;
-                double2 pn, xn_;
-                pn.x = di.x * q.r.x + beta * q.p.x; pn.y = di.y * q.r.y + beta * q.p.y;      // p_i = u_i + beta_i p_{i-1}
-                xn_.x = q.x.x + alpha * pn.x; xn_.y = q.x.y + alpha * pn.y;
-                reinterpret_cast<double2 *>(v.p)[a] = pn;
-                reinterpret_cast<double2 *>(v.x)[a] = xn_;
-                reinterpret_cast<double2 *>(v.r_out)[a] = rn;
-                reinterpret_cast<double2 *>(v.s_out)[a] = sn;
-                dots[0] += rn.x * un.x; dots[0] += rn.y * un.y;
-                dots[2] += rn.x * rn.x; dots[2] += rn.y * rn.y;
-            }
-            return un;
-        };
-        auto ucol = [&](int c, bool mine) -> double2 {
-            Raw q;
-            load_raw(c, mine, q);
-            return finish_raw(c, mine, q);
-        };
-        auto in_seg = [&](int c) { return c >= sa && c < sb; };
-
-        if (DIST) {
-            // boundary columns first: the neighbours' edge segments wait for them.  The first owned column is the first
-            // column of segment 0 anyway (pushed below, right after it is computed); the last owned column is reached
-            // only at the end of the last segment's march, so its u is computed here once more, without the stores.
-            if (seg == g.G - 1 && ps.has_right && owned_cols > 0) {
-                const double2 ub = ucol(own1 - 1, false);
-                if (owned) cg_ll_store(v.ll_to_right + 4 * (size_t)j, ub, ps.seq);
-            }
-        }
-        auto load_col = [&](int s, double (&F)[SL_NC]) {
-            const double *p = sv + (size_t)s * cstride + j;
-#pragma unroll
-            for (int k = 0; k < 3; ++k) F[k] = sl_ld(p + k * mp, owned);
-#pragma unroll
-            for (int k = 3; k < 7; ++k) F[k] = sl_ld(p + k * mp, lo);
-#pragma unroll
-            for (int k = 7; k < 11; ++k) F[k] = sl_ld(p + k * mp, hi);
-#pragma unroll
-            for (int k = 11; k < 15; ++k) F[k] = sl_ld(p + k * mp, owned);
-#pragma unroll
-            for (int k = 15; k < 19; ++k) F[k] = sl_ld(p + k * mp, lo);
-        };
-        auto phaseP = [&](const double (&F)[SL_NC], const double2 xc, double &p0, double &p1) {
-            double c0 = 0.0, c1 = 0.0;
-            c0 += F[15] * xc.x; c0 += F[17] * xc.y;
-            c1 += F[16] * xc.x; c1 += F[18] * xc.y;
-            c0 = __shfl_up_sync(FULL, c0, 1); c1 = __shfl_up_sync(FULL, c1, 1);
-            c0 += F[11] * xc.x; c0 += F[13] * xc.y;
-            c1 += F[12] * xc.x; c1 += F[14] * xc.y;
-            c0 = __shfl_up_sync(FULL, c0, 1); c1 = __shfl_up_sync(FULL, c1, 1);
-            c0 += F[7] * xc.x; c0 += F[9] * xc.y;
-            c1 += F[8] * xc.x; c1 += F[10] * xc.y;
-            p0 = __shfl_down_sync(FULL, c0, 2); p1 = __shfl_down_sync(FULL, c1, 2);
-        };
-        double Fc[SL_NC], Fn[SL_NC];
-        double p0 = 0.0, p1 = 0.0;
-        // own data first, the column before the segment (possibly a neighbour GPU's) last
-        double2 xc = ucol(sa, true);
-        if (DIST && seg == 0 && ps.has_left && owned && owned_cols > 0) cg_ll_store(v.ll_to_left + 4 * (size_t)j, xc, ps.seq);
-        double2 xn = ucol(sa + 1, in_seg(sa + 1));
-        Raw raw;
-        load_raw(sa + 2, in_seg(sa + 2), raw);
-        load_col(sa, Fc);
-        if (sa > 0) {   // pre-step: chain heads from the column before the segment (another segment's, or the left halo column)
-            double Fp[SL_NC];
-            const double *p = sv + (size_t)(sa - 1) * cstride + j;
-#pragma unroll
-            for (int k = 0; k < 7; ++k) Fp[k] = 0.0;
-#pragma unroll
-            for (int k = 7; k < 11; ++k) Fp[k] = sl_ld(p + k * mp, hi);
-#pragma unroll
-            for (int k = 11; k < 15; ++k) Fp[k] = sl_ld(p + k * mp, owned);
-#pragma unroll
-            for (int k = 15; k < 19; ++k) Fp[k] = sl_ld(p + k * mp, lo);
-            phaseP(Fp, ucol(sa - 1, false), p0, p1);
-        }
-        for (int s = sa; s < sb; ++s) {
-            const bool more = s + 1 < sb;
-            if (more) load_col(s + 1, Fn);
-            // u of column s+2 (needed as x(s+1)'s right... as xn of the next step) from the loads of the previous step;
-            // the loads of column s+3 go out now and have this whole step to arrive
-            double2 xnn = make_double2(0.0, 0.0);
-            if (more) {
-                xnn = finish_raw(s + 2, in_seg(s + 2), raw);
-                if (s + 3 <= sb) load_raw(s + 3, in_seg(s + 3), raw);
-            }
-            double s0 = p0, s1 = p1;
-            s0 += Fc[3] * xc.x; s0 += Fc[5] * xc.y;
-            s1 += Fc[4] * xc.x; s1 += Fc[6] * xc.y;
-            s0 = __shfl_up_sync(FULL, s0, 1); s1 = __shfl_up_sync(FULL, s1, 1);
-            double2 xr, xnl, xnr;
-            xr.x = __shfl_down_sync(FULL, xc.x, 1); xr.y = __shfl_down_sync(FULL, xc.y, 1);
-            xnl.x = __shfl_up_sync(FULL, xn.x, 1); xnl.y = __shfl_up_sync(FULL, xn.y, 1);
-            xnr.x = __shfl_down_sync(FULL, xn.x, 1); xnr.y = __shfl_down_sync(FULL, xn.y, 1);
-            s0 += Fc[0] * xc.x; s0 += Fc[1] * xc.y;
-            s1 += Fc[1] * xc.x; s1 += Fc[2] * xc.y;
-            s0 += Fc[3] * xr.x; s0 += Fc[4] * xr.y;
-            s1 += Fc[5] * xr.x; s1 += Fc[6] * xr.y;
-            s0 += Fc[7] * xnl.x; s0 += Fc[8] * xnl.y;
-            s1 += Fc[9] * xnl.x; s1 += Fc[10] * xnl.y;
-            s0 += Fc[11] * xn.x; s0 += Fc[12] * xn.y;
-            s1 += Fc[13] * xn.x; s1 += Fc[14] * xn.y;
-            s0 += Fc[15] * xnr.x; s0 += Fc[16] * xnr.y;
-            s1 += Fc[17] * xnr.x; s1 += Fc[18] * xnr.y;
-            if (owned) {
-                const size_t a = (size_t)(s - own0) * g.m + j;
-                reinterpret_cast<double2 *>(v.w_out)[a] = make_double2(s0, s1);
-                dots[1] += xc.x * s0; dots[1] += xc.y * s1;
-            }
-            if (more) {
-                phaseP(Fc, xc, p0, p1);
-#pragma unroll
-                for (int k = 0; k < SL_NC; ++k) Fc[k] = Fn[k];
-                xc = xn; xn = xnn;
-            }
-        }
-    }
-    double total[3];
-    if (grid_sum<SL_THREADS, 3>(dots, partials, counter, red, total)) {
-        if (DIST) {
-            peer_publish<3>(ps, 1, total);
-            double gsum[3];
-            peer_wait_sum<3>(ps, 1, ps.seq, gsum);
-            total[0] = gsum[0]; total[1] = gsum[1]; total[2] = gsum[2];
-        }
-        const double gamma_new = total[0], delta = total[1];
-        const double beta_new = gamma_new / ctl->gamma;
-        const double den = delta - beta_new * gamma_new / alpha;
-        ctl->gamma = gamma_new;
-        ctl->delta = delta;
-        ctl->rr = total[2];
-        ctl->iters += 1;
-        ctl->beta = beta_new;
-        ctl->alpha = gamma_new / den;
-        if (total[2] <= ctl->tol2) ctl->done = 1;
-        else if (!(den > 0.0) || !(gamma_new > 0.0)) { ctl->done = 1; ctl->status = 2; }
-        __threadfence();
-    }
-}
-
-
 // ---------------------------------------------------------------------------------------------
-// The same iteration with the operands staged through shared memory by bulk async copies (TMA) + mbarriers.
+// The operands are staged through shared memory by bulk async copies (TMA) + mbarriers.
 //
-// The register-prefetch version above is latency bound (ncu, gpurun_out/r2d: 8 warps per SM at 182 registers, 7 long-
-// scoreboard stalls per issue, 4.2 TB/s).  Here a CTA = one producer warp + four consumer warps that own four adjacent
-// 28-row strips of one column segment.  Per lattice column the producer issues 24 bulk copies (cp.async.bulk, completion
+// A first version that prefetched the next column into registers like spmv_sl_kernel was latency bound (ncu,
+// profiles/r2d_cg_regprefetch.md: 8 warps per SM at 182 registers, 7 long-scoreboard stalls per issue, 4.2 TB/s, 1.24 ms per
+// iteration at C4 -- slower than the three classic kernels).  Here a CTA = one producer warp + four consumer warps that own
+// four adjacent 28-row strips of one column segment.  Per lattice column the producer issues 24 bulk copies (cp.async.bulk, completion
 // on an mbarrier) of the CTA's 116-row window: the 17 off-diagonal components of column c, the two diagonal components of
 // column c+1, and r, w, s, p of column c+1 -- into a 3-stage ring, two columns ahead of the consumers.  Nothing is
 // prefetched in registers (98 registers instead of 182), the loads in flight no longer depend on occupancy.
@@ -300,14 +92,15 @@ struct CgStage {
 template <bool DINV_VEC, bool DIST>
 __global__ void __launch_bounds__(CGT_THREADS, 2)
 cg_sl_tma_kernel(const double *__restrict__ sv, const SlGeom g, const CgVec v, CgCtl *__restrict__ ctl, double *__restrict__ partials,
-                 unsigned int *counter, const PeerSync ps, const int n_groups) {
+                 unsigned int *counter, const PeerSync ps, const int n_groups, const int defer_x) {
     extern __shared__ __align__(128) unsigned char cg_smem[];
     __shared__ double red[CGT_THREADS / 32];
     __shared__ uint64_t full_bar[CGT_STAGES], empty_bar[CGT_STAGES];
     CgStage *stages = reinterpret_cast<CgStage *>(cg_smem);
     pdl_enter();
     if (ctl->done) return;
-    const double alpha = ctl->alpha, beta = ctl->beta;
+    const double alpha = ctl->alpha, beta = ctl->beta, a_pend = ctl->alpha_pend;
+    const bool skip_x = defer_x && a_pend == 0.0;   // this iteration leaves x alone; the next one adds both steps
     constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
     const int gidx = blockIdx.x % n_groups, seg = blockIdx.x / n_groups;
@@ -397,7 +190,7 @@ cg_sl_tma_kernel(const double *__restrict__ sv, const SlGeom g, const CgVec v, C
             const bool mineV = in_seg(cV);
             // x of the NEXT vector column (plain load: x is the caller's buffer, not padded for window copies)
             double2 xnext = make_double2(0.0, 0.0);
-            if (owned && in_seg(cV + 1)) xnext = *xaddr(cV + 1);
+            if (!skip_x && owned && in_seg(cV + 1)) xnext = *xaddr(cV + 1);
             mbar_wait(&full_bar[st], (q / CGT_STAGES) & 1);
             const CgStage &S = stages[st];
             // ---- u of column cV (+ the pointwise updates of the nodes this lane owns) ----
@@ -418,11 +211,14 @@ cg_sl_tma_kernel(const double *__restrict__ sv, const SlGeom g, const CgVec v, C
                     if (mineV && owned) {
                         const size_t a = (size_t)(cV - own0) * g.m + j;
                         const double2 p_ = S.P[wrow];
-                        double2 pn, xn_;
+                        double2 pn;
                         pn.x = di.x * r_.x + beta * p_.x; pn.y = di.y * r_.y + beta * p_.y;      // p_i = u_i + beta_i p_{i-1}
-                        xn_.x = xpre.x + alpha * pn.x; xn_.y = xpre.y + alpha * pn.y;
                         reinterpret_cast<double2 *>(v.p)[a] = pn;
-                        reinterpret_cast<double2 *>(v.x)[a] = xn_;
+                        if (!skip_x) {   // x += alpha_{i-1} p_{i-1} (pending from the previous iteration, or 0) + alpha_i p_i
+                            double2 xn_;
+                            xn_.x = (xpre.x + a_pend * p_.x) + alpha * pn.x; xn_.y = (xpre.y + a_pend * p_.y) + alpha * pn.y;
+                            reinterpret_cast<double2 *>(v.x)[a] = xn_;
+                        }
                         reinterpret_cast<double2 *>(v.r_out)[a] = rn;
                         reinterpret_cast<double2 *>(v.s_out)[a] = sn;
                         dots[0] += rn.x * un.x; dots[0] += rn.y * un.y;
@@ -502,11 +298,20 @@ cg_sl_tma_kernel(const double *__restrict__ sv, const SlGeom g, const CgVec v, C
         ctl->iters += 1;
         ctl->beta = beta_new;
         ctl->alpha = gamma_new / den;
+        ctl->alpha_pend = skip_x ? alpha : 0.0;
         if (total[2] <= ctl->tol2) ctl->done = 1;
         else if (!(den > 0.0) || !(gamma_new > 0.0)) { ctl->done = 1; ctl->status = 2; }
         __threadfence();
     }
 }
+
+// the pending half of the deferred x update: x += alpha_pend * p (then alpha_pend = 0); run before x is read
+__global__ void cg_finish_x_kernel(int64_t n, double *__restrict__ x, const double *__restrict__ p, const CgCtl *__restrict__ ctl) {
+    const double a = ctl->alpha_pend;
+    if (a == 0.0) return;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) x[i] += a * p[i];
+}
+__global__ void cg_clear_pend_kernel(CgCtl *ctl) { ctl->alpha_pend = 0.0; }
 
 // start of a solve: gamma_0, delta_0 are in place (pcg_init_kernel: p = u_0 = D^-1 r_0, {r.u, r.r, b.b}; the SpMV: w_0 = A u_0,
 // delta_0 = u_0 . w_0); alpha_0 = gamma_0 / delta_0, beta_0 = 0
@@ -517,6 +322,7 @@ __global__ void cg_start_ctl_kernel(CgCtl *ctl, const double *init3 /* r.u, r.r,
     ctl->tol2 = rtol * rtol * bb;
     ctl->beta = 0.0;
     ctl->alpha = gamma / d;
+    ctl->alpha_pend = 0.0;
     ctl->iters = 0;
     ctl->status = 0;
     ctl->done = (bb == 0.0 || rr <= ctl->tol2) ? 1 : 0;

@@ -1778,7 +1778,7 @@ namespace {
 bool cg_sl_ok(const psfem_csr *A, bool strip) {
     static const bool off = getenv("PSFEM_NO_SYMLATTICE") != nullptr;
     SlGeom g;
-    return !off && A && A->sl_vals && A->sl_src_vals == A->vals && sl_geometry(A, &g, 148, PSFEM_CG_CTAS) && (strip || A->sl_roff == 0) &&
+    return !off && A && A->sl_vals && A->sl_src_vals == A->vals && sl_geometry(A, &g, 148, 2) && (strip || A->sl_roff == 0) &&
            (!strip || A->sl_roff == 0 || A->sl_roff == A->sl_m);
 }
 int cg_sl_launch(const psfem_csr *A, double *d_x, const CgWs &w, bool masked, int64_t it, const PeerSync *peer, const CgVec *halo, cudaStream_t stream) {
@@ -1786,7 +1786,7 @@ int cg_sl_launch(const psfem_csr *A, double *d_x, const CgWs &w, bool masked, in
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     SlGeom g;
-    PSFEM_REQUIRE(sl_geometry(A, &g, sms, PSFEM_CG_CTAS), "cg_sl: operand has no symmetric-lattice geometry");
+    PSFEM_REQUIRE(sl_geometry(A, &g, sms, 2), "cg_sl: operand has no symmetric-lattice geometry");
     const int cur = (int)(it & 1);
     CgVec v;
     memset(&v, 0, sizeof(v));
@@ -1798,37 +1798,25 @@ int cg_sl_launch(const psfem_csr *A, double *d_x, const CgWs &w, bool masked, in
     PeerSync ps;
     memset(&ps, 0, sizeof(ps));
     if (peer) ps = *peer;
-    static const bool no_tma = getenv("PSFEM_CG_NO_TMA") != nullptr;   // A/B switch: the register-prefetch kernel
-    if (!no_tma) {
-        // TMA-staged kernel: CTAs of four strips; one resident wave of 2 CTAs per SM
-        const int n_groups = (int)ceil_div(g.n_strips, CGT_CONSUMERS);
-        int64_t G = (int64_t)sms * 2 / n_groups;
-        const int64_t owned_cols = g.S - g.pre;
-        if (G > owned_cols / 4) G = owned_cols / 4;
-        if (G < 1) G = 1;
-        g.G = (int)G;
-        const unsigned grid = (unsigned)(n_groups * g.G);
-        PSFEM_REQUIRE(grid <= 148 * 8, "cg_sl: grid larger than the partial-sum buffer");
-        const size_t smem = sizeof(CgStage) * CGT_STAGES + 128;
+    static const int defer_x = getenv("PSFEM_CG_NO_DEFER") == nullptr ? 1 : 0;   // A/B switch: x updated every iteration
+    // CTAs of four strips; one resident wave of 2 CTAs per SM
+    const int n_groups = (int)ceil_div(g.n_strips, CGT_CONSUMERS);
+    int64_t G = (int64_t)sms * 2 / n_groups;
+    const int64_t owned_cols = g.S - g.pre;
+    if (G > owned_cols / 4) G = owned_cols / 4;
+    if (G < 1) G = 1;
+    g.G = (int)G;
+    const unsigned grid = (unsigned)(n_groups * g.G);
+    PSFEM_REQUIRE(grid <= 148 * 8, "cg_sl: grid larger than the partial-sum buffer");
+    const size_t smem = sizeof(CgStage) * CGT_STAGES + 128;
 #define PSFEM_CG_LAUNCH(D, P_)                                                                                                         \
     do {                                                                                                                              \
         PSFEM_CUDA_CHECK(cudaFuncSetAttribute(cg_sl_tma_kernel<D, P_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
-        PSFEM_CUDA_CHECK(launch_pdl(cg_sl_tma_kernel<D, P_>, grid, CGT_THREADS, smem, stream, A->sl_vals, g, v, w.ctl, w.partials, w.counter, ps, n_groups)); \
+        PSFEM_CUDA_CHECK(launch_pdl(cg_sl_tma_kernel<D, P_>, grid, CGT_THREADS, smem, stream, A->sl_vals, g, v, w.ctl, w.partials, w.counter, ps, n_groups, defer_x)); \
     } while (0)
-        if (peer) { if (masked) PSFEM_CG_LAUNCH(true, true); else PSFEM_CG_LAUNCH(false, true); }
-        else { if (masked) PSFEM_CG_LAUNCH(true, false); else PSFEM_CG_LAUNCH(false, false); }
+    if (peer) { if (masked) PSFEM_CG_LAUNCH(true, true); else PSFEM_CG_LAUNCH(false, true); }
+    else { if (masked) PSFEM_CG_LAUNCH(true, false); else PSFEM_CG_LAUNCH(false, false); }
 #undef PSFEM_CG_LAUNCH
-        return PSFEM_OK;
-    }
-    const unsigned grid = (unsigned)ceil_div((int64_t)g.n_strips * g.G, SL_WARPS);
-    PSFEM_REQUIRE(grid <= 148 * 8, "cg_sl: grid larger than the partial-sum buffer");
-    if (peer) {
-        if (masked) PSFEM_CUDA_CHECK(launch_pdl(cg_sl_kernel<true, true>, grid, SL_THREADS, 0, stream, A->sl_vals, g, v, w.ctl, w.partials, w.counter, ps));
-        else PSFEM_CUDA_CHECK(launch_pdl(cg_sl_kernel<false, true>, grid, SL_THREADS, 0, stream, A->sl_vals, g, v, w.ctl, w.partials, w.counter, ps));
-    } else {
-        if (masked) PSFEM_CUDA_CHECK(launch_pdl(cg_sl_kernel<true, false>, grid, SL_THREADS, 0, stream, A->sl_vals, g, v, w.ctl, w.partials, w.counter, ps));
-        else PSFEM_CUDA_CHECK(launch_pdl(cg_sl_kernel<false, false>, grid, SL_THREADS, 0, stream, A->sl_vals, g, v, w.ctl, w.partials, w.counter, ps));
-    }
     return PSFEM_OK;
 }
 }  // namespace
@@ -1906,6 +1894,18 @@ extern "C" int psfem_cg_sl_state(void *d_ws, int64_t n, double *h_info, void *st
     return PSFEM_OK;
 }
 
+extern "C" int psfem_cg_sl_finish(double *d_x, int64_t n, void *d_ws, void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    PSFEM_REQUIRE(d_x && d_ws && n >= 0, "cg_sl_finish: bad arguments");
+    CgWs w = carve_cg(d_ws, n);
+    if (n > 0) {
+        cg_finish_x_kernel<<<ew_grid(n), EW_THREADS, 0, stream>>>(n, d_x, w.p, w.ctl);
+        cg_clear_pend_kernel<<<1, 1, 0, stream>>>(w.ctl);
+        PSFEM_LAUNCH_CHECK();
+    }
+    return PSFEM_OK;
+}
+
 extern "C" int psfem_cg_sl_solve(const psfem_csr *A, const double *d_b, double *d_x, const int32_t *d_new_id, double rtol, int64_t maxit,
                                  int64_t check_every, double *h_info, void *d_ws, size_t ws_bytes, void *stream_) {
     PSFEM_REQUIRE(h_info, "cg_sl_solve: null argument");
@@ -1924,6 +1924,8 @@ extern "C" int psfem_cg_sl_solve(const psfem_csr *A, const double *d_b, double *
         if (rc) return rc;
         launched += batch;
     }
+    rc = psfem_cg_sl_finish(d_x, A->n_rows, d_ws, stream_);
+    if (rc) return rc;
     h_info[0] = st[0]; h_info[1] = st[1]; h_info[2] = st[2];
     if (st[4] != 0.0) { set_error("cg_sl: breakdown (matrix not positive definite?) after %.0f iterations, relres %.3e", st[0], st[1]); return PSFEM_ENOCONV; }
     if (!(st[1] <= rtol) && st[2] > 0) { set_error("pcg: not converged (relres %.3e after %.0f iterations)", st[1], st[0]); return PSFEM_ENOCONV; }

@@ -609,6 +609,11 @@ class FusedCG:
              ptr(self.ws), self.ws_bytes, stream_ptr())
         self.launched += int(k)
 
+    def finish(self):
+        """x is written every other iteration only; adds the pending half of the update (call before reading x)."""
+        if self.x is not None:
+            call("psfem_cg_sl_finish", ptr(self.x), self.n, ptr(self.ws), stream_ptr())
+
     def state(self):
         h = (C.c_double * 5)()
         call("psfem_cg_sl_state", ptr(self.ws), self.n, h, stream_ptr())

@@ -527,9 +527,10 @@ class StripProblem:
     def iteration_bytes(self, spmv_bytes):
         """algorithmic HBM bytes of one PCG iteration on this rank.  Classic: the SpMV + update (q, r, dinv read, r
         written) + p-update (p, x, r, dinv read, p, x written) = spmv + 80 B per DOF.  Fused: 152 B of matrix per node +
-        r, w, s, p, x read and r, s, w, p, x written = 152 + 160 B per node (D^-1 comes from the streamed diagonal)."""
+        r, w, s, p read and r, s, w, p written (128) + x read and written every other iteration (16) = 296 B per node
+        (D^-1 comes from the streamed diagonal)."""
         if self.kernels_per_iteration == 1:
-            return (152 + 160) * (self.n_owned_free // 2)
+            return (152 + 128 + 16) * (self.n_owned_free // 2)
         return spmv_bytes + (4 + 6) * 8 * self.n_owned_free
 
     @staticmethod
@@ -603,11 +604,17 @@ class StripProblem:
         r, b = self.residual()
         return dict(iterations=self.st["iters"], relres=r / b if b > 0 else 0.0, seconds=time.perf_counter() - t0)
 
+    def finish_x(self):
+        """The fused PCG writes x every other iteration; add the pending half before x is read."""
+        if getattr(self, "fused", None) is not None:
+            self.fused.finish()
+
     def gather_solution(self, dst=0):
         """Global displacement vector (zeros at constrained DOFs, like reconstruct_full_vector Polygones.py:913-921)
         on rank `dst` (None elsewhere): every rank contributes the free DOFs of its owned node columns."""
         torch = _capi.torch_cuda()
         lo, hi = self.plan["own"]
+        self.finish_x()
         torch.cuda.synchronize()
         if self.masked:
             ids = np.arange(lo, hi, dtype=np.int64) + self.part.dof_shift

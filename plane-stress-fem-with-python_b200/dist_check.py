@@ -33,6 +33,7 @@ def run_checks(world, rank):
                              prob.K_red.col_idx[int(rp[0]):int(rp[-1])].cpu().numpy().astype(np.int64) - prob.plan["own"][0])
         prob.cg_iterations(iters)
         r, b = prob.residual()
+        prob.finish_x()
         res[transport] = (prob.st["x"].cpu().numpy().copy(), r, b)
         if transport == "peer":                                    # restart on the same boards, solve to 1e-9
             info = prob.full_solve(1e-9)
@@ -52,6 +53,7 @@ def run_checks(world, rank):
     # single-GPU solver on the whole plate (every rank repeats it; small)
     one = StripProblem(rank=0, world=1, **kw).setup()
     one.cg_iterations(iters)
+    one.finish_x()
     x1 = one.st["x"].cpu().numpy()
     r1, b1 = one.residual()
     # owned free DOFs of this rank inside the global free vector: rank 0 starts at 0, sizes are gathered
@@ -76,6 +78,7 @@ def run_checks(world, rank):
         rpo = pr.K_red.row_ptr.cpu().numpy().astype(np.int64)
         vals_own = pr.K_red.vals[int(rpo[0]):int(rpo[-1])].cpu().numpy().copy()
         pr.cg_iterations(25)
+        pr.finish_x()
         x_own = pr.st["x"].cpu().numpy().copy()
         pr.release()
         o1 = StripProblem(rank=0, world=1, **kw2).setup()
@@ -86,6 +89,7 @@ def run_checks(world, rank):
         rp1 = o1.K_red.row_ptr.cpu().numpy().astype(np.int64)
         assert np.array_equal(rpo - rpo[0], rp1[off2:off2 + len(x_own) + 1] - rp1[off2]), (et, mt)
         assert np.array_equal(vals_own, o1.K_red.vals[int(rp1[off2]):int(rp1[off2 + len(x_own)])].cpu().numpy()), (et, mt)
+        o1.finish_x()
         x1_ = o1.st["x"].cpu().numpy()
         assert np.abs(x_own - x1_[off2:off2 + len(x_own)]).max() <= 1e-9 * np.abs(x1_).max(), (et, mt)
         o1.release()
