@@ -397,6 +397,34 @@ int psfem_dist_pcg_profile(const psfem_csr *A, const psfem_dist_ctx *ctx, int64_
 /* global {r.z, r.r, b.b} of the step with sequence number seq (b.b is valid for the start step only); synchronises */
 int psfem_dist_pcg_residual(const psfem_dist_ctx *ctx, uint64_t seq, double *h_out3, void *stream);
 
+/* ---- the fused one-kernel PCG iteration (psfem_cg_sl_*) on a strip of the multi-GPU partition --------------------------
+ * One launch per iteration and ONE cross-GPU scalar exchange ({r.u, w.u, r.r} through the peer boards, LL words); the halo
+ * is u of the first / last owned lattice column, computed first by the edge column segments and stored into the
+ * neighbour's LL halo buffer ({32 data bits | 32-bit sequence number} words polled by exactly the lanes that need them:
+ * no fence, no flag).  Replaces psfem_dist_pcg_* (three launches, two exchanges) when the strip operand carries its
+ * symmetric-lattice storage.  State lives in a psfem_cg_sl_workspace block; psfem_cg_sl_finish adds the pending x half.
+ *   psfem_dist_cg_halo_bytes  size of a rank's LL halo buffer (psfem_peer_alloc, zero-filled) for column height m
+ *   psfem_dist_cg_start       x = 0, r = b and the start pass (launch 0, sequence number seq >= 1); masked strips pass D^-1
+ *                             of the owned rows with zeros at constrained DOFs
+ *   psfem_dist_cg_iterations  k launches; launches_done counts launches since the start (>= 1), seq_first = seq + launches_done
+ *   psfem_dist_cg_state       {iterations, relative residual, ||b||, done, status}, global; reports a peer time-out */
+typedef struct psfem_dist_cg_ctx {
+    int32_t rank, world, has_left, has_right;
+    void *board[PSFEM_MAX_RANKS];          /* psfem_peer_board_bytes boards, board[rank] is this rank's own                */
+    void *ll_mine;                         /* this rank's LL halo buffer                                                  */
+    void *ll_left, *ll_right;              /* the neighbours' LL halo buffers (peer mapped) or NULL                        */
+    int64_t m;                             /* nodes per lattice column                                                    */
+    double *x;                             /* owned rows of the solution                                                  */
+    uint32_t *counter;                     /* 4 zero-initialised uint32; [3] = peer time-out flag                          */
+    int32_t masked;
+} psfem_dist_cg_ctx;
+int psfem_dist_cg_halo_bytes(int64_t m, size_t *bytes);
+int psfem_dist_cg_start(const psfem_csr *A, const psfem_dist_cg_ctx *ctx, const double *d_b, const double *d_dinv_masked,
+                        double rtol, uint64_t seq, void *d_ws, size_t ws_bytes, void *stream);
+int psfem_dist_cg_iterations(const psfem_csr *A, const psfem_dist_cg_ctx *ctx, int64_t k, int64_t launches_done,
+                             uint64_t seq_first, void *d_ws, size_t ws_bytes, void *stream);
+int psfem_dist_cg_state(const psfem_dist_cg_ctx *ctx, int64_t n, void *d_ws, double *h_info /* [5] */, void *stream);
+
 /* ---- BLAS-1 helpers for the drivers (Lanczos, K_eff = K + c M, energies) ------------------ */
 int psfem_axpby(int64_t n, double a, const double *d_x, double b, const double *d_y /* may be NULL */,
                 double *d_out, void *stream);

@@ -43,6 +43,12 @@ class psfem_dist_ctx(C.Structure):
                 ("partials", C.c_void_p), ("counter", C.c_void_p), ("masked", C.c_int32)]
 
 
+class psfem_dist_cg_ctx(C.Structure):
+    _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("has_left", C.c_int32), ("has_right", C.c_int32),
+                ("board", C.c_void_p * MAX_RANKS), ("ll_mine", C.c_void_p), ("ll_left", C.c_void_p), ("ll_right", C.c_void_p),
+                ("m", C.c_int64), ("x", C.c_void_p), ("counter", C.c_void_p), ("masked", C.c_int32)]
+
+
 if not os.path.exists(LIB_PATH):
     raise ImportError(
         f"{LIB_PATH} is missing: build the CUDA library first (python -c 'import __graft_entry__ as g; g.build()' "
@@ -57,6 +63,7 @@ _psz = C.POINTER(C.c_size_t)
 _pcsr = C.POINTER(psfem_csr)
 _pctx = C.POINTER(psfem_dist_ctx)
 _u64 = C.c_uint64
+_pcgctx = C.POINTER(psfem_dist_cg_ctx)
 
 # name -> argtypes; must list every symbol include/psfem.h declares (tests/test_capi_symbols.py checks)
 SIGNATURES = {
@@ -128,6 +135,10 @@ SIGNATURES = {
     "psfem_dist_pcg_iterations": [_pcsr, _pctx, _i64, _u64, _ptr],
     "psfem_dist_pcg_profile": [_pcsr, _pctx, _i64, _u64, _pdbl, _ptr],
     "psfem_dist_pcg_residual": [_pctx, _u64, _pdbl, _ptr],
+    "psfem_dist_cg_halo_bytes": [_i64, _psz],
+    "psfem_dist_cg_start": [_pcsr, _pcgctx, _ptr, _ptr, _dbl, _u64, _ptr, _sz, _ptr],
+    "psfem_dist_cg_iterations": [_pcsr, _pcgctx, _i64, _i64, _u64, _ptr, _sz, _ptr],
+    "psfem_dist_cg_state": [_pcgctx, _i64, _ptr, _pdbl, _ptr],
     "psfem_axpby": [_i64, _dbl, _ptr, _dbl, _ptr, _ptr, _ptr],
     "psfem_dot_workspace": [_i64, _psz],
     "psfem_dot": [_i64, _ptr, _ptr, _pdbl, _ptr, _sz, _ptr],

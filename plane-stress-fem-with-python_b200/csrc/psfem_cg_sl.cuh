@@ -290,17 +290,31 @@ cg_sl_tma_kernel(const double *__restrict__ sv, const SlGeom g, const CgVec v, C
             total[0] = gsum[0]; total[1] = gsum[1]; total[2] = gsum[2];
         }
         const double gamma_new = total[0], delta = total[1];
-        const double beta_new = gamma_new / ctl->gamma;
-        const double den = delta - beta_new * gamma_new / alpha;
-        ctl->gamma = gamma_new;
-        ctl->delta = delta;
-        ctl->rr = total[2];
-        ctl->iters += 1;
-        ctl->beta = beta_new;
-        ctl->alpha = gamma_new / den;
-        ctl->alpha_pend = skip_x ? alpha : 0.0;
-        if (total[2] <= ctl->tol2) ctl->done = 1;
-        else if (!(den > 0.0) || !(gamma_new > 0.0)) { ctl->done = 1; ctl->status = 2; }
+        if (ctl->iters < 0) {
+            // START PASS (psfem_dist_cg_start): launched with r = b, w = s = p = x = 0, alpha = beta = 0, the kernel has
+            // just produced u_0 = D^-1 b (left in p), w_0 = A u_0 (halo exchange included), gamma_0, delta_0 and b.b
+            ctl->gamma = gamma_new; ctl->delta = delta; ctl->rr = total[2]; ctl->bb = total[2];
+            ctl->tol2 = ctl->tol2 * total[2];          // rtol^2 was parked here
+            ctl->beta = 0.0;
+            ctl->alpha = gamma_new / delta;
+            ctl->alpha_pend = 0.0;
+            ctl->iters = 0;
+            ctl->status = 0;
+            ctl->done = (total[2] == 0.0 || total[2] <= ctl->tol2) ? 1 : 0;
+            if (!ctl->done && !(delta > 0.0)) { ctl->done = 1; ctl->status = 2; }
+        } else {
+            const double beta_new = gamma_new / ctl->gamma;
+            const double den = delta - beta_new * gamma_new / alpha;
+            ctl->gamma = gamma_new;
+            ctl->delta = delta;
+            ctl->rr = total[2];
+            ctl->iters += 1;
+            ctl->beta = beta_new;
+            ctl->alpha = gamma_new / den;
+            ctl->alpha_pend = skip_x ? alpha : 0.0;
+            if (total[2] <= ctl->tol2) ctl->done = 1;
+            else if (!(den > 0.0) || !(gamma_new > 0.0)) { ctl->done = 1; ctl->status = 2; }
+        }
         __threadfence();
     }
 }
@@ -327,4 +341,14 @@ __global__ void cg_start_ctl_kernel(CgCtl *ctl, const double *init3 /* r.u, r.r,
     ctl->status = 0;
     ctl->done = (bb == 0.0 || rr <= ctl->tol2) ? 1 : 0;
     if (!ctl->done && !(d > 0.0)) { ctl->done = 1; ctl->status = 2; }
+}
+
+// control block of a start pass (see the last block of cg_sl_tma_kernel)
+__global__ void cg_start_pass_ctl_kernel(CgCtl *ctl, double rtol) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    ctl->gamma = 1.0; ctl->delta = 0.0; ctl->rr = 0.0; ctl->bb = 0.0;
+    ctl->tol2 = rtol * rtol;
+    ctl->alpha = 0.0; ctl->beta = 0.0; ctl->alpha_pend = 0.0;
+    ctl->iters = -1;
+    ctl->done = 0; ctl->status = 0;
 }

@@ -1823,7 +1823,7 @@ int cg_sl_launch(const psfem_csr *A, double *d_x, const CgWs &w, bool masked, in
 
 extern "C" int psfem_cg_sl_usable(const psfem_csr *A, int *h_usable) {
     PSFEM_REQUIRE(A && h_usable, "cg_sl_usable: null argument");
-    *h_usable = cg_sl_ok(A, false) ? 1 : 0;
+    *h_usable = cg_sl_ok(A, false) ? 1 : (cg_sl_ok(A, true) ? 2 : 0);   // 2: as a strip of a partition only (psfem_dist_cg_*)
     return PSFEM_OK;
 }
 
@@ -1929,5 +1929,99 @@ extern "C" int psfem_cg_sl_solve(const psfem_csr *A, const double *d_b, double *
     h_info[0] = st[0]; h_info[1] = st[1]; h_info[2] = st[2];
     if (st[4] != 0.0) { set_error("cg_sl: breakdown (matrix not positive definite?) after %.0f iterations, relres %.3e", st[0], st[1]); return PSFEM_ENOCONV; }
     if (!(st[1] <= rtol) && st[2] > 0) { set_error("pcg: not converged (relres %.3e after %.0f iterations)", st[1], st[0]); return PSFEM_ENOCONV; }
+    return PSFEM_OK;
+}
+
+// ---- the fused iteration on a strip of a multi-GPU partition: halo columns of u as LL words, one scalar exchange ----
+namespace {
+int dist_cg_check(const psfem_csr *A, const psfem_dist_cg_ctx *c) {
+    PSFEM_REQUIRE(A && c && c->world >= 1 && c->world <= PSFEM_MAX_RANKS && c->rank >= 0 && c->rank < c->world, "dist_cg: bad rank/world");
+    PSFEM_REQUIRE(cg_sl_ok(A, true), "dist_cg: the strip operand needs its symmetric-lattice storage");
+    PSFEM_REQUIRE(c->x && c->counter && c->ll_mine && c->m == A->sl_m, "dist_cg: null buffers / column height mismatch");
+    PSFEM_REQUIRE(!c->has_left || (c->ll_left && c->rank > 0 && A->sl_roff == A->sl_m), "dist_cg: left neighbour not mapped (or no halo column in the storage)");
+    PSFEM_REQUIRE(!c->has_right || (c->ll_right && c->rank < c->world - 1), "dist_cg: right neighbour not mapped");
+    for (int w = 0; w < c->world; ++w) PSFEM_REQUIRE(c->board[w], "dist_cg: board of rank %d not mapped", w);
+    return PSFEM_OK;
+}
+void dist_cg_setup(const psfem_dist_cg_ctx *c, uint64_t seq, PeerSync *ps, CgVec *halo) {
+    memset(ps, 0, sizeof(*ps));
+    for (int w = 0; w < c->world && w < PSFEM_MAX_RANKS; ++w) ps->board[w] = static_cast<PeerBoard *>(c->board[w]);
+    ps->world = c->world; ps->rank = c->rank; ps->has_left = c->has_left; ps->has_right = c->has_right;
+    ps->seq = seq;
+    ps->err = reinterpret_cast<int *>(c->counter + 3);
+    memset(halo, 0, sizeof(*halo));
+    unsigned long long *mine = static_cast<unsigned long long *>(c->ll_mine);
+    const size_t side = (size_t)c->m * 4;
+    halo->ll_from_left = mine;                  // side 0 of my buffer: written by my left neighbour
+    halo->ll_from_right = mine + side;          // side 1: written by my right neighbour
+    if (c->has_left) halo->ll_to_left = static_cast<unsigned long long *>(c->ll_left) + side;   // I am its right neighbour
+    if (c->has_right) halo->ll_to_right = static_cast<unsigned long long *>(c->ll_right);       // I am its left neighbour
+}
+}  // namespace
+
+extern "C" int psfem_dist_cg_halo_bytes(int64_t m, size_t *bytes) {
+    PSFEM_REQUIRE(bytes && m > 0, "dist_cg_halo_bytes: bad arguments");
+    *bytes = align_up((size_t)m * 4 * sizeof(unsigned long long) * 2);
+    return PSFEM_OK;
+}
+
+// x = 0, r = b, then ONE launch of the iteration kernel in start mode: u_0 = D^-1 b, w_0 = A u_0 (halo exchanged inside the
+// kernel), gamma_0, delta_0, b.b, alpha_0.  Launch 0 of the solve, sequence number seq; the iterations follow with
+// launches_done = 1, 2, ... and seq + 1, seq + 2, ...
+extern "C" int psfem_dist_cg_start(const psfem_csr *A, const psfem_dist_cg_ctx *c, const double *d_b, const double *d_dinv_masked,
+                                   double rtol, uint64_t seq, void *d_ws, size_t ws_bytes, void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (int rc = dist_cg_check(A, c)) return rc;
+    PSFEM_REQUIRE(d_b && d_ws && seq >= 1, "dist_cg_start: bad arguments");
+    PSFEM_REQUIRE(!c->masked || d_dinv_masked, "dist_cg_start: masked strips pass D^-1 with zeros at the constrained rows");
+    const int64_t n = A->n_rows;
+    CgWs w = carve_cg(d_ws, n);
+    PSFEM_REQUIRE(ws_bytes >= w.total, "dist_cg_start: workspace too small (%zu < %zu)", ws_bytes, w.total);
+    const size_t nb = (size_t)n * sizeof(double);
+    PSFEM_CUDA_CHECK(cudaMemsetAsync(w.counter, 0, 3 * sizeof(unsigned int), stream));
+    PSFEM_CUDA_CHECK(cudaMemcpyAsync(w.r[0], d_b, nb, cudaMemcpyDeviceToDevice, stream));
+    PSFEM_CUDA_CHECK(cudaMemsetAsync(w.w[0], 0, nb, stream));
+    PSFEM_CUDA_CHECK(cudaMemsetAsync(w.s[0], 0, nb, stream));
+    PSFEM_CUDA_CHECK(cudaMemsetAsync(w.p, 0, nb, stream));
+    PSFEM_CUDA_CHECK(cudaMemsetAsync(c->x, 0, nb, stream));
+    if (c->masked) PSFEM_CUDA_CHECK(cudaMemcpyAsync(w.dinv, d_dinv_masked, nb, cudaMemcpyDeviceToDevice, stream));
+    cg_start_pass_ctl_kernel<<<1, 32, 0, stream>>>(w.ctl, rtol);
+    PSFEM_LAUNCH_CHECK();
+    PeerSync ps;
+    CgVec halo;
+    dist_cg_setup(c, seq, &ps, &halo);
+    // the kernel's own counter lives in the workspace; the error flag in the caller's counter block
+    return cg_sl_launch(A, c->x, w, c->masked != 0, 0, &ps, &halo, stream);
+}
+
+extern "C" int psfem_dist_cg_iterations(const psfem_csr *A, const psfem_dist_cg_ctx *c, int64_t k, int64_t launches_done, uint64_t seq_first,
+                                        void *d_ws, size_t ws_bytes, void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (int rc = dist_cg_check(A, c)) return rc;
+    PSFEM_REQUIRE(d_ws && k >= 0 && launches_done >= 1 && seq_first >= 2, "dist_cg_iterations: bad arguments");
+    CgWs w = carve_cg(d_ws, A->n_rows);
+    PSFEM_REQUIRE(ws_bytes >= w.total, "dist_cg_iterations: workspace too small");
+    for (int64_t j = 0; j < k; ++j) {
+        PeerSync ps;
+        CgVec halo;
+        dist_cg_setup(c, seq_first + (uint64_t)j, &ps, &halo);
+        int rc = cg_sl_launch(A, c->x, w, c->masked != 0, launches_done + j, &ps, &halo, stream);
+        if (rc) return rc;
+    }
+    PSFEM_LAUNCH_CHECK();
+    return PSFEM_OK;
+}
+
+// {iterations, relative residual, ||b||, done, status} of the strip solve (global values, identical on every rank) and the
+// peer time-out flag; synchronises
+extern "C" int psfem_dist_cg_state(const psfem_dist_cg_ctx *c, int64_t n, void *d_ws, double *h_info, void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    PSFEM_REQUIRE(c && d_ws && h_info && c->counter, "dist_cg_state: null argument");
+    int rc = psfem_cg_sl_state(d_ws, n, h_info, stream_);
+    if (rc) return rc;
+    int err = 0;
+    PSFEM_CUDA_CHECK(cudaMemcpyAsync(&err, c->counter + 3, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    PSFEM_CUDA_CHECK(cudaStreamSynchronize(stream));
+    if (err) { set_error("dist_cg: a wait on a peer rank timed out"); return PSFEM_ECUDA; }
     return PSFEM_OK;
 }

@@ -216,11 +216,14 @@ class PeerFabric:
             call("psfem_peer_board_bytes", C.byref(sz))
             self.board_ptr, hb = self._alloc(sz.value)
             self.p_ptr, hp = self._alloc(max(self.n_ext_free, 1) * 8)
+            call("psfem_dist_cg_halo_bytes", part.m, C.byref(sz))      # LL halo buffer of the fused one-kernel iteration
+            self.ll_ptr, hl = self._alloc(sz.value)
         except Exception as e:                                # noqa: BLE001 -- any failure means "no peer transport"
             err = str(e)
+            hl = None
         agree(err)
         # stage 2 (collective): swap the IPC handles and the halo sizes
-        mine = dict(board=hb, p=hp, lo=lo, hi=hi, n_ext_free=self.n_ext_free,
+        mine = dict(board=hb, p=hp, ll=hl, lo=lo, hi=hi, n_ext_free=self.n_ext_free,
                     send_left=plan["send_left"], send_right=plan["send_right"])
         everyone = [None] * world
         dist_module.all_gather_object(everyone, mine)
@@ -231,11 +234,13 @@ class PeerFabric:
             for w in range(world):
                 self.boards[w] = self.board_ptr if w == rank else self._open(everyone[w]["board"])
             self.left_p = self.right_p = None
+            self.left_ll = self.right_ll = None
             self.left_dst_off = self.right_dst_off = 0
             self.send_left_n = self.send_right_n = 0
             if part.left is not None:
                 nb = everyone[part.left]
                 self.left_p = self._open(nb["p"])
+                self.left_ll = self._open(nb["ll"])
                 self.left_dst_off = nb["hi"]                                   # its recv_right region [hi, n_ext_free)
                 self.send_left_n = plan["send_left"][1] - plan["send_left"][0]
                 if self.send_left_n != nb["n_ext_free"] - nb["hi"] or plan["send_left"][0] != lo:
@@ -243,6 +248,7 @@ class PeerFabric:
             if part.right is not None:
                 nb = everyone[part.right]
                 self.right_p = self._open(nb["p"])
+                self.right_ll = self._open(nb["ll"])
                 self.right_dst_off = 0                                           # its recv_left region [0, lo)
                 self.send_right_n = plan["send_right"][1] - plan["send_right"][0]
                 if self.send_right_n != nb["lo"] or plan["send_right"][1] != hi:
@@ -472,6 +478,30 @@ class StripProblem:
             c.out3 = st["out3"].data_ptr()
             c.partials, c.counter = self.ops.partials.data_ptr(), self.ops.counter.data_ptr()
             c.masked = int(self.masked)
+        # strips with the peer transport and symmetric-lattice storage: the fused one-kernel iteration with the halo of u and
+        # ONE scalar exchange inside it (psfem_dist_cg_*); PSFEM_PCG=classic keeps the three-kernel strip solver
+        self.fused_dist = False
+        if self.fabric and self.sym_lattice and not (self.masked and lo % 2):
+            from .device import FusedCG, fused_cg_enabled, workspace
+            ok = C.c_int(0)
+            call("psfem_cg_sl_usable", C.byref(self.A), C.byref(ok))
+            if fused_cg_enabled() and ok.value in (1, 2):
+                sz = C.c_size_t(0)
+                call("psfem_cg_sl_workspace", n, C.byref(sz))
+                self.cg_ws, self.cg_ws_bytes = workspace(sz.value), sz.value
+                g = self.cg_ctx = _capi.psfem_dist_cg_ctx()
+                fb = self.fabric
+                g.rank, g.world = self.rank, self.world
+                g.has_left, g.has_right = int(p.left is not None), int(p.right is not None)
+                for w_ in range(self.world):
+                    g.board[w_] = fb.boards[w_]
+                g.ll_mine, g.ll_left, g.ll_right = fb.ll_ptr, fb.left_ll, fb.right_ll
+                g.m = p.m
+                g.x = self.st["x"].data_ptr()
+                g.counter = self.ops.counter.data_ptr()
+                g.masked = int(self.masked)
+                self.fused_dist = True
+                self.launches = 0
         # one GPU, symmetric-lattice operand: the whole iteration is one kernel (psfem_cg_sl.cuh)
         self.fused = None
         if self.world == 1 and self.sym_lattice:
@@ -492,6 +522,19 @@ class StripProblem:
             self.st["x"].zero_()
             self.fused.start(self.b_own, self.st["x"], rtol=0.0)
             self.st["iters"] = 0
+            return
+        if self.fused_dist:
+            torch = _capi.torch_cuda()
+            if self.seq > 0:                      # restart on live boards / halo buffers: everybody has consumed the previous sequence
+                import torch.distributed as dist
+                torch.cuda.synchronize()
+                dist.barrier()
+            self.seq += 1
+            call("psfem_dist_cg_start", C.byref(self.A), C.byref(self.cg_ctx), ptr(self.b_own), ptr(self.st["dinv"] if self.masked else None),
+                 0.0, self.seq, ptr(self.cg_ws), self.cg_ws_bytes, stream_ptr())
+            self.launches = 1
+            self.st["iters"] = 0
+            self._bb = None
             return
         if self.fabric:
             if self.seq > 0:
@@ -565,6 +608,13 @@ class StripProblem:
             self.fused.iterations(k)
             self.st["iters"] += int(k)
             return
+        if self.fused_dist:   # one kernel per iteration: halo of u and the scalar exchange inside it
+            call("psfem_dist_cg_iterations", C.byref(self.A), C.byref(self.cg_ctx), int(k), self.launches, self.seq + 1,
+                 ptr(self.cg_ws), self.cg_ws_bytes, stream_ptr())
+            self.seq += int(k)
+            self.launches += int(k)
+            self.st["iters"] += int(k)
+            return
         if self.fabric:   # three kernels per iteration, no collective launches: scalars and halo go through peer memory
             call("psfem_dist_pcg_iterations", C.byref(self.A), C.byref(self.ctx), int(k), self.seq + 1, stream_ptr())
             self.seq += int(k)
@@ -583,6 +633,10 @@ class StripProblem:
         if self.fused is not None:
             st = self.fused.state()
             return st["relres"] * st["bnorm"], st["bnorm"]
+        if self.fused_dist:
+            h = (C.c_double * 5)()
+            call("psfem_dist_cg_state", C.byref(self.cg_ctx), self.n_owned_free, ptr(self.cg_ws), h, stream_ptr())
+            return float(h[1] * h[2]), float(h[2])
         if self.fabric:
             h = (C.c_double * 3)()
             call("psfem_dist_pcg_residual", C.byref(self.ctx), self.seq, h, stream_ptr())
@@ -608,6 +662,8 @@ class StripProblem:
         """The fused PCG writes x every other iteration; add the pending half before x is read."""
         if getattr(self, "fused", None) is not None:
             self.fused.finish()
+        elif getattr(self, "fused_dist", False):
+            call("psfem_cg_sl_finish", ptr(self.st["x"]), self.n_owned_free, ptr(self.cg_ws), stream_ptr())
 
     def gather_solution(self, dst=0):
         """Global displacement vector (zeros at constrained DOFs, like reconstruct_full_vector Polygones.py:913-921)
@@ -678,7 +734,7 @@ class StripProblem:
             self.st["p_ext"] = None
             self.fabric.close()
             self.fabric = None
-        for k in ("asm", "K_vals", "K_ext_red", "K_red", "fm", "st", "ops", "A", "b_own", "nodes", "conn", "ctx", "_cd_owned", "fused"):
+        for k in ("asm", "K_vals", "K_ext_red", "K_red", "fm", "st", "ops", "A", "b_own", "nodes", "conn", "ctx", "_cd_owned", "fused", "cg_ws", "cg_ctx"):
             if hasattr(self, k):
                 delattr(self, k)
 

@@ -22,11 +22,27 @@ def run_checks(world, rank):
     N, M, iters = 96 * world, 80, 40
     kw = dict(L=N * 1e-2, l=M * 1e-2, N=N, M=M, E=210e9, nu=0.3, t=0.1)
     res = {}
-    for transport in ("peer", "nccl"):
-        prob = StripProblem(rank=rank, world=world, transport=transport, **kw).setup()
-        assert prob.transport == transport, f"transport {transport} not available: fell back to {prob.transport}"
-        assert (prob.fabric is not None) == (transport == "peer")
+    for transport in ("peer", "peer-classic", "nccl"):
+        # "peer": the fused one-kernel iteration (halo + one scalar exchange inside it); "peer-classic": the three-kernel
+        # strip solver over the same boards (PSFEM_PCG=classic); "nccl": the three kernels with NCCL calls between them
+        saved = os.environ.get("PSFEM_PCG")
+        if transport == "peer-classic":
+            os.environ["PSFEM_PCG"] = "classic"
+        try:
+            prob = StripProblem(rank=rank, world=world, transport=transport.split("-")[0], **kw).setup()
+        finally:
+            if transport == "peer-classic":
+                if saved is None:
+                    os.environ.pop("PSFEM_PCG", None)
+                else:
+                    os.environ["PSFEM_PCG"] = saved
+        assert prob.transport == transport.split("-")[0], f"transport {transport} not available: fell back to {prob.transport}"
+        assert (prob.fabric is not None) == transport.startswith("peer")
         assert prob.sym_lattice or os.environ.get("PSFEM_NO_SYMLATTICE")   # the strips run the symmetric-lattice SpMV
+        if transport == "peer" and saved != "classic" and not os.environ.get("PSFEM_NO_SYMLATTICE"):
+            assert prob.fused_dist and prob.kernels_per_iteration == 1
+        if transport == "peer-classic":
+            assert not prob.fused_dist and prob.kernels_per_iteration == 3
         if transport == "peer":                                    # assembled + reduced rows this rank owns
             rp = prob.K_red.row_ptr.cpu().numpy().astype(np.int64)
             res["K_rows"] = (rp - rp[0], prob.K_red.vals[int(rp[0]):int(rp[-1])].cpu().numpy().copy(),
@@ -35,21 +51,26 @@ def run_checks(world, rank):
         r, b = prob.residual()
         prob.finish_x()
         res[transport] = (prob.st["x"].cpu().numpy().copy(), r, b)
-        if transport == "peer":                                    # restart on the same boards, solve to 1e-9
+        if transport.startswith("peer"):                           # restart on the same boards, solve to 1e-9
             info = prob.full_solve(1e-9)
             assert info["relres"] <= 1e-9, info
-            res["solve_iters"] = info["iterations"]
+            res["solve_iters" if transport == "peer" else "solve_iters_classic"] = info["iterations"]
         lo_hi = (prob.part.dof_shift, prob.plan["own"])
         prob.release()
     xp, rp, bp = res["peer"]
+    xc, rc, bc_ = res["peer-classic"]
     xn, rn, bn = res["nccl"]
     scale = np.abs(xn).max()
-    if world == 2:
-        assert np.array_equal(xp, xn), np.abs(xp - xn).max() / scale
-        assert rp == rn and bp == bn
+    if world == 2:      # classic recurrence: the peer boards and NCCL add the two partials in the same order
+        assert np.array_equal(xc, xn), np.abs(xc - xn).max() / scale
+        assert rc == rn and bc_ == bn
     else:
-        assert np.abs(xp - xn).max() <= 1e-9 * scale
-        assert abs(rp - rn) <= 1e-6 * rn
+        assert np.abs(xc - xn).max() <= 1e-9 * scale
+        assert abs(rc - rn) <= 1e-6 * rn
+    # the fused iteration is the same Krylov method in another recurrence: equal up to rounding
+    assert np.abs(xp - xn).max() <= 1e-8 * scale, np.abs(xp - xn).max() / scale
+    assert abs(rp - rn) <= 1e-4 * rn and abs(bp - bn) <= 1e-12 * bn
+    assert abs(res["solve_iters"] - res["solve_iters_classic"]) <= max(3, 0.05 * res["solve_iters_classic"])
     # single-GPU solver on the whole plate (every rank repeats it; small)
     one = StripProblem(rank=0, world=1, **kw).setup()
     one.cg_iterations(iters)
