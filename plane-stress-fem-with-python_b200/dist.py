@@ -667,28 +667,33 @@ class StripProblem:
 
     def gather_solution(self, dst=0):
         """Global displacement vector (zeros at constrained DOFs, like reconstruct_full_vector Polygones.py:913-921)
-        on rank `dst` (None elsewhere): every rank contributes the free DOFs of its owned node columns."""
+        on rank `dst` (None elsewhere).  Ranks own contiguous, ascending DOF ranges, so the owned solutions concatenated in
+        rank order ARE the reduced global vector: one NCCL gather of device buffers, one scatter over the free DOFs on the
+        device (psfem_scatter_free), one D2H into page-locked memory."""
         torch = _capi.torch_cuda()
-        lo, hi = self.plan["own"]
+        from .device import FreeMap, to_host
         self.finish_x()
-        torch.cuda.synchronize()
-        if self.masked:
-            ids = np.arange(lo, hi, dtype=np.int64) + self.part.dof_shift
-        else:
-            ids = (self.fm.free_dofs[lo:hi].cpu().numpy().astype(np.int64) + self.part.dof_shift)
-        vals = self.st["x"].cpu().numpy()
+        x = self.st["x"]
         if self.world == 1:
-            parts = [(ids, vals)]
+            red = x
         else:
             import torch.distributed as dist
-            parts = [None] * self.world if self.rank == dst else None
-            dist.gather_object((ids, vals), parts, dst=dst)
-            if self.rank != dst:
+            sizes = [None] * self.world
+            dist.all_gather_object(sizes, int(x.numel()))
+            if self.rank == dst:
+                red = torch.empty(sum(sizes), dtype=torch.float64, device="cuda")
+                dist.gather(x, gather_list=list(red.split(sizes)), dst=dst)
+            else:
+                dist.gather(x, dst=dst)
                 return None
-        U = np.zeros(self.n_dof_global)
-        for i, v in parts:
-            U[i] = v
-        return U
+        if self.masked:                      # masked strips keep every DOF of their columns (zeros at the constrained ones)
+            full = red
+        else:
+            fm = FreeMap(self.n_dof_global, self.constrained_global)
+            full = fm.expand(red)
+        h = to_host(full)
+        torch.cuda.current_stream().synchronize()
+        return h.numpy()
 
     def full_solve(self, rtol):
         torch = _capi.torch_cuda()
@@ -787,7 +792,7 @@ def static_solve(L, l, N, M=0, bc=None, F=None, E=210e9, nu=0.3, t=0.1, element_
     info["transport"] = prob.transport if world > 1 else "single GPU"
     U = prob.gather_solution(dst=dst)
     info["h2d_bytes"] = int(h2d)
-    info["d2h_bytes"] = int(8 * prob.n_owned_free)
+    info["d2h_bytes"] = int(8 * prob.n_dof_global) if rank == dst else 0       # the gathered vector leaves the device on rank dst only
     prob.release()
     if raise_on_fail and not info["converged"]:
         raise _capi.ConvergenceError(f"strip PCG: relres {info['relres']:.3e} after {info['iterations']} iterations")
