@@ -262,7 +262,8 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        import datetime
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=150))   # a rank that dies must not hold the others (and the GPUs) for NCCL's default 10 minutes
     hbm_peak, peak_src = peaks()
     cells = args.cells
 

@@ -668,8 +668,8 @@ class StripProblem:
     def gather_solution(self, dst=0):
         """Global displacement vector (zeros at constrained DOFs, like reconstruct_full_vector Polygones.py:913-921)
         on rank `dst` (None elsewhere).  Ranks own contiguous, ascending DOF ranges, so the owned solutions concatenated in
-        rank order ARE the reduced global vector: one NCCL gather of device buffers, one scatter over the free DOFs on the
-        device (psfem_scatter_free), one D2H into page-locked memory."""
+        rank order ARE the reduced global vector: NCCL transfers of the device buffers into one buffer on `dst`, one scatter
+        over the free DOFs on the device (psfem_scatter_free), one D2H into page-locked memory."""
         torch = _capi.torch_cuda()
         from .device import FreeMap, to_host
         self.finish_x()
@@ -680,11 +680,18 @@ class StripProblem:
             import torch.distributed as dist
             sizes = [None] * self.world
             dist.all_gather_object(sizes, int(x.numel()))
+            # the strips own different numbers of columns (the last one also owns the right edge): point-to-point
+            # transfers into slices of one device buffer (a NCCL gather wants equal sizes)
             if self.rank == dst:
                 red = torch.empty(sum(sizes), dtype=torch.float64, device="cuda")
-                dist.gather(x, gather_list=list(red.split(sizes)), dst=dst)
+                parts = list(red.split(sizes))
+                parts[dst].copy_(x)
+                ops = [dist.P2POp(dist.irecv, parts[r], r) for r in range(self.world) if r != dst]
+                for w_ in dist.batch_isend_irecv(ops):
+                    w_.wait()
             else:
-                dist.gather(x, dst=dst)
+                for w_ in dist.batch_isend_irecv([dist.P2POp(dist.isend, x, dst)]):
+                    w_.wait()
                 return None
         if self.masked:                      # masked strips keep every DOF of their columns (zeros at the constrained ones)
             full = red

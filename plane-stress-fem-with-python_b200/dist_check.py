@@ -19,6 +19,17 @@ def run_checks(world, rank):
     import torch.distributed as dist
     import psfem_b200
     from psfem_b200.dist import StripProblem, static_solve
+    import torch
+    fails = []
+
+    def chk(cond, what=""):
+        """a failed check is RECORDED, not raised: an exception on one rank would leave the others waiting in the next
+        collective; all ranks agree on the outcome at the end"""
+        if not cond:
+            try:
+                fails.append(str(what() if callable(what) else what))
+            except Exception as e:                      # noqa: BLE001
+                fails.append(f"check failed ({e})")
     N, M, iters = 96 * world, 80, 40
     kw = dict(L=N * 1e-2, l=M * 1e-2, N=N, M=M, E=210e9, nu=0.3, t=0.1)
     res = {}
@@ -36,13 +47,13 @@ def run_checks(world, rank):
                     os.environ.pop("PSFEM_PCG", None)
                 else:
                     os.environ["PSFEM_PCG"] = saved
-        assert prob.transport == transport.split("-")[0], f"transport {transport} not available: fell back to {prob.transport}"
-        assert (prob.fabric is not None) == transport.startswith("peer")
-        assert prob.sym_lattice or os.environ.get("PSFEM_NO_SYMLATTICE")   # the strips run the symmetric-lattice SpMV
+        chk(prob.transport == transport.split("-")[0], lambda: f"transport {transport} not available: fell back to {prob.transport}")
+        chk((prob.fabric is not None) == transport.startswith("peer"), "(prob.fabric is not None) == transport.startswith('peer')")
+        chk(prob.sym_lattice or os.environ.get("PSFEM_NO_SYMLATTICE"), "the strips run the symmetric-lattice SpMV")
         if transport == "peer" and saved != "classic" and not os.environ.get("PSFEM_NO_SYMLATTICE"):
-            assert prob.fused_dist and prob.kernels_per_iteration == 1
+            chk(prob.fused_dist and prob.kernels_per_iteration == 1, "prob.fused_dist and prob.kernels_per_iteration == 1")
         if transport == "peer-classic":
-            assert not prob.fused_dist and prob.kernels_per_iteration == 3
+            chk(not prob.fused_dist and prob.kernels_per_iteration == 3, "not prob.fused_dist and prob.kernels_per_iteration == 3")
         if transport == "peer":                                    # assembled + reduced rows this rank owns
             rp = prob.K_red.row_ptr.cpu().numpy().astype(np.int64)
             res["K_rows"] = (rp - rp[0], prob.K_red.vals[int(rp[0]):int(rp[-1])].cpu().numpy().copy(),
@@ -53,7 +64,7 @@ def run_checks(world, rank):
         res[transport] = (prob.st["x"].cpu().numpy().copy(), r, b)
         if transport.startswith("peer"):                           # restart on the same boards, solve to 1e-9
             info = prob.full_solve(1e-9)
-            assert info["relres"] <= 1e-9, info
+            chk(info["relres"] <= 1e-9, lambda: f"info['relres'] <= 1e-9: {info}")
             res["solve_iters" if transport == "peer" else "solve_iters_classic"] = info["iterations"]
         lo_hi = (prob.part.dof_shift, prob.plan["own"])
         prob.release()
@@ -62,15 +73,15 @@ def run_checks(world, rank):
     xn, rn, bn = res["nccl"]
     scale = np.abs(xn).max()
     if world == 2:      # classic recurrence: the peer boards and NCCL add the two partials in the same order
-        assert np.array_equal(xc, xn), np.abs(xc - xn).max() / scale
-        assert rc == rn and bc_ == bn
+        chk(np.array_equal(xc, xn), lambda: f"np.array_equal(xc, xn): {np.abs(xc - xn).max() / scale}")
+        chk(rc == rn and bc_ == bn, "rc == rn and bc_ == bn")
     else:
-        assert np.abs(xc - xn).max() <= 1e-9 * scale
-        assert abs(rc - rn) <= 1e-6 * rn
+        chk(np.abs(xc - xn).max() <= 1e-9 * scale, "np.abs(xc - xn).max() <= 1e-9 * scale")
+        chk(abs(rc - rn) <= 1e-6 * rn, "abs(rc - rn) <= 1e-6 * rn")
     # the fused iteration is the same Krylov method in another recurrence: equal up to rounding
-    assert np.abs(xp - xn).max() <= 1e-8 * scale, np.abs(xp - xn).max() / scale
-    assert abs(rp - rn) <= 1e-4 * rn and abs(bp - bn) <= 1e-12 * bn
-    assert abs(res["solve_iters"] - res["solve_iters_classic"]) <= max(3, 0.05 * res["solve_iters_classic"])
+    chk(np.abs(xp - xn).max() <= 1e-8 * scale, lambda: f"np.abs(xp - xn).max() <= 1e-8 * scale: {np.abs(xp - xn).max() / scale}")
+    chk(abs(rp - rn) <= 1e-4 * rn and abs(bp - bn) <= 1e-12 * bn, "abs(rp - rn) <= 1e-4 * rn and abs(bp - bn) <= 1e-12 * bn")
+    chk(abs(res["solve_iters"] - res["solve_iters_classic"]) <= max(3, 0.05 * res["solve_iters_classic"]), "abs(res['solve_iters'] - res['solve_iters_classic']) <= max(3, 0.05 * res['solve_iters_classic'])")
     # single-GPU solver on the whole plate (every rank repeats it; small)
     one = StripProblem(rank=0, world=1, **kw).setup()
     one.cg_iterations(iters)
@@ -81,16 +92,16 @@ def run_checks(world, rank):
     sizes = [None] * world
     dist.all_gather_object(sizes, len(xp))
     off = sum(sizes[:rank])
-    assert sum(sizes) == len(x1)
+    chk(sum(sizes) == len(x1), "sum(sizes) == len(x1)")
     # the strip's owned rows of K are the single-GPU rows BIT FOR BIT (pattern, values; columns up to the strip offset)
     rp1 = one.K_red.row_ptr.cpu().numpy().astype(np.int64)
     a, b_ = int(rp1[off]), int(rp1[off + len(xp)])
     rel_ptr, vals, cols = res["K_rows"]
-    assert np.array_equal(rel_ptr, rp1[off:off + len(xp) + 1] - a)
-    assert np.array_equal(vals, one.K_red.vals[a:b_].cpu().numpy())
-    assert np.array_equal(cols + off, one.K_red.col_idx[a:b_].cpu().numpy().astype(np.int64))
-    assert np.abs(xp - x1[off:off + len(xp)]).max() <= 1e-8 * np.abs(x1).max()
-    assert abs(rp - r1) <= 1e-5 * r1 and abs(bp - b1) <= 1e-12 * b1
+    chk(np.array_equal(rel_ptr, rp1[off:off + len(xp) + 1] - a), "np.array_equal(rel_ptr, rp1[off:off + len(xp) + 1] - a)")
+    chk(np.array_equal(vals, one.K_red.vals[a:b_].cpu().numpy()), "np.array_equal(vals, one.K_red.vals[a:b_].cpu().numpy())")
+    chk(np.array_equal(cols + off, one.K_red.col_idx[a:b_].cpu().numpy().astype(np.int64)), "np.array_equal(cols + off, one.K_red.col_idx[a:b_].cpu().numpy().astype(np.int64))")
+    chk(np.abs(xp - x1[off:off + len(xp)]).max() <= 1e-8 * np.abs(x1).max(), "np.abs(xp - x1[off:off + len(xp)]).max() <= 1e-8 * np.abs(x1).max()")
+    chk(abs(rp - r1) <= 1e-5 * r1 and abs(bp - b1) <= 1e-12 * b1, "abs(rp - r1) <= 1e-5 * r1 and abs(bp - b1) <= 1e-12 * b1")
     # 3b. the other element types (T3, and the quadratic T6 / Q9 of mesh_type='fine', whose strips carry a two-column
     #     left halo): owned matrix rows bit-identical to the single-GPU rows, same iterates
     for et, mt, n_, m_ in (("tri", "coarse", 40 * world, 60), ("quad", "fine", 24 * world, 20), ("tri", "fine", 24 * world, 20)):
@@ -108,11 +119,11 @@ def run_checks(world, rank):
         dist.all_gather_object(sizes2, len(x_own))
         off2 = sum(sizes2[:rank])
         rp1 = o1.K_red.row_ptr.cpu().numpy().astype(np.int64)
-        assert np.array_equal(rpo - rpo[0], rp1[off2:off2 + len(x_own) + 1] - rp1[off2]), (et, mt)
-        assert np.array_equal(vals_own, o1.K_red.vals[int(rp1[off2]):int(rp1[off2 + len(x_own)])].cpu().numpy()), (et, mt)
+        chk(np.array_equal(rpo - rpo[0], rp1[off2:off2 + len(x_own) + 1] - rp1[off2]), lambda: f"np.array_equal(rpo - rpo[0], rp1[off2:off2 + len(x_own) + 1] - rp1[off2]): {(et, mt)}")
+        chk(np.array_equal(vals_own, o1.K_red.vals[int(rp1[off2]):int(rp1[off2 + len(x_own)])].cpu().numpy()), lambda: f"np.array_equal(vals_own, o1.K_red.vals[int(rp1[off2]):int(rp1[off2 + len(x_own)])].cpu().numpy()): {(et, mt)}")
         o1.finish_x()
         x1_ = o1.st["x"].cpu().numpy()
-        assert np.abs(x_own - x1_[off2:off2 + len(x_own)]).max() <= 1e-9 * np.abs(x1_).max(), (et, mt)
+        chk(np.abs(x_own - x1_[off2:off2 + len(x_own)]).max() <= 1e-9 * np.abs(x1_).max(), lambda: f"np.abs(x_own - x1_[off2:off2 + len(x_own)]).max() <= 1e-9 * np.abs(x1_).max(): {(et, mt)}")
         o1.release()
     # 4. general boundary conditions and loads: rollers along the bottom edge (single DOFs constrained: the reduced
     #    matrix would lose its node-block structure, so the strips keep them as masked rows), one pinned node, load on the top edge; the gathered
@@ -123,11 +134,17 @@ def run_checks(world, rank):
     Fg = P.edgeForces(np.zeros(2 * len(nodes)), [2e5, -1e6], "top", kw["L"], N, M)
     Ug, info = static_solve(kw["L"], kw["l"], N, M, bc=bc, F=Fg, E=kw["E"], nu=kw["nu"], t=kw["t"], rtol=1e-11, maxit=40000,
                             check_every=200, transport="peer")
-    assert info["relres"] <= 1e-11 and info["transport"] == "peer", info
+    chk(info["relres"] <= 1e-11 and info["transport"] == "peer", lambda: f"info['relres'] <= 1e-11 and info['transport'] == 'peer': {info}")
     if rank == 0:
-        K = P.global_stiffness_matrix(nodes, elements, kw["E"], kw["nu"], kw["t"], "quad")
-        U1, _, cd, _ = psfem_b200.static_solve(K, Fg, bc, rtol=1e-11, check_every=200)
-        assert np.all(Ug[cd] == 0)
-        assert np.abs(Ug - U1).max() <= 1e-8 * np.abs(U1).max(), np.abs(Ug - U1).max() / np.abs(U1).max()
-    dist.barrier()
+        try:                                             # rank-0-only work must not raise past the collective below
+            K = P.global_stiffness_matrix(nodes, elements, kw["E"], kw["nu"], kw["t"], "quad")
+            U1, _, cd, _ = psfem_b200.static_solve(K, Fg, bc, rtol=1e-11, check_every=200)
+            chk(Ug is not None and Ug.shape == U1.shape and np.all(Ug[cd] == 0), "gathered solution: shape / zeros at constrained DOFs")
+            chk(np.abs(Ug - U1).max() <= 1e-8 * np.abs(U1).max(), lambda: f"gathered strip solution vs single-GPU static_solve: {np.abs(Ug - U1).max() / np.abs(U1).max()}")
+        except Exception as e:                           # noqa: BLE001
+            chk(False, f"single-GPU comparison raised {type(e).__name__}: {e}")
+    bad = torch.tensor([len(fails)], dtype=torch.int32, device="cuda")
+    dist.all_reduce(bad)
+    if int(bad.item()):
+        raise AssertionError(f"dist check: {int(bad.item())} failed checks over all ranks; rank {rank}: {fails[:4]}")
     return dict(world=world, iters=iters, relres=rp / bp, full_solve_iterations=res["solve_iters"])

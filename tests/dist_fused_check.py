@@ -16,7 +16,8 @@ def main():
 
     world, rank, local = int(os.environ["WORLD_SIZE"]), int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import datetime
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=150))
     out = run_checks(world, rank)
     if rank == 0:
         print(f"dist_fused_check OK: world={world} iters={out['iters']} relres={out['relres']:.3e} "
