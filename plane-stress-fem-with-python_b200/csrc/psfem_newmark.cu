@@ -13,7 +13,7 @@
 namespace psfem {
 int pcg_solve(const psfem_csr *A, const double *d_b, double *d_x, double rtol, int64_t maxit, int64_t check_every,
               double *h_info, double *d_info, double *h_acc, void *d_ws, size_t ws_bytes, bool have_dinv, cudaStream_t stream,
-              bool masked);
+              bool masked, const int32_t *d_new_id);
 double *pcg_dinv_ptr(void *d_ws, int64_t n, int64_t n_blocks);
 }
 using namespace psfem;
@@ -424,6 +424,7 @@ static int time_loop(const psfem_csr *K, const psfem_csr *M, const psfem_csr *Ke
             if (ok) first_step = n_steps;   // every step done
         }
     }
+    int64_t pcg_batch = 50;
     for (int64_t i = first_step; i < n_steps; ++i) {
         predictor_kernel<<<g, NT, 0, stream>>>(n, w.u, w.v, w.a, dt, c_u_pred, c_v_pred, beta_R, w.up, w.vp, w.w1);
         PSFEM_LAUNCH_CHECK();
@@ -437,7 +438,10 @@ static int time_loop(const psfem_csr *K, const psfem_csr *M, const psfem_csr *Ke
             rc = psfem_spmv2(K, d_M_vals, w.w1, w.vp, -1.0, -alpha_R, h_fscale[i], d_fshape, w.rhs, stream);
         }
         if (rc) return rc;
-        rc = pcg_solve(&Keff, w.rhs, w.a, rtol, maxit, 50, nullptr, w.info, h_acc, w.pcg, w.pcg_bytes, true, stream, false);  // :314
+        // batches sized by the previous step's iteration count (warm start: a handful of iterations per step)
+        const double it_before = h_acc[0];
+        rc = pcg_solve(&Keff, w.rhs, w.a, rtol, maxit, pcg_batch, nullptr, w.info, h_acc, w.pcg, w.pcg_bytes, true, stream, false, nullptr);  // :314
+        if (h_acc[0] > it_before) { const int64_t used = (int64_t)(h_acc[0] - it_before); pcg_batch = used + 3 < 50 ? used + 3 : 50; }
         if (rc && rc != PSFEM_ENOCONV) return rc;
         corrector_kernel<<<g, NT, 0, stream>>>(n, w.up, w.vp, w.a, c_v_corr, c_u_corr, w.u, w.v, w.partials, w.counter, w.ctl, i, lc.thresh);
         PSFEM_LAUNCH_CHECK();

@@ -1220,6 +1220,8 @@ CgWs carve_cg(void *ws, int64_t n) {
     return w;
 }
 
+bool cg_sl_ok(const psfem_csr *A, bool strip);   // defined with the fused-iteration entry points below
+
 struct PcgWs {
     double *r, *p, *q, *dinv, *partials, *scal;
     PcgCtl *ctl;
@@ -1431,7 +1433,8 @@ extern "C" int psfem_extract_diag(const psfem_csr *A, int64_t col_offset, int in
 
 extern "C" int psfem_pcg_workspace(int64_t n, int64_t n_blocks, size_t *bytes) {
     PSFEM_REQUIRE(bytes && n >= 0, "pcg_workspace: bad arguments");
-    *bytes = carve_pcg(nullptr, n, n_blocks).total;
+    const size_t classic = carve_pcg(nullptr, n, n_blocks).total, fused = carve_cg(nullptr, n).total;
+    *bytes = classic > fused ? classic : fused;     // either recurrence runs in a work space of this size (pcg_solve picks)
     return PSFEM_OK;
 }
 
@@ -1629,8 +1632,20 @@ double *pcg_dinv_ptr(void *d_ws, int64_t n, int64_t n_blocks) { return carve_pcg
 // h_acc (optional): host accumulators of the multi-kernel path (sum of iterations, max relres, status).
 int pcg_solve(const psfem_csr *A, const double *d_b, double *d_x, double rtol, int64_t maxit, int64_t check_every,
               double *h_info, double *d_info, double *h_acc, void *d_ws, size_t ws_bytes, bool have_dinv,
-              cudaStream_t stream, bool masked) {
+              cudaStream_t stream, bool masked, const int32_t *d_new_id) {
     const int64_t n = A->n_rows;
+    {
+        // operands that carry their symmetric-lattice storage: one kernel per iteration (psfem_cg_sl.cuh)
+        const char *mode = getenv("PSFEM_PCG");
+        const bool classic = mode && strcmp(mode, "classic") == 0;
+        if (!classic && n > SMALL_MAX_N && cg_sl_ok(A, false) && (!masked || d_new_id) && ws_bytes >= carve_cg(nullptr, n).total) {
+            double info3[4] = {0, 0, 0, 0};
+            const int rc = psfem_cg_sl_solve(A, d_b, d_x, masked ? d_new_id : nullptr, rtol, maxit, check_every, info3, d_ws, ws_bytes, stream);
+            if (h_info) { h_info[0] = info3[0]; h_info[1] = info3[1]; h_info[2] = info3[2]; }
+            if (h_acc) { h_acc[0] += info3[0]; if (info3[1] > h_acc[1]) h_acc[1] = info3[1]; if (rc == PSFEM_ENOCONV) h_acc[2] = 1.0; }
+            return rc;
+        }
+    }
     PSFEM_REQUIRE(!masked || n > SMALL_MAX_N, "pcg: the masked solve is for systems above %d rows (reduce smaller ones)", SMALL_MAX_N);
     PcgWs w = carve_pcg(d_ws, n, A->n_blocks);
     PSFEM_REQUIRE(ws_bytes >= w.total, "pcg: workspace too small (%zu < %zu)", ws_bytes, w.total);
@@ -1702,7 +1717,7 @@ extern "C" int psfem_pcg_jacobi(const psfem_csr *A, const double *d_b, double *d
     PcgWs w = carve_pcg(d_ws, A->n_rows, A->n_blocks);
     PSFEM_REQUIRE(ws_bytes >= w.total, "pcg_jacobi: workspace too small (%zu < %zu)", ws_bytes, w.total);
     PSFEM_CUDA_CHECK(cudaMemsetAsync(w.scal, 0, 16 * sizeof(double), stream));
-    return psfem::pcg_solve(A, d_b, d_x, rtol, maxit, check_every, h_info, w.scal, nullptr, d_ws, ws_bytes, false, stream, false);
+    return psfem::pcg_solve(A, d_b, d_x, rtol, maxit, check_every, h_info, w.scal, nullptr, d_ws, ws_bytes, false, stream, false, nullptr);
 }
 
 __global__ void mask_dinv_kernel(int64_t n, const int32_t *__restrict__ new_id, double *__restrict__ dinv) {
@@ -1722,7 +1737,7 @@ extern "C" int psfem_pcg_jacobi_masked(const psfem_csr *A, const double *d_b, do
     if (rc) return rc;
     mask_dinv_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, stream>>>(n, d_new_id, w.dinv);
     PSFEM_LAUNCH_CHECK();
-    return psfem::pcg_solve(A, d_b, d_x, rtol, maxit, check_every, h_info, w.scal, nullptr, d_ws, ws_bytes, true, stream, true);
+    return psfem::pcg_solve(A, d_b, d_x, rtol, maxit, check_every, h_info, w.scal, nullptr, d_ws, ws_bytes, true, stream, true, d_new_id);
 }
 
 extern "C" int psfem_axpby(int64_t n, double a, const double *d_x, double b, const double *d_y, double *d_out, void *stream_) {
@@ -1844,15 +1859,19 @@ extern "C" int psfem_cg_sl_start(const psfem_csr *A, const double *d_b, double *
     PSFEM_CUDA_CHECK(cudaMemsetAsync(w.counter, 0, 4 * sizeof(unsigned int), stream));
     PSFEM_CUDA_CHECK(cudaMemsetAsync(w.scal, 0, 16 * sizeof(double), stream));
     PSFEM_CUDA_CHECK(cudaMemsetAsync(w.ctl, 0, sizeof(CgCtl), stream));
-    int rc = psfem_extract_diag(A, 0, 1, w.dinv, stream);
-    if (rc) return rc;
+    {
+        SlGeom g;
+        PSFEM_REQUIRE(sl_geometry(A, &g, 148, 2), "cg_sl_start: operand has no symmetric-lattice geometry");
+        cg_sl_dinv_kernel<<<ew_grid(n / 2), EW_THREADS, 0, stream>>>(A->sl_vals, g, w.dinv);
+        PSFEM_LAUNCH_CHECK();
+    }
     const bool masked = d_new_id != nullptr;
     if (masked) {
         mask_dinv_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, stream>>>(n, d_new_id, w.dinv);
         PSFEM_LAUNCH_CHECK();
     }
     // r_0 = b - A x_0 ; u_0 = D^-1 r_0 (parked in p) ; w_0 = A u_0 ; gamma_0 = r.u, delta_0 = u.w ; s = 0
-    rc = launch_spmv(A, nullptr, d_x, nullptr, -1.0, 0.0, 1.0, d_b, w.r[0], nullptr, nullptr, nullptr, nullptr, nullptr, stream);
+    int rc = launch_spmv(A, nullptr, d_x, nullptr, -1.0, 0.0, 1.0, d_b, w.r[0], nullptr, nullptr, nullptr, nullptr, nullptr, stream);
     if (rc) return rc;
     pcg_init_kernel<<<ew_grid(n), EW_THREADS, 0, stream>>>(n, w.r[0], w.dinv, d_b, w.p, w.scal, w.partials, w.counter, nullptr, rtol, masked ? 1 : 0);
     PSFEM_LAUNCH_CHECK();
