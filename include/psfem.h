@@ -181,6 +181,16 @@ int psfem_assemble_lattice(const double *d_nodes, int64_t n, int64_t m, int etyp
                            double *d_K_vals, double *d_M_vals, void *d_ws, size_t ws_bytes,
                            int64_t *h_bad_element, void *stream);
 
+/* The same numeric assembly (Q4 lattices: global_stiffness_matrix :710-728 / global_mass_matrix :1344-1364) written STRAIGHT
+ * INTO the symmetric-lattice operand of the solvers (psfem_spmv_sl_build's layout: 19 doubles per node): for flows that
+ * only solve, K never exists as CSR -- no value array, no column indices, no reduced copy (2.55 instead of ~12 GB and ~15 ms
+ * of set-up at the 4096 x 4096 plate; the 16384 x 4096 strip fits ONE GPU).  Stores the node columns [c_lo, c_lo + S);
+ * c_lo = 1 is the reduction by a clamped first column.  d_sl_vals: S * 19 * ((m+3)&~3) doubles.  what: 1 = K, 2 = M.
+ * Bit-identical to psfem_assemble_lattice + psfem_spmv_sl_build.  d_ws >= 32 bytes.  Synchronises. */
+int psfem_assemble_lattice_sl(const double *d_nodes, int64_t n, int64_t m, int etype, double E, double nu, double rho, double t,
+                              int what, int64_t c_lo, int64_t S, double *d_sl_vals, size_t bytes, void *d_ws, size_t ws_bytes,
+                              int64_t *h_bad_element, void *stream);
+
 /* element matrices only: Polygones.element_stiffness_matrix :566, element_mass_matrix :1250.
  * d_Ke / d_Me: nel*(2npe)^2 doubles, one row-major (2npe x 2npe) matrix per element.
  * Work space: psfem_assemble_workspace(nel, etype, what). */
@@ -404,8 +414,8 @@ int psfem_dist_pcg_residual(const psfem_dist_ctx *ctx, uint64_t seq, double *h_o
  * no fence, no flag).  Replaces psfem_dist_pcg_* (three launches, two exchanges) when the strip operand carries its
  * symmetric-lattice storage.  State lives in a psfem_cg_sl_workspace block; psfem_cg_sl_finish adds the pending x half.
  *   psfem_dist_cg_halo_bytes  size of a rank's LL halo buffer (psfem_peer_alloc, zero-filled) for column height m
- *   psfem_dist_cg_start       x = 0, r = b and the start pass (launch 0, sequence number seq >= 1); masked strips pass D^-1
- *                             of the owned rows with zeros at constrained DOFs
+ *   psfem_dist_cg_start       x = 0, r = b and the start pass (launch 0, sequence number seq >= 1); masked strips pass the free
+ *                             map of their owned rows (d_new_id[i] < 0: constrained DOF kept in the matrix)
  *   psfem_dist_cg_iterations  k launches; launches_done counts launches since the start (>= 1), seq_first = seq + launches_done
  *   psfem_dist_cg_state       {iterations, relative residual, ||b||, done, status}, global; reports a peer time-out */
 typedef struct psfem_dist_cg_ctx {
@@ -419,7 +429,7 @@ typedef struct psfem_dist_cg_ctx {
     int32_t masked;
 } psfem_dist_cg_ctx;
 int psfem_dist_cg_halo_bytes(int64_t m, size_t *bytes);
-int psfem_dist_cg_start(const psfem_csr *A, const psfem_dist_cg_ctx *ctx, const double *d_b, const double *d_dinv_masked,
+int psfem_dist_cg_start(const psfem_csr *A, const psfem_dist_cg_ctx *ctx, const double *d_b, const int32_t *d_new_id,
                         double rtol, uint64_t seq, void *d_ws, size_t ws_bytes, void *stream);
 int psfem_dist_cg_iterations(const psfem_csr *A, const psfem_dist_cg_ctx *ctx, int64_t k, int64_t launches_done,
                              uint64_t seq_first, void *d_ws, size_t ws_bytes, void *stream);

@@ -85,6 +85,7 @@ SIGNATURES = {
     "psfem_lattice_detect": [_ptr, _i64, _i32, _i64, _pi64, _ptr, _sz, _ptr],
     "psfem_lattice_pattern": [_i64, _i64, _i32, _ptr, _ptr, _ptr, _pi64, _ptr],
     "psfem_assemble_lattice": [_ptr, _i64, _i64, _i32, _dbl, _dbl, _dbl, _dbl, _i32, _ptr, _ptr, _ptr, _sz, _pi64, _ptr],
+    "psfem_assemble_lattice_sl": [_ptr, _i64, _i64, _i32, _dbl, _dbl, _dbl, _dbl, _i32, _i64, _i64, _ptr, _sz, _ptr, _sz, _pi64, _ptr],
     "psfem_element_matrices": [_ptr, _ptr, _i64, _i32, _dbl, _dbl, _dbl, _dbl, _i32, _ptr, _ptr, _ptr, _sz, _pi64, _ptr],
     "psfem_b_matrix_at_point": [_ptr, _ptr, _i32, _dbl, _dbl, _ptr, _pdbl, _ptr],
     "psfem_scan_workspace": [_i64, _psz],

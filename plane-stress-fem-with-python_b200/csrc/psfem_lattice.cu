@@ -167,10 +167,21 @@ __device__ __forceinline__ uint32_t l_smem_u32(const void *p) { return (uint32_t
 // pairs of the nodes 0..j-1 of one node column, per neighbour column (the column has 3m-2 in total)
 __device__ __forceinline__ int colq(int j, int m) { return 3 * j - (j > 0) - (j == m); }
 
-template <bool IS_K, int WARPS, int MINB>
+// Symmetric-lattice output (SL_OUT): instead of the CSR node blocks, a finished node writes its diagonal block and its four
+// forward blocks -- 19 doubles -- straight into the structure-of-arrays storage of psfem_spmv_sl.cuh / psfem_cg_sl.cuh,
+// sv[((ci - c_lo) * 19 + k) * mpad + j], for the node columns [c_lo, c_lo + S).  Same registers, same sums, same bits as
+// psfem_spmv_sl_build on the CSR values; no CSR is ever written.
+struct SlTarget { double *sv; int c_lo, S, mpad; };
+__device__ __forceinline__ void sl_put3(double *o, size_t mp, const KB &b) { o[0] = b.x; o[mp] = b.y; o[2 * mp] = b.w; }
+__device__ __forceinline__ void sl_put3(double *o, size_t mp, const MB &b) { o[0] = b.x; o[mp] = 0.0; o[2 * mp] = b.x; }
+__device__ __forceinline__ void sl_put4(double *o, size_t mp, const KB &b) { o[0] = b.x; o[mp] = b.y; o[2 * mp] = b.z; o[3 * mp] = b.w; }
+__device__ __forceinline__ void sl_put4(double *o, size_t mp, const MB &b) { o[0] = b.x; o[mp] = 0.0; o[2 * mp] = 0.0; o[3 * mp] = b.x; }
+
+template <bool IS_K, int WARPS, int MINB, bool SL_OUT = false>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 lattice_q4_kernel(const double2 *__restrict__ nodes, Mat mat, int n, int m, int seg_len, int n_seg, int n_strips,
-                  double *__restrict__ vals, unsigned long long *__restrict__ bad, unsigned int *__restrict__ counter) {
+                  double *__restrict__ vals, unsigned long long *__restrict__ bad, unsigned int *__restrict__ counter,
+                  const SlTarget sl = SlTarget{nullptr, 0, 0, 0}) {
     using B = typename BlockOf<IS_K>::type;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -225,6 +236,18 @@ lattice_q4_kernel(const double2 *__restrict__ nodes, Mat mat, int n, int m, int 
                 add(acc[3], b30); acc[6] = b31; acc[7] = b32; add(acc[4], b33);
                 add(acc[4], blk<IS_K>(el, 0, 0, mat)); add(acc[7], blk<IS_K>(el, 0, 1, mat));
                 acc[8] = blk<IS_K>(el, 0, 2, mat); add(acc[5], blk<IS_K>(el, 0, 3, mat));
+                if constexpr (SL_OUT) {
+                    const int sc = ci - sl.c_lo;
+                    if (node_out && sc >= 0 && sc < sl.S) {
+                        const size_t mp = (size_t)sl.mpad;
+                        double *o = sl.sv + ((size_t)sc * 19) * mp + jl;
+                        sl_put3(o, mp, acc[4]);               // diagonal block: D00, D01, D11
+                        sl_put4(o + 3 * mp, mp, acc[5]);      // F1 -> (i, j+1)
+                        sl_put4(o + 7 * mp, mp, acc[6]);      // F2 -> (i+1, j-1)
+                        sl_put4(o + 11 * mp, mp, acc[7]);     // F3 -> (i+1, j)
+                        sl_put4(o + 15 * mp, mp, acc[8]);     // F4 -> (i+1, j+1)
+                    }
+                } else {
                 // the bulk store that read this buffer two steps ago has finished reading
                 if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                 __syncwarp();
@@ -261,6 +284,7 @@ lattice_q4_kernel(const double2 *__restrict__ nodes, Mat mat, int n, int m, int 
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
                 parity ^= 1;
+                }
             }
             // ---- open node column ci+1: rows 2 of the element below (lane-1), then rows 1 of mine ----
             {
@@ -413,10 +437,10 @@ int launch_lattice_t3(const double *d_nodes, const Mat &mat, int n, int m, int s
     return PSFEM_OK;
 }
 
-template <bool IS_K, int WARPS, int MINB>
+template <bool IS_K, int WARPS, int MINB, bool SL_OUT = false>
 int launch_lattice_q4(const double *d_nodes, const Mat &mat, int n, int m, int seg_len, double *vals, unsigned long long *bad,
-                      unsigned int *counter, cudaStream_t stream) {
-    auto kern = lattice_q4_kernel<IS_K, WARPS, MINB>;
+                      unsigned int *counter, cudaStream_t stream, SlTarget sl = SlTarget{nullptr, 0, 0, 0}) {
+    auto kern = lattice_q4_kernel<IS_K, WARPS, MINB, SL_OUT>;
     const size_t smem = (size_t)WARPS * 2 * LBUF_BYTES;
     PSFEM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int dev = 0, sms = 148, per_sm = 1;
@@ -434,7 +458,7 @@ int launch_lattice_q4(const double *d_nodes, const Mat &mat, int n, int m, int s
     if (grid * WARPS > n_items) grid = ceil_div(n_items, WARPS);
     PSFEM_CUDA_CHECK(cudaMemsetAsync(counter, 0, sizeof(unsigned int), stream));
     kern<<<(unsigned)grid, WARPS * 32, smem, stream>>>(reinterpret_cast<const double2 *>(d_nodes), mat, n, m, seg_len, n_seg, n_strips,
-                                                       vals, bad, counter);
+                                                       vals, bad, counter, sl);
     PSFEM_LAUNCH_CHECK();
     return PSFEM_OK;
 }
@@ -523,6 +547,47 @@ extern "C" int psfem_assemble_lattice(const double *d_nodes, int64_t n, int64_t 
         rc = launch_lattice_q4<false, 4, 3>(d_nodes, mat, (int)n, (int)m, seg_len, d_M_vals, bad, counter, stream);
         if (rc) return rc;
     }
+    unsigned long long hb = 0;
+    PSFEM_CUDA_CHECK(cudaMemcpyAsync(&hb, bad, sizeof(hb), cudaMemcpyDeviceToHost, stream));
+    PSFEM_CUDA_CHECK(cudaStreamSynchronize(stream));
+    if (hb != ~0ull) {
+        if (h_bad_element) *h_bad_element = (int64_t)hb;
+        set_error("Jacobian determinant near zero for element %llu", hb);
+        return PSFEM_EJACOBIAN;
+    }
+    return PSFEM_OK;
+}
+
+// Numeric assembly of a Q4 lattice STRAIGHT INTO the symmetric-lattice operand of the PCG (no CSR values, no column
+// indices, no reduction copy): the node columns [c_lo, c_lo + S) of the lattice (n node columns, m nodes per column),
+// 19 doubles per node.  c_lo = 1 drops a clamped first column (K[np.ix_(free, free)] of Polygones.py:1003 for
+// boundary('left', [0, 0], ...): the forward blocks of the remaining columns are untouched by the reduction); in a strip of
+// the multi-GPU partition the first stored column is the halo column before the owned ones.
+extern "C" int psfem_assemble_lattice_sl(const double *d_nodes, int64_t n, int64_t m, int etype, double E, double nu, double rho, double t,
+                                         int what, int64_t c_lo, int64_t S, double *d_sl_vals, size_t bytes, void *d_ws, size_t ws_bytes,
+                                         int64_t *h_bad_element, void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    PSFEM_REQUIRE(etype == PSFEM_Q4, "assemble_lattice_sl: Q4 lattices only");
+    PSFEM_REQUIRE(what == 1 || what == 2, "assemble_lattice_sl: what must be 1 (K) or 2 (M)");
+    PSFEM_REQUIRE(d_nodes && d_sl_vals && n >= 2 && m >= 2 && n * m < (1ll << 31) && c_lo >= 0 && S >= 1 && c_lo + S <= n,
+                  "assemble_lattice_sl: bad lattice / column range");
+    PSFEM_REQUIRE(d_ws && ws_bytes >= 32, "assemble_lattice_sl: workspace too small");
+    const int64_t mpad = (m + 3) & ~3ll;
+    const size_t want = (size_t)S * 19 * (size_t)mpad * sizeof(double);
+    PSFEM_REQUIRE(bytes >= want, "assemble_lattice_sl: storage too small (%zu < %zu)", bytes, want);
+    if (h_bad_element) *h_bad_element = -1;
+    const Mat mat = make_mat(E, nu, rho, t, etype);
+    unsigned long long *bad = static_cast<unsigned long long *>(d_ws);
+    unsigned int *counter = reinterpret_cast<unsigned int *>(bad + 1);
+    PSFEM_CUDA_CHECK(cudaMemsetAsync(bad, 0xff, sizeof(unsigned long long), stream));
+    PSFEM_CUDA_CHECK(cudaMemsetAsync(d_sl_vals, 0, want, stream));        // pad rows
+    const char *seg_env = getenv("PSFEM_LATTICE_SEG");
+    int seg_len = seg_env ? atoi(seg_env) : 64;
+    if (seg_len < 1) seg_len = 64;
+    SlTarget sl{d_sl_vals, (int)c_lo, (int)S, (int)mpad};
+    int rc = what == 1 ? launch_lattice_q4<true, 4, 2, true>(d_nodes, mat, (int)n, (int)m, seg_len, nullptr, bad, counter, stream, sl)
+                       : launch_lattice_q4<false, 4, 3, true>(d_nodes, mat, (int)n, (int)m, seg_len, nullptr, bad, counter, stream, sl);
+    if (rc) return rc;
     unsigned long long hb = 0;
     PSFEM_CUDA_CHECK(cudaMemcpyAsync(&hb, bad, sizeof(hb), cudaMemcpyDeviceToHost, stream));
     PSFEM_CUDA_CHECK(cudaStreamSynchronize(stream));

@@ -717,13 +717,16 @@ bool sl_usable(const psfem_csr *A, bool dual, const double *x1, const double *y,
 int launch_spmv(const psfem_csr *A, const double *v2, const double *x1, const double *x2, double alpha, double beta,
                 double gamma, const double *z, double *y, const double *xdot, double *dot_out, double *partials,
                 unsigned int *counter, const int *done, cudaStream_t stream, const PeerSync *peer = nullptr) {
-    PSFEM_REQUIRE(A && A->rowblk && A->n_blocks > 0, "spmv: matrix has no row-block plan (psfem_spmv_plan)");
+    PSFEM_REQUIRE(A, "spmv: null matrix");
     PeerSync ps;
     memset(&ps, 0, sizeof(ps));
     if (peer) ps = *peer;
+    const bool dual = v2 != nullptr, dot = dot_out != nullptr;
+    // operands assembled straight into the symmetric-lattice storage (psfem_assemble_lattice_sl) have no CSR side at all
+    PSFEM_REQUIRE((A->rowblk && A->n_blocks > 0) || sl_usable(A, dual, x1, y, z, xdot, dot),
+                  "spmv: matrix has no row-block plan (psfem_spmv_plan) and no usable symmetric-lattice storage");
     const size_t smem = (size_t)(SPMV_T + A->max_row_nnz + 8) * sizeof(double);
     PSFEM_REQUIRE(smem <= 200 * 1024, "spmv: a row with %lld non-zeros does not fit the shared-memory stage", (long long)A->max_row_nnz);
-    const bool dual = v2 != nullptr, dot = dot_out != nullptr;
     static const bool nb_off = getenv("PSFEM_NO_NODEBLOCK") != nullptr;   // A/B switch for measurements
     // symmetric-lattice storage of exactly these values (psfem_spmv_sl_build): half the HBM traffic, same result
     PSFEM_REQUIRE(!ps.halo_in_spmv || sl_usable(A, dual, x1, y, z, xdot, dot), "spmv: the halo wait was delegated to a kernel that does not run");
@@ -1987,12 +1990,12 @@ extern "C" int psfem_dist_cg_halo_bytes(int64_t m, size_t *bytes) {
 // x = 0, r = b, then ONE launch of the iteration kernel in start mode: u_0 = D^-1 b, w_0 = A u_0 (halo exchanged inside the
 // kernel), gamma_0, delta_0, b.b, alpha_0.  Launch 0 of the solve, sequence number seq; the iterations follow with
 // launches_done = 1, 2, ... and seq + 1, seq + 2, ...
-extern "C" int psfem_dist_cg_start(const psfem_csr *A, const psfem_dist_cg_ctx *c, const double *d_b, const double *d_dinv_masked,
+extern "C" int psfem_dist_cg_start(const psfem_csr *A, const psfem_dist_cg_ctx *c, const double *d_b, const int32_t *d_new_id,
                                    double rtol, uint64_t seq, void *d_ws, size_t ws_bytes, void *stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (int rc = dist_cg_check(A, c)) return rc;
     PSFEM_REQUIRE(d_b && d_ws && seq >= 1, "dist_cg_start: bad arguments");
-    PSFEM_REQUIRE(!c->masked || d_dinv_masked, "dist_cg_start: masked strips pass D^-1 with zeros at the constrained rows");
+    PSFEM_REQUIRE(!c->masked || d_new_id, "dist_cg_start: masked strips pass the free map of their owned rows (negative = constrained)");
     const int64_t n = A->n_rows;
     CgWs w = carve_cg(d_ws, n);
     PSFEM_REQUIRE(ws_bytes >= w.total, "dist_cg_start: workspace too small (%zu < %zu)", ws_bytes, w.total);
@@ -2003,7 +2006,13 @@ extern "C" int psfem_dist_cg_start(const psfem_csr *A, const psfem_dist_cg_ctx *
     PSFEM_CUDA_CHECK(cudaMemsetAsync(w.s[0], 0, nb, stream));
     PSFEM_CUDA_CHECK(cudaMemsetAsync(w.p, 0, nb, stream));
     PSFEM_CUDA_CHECK(cudaMemsetAsync(c->x, 0, nb, stream));
-    if (c->masked) PSFEM_CUDA_CHECK(cudaMemcpyAsync(w.dinv, d_dinv_masked, nb, cudaMemcpyDeviceToDevice, stream));
+    if (c->masked) {   // D^-1 from the lattice diagonal, zero at the constrained rows
+        SlGeom g;
+        PSFEM_REQUIRE(sl_geometry(A, &g, 148, 2), "dist_cg_start: operand has no symmetric-lattice geometry");
+        cg_sl_dinv_kernel<<<ew_grid(n / 2), EW_THREADS, 0, stream>>>(A->sl_vals, g, w.dinv);
+        mask_dinv_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, stream>>>(n, d_new_id, w.dinv);
+        PSFEM_LAUNCH_CHECK();
+    }
     cg_start_pass_ctl_kernel<<<1, 32, 0, stream>>>(w.ctl, rtol);
     PSFEM_LAUNCH_CHECK();
     PeerSync ps;

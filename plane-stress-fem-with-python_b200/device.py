@@ -568,6 +568,58 @@ class FreeMap:
 SL_MIN_ROWS = 16384       # systems up to this size run in the single-CTA solver
 
 
+class LatticeOperand:
+    """A K (or M) of a Q4 lattice that exists ONLY as the symmetric-lattice operand of the solvers (psfem_assemble_lattice_sl):
+    19 doubles per node, no CSR values, no column indices.  Quacks like a DeviceCSR for the fused PCG and the SpMV."""
+
+    def __init__(self, n_rows, m, roff_nodes, x_nodes, sl_vals, keep=None):
+        self.n_rows, self.n_cols, self.nnz = int(n_rows), 2 * int(x_nodes), 0
+        self.vals = None
+        self._sl = dict(vals=sl_vals, src=None, m=int(m), roff=int(roff_nodes), x_nodes=int(x_nodes), tol=0.0)
+        self._keep = keep
+
+    def plan(self):
+        return (None, 0, 0, None)
+
+    def sym_lattice(self, row_node_offset=0, tol=None):
+        return True
+
+    def struct(self):
+        s = _capi.psfem_csr()
+        s.n_rows, s.nnz = self.n_rows, 0
+        sl = self._sl
+        s.sl_vals, s.sl_src_vals = sl["vals"].data_ptr(), None          # vals is NULL as well: "storage of exactly these values"
+        s.sl_m, s.sl_roff, s.sl_x_nodes = sl["m"], sl["roff"], sl["x_nodes"]
+        return s
+
+    def matvec(self, x, alpha=1.0, gamma=0.0, z=None, out=None):
+        torch = _capi.torch_cuda()
+        _capi.bind_device()
+        if out is None:
+            out = torch.empty(self.n_rows, dtype=torch.float64, device="cuda")
+        s = self.struct()
+        call("psfem_spmv", C.byref(s), ptr(x), float(alpha), float(gamma), ptr(z), ptr(out), stream_ptr())
+        return out
+
+
+def assemble_lattice_sl(nodes_dev, n, m, c_lo, S, E=0.0, nu=0.0, rho=0.0, t=1.0, what=1):
+    """Q4 lattice (n node columns x m rows, coordinates nodes_dev) assembled straight into symmetric-lattice storage for the
+    node columns [c_lo, c_lo + S) (psfem_assemble_lattice_sl).  Returns the storage tensor (padded for the window copies of
+    the fused PCG kernel)."""
+    torch = _capi.torch_cuda()
+    _capi.bind_device()
+    mpad = (int(m) + 3) & ~3
+    nd = int(S) * 19 * mpad
+    whole = torch.empty(nd + 32 + 256, dtype=torch.float64, device="cuda")
+    buf = whole[32:]
+    ws = workspace(256)
+    bad = C.c_int64(-1)
+    rc = lib.psfem_assemble_lattice_sl(ptr(nodes_dev), int(n), int(m), _capi.Q4, float(E), float(nu), float(rho), float(t), int(what),
+                                       int(c_lo), int(S), ptr(buf), nd * 8, ptr(ws), 256, C.byref(bad), stream_ptr())
+    check(rc, bad.value)
+    return buf
+
+
 def fused_cg_enabled():
     """PSFEM_PCG=classic selects the three-kernel recurrence everywhere (A/B measurements, bit-comparison with the oracle's PCG)."""
     return os.environ.get("PSFEM_PCG", "fused") != "classic"

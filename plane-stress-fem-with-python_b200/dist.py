@@ -361,12 +361,17 @@ class StripProblem:
         self.part = StripPartition(N, M, world, rank, fine=(mesh_type == "fine"))
 
     # -- set-up ---------------------------------------------------------------------------------
-    def setup(self, nodes_conn=None):
+    def setup(self, nodes_conn=None, lattice_only=False):
+        """lattice_only (Q4 meshes): K is assembled straight into the symmetric-lattice operand of the fused PCG
+        (psfem_assemble_lattice_sl) -- no CSR values, column indices, reduction copy or SpMV plans exist; solve-only flows."""
         from .device import Assembler, FreeMap, device_mesh
         from ._capi import ETYPE
         torch = _capi.torch_cuda()
         _capi.bind_device()
         p = self.part
+        self.lattice_only = bool(lattice_only)
+        if lattice_only:
+            return self._setup_lattice_only(nodes_conn)
         if nodes_conn is None:
             self.nodes, self.conn = device_mesh(self.L, self.l, self.N, self.M, 0, 0, self.element_type, self.mesh_type,
                                                 col0=p.e0, ncols=p.e1 - p.e0, cell0=p.cell0, ncells=p.cell1 - p.cell0)
@@ -443,6 +448,91 @@ class StripProblem:
         per_cell = 2 if self.element_type == "tri" else 1
         self.nel_global = self.N * self.M * per_cell
         self.nel_owned = self.asm.nel
+        return self._setup_solver(lo, nb)
+
+    def _setup_lattice_only(self, nodes_conn):
+        """Solve-only strip: mesh -> K in symmetric-lattice storage -> fused PCG state.  The default boundary condition (left
+        edge clamped) is the reduction of Polygones.py:1003 by dropping node column 0 from the stored columns; any other
+        `bc` keeps its DOFs in the system as masked rows."""
+        from .device import LatticeOperand, assemble_lattice_sl, device_mesh, fused_cg_enabled
+        torch = _capi.torch_cuda()
+        p = self.part
+        if (self.element_type, self.mesh_type) != ("quad", "coarse"):
+            raise ValueError("lattice_only: Q4 meshes only")
+        if not fused_cg_enabled():
+            raise RuntimeError("lattice_only needs the fused PCG (PSFEM_PCG=classic is set)")
+        if nodes_conn is None:
+            self.nodes, _ = device_mesh(self.L, self.l, self.N, self.M, 0, 0, self.element_type, self.mesh_type,
+                                        col0=p.e0, ncols=p.e1 - p.e0, cell0=p.cell0, ncells=0)
+        else:
+            self.nodes = nodes_conn[0]
+        self.conn = None
+        f64 = dict(dtype=torch.float64, device="cuda")
+        m = p.m
+        if self.bc is None:
+            cd_global = np.arange(2 * m, dtype=np.int64)
+        else:
+            from .device import constrained_dofs_of
+            cd_global = np.asarray(constrained_dofs_of(self.bc), dtype=np.int64)
+        self.constrained_global = cd_global
+        cd_local = p.local_constrained(cd_global)
+        pre = p.left_halo_cols                               # 0 or 1 node columns before the owned ones
+        drop0 = 1 if (self.bc is None and p.c0 == 0) else 0  # the clamped column 0 leaves the system
+        own_first = (p.c0 - p.e0) + drop0                    # strip-local index of the first owned node column
+        c_lo = own_first - pre
+        n_loc = p.e1 - p.e0
+        own_end = p.c1 - p.e0
+        S = own_end - c_lo
+        n_cols_own = S - pre
+        if n_cols_own < 1:
+            raise ValueError("lattice_only: a rank without owned node columns")
+        n = 2 * m * n_cols_own
+        self.masked = self.bc is not None
+        sl = assemble_lattice_sl(self.nodes, n_loc, m, c_lo, S, E=self.E, nu=self.nu, t=self.t, what=1)
+        self.K_red = LatticeOperand(n, m, pre * m, (S + p.right_halo_cols) * m, sl)
+        self.K_vals = self.K_ext_red = self.fm = self.asm = None
+        self.sym_lattice = True
+        self.A = self.K_red.struct()
+        dof0, dof1 = 2 * m * own_first, 2 * m * own_end      # owned DOFs in strip-local numbering
+        if self.masked:
+            own_cd = np.unique(cd_local[(cd_local >= dof0) & (cd_local < dof1)]) - dof0
+            self._cd_owned = torch.from_numpy(own_cd).cuda()
+            count_free = lambda a, b: b - a
+        else:
+            c0a, c0b = (0, 2 * m) if (p.e0 == 0) else (0, 0)  # strip-local DOFs of the clamped global column 0
+
+            def count_free(a, b):
+                return (b - a) - max(0, min(b, c0b) - max(a, c0a))
+        self.plan = p.halo_plan(count_free=count_free)
+        lo, hi = self.plan["own"]
+        assert hi - lo == n, (lo, hi, n)
+        self.n_owned_free = n
+        self.n_ext_free = self.plan["n_ext_free"]
+        if self.F is None:
+            F_ext = torch.zeros(p.n_ext_dof, **f64)
+            if p.e1 == p.n:
+                k0 = (p.n - 1 - p.e0) * m
+                F_ext[2 * k0:2 * (k0 + m):2] = self.load[0] * self.l / (m - 1)
+                F_ext[2 * k0 + 1:2 * (k0 + m):2] = self.load[1] * self.l / (m - 1)
+        else:
+            a, b = p.dof_shift, p.dof_shift + p.n_ext_dof
+            Fh = self.F(a, b) if callable(self.F) else np.asarray(self.F)[a:b]
+            F_ext = torch.from_numpy(np.ascontiguousarray(Fh, dtype=np.float64)).cuda()
+        self.b_own = F_ext[dof0:dof1].clone()
+        if self.masked:
+            self.b_own[self._cd_owned] = 0.0
+        self.n_dof_global = 2 * p.n * p.m
+        cdg = cd_global[(cd_global >= 0) & (cd_global < self.n_dof_global)]
+        self.n_free_global = self.n_dof_global - len(np.unique(cdg))
+        self.nel_global = self.N * self.M
+        self.nel_owned = (n_loc - 1) * self.M
+        return self._setup_solver(lo, 0)
+
+    def _setup_solver(self, lo, nb):
+        """PCG state, peer fabric and the fused / classic iteration contexts (shared by the CSR and the lattice-only set-up)."""
+        torch = _capi.torch_cuda()
+        p = self.part
+        f64 = dict(dtype=torch.float64, device="cuda")
         # PCG state
         self.ops = CudaOps(self.A, self.n_owned_free, nb, masked=self.masked)
         import torch.distributed as dist
@@ -460,10 +550,15 @@ class StripProblem:
                        dinv=torch.empty(n, **f64), p_ext=p_ext,
                        rz=torch.zeros(2, **f64), pq=torch.zeros(1, **f64), out2=torch.zeros(2, **f64),
                        out3=torch.zeros(8, **f64), parity=0, iters=0)
-        call("psfem_extract_diag", C.byref(self.A), lo, 1, ptr(self.st["dinv"]), stream_ptr())
-        if self.masked:
-            self.st["dinv"][self._cd_owned] = 0.0
-        if self.fabric:
+        if not self.lattice_only:
+            call("psfem_extract_diag", C.byref(self.A), lo, 1, ptr(self.st["dinv"]), stream_ptr())
+            if self.masked:
+                self.st["dinv"][self._cd_owned] = 0.0
+        self._new_id = None
+        if self.masked:                                   # free map of the owned rows for the fused kernels (negative = constrained)
+            self._new_id = torch.zeros(n, dtype=torch.int32, device="cuda")
+            self._new_id[self._cd_owned] = -1
+        if self.fabric and not self.lattice_only:
             fb, st = self.fabric, self.st
             c = self.ctx = _capi.psfem_dist_ctx()
             c.rank, c.world = self.rank, self.world
@@ -507,14 +602,13 @@ class StripProblem:
         if self.world == 1 and self.sym_lattice:
             from .device import FusedCG
             if FusedCG.usable(self.K_red):
-                new_id = None
-                if self.masked:
-                    new_id = torch.zeros(n, dtype=torch.int32, device="cuda")
-                    new_id[self._cd_owned] = -1
-                self.fused = FusedCG(self.K_red, new_id=new_id)
+                self.fused = FusedCG(self.K_red, new_id=self._new_id)
+        if self.lattice_only and self.fused is None and not self.fused_dist:
+            raise RuntimeError("lattice_only: the fused PCG is not available for this strip (no peer transport / operand rejected)")
         self.start()
         torch.cuda.synchronize()
         return self
+
 
     def start(self):
         """x = 0, r = b, p = D^-1 r with its halo, r.z / r.r / b.b."""
@@ -530,7 +624,7 @@ class StripProblem:
                 torch.cuda.synchronize()
                 dist.barrier()
             self.seq += 1
-            call("psfem_dist_cg_start", C.byref(self.A), C.byref(self.cg_ctx), ptr(self.b_own), ptr(self.st["dinv"] if self.masked else None),
+            call("psfem_dist_cg_start", C.byref(self.A), C.byref(self.cg_ctx), ptr(self.b_own), ptr(self._new_id),
                  0.0, self.seq, ptr(self.cg_ws), self.cg_ws_bytes, stream_ptr())
             self.launches = 1
             self.st["iters"] = 0
@@ -755,7 +849,8 @@ class StripProblem:
 # public multi-GPU entry point
 # ------------------------------------------------------------------------------------------------
 def static_solve(L, l, N, M=0, bc=None, F=None, E=210e9, nu=0.3, t=0.1, element_type="quad", mesh_type="coarse",
-                 nodes=None, rtol=1e-8, maxit=200000, check_every=100, dst=0, raise_on_fail=True, transport=None):
+                 nodes=None, rtol=1e-8, maxit=200000, check_every=100, dst=0, raise_on_fail=True, transport=None,
+                 lattice_only=None):
     """Static solve of a `Polygones.mesh(L, l, N, M, element_type=..., mesh_type=...)` plate on ALL ranks of the default
     torch.distributed process group (one process per GPU): the multi-GPU counterpart of `drivers.static_solve`, i.e. of
     mesh -> global_stiffness_matrix -> apply_boundary_conditions -> solve -> reconstruct (Statictest.py:49-75).
@@ -767,6 +862,8 @@ def static_solve(L, l, N, M=0, bc=None, F=None, E=210e9, nu=0.3, t=0.1, element_
              uploads only the rows of its strip.
     The strip of each rank is meshed, assembled and reduced on its GPU without communication; the PCG runs with the
     collectives fused into its kernels over peer memory (NCCL when peer access is unavailable).
+    lattice_only (default: on for Q4 meshes when the fused PCG can run): K is assembled straight into the symmetric-lattice
+    operand of the solver and never exists as CSR (StripProblem.setup(lattice_only=True)); same iterates, bit for bit.
     Returns (U, info): U = the global displacement vector with zeros at constrained DOFs (reconstruct_full_vector,
     Polygones.py:913-921) on rank `dst`, None elsewhere; info = dict(iterations, relres, converged, seconds, transport,
     h2d_bytes, d2h_bytes of this rank)."""
@@ -791,12 +888,25 @@ def static_solve(L, l, N, M=0, bc=None, F=None, E=210e9, nu=0.3, t=0.1, element_
         nd = torch.from_numpy(part).to("cuda", non_blocking=True)
         h2d += part.nbytes
         nodes_conn = (nd, conn)
-    prob.setup(nodes_conn)
+    from .device import fused_cg_enabled
+    if lattice_only is None:
+        lattice_only = ((element_type, mesh_type) == ("quad", "coarse") and fused_cg_enabled()
+                        and (world == 1 or prob.transport == "peer"))
+    if lattice_only:
+        try:
+            prob.setup(nodes_conn, lattice_only=True)
+        except RuntimeError as e:                           # no peer transport on this box (decided by ALL ranks together)
+            if "lattice_only" not in str(e):
+                raise
+            prob.setup(nodes_conn)
+    else:
+        prob.setup(nodes_conn)
     if F is not None:
         h2d += 8 * prob.part.n_ext_dof
     info = prob.solve(rtol=rtol, maxit=maxit, check_every=check_every)
     info["converged"] = bool(info["relres"] <= rtol)
     info["transport"] = prob.transport if world > 1 else "single GPU"
+    info["lattice_only"] = bool(getattr(prob, "lattice_only", False))
     U = prob.gather_solution(dst=dst)
     info["h2d_bytes"] = int(h2d)
     info["d2h_bytes"] = int(8 * prob.n_dof_global) if rank == dst else 0       # the gathered vector leaves the device on rank dst only

@@ -143,6 +143,20 @@ def run_checks(world, rank):
             chk(np.abs(Ug - U1).max() <= 1e-8 * np.abs(U1).max(), lambda: f"gathered strip solution vs single-GPU static_solve: {np.abs(Ug - U1).max() / np.abs(U1).max()}")
         except Exception as e:                           # noqa: BLE001
             chk(False, f"single-GPU comparison raised {type(e).__name__}: {e}")
+    # 5. the same problem with K assembled straight into the symmetric-lattice operand (no CSR anywhere): bit-identical
+    #    solution; and the default clamped / loaded plate through both set-ups
+    chk(info.get("lattice_only") is True, "dist.static_solve takes the lattice-only set-up by default on Q4 meshes")
+    Uc, info_c = static_solve(kw["L"], kw["l"], N, M, bc=bc, F=Fg, E=kw["E"], nu=kw["nu"], t=kw["t"], rtol=1e-11, maxit=40000,
+                              check_every=200, transport="peer", lattice_only=False)
+    chk(info_c["iterations"] == info["iterations"], lambda: f"CSR vs lattice-only iterations: {info_c['iterations']} {info['iterations']}")
+    if rank == 0:
+        chk(np.array_equal(Uc, Ug), lambda: f"CSR vs lattice-only strip solution: {np.abs(Uc - Ug).max()}")
+    Ua, ia = static_solve(kw["L"], kw["l"], N, M, E=kw["E"], nu=kw["nu"], t=kw["t"], rtol=1e-9, maxit=40000, check_every=100)
+    Ub, ib = static_solve(kw["L"], kw["l"], N, M, E=kw["E"], nu=kw["nu"], t=kw["t"], rtol=1e-9, maxit=40000, check_every=100,
+                          lattice_only=False)
+    chk(ia["lattice_only"] and not ib["lattice_only"] and ia["iterations"] == ib["iterations"], lambda: f"clamped plate: {ia} {ib}")
+    if rank == 0:
+        chk(np.array_equal(Ua, Ub) and np.all(Ua[:2 * (M + 1)] == 0) and np.abs(Ua).max() > 0, "clamped plate: lattice-only == CSR set-up")
     bad = torch.tensor([len(fails)], dtype=torch.int32, device="cuda")
     dist.all_reduce(bad)
     if int(bad.item()):
