@@ -531,6 +531,14 @@ def extras_leg(psfem_b200, prob, cells, hbm_peak):
     out["assembly_KM"] = {"ms": ms, "elements_per_s": nel / ms * 1e3, "bytes_per_element": bkm,
                           "hbm_frac": bkm * nel / (ms * 1e-3) / 1e9 / hbm_peak}
     del K2
+    # K straight into the solver's symmetric-lattice operand (what a solve-only flow runs instead of the CSR assembly)
+    from psfem_b200.device import assemble_lattice_sl
+    n_cols, m_rows = prob.part.e1 - prob.part.e0, prob.part.m
+    ms = best(lambda: assemble_lattice_sl(prob.nodes, n_cols, m_rows, 1, n_cols - 1, E=E, nu=NU, t=T, what=1))
+    bsl = 16 + 19 * 8
+    out["assembly_SL"] = {"ms": ms, "elements_per_s": nel / ms * 1e3, "bytes_per_element": bsl,
+                          "hbm_frac": bsl * nel / (ms * 1e-3) / 1e9 / hbm_peak,
+                          "what": "psfem_assemble_lattice_sl: the clamped plate's K as 19 doubles per node, no CSR values / indices / reduction"}
     # symbolic phase of the lattice (topology check + closed-form pattern), once per mesh
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -568,6 +576,25 @@ def extras_leg(psfem_b200, prob, cells, hbm_peak):
         out["newmark_step"] = f"skipped: {type(e).__name__}: {e}"[:300]
     del M_vals
     torch.cuda.empty_cache()
+    # BASELINE's C5 strip (16384 x 4096, 134 M DOF) on ONE GPU: possible because the solve-only set-up never builds the CSR
+    # side (2.4e9 non-zeros would not fit int32 indices); 10.2 GB of matrix
+    try:
+        from psfem_b200.dist import StripProblem
+        prob.release()
+        torch.cuda.empty_cache()
+        t0 = time.perf_counter()
+        big = StripProblem(L=4 * cells * 1e-3, l=cells * 1e-3, N=4 * cells, M=cells, rank=0, world=1, E=E, nu=NU, t=T).setup(lattice_only=True)
+        torch.cuda.synchronize()
+        t_setup = time.perf_counter() - t0
+        ms = best(lambda: big.cg_iterations(20), reps=3) / 20
+        out["c5_single_gpu_lattice_only"] = {"plate": f"{4 * cells}x{cells}", "free_dof": int(big.n_free_global), "ms_per_iter": ms,
+                                             "dof_iter_per_s": big.n_free_global / (ms * 1e-3), "setup_s": t_setup,
+                                             "device_memory_gb": torch.cuda.max_memory_allocated() / 1e9}
+        big.release()
+        del big
+        torch.cuda.empty_cache()
+    except Exception as e:                                 # noqa: BLE001
+        out["c5_single_gpu_lattice_only"] = f"skipped: {type(e).__name__}: {e}"[:300]
     # BASELINE configs 2 and 3 end to end (mesh -> K, M -> driver), wall clock, second of two runs
     try:
         L, l, N, G = 20, 2, 20, 2

@@ -307,6 +307,11 @@ int psfem_direct_limits(int64_t *max_rows, int64_t *max_half_bandwidth);
 int psfem_direct_workspace(int64_t n, int64_t half_bandwidth, size_t *bytes);
 int psfem_direct_solve(const psfem_csr *A, const double *d_b, double *d_x, int64_t half_bandwidth, int refine_rounds,
                        double *h_info /* [5] */, void *d_ws, size_t ws_bytes, void *stream);
+/* the factorisation alone (it stays in d_ws) and solves with it: K is factored ONCE for the shift-invert Lanczos of the modal
+ * driver (freeModes.py:74 / Beamexemple.py:109 do the same through LAPACK / ARPACK) */
+int psfem_direct_factor(const psfem_csr *A, int64_t half_bandwidth, void *d_ws, size_t ws_bytes, void *stream);
+int psfem_direct_substitute(const psfem_csr *A, const double *d_b, double *d_x, int64_t half_bandwidth, int refine_rounds,
+                            double *h_info /* [5] */, void *d_ws, size_t ws_bytes, void *stream);
 int psfem_residual_dd(const psfem_csr *A, const double *d_x, const double *d_b, double *d_r, void *stream);
 
 /* np.allclose(A, A.T, rtol, atol) on CSR -- the symmetry test of main.py:65-66, Beamexemple.py:48, SparseTest.py:37 without

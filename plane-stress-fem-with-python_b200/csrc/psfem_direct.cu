@@ -102,6 +102,7 @@ __global__ void csr_symmetry_kernel(int64_t n, const int32_t *__restrict__ row_p
 
 struct DsArgs {
     int n, hb, rounds;
+    int do_factor, do_solve;   // the factor stays in the work space: psfem_direct_factor once, psfem_direct_substitute many times
     const int32_t *row_ptr, *col_idx;
     const double *vals, *b;
     double *x;
@@ -124,8 +125,10 @@ band_cholesky_kernel(const DsArgs g) {
         __syncthreads();
         return o;
     };
-    for (int64_t i = t; i < (int64_t)n * w; i += DS_T) Lb[i] = 0.0;
     if (t == 0) fail = 0;
+    __syncthreads();
+    if (g.do_factor) {
+    for (int64_t i = t; i < (int64_t)n * w; i += DS_T) Lb[i] = 0.0;
     __syncthreads();
     for (int r = t; r < n; r += DS_T)
         for (int k = g.row_ptr[r]; k < g.row_ptr[r + 1]; ++k) {
@@ -156,6 +159,8 @@ band_cholesky_kernel(const DsArgs g) {
         __syncthreads();
     }
     if (fail) { if (t == 0) g.info[3] = 1.0; return; }
+    }
+    if (!g.do_solve) return;
     double lbb = 0.0;
     for (int i = t; i < n; i += DS_T) { g.x[i] = 0.0; lbb += g.b[i] * g.b[i]; }
     const double bb = bsum(lbb);
@@ -267,10 +272,10 @@ extern "C" int psfem_direct_workspace(int64_t n, int64_t half_bandwidth, size_t 
     return PSFEM_OK;
 }
 
-extern "C" int psfem_direct_solve(const psfem_csr *A, const double *d_b, double *d_x, int64_t half_bandwidth, int refine_rounds,
-                                  double *h_info, void *d_ws, size_t ws_bytes, void *stream_) {
+static int direct_run(const psfem_csr *A, const double *d_b, double *d_x, int64_t half_bandwidth, int refine_rounds, int mode,
+                      double *h_info, void *d_ws, size_t ws_bytes, void *stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    PSFEM_REQUIRE(A && d_b && d_x && h_info && d_ws, "direct_solve: null argument");
+    PSFEM_REQUIRE(A && h_info && d_ws && ((mode & 2) == 0 || (d_b && d_x)), "direct_solve: null argument");
     PSFEM_REQUIRE(A->n_rows > 0 && A->n_rows <= DS_MAX_N && half_bandwidth >= 0 && half_bandwidth <= DS_MAX_HB && refine_rounds >= 0 &&
                       refine_rounds <= 8,
                   "direct_solve: the band solver takes up to %d rows, a half bandwidth up to %d and up to 8 refinement rounds",
@@ -280,6 +285,7 @@ extern "C" int psfem_direct_solve(const psfem_csr *A, const double *d_b, double 
     PSFEM_CUDA_CHECK(cudaMemsetAsync(w.info, 0, 8 * sizeof(double), stream));
     DsArgs g;
     g.n = (int)A->n_rows; g.hb = (int)half_bandwidth; g.rounds = refine_rounds;
+    g.do_factor = mode & 1; g.do_solve = (mode >> 1) & 1;
     g.row_ptr = A->row_ptr; g.col_idx = A->col_idx; g.vals = A->vals; g.b = d_b; g.x = d_x;
     g.Lb = w.Lb; g.invd = w.invd; g.y = w.y; g.info = w.info;
     band_cholesky_kernel<<<1, DS_T, 0, stream>>>(g);
@@ -290,6 +296,23 @@ extern "C" int psfem_direct_solve(const psfem_csr *A, const double *d_b, double 
     for (int q = 0; q < 5; ++q) h_info[q] = h[q];
     if (h[3] != 0.0) { set_error("direct_solve: the matrix is not positive definite (Cholesky pivot <= 0)"); return PSFEM_ENOCONV; }
     return PSFEM_OK;
+}
+
+extern "C" int psfem_direct_solve(const psfem_csr *A, const double *d_b, double *d_x, int64_t half_bandwidth, int refine_rounds,
+                                  double *h_info, void *d_ws, size_t ws_bytes, void *stream_) {
+    return direct_run(A, d_b, d_x, half_bandwidth, refine_rounds, 3, h_info, d_ws, ws_bytes, stream_);
+}
+
+// the factorisation alone (kept in d_ws) and solves with it: the shift-invert Lanczos of the modal driver factors K once and
+// substitutes per step, like scipy's eigsh(sigma=0) / the reference's eigh do with LAPACK
+extern "C" int psfem_direct_factor(const psfem_csr *A, int64_t half_bandwidth, void *d_ws, size_t ws_bytes, void *stream_) {
+    double info[5];
+    return direct_run(A, nullptr, nullptr, half_bandwidth, 0, 1, info, d_ws, ws_bytes, stream_);
+}
+
+extern "C" int psfem_direct_substitute(const psfem_csr *A, const double *d_b, double *d_x, int64_t half_bandwidth, int refine_rounds,
+                                       double *h_info, void *d_ws, size_t ws_bytes, void *stream_) {
+    return direct_run(A, d_b, d_x, half_bandwidth, refine_rounds, 2, h_info, d_ws, ws_bytes, stream_);
 }
 
 extern "C" int psfem_residual_dd(const psfem_csr *A, const double *d_x, const double *d_b, double *d_r, void *stream_) {

@@ -246,6 +246,10 @@ lattice_q4_kernel(const double2 *__restrict__ nodes, Mat mat, int n, int m, int 
                         sl_put4(o + 7 * mp, mp, acc[6]);      // F2 -> (i+1, j-1)
                         sl_put4(o + 11 * mp, mp, acc[7]);     // F3 -> (i+1, j)
                         sl_put4(o + 15 * mp, mp, acc[8]);     // F4 -> (i+1, j+1)
+                        if (jl == m - 1)                      // pad rows m .. mpad-1 of this column (never used; kept finite)
+                            for (int r = 1; r < sl.mpad - jl; ++r)
+#pragma unroll
+                                for (int k = 0; k < 19; ++k) o[(size_t)k * mp + r] = 0.0;
                     }
                 } else {
                 // the bulk store that read this buffer two steps ago has finished reading
@@ -580,7 +584,6 @@ extern "C" int psfem_assemble_lattice_sl(const double *d_nodes, int64_t n, int64
     unsigned long long *bad = static_cast<unsigned long long *>(d_ws);
     unsigned int *counter = reinterpret_cast<unsigned int *>(bad + 1);
     PSFEM_CUDA_CHECK(cudaMemsetAsync(bad, 0xff, sizeof(unsigned long long), stream));
-    PSFEM_CUDA_CHECK(cudaMemsetAsync(d_sl_vals, 0, want, stream));        // pad rows
     const char *seg_env = getenv("PSFEM_LATTICE_SEG");
     int seg_len = seg_env ? atoi(seg_env) : 64;
     if (seg_len < 1) seg_len = 64;

@@ -301,16 +301,58 @@ def explicit_euler(K, M, bc, f_shape, f_scale, dt=1e-3, store_every=1, energies=
 # ---------------------------------------------------------------------------------------------
 # modal (freeModes.py)
 # ---------------------------------------------------------------------------------------------
-def modal(K, M, bc, k=20, tol=1e-10, max_lanczos=None, pcg_rtol=1e-14):
+class _ShiftInvertOperator:
+    """w = K_hat^-1 y for the Lanczos iteration.  Small banded systems: K_hat is factored ONCE (banded Cholesky,
+    psfem_direct_factor) and every application is two substitutions plus one refinement round on a double-double residual
+    -- what the reference gets from LAPACK inside eigh / eigsh(sigma=0).  Everything else: a Jacobi-PCG solve per application
+    (the fused one-kernel iteration on symmetric-lattice operands)."""
+
+    def __init__(self, Kh: DeviceCSR, pcg_rtol):
+        torch = _capi.torch_cuda()
+        self.Kh, self.pcg_rtol = Kh, pcg_rtol
+        self.pcg_iterations = 0
+        self.direct = False
+        max_rows, max_hb = direct_limits()
+        if 0 < Kh.n_rows <= max_rows:
+            hb = half_bandwidth(Kh)
+            if hb <= max_hb:
+                sz = C.c_size_t(0)
+                call("psfem_direct_workspace", Kh.n_rows, hb, C.byref(sz))
+                self.ws, self.ws_bytes, self.hb = workspace(sz.value), sz.value, hb
+                s_ = Kh.struct()
+                rc = lib.psfem_direct_factor(C.byref(s_), hb, ptr(self.ws), sz.value, stream_ptr())
+                if rc == _capi.OK:
+                    self.direct = True
+                elif rc != _capi.ENOCONV:                     # ENOCONV: not positive definite -> let PCG report it
+                    check(rc)
+        self.out = torch.empty(Kh.n_rows, dtype=torch.float64, device="cuda")
+
+    def __call__(self, y):
+        if self.direct:
+            torch = _capi.torch_cuda()
+            x = torch.empty_like(y)
+            info = (C.c_double * 5)()
+            s_ = self.Kh.struct()
+            call("psfem_direct_substitute", C.byref(s_), ptr(y), ptr(x), self.hb, 1, info, ptr(self.ws), self.ws_bytes, stream_ptr())
+            return x
+        x, inf = pcg_jacobi(self.Kh, y, rtol=self.pcg_rtol)
+        self.pcg_iterations += inf["iterations"]
+        return x
+
+
+def modal(K, M, bc, k=20, tol=1e-10, max_lanczos=None, pcg_rtol=1e-14, max_restarts=200):
     """First k natural frequencies and mode shapes.
 
-    freeModes.py:53-77: reduce, scale K and M by their largest |diagonal| entry, generalized
-    symmetric eigenproblem, clip at 0, f = sqrt(lambda * k_max/m_max)/(2 pi), modes rebuilt to
-    full length as rows.  The dense LAPACK `eigh` (:74, all modes, O(n^3)) is replaced by a
-    shift-invert Lanczos iteration (sigma = 0) in the M-inner product with full
-    reorthogonalisation; every operator application is a device SpMV and a Jacobi-PCG solve.
-    Eigenvectors are M_hat-orthonormal like LAPACK's (sign arbitrary).
-    Returns (frequencies (k,), modes (k, total_dofs), constrained_dofs, info)."""
+    freeModes.py:53-77: reduce, scale K and M by their largest |diagonal| entry, generalized symmetric eigenproblem, clip
+    at 0, f = sqrt(lambda * k_max/m_max)/(2 pi), modes rebuilt to full length as rows.  The dense LAPACK `eigh` (:74, all
+    modes, O(n^3)) is replaced by a THICK-RESTART shift-invert Lanczos iteration (sigma = 0) in the M-inner product with
+    full reorthogonalisation: the basis is bounded (`max_lanczos`, default max(2k + 20, 60) vectors -- 2 x 61 vectors of
+    n doubles instead of an unbounded Krylov basis), after every cycle the best k + 10 Ritz vectors are kept and the
+    iteration continues from them.  Operator applications: device SpMV with M_hat and a solve with K_hat (factored once
+    for small banded systems, Jacobi-PCG otherwise).  Eigenvectors are M_hat-orthonormal like LAPACK's (sign arbitrary).
+    Returns (frequencies (k,), modes (k, total_dofs), constrained_dofs, info); warns when the Ritz values have not
+    converged to `tol` within `max_restarts` cycles."""
+    import warnings
     torch = _capi.torch_cuda()
     _capi.bind_device()
     constrained = constrained_dofs_of(bc)
@@ -323,72 +365,99 @@ def modal(K, M, bc, k=20, tol=1e-10, max_lanczos=None, pcg_rtol=1e-14):
     f64 = dict(dtype=torch.float64, device="cuda")
     blas = Blas()
     torch.cuda.current_stream().synchronize()
-    k_max = float(np.max(np.abs(K_red.diagonal().cpu().numpy())))  # freeModes.py:58-59
-    m_max = float(np.max(np.abs(M_red.diagonal().cpu().numpy())))
+    k_max = float(torch.max(torch.abs(K_red.diagonal())).item())   # freeModes.py:58-59
+    m_max = float(torch.max(torch.abs(M_red.diagonal())).item())
     scaling = k_max / m_max                                        # :60
     Kh = K_red.with_vals(_scaled(K_red.vals, 1.0 / k_max))         # :62-63
     Mh = M_red.with_vals(_scaled(M_red.vals, 1.0 / m_max))
-    m_lanczos = min(n, max_lanczos or max(4 * k + 40, 100))
-    Vb = torch.zeros((m_lanczos + 1, n), **f64)                    # Lanczos basis (rows), M-orthonormal
-    MV = torch.zeros((m_lanczos + 1, n), **f64)                    # M_hat @ basis
-    coef = torch.empty(m_lanczos + 1, **f64)
-    alphas, betas = [], []
+    if n > SL_MIN_ROWS:
+        Mh.sym_lattice()
+    op = _ShiftInvertOperator(Kh, pcg_rtol)
+    m_max_basis = int(min(n, max_lanczos or max(2 * k + 20, 60)))
+    keep = min(k + 10, max(m_max_basis - 2, k))                    # Ritz vectors kept at a restart
+    Vb = torch.zeros((m_max_basis + 1, n), **f64)                  # basis (rows), M-orthonormal
+    MV = torch.zeros((m_max_basis + 1, n), **f64)                  # M_hat @ basis
+    coef = torch.empty(m_max_basis + 1, **f64)
+    H = np.zeros((m_max_basis + 1, m_max_basis + 1))               # projected operator V^T M (K^-1 M) V, built column by column
     rng = np.random.default_rng(12345)
     v = torch.from_numpy(rng.standard_normal(n)).cuda()
-    # start in range(K^-1 M): removes components in the null space of M
-    mv = Mh.matvec(v)
-    v, _ = pcg_jacobi(Kh, mv, rtol=pcg_rtol)
+    v = op(Mh.matvec(v))                                           # start in range(K^-1 M): no components in the null space of M
     mv = Mh.matvec(v)
     nrm = np.sqrt(blas.dot(v, mv))
     _scaled(v, 1.0 / nrm, Vb[0])
     _scaled(mv, 1.0 / nrm, MV[0])
-    total_pcg = 0
-    theta = None
+    theta, Ssel, resid = None, None, None
     converged = False
-    j_used = 0
-    for j in range(m_lanczos):
-        # w = K^-1 M v_j
-        w, inf = pcg_jacobi(Kh, MV[j], rtol=pcg_rtol)
-        total_pcg += inf["iterations"]
-        # full reorthogonalisation against v_0..v_j in the M inner product (twice is enough)
+    j, steps, restarts = 0, 0, 0
+    while True:
+        # ---- one Lanczos step: w = K^-1 M v_j, orthogonalised against v_0..v_j in the M inner product (twice) ----
+        w = op(MV[j])
+        col = np.zeros(j + 1)
         for _ in range(2):
             blas.multi_dot(MV, j + 1, w, coef)
-            if _ == 0:
-                alphas.append(float(coef[j].item()))
+            col += coef[: j + 1].cpu().numpy()                     # one host read per pass: the column of H (and the loop needs beta)
             blas.multi_axpy(Vb, j + 1, coef, w)
+        H[: j + 1, j] = col
         mw = Mh.matvec(w)
-        b2 = blas.dot(w, mw)
-        b = np.sqrt(max(b2, 0.0))
-        j_used = j + 1
-        # Ritz values of T (eigenvalues of K^-1 M = 1/lambda): check every few steps
-        if j_used >= k and (j_used % 5 == 0 or j_used == m_lanczos or b < 1e-300):
-            T = np.diag(alphas) + np.diag(betas, 1) + np.diag(betas, -1)
-            th, S = np.linalg.eigh(T)
-            order = np.argsort(-th)[:k]
-            resid = np.abs(b * S[-1, order]) / np.abs(th[order])
-            theta, Ssel = th[order], S[:, order]
-            if np.all(resid < tol) or b < 1e-300:
-                converged = True
-                break
-        if j + 1 < m_lanczos + 1 and b > 0:
-            betas.append(b)
-            _scaled(w, 1.0 / b, Vb[j + 1])
-            _scaled(mw, 1.0 / b, MV[j + 1])
+        b = float(np.sqrt(max(blas.dot(w, mw), 0.0)))
+        steps += 1
+        jn = j + 1                                                  # vectors in the basis
+        full = jn == m_max_basis or b < 1e-300
+        if jn >= k and (jn % 5 == 0 or full):
+            Hs = 0.5 * (H[:jn, :jn] + H[:jn, :jn].T)
+            th, S = np.linalg.eigh(Hs)
+            order = np.argsort(-th)
+            th, S = th[order], S[:, order]
+            if np.all(th[:k] > 0):
+                resid = np.abs(b * S[-1, :k]) / np.abs(th[:k])
+                theta, Ssel = th[:k], S[:, :k]
+                if np.all(resid < tol) or b < 1e-300:
+                    converged = True
+                    break
+            if full:
+                if restarts >= max_restarts:
+                    break
+                # ---- thick restart: keep the best `keep` Ritz vectors, continue from the next Lanczos vector ----
+                l = min(keep, jn - 1)
+                Y = torch.zeros((l, n), **f64)
+                MY = torch.zeros((l, n), **f64)
+                Sd = torch.from_numpy(np.ascontiguousarray(-S[:, :l].T)).cuda()      # negated: multi_axpy subtracts
+                for i in range(l):
+                    call("psfem_multi_axpy", jn, n, ptr(Vb), ptr(Sd[i]), ptr(Y[i]), stream_ptr())
+                    call("psfem_multi_axpy", jn, n, ptr(MV), ptr(Sd[i]), ptr(MY[i]), stream_ptr())
+                Vb[:l].copy_(Y)
+                MV[:l].copy_(MY)
+                _scaled(w, 1.0 / b, Vb[l])
+                _scaled(mw, 1.0 / b, MV[l])
+                H[:] = 0.0
+                H[np.arange(l), np.arange(l)] = th[:l]
+                H[l, :l] = b * S[-1, :l]                                   # K^-1 M y_i = theta_i y_i + (beta s_mi) v_next
+                del Y, MY, Sd
+                j = l
+                restarts += 1
+                continue
+        if b < 1e-300:
+            break
+        H[jn, j] = b
+        _scaled(w, 1.0 / b, Vb[jn])
+        _scaled(mw, 1.0 / b, MV[jn])
+        j = jn
     if theta is None:
-        T = np.diag(alphas) + np.diag(betas[: len(alphas) - 1], 1) + np.diag(betas[: len(alphas) - 1], -1)
-        th, S = np.linalg.eigh(T)
-        order = np.argsort(-th)[:k]
-        theta, Ssel = th[order], S[:, order]
-    lam = 1.0 / theta                                              # eigenvalues of (K_hat, M_hat), ascending
+        raise _capi.ConvergenceError("modal: no positive Ritz values (K or M not positive definite on the free DOFs?)")
+    if not converged:
+        warnings.warn(f"modal: Ritz values not converged to {tol:g} after {steps} Lanczos steps and {restarts} restarts "
+                      f"(largest relative residual {float(np.max(resid)):.2e})")
+    lam = 1.0 / theta                                              # eigenvalues of (K_hat, M_hat), ascending; theta > 0 checked above
     lam = np.maximum(lam, 0)                                       # freeModes.py:75
     freqs = np.sqrt(lam * scaling) / (2 * np.pi)                   # :76
-    # Ritz vectors: modes = S^T V  (rows), M_hat-orthonormal
-    S_dev = torch.from_numpy(np.ascontiguousarray(-Ssel.T)).cuda()  # (k, j_used), negated: multi_axpy subtracts
+    jn = Ssel.shape[0]
+    S_dev = torch.from_numpy(np.ascontiguousarray(-Ssel.T)).cuda()  # (k, jn), negated: multi_axpy subtracts
     modes_red = torch.zeros((k, n), **f64)
     for i in range(k):
-        # modes_red[i] = sum_j S[j,i] V[j]
-        call("psfem_multi_axpy", S_dev.shape[1], n, ptr(Vb), ptr(S_dev[i]), ptr(modes_red[i]), stream_ptr())
+        call("psfem_multi_axpy", jn, n, ptr(Vb), ptr(S_dev[i]), ptr(modes_red[i]), stream_ptr())
     modes_full = fm.expand(modes_red.contiguous(), nvec=k) if k > 1 else fm.expand(modes_red[0]).reshape(1, -1)
     torch.cuda.current_stream().synchronize()
-    info = dict(lanczos_steps=j_used, pcg_iterations=total_pcg, converged=bool(converged), k_max=k_max, m_max=m_max)
+    info = dict(lanczos_steps=steps, restarts=restarts, basis_vectors=m_max_basis, pcg_iterations=op.pcg_iterations,
+                direct_factorisation=op.direct, converged=bool(converged), k_max=k_max, m_max=m_max,
+                max_residual=float(np.max(resid)) if resid is not None else None)
     return freqs, modes_full.cpu().numpy().reshape(k, -1), constrained, info
