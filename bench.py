@@ -582,6 +582,7 @@ def extras_leg(psfem_b200, prob, cells, hbm_peak):
         from psfem_b200.dist import StripProblem
         prob.release()
         torch.cuda.empty_cache()
+        torch.cuda.reset_peak_memory_stats()
         t0 = time.perf_counter()
         big = StripProblem(L=4 * cells * 1e-3, l=cells * 1e-3, N=4 * cells, M=cells, rank=0, world=1, E=E, nu=NU, t=T).setup(lattice_only=True)
         torch.cuda.synchronize()
