@@ -483,12 +483,24 @@ def strong_leg(StripProblem, world, rank, cells, cg_iters, barrier, maxr):
     one.release()
     torch.cuda.empty_cache()
     out["single_gpu_c4_ms_per_iter"] = t1
+    t1_c5 = None
+    try:     # the C5 strip fits ONE GPU in the solve-only set-up (no CSR): its single-GPU iteration is measured, not extrapolated
+        big = StripProblem(L=4 * cells * 1e-3, l=cells * 1e-3, N=4 * cells, M=cells, rank=0, world=1, E=E, nu=NU, t=T).setup(lattice_only=True)
+        t1_c5 = time_iters(big, reps=3, iters=20)
+        big.release()
+        del big
+        torch.cuda.empty_cache()
+        out["single_gpu_c5_ms_per_iter"] = t1_c5
+    except Exception as e:                                 # noqa: BLE001
+        out["single_gpu_c5_ms_per_iter"] = f"skipped: {type(e).__name__}: {e}"[:200]
     for name, cols in (("c4", cells), ("c5", 4 * cells)):
         if cols // world < 2:
             continue
         p = StripProblem(L=cols * 1e-3, l=cells * 1e-3, N=cols, M=cells, rank=rank, world=world, E=E, nu=NU, t=T).setup()
         tn = time_iters(p)
         ref = t1 * (cols // cells)
+        if name == "c5" and t1_c5:
+            ref = t1_c5
         out[name] = {"plate": f"{cols}x{cells}", "free_dof": int(p.n_free_global), "ms_per_iter": tn,
                      "dof_iter_per_s": p.n_free_global / (tn * 1e-3), "speedup_vs_one_gpu": ref / tn,
                      "one_gpu_reference_ms": ref, "transport": p.transport, "pcg": p.pcg_variant,
@@ -521,9 +533,23 @@ def extras_leg(psfem_b200, prob, cells, hbm_peak):
     out = {}
     nel = prob.nel_owned
     asm = prob.asm
+    import ctypes as C
+    from psfem_b200._capi import call, ptr, stream_ptr, workspace
+    tf = C.c_double(0.0)
+    ws_ = workspace(256)
+    call("psfem_fp64_peak", C.byref(tf), ptr(ws_), 256, stream_ptr())
+    out["fp64_peak_tflops_measured"] = tf.value
     M_vals = torch.empty(asm.nnz, **f64)
     K2 = torch.empty(asm.nnz, **f64)
     ms = best(lambda: asm.assemble(prob.nodes, rho=RHO, t=T, what=2, M_out=M_vals))
+    k_ms = best(lambda: asm.assemble(prob.nodes, E=E, nu=NU, t=T, what=1, K_out=prob.K_vals))
+    # SASS of lattice_q4_kernel<true,4,2,false> (profiles/r2_sass.md): 219 DFMA + 179 DMUL + 143 DADD per marching step of a
+    # lane = 760 flop per element; one halo lane in 32 and one halo column per 64-column segment recompute elements (x 1.05)
+    flop_per_el = (2 * 219 + 179 + 143) * 1.05
+    out["assembly_K_isolated"] = {"ms": k_ms, "elements_per_s": nel / k_ms * 1e3, "hbm_frac": ASM_BYTES_PER_Q4 * nel / (k_ms * 1e-3) / 1e9 / hbm_peak,
+                                  "fp64_tflops": flop_per_el * nel / (k_ms * 1e-3) / 1e12,
+                                  "fp64_frac_of_measured_peak": flop_per_el * nel / (k_ms * 1e-3) / 1e12 / max(tf.value, 1e-9),
+                                  "note": "back-to-back launches outside the PCG loop; co-bound by HBM and the fp64 pipe (ncu r1: 64 % of the pipe)"}
     out["assembly_M"] = {"ms": ms, "elements_per_s": nel / ms * 1e3, "bytes_per_element": ASM_BYTES_PER_Q4,
                          "hbm_frac": ASM_BYTES_PER_Q4 * nel / (ms * 1e-3) / 1e9 / hbm_peak}
     ms = best(lambda: asm.assemble(prob.nodes, E=E, nu=NU, rho=RHO, t=T, what=3, K_out=K2, M_out=M_vals))

@@ -313,6 +313,10 @@ int psfem_direct_factor(const psfem_csr *A, int64_t half_bandwidth, void *d_ws, 
 int psfem_direct_substitute(const psfem_csr *A, const double *d_b, double *d_x, int64_t half_bandwidth, int refine_rounds,
                             double *h_info /* [5] */, void *d_ws, size_t ws_bytes, void *stream);
 int psfem_residual_dd(const psfem_csr *A, const double *d_x, const double *d_b, double *d_r, void *stream);
+/* measured fp64 FMA throughput of the current device in TFLOP/s (a short micro-kernel on all SMs; d_ws >= 16 bytes): the
+ * assembly kernels (Polygones.py:566-708 element arithmetic) are co-bound by the fp64 pipe, so bench.py reports them against
+ * the HBM roofline AND against this peak.  Synchronises. */
+int psfem_fp64_peak(double *h_tflops, void *d_ws, size_t ws_bytes, void *stream);
 
 /* np.allclose(A, A.T, rtol, atol) on CSR -- the symmetry test of main.py:65-66, Beamexemple.py:48, SparseTest.py:37 without
  * a dense transpose: every stored entry is compared with its mirror entry (0 when not stored).  *h_violations = entries

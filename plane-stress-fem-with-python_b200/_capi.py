@@ -115,6 +115,7 @@ SIGNATURES = {
     "psfem_direct_solve": [_pcsr, _ptr, _ptr, _i64, _i32, _pdbl, _ptr, _sz, _ptr],
     "psfem_direct_factor": [_pcsr, _i64, _ptr, _sz, _ptr],
     "psfem_direct_substitute": [_pcsr, _ptr, _ptr, _i64, _i32, _pdbl, _ptr, _sz, _ptr],
+    "psfem_fp64_peak": [_pdbl, _ptr, _sz, _ptr],
     "psfem_residual_dd": [_pcsr, _ptr, _ptr, _ptr, _ptr],
     "psfem_csr_symmetry": [_pcsr, _dbl, _dbl, _pi64, _pdbl, _ptr, _sz, _ptr],
     "psfem_cg_sl_usable": [_pcsr, C.POINTER(C.c_int)],

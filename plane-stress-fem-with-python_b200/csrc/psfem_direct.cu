@@ -100,6 +100,18 @@ __global__ void csr_symmetry_kernel(int64_t n, const int32_t *__restrict__ row_p
     if (worst > 0.0) atomicMax(out + 1, (unsigned long long)__double_as_longlong(worst));   // non-negative doubles order like integers
 }
 
+// fp64 FMA throughput of this device: 8 independent chains per thread, all SMs (the assembly kernels are co-bound by the fp64
+// pipe: their roofline is reported against HBM AND against this measured peak)
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters, double a, double b) {
+    double x0 = threadIdx.x * 1e-9, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+        x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+        x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+    const double s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (s == 1234.5678) out[0] = s;   // never true: keeps the chains alive
+}
+
 struct DsArgs {
     int n, hb, rounds;
     int do_factor, do_solve;   // the factor stays in the work space: psfem_direct_factor once, psfem_direct_substitute many times
@@ -341,5 +353,32 @@ extern "C" int psfem_csr_symmetry(const psfem_csr *A, double rtol, double atol, 
     double w;
     memcpy(&w, &h[1], sizeof(w));
     *h_max_abs_diff = w;
+    return PSFEM_OK;
+}
+
+extern "C" int psfem_fp64_peak(double *h_tflops, void *d_ws, size_t ws_bytes, void *stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    PSFEM_REQUIRE(h_tflops && d_ws && ws_bytes >= 16, "fp64_peak: bad arguments");
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int iters = 1 << 15, threads = 256, blocks = sms * 8;
+    cudaEvent_t e0, e1;
+    PSFEM_CUDA_CHECK(cudaEventCreate(&e0));
+    PSFEM_CUDA_CHECK(cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {
+        PSFEM_CUDA_CHECK(cudaEventRecord(e0, stream));
+        fp64_peak_kernel<<<blocks, threads, 0, stream>>>(static_cast<double *>(d_ws), iters, 0.999999, 1e-9);
+        PSFEM_CUDA_CHECK(cudaEventRecord(e1, stream));
+        PSFEM_CUDA_CHECK(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double tf = 2.0 * 8.0 * iters * (double)threads * blocks / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    PSFEM_LAUNCH_CHECK();
+    *h_tflops = best;
     return PSFEM_OK;
 }
