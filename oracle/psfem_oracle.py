@@ -449,18 +449,21 @@ def jacobi_pcg(A, b, rtol=1e-8, maxit=100000, x0=None):
     return x, it, float(np.sqrt(r @ r) / bnorm)
 
 
-def jacobi_pcg_threads(A, b, iters, nthreads):
+def row_blocks(A, nthreads):
+    """The row-block split jacobi_pcg_threads multiplies with (set-up, reusable across calls)."""
+    A = A.tocsr()
+    bounds = np.linspace(0, A.shape[0], nthreads + 1).astype(np.int64)
+    return bounds, [A[bounds[i]:bounds[i + 1]] for i in range(nthreads)], 1.0 / A.diagonal()
+
+
+def jacobi_pcg_threads(A, b, iters, nthreads, split=None):
     """The recurrence of jacobi_pcg for a FIXED number of iterations with the SpMV and the vector
     updates split over `nthreads` row blocks (SciPy's CSR mat-vec and NumPy's element-wise loops
     release the GIL).  Only used to time the CPU side of bench.py with every host core busy.
     Returns (x, relres, seconds spent in the iteration loop -- the row-block split is set-up)."""
     from concurrent.futures import ThreadPoolExecutor
-    A = A.tocsr()
-    n = A.shape[0]
-    bounds = np.linspace(0, n, nthreads + 1).astype(np.int64)
-    blocks = [A[bounds[i]:bounds[i + 1]] for i in range(nthreads)]
+    bounds, blocks, dinv = split if split is not None else row_blocks(A, nthreads)
     sl = [slice(bounds[i], bounds[i + 1]) for i in range(nthreads)]
-    dinv = 1.0 / A.diagonal()
     x = np.zeros_like(b)
     r = b.copy()
     z = dinv * r
