@@ -82,7 +82,45 @@ class NumpyOps:
         dst.numpy()[:] = src.numpy()
 
 
-def _worker(rank, world, port, N, M, iters, out_dir, rollers=False, et="quad"):
+def _fused_strip_iterations(A_own, lo, hi, b_own, dinv, comm, dist, torch, iters, defer_x=True):
+    """NumPy restatement of what cg_sl_tma_kernel<., DIST> does on one strip (csrc/psfem_cg_sl.cuh), with the SAME exchange
+    structure: per launch ONE halo exchange (u of the first / last owned column, i.e. comm.halo on the extended u vector)
+    and ONE all-reduce of {r.u, w.u, r.r}; the start of a solve is the same launch in start mode; x is written every other
+    iteration (alpha_pend).  Returns (x, ctl) with x finished (psfem_cg_sl_finish)."""
+    n = hi - lo
+    mask = (dinv != 0.0).astype(np.float64)
+    x, p, s, w = np.zeros(n), np.zeros(n), np.zeros(n), np.zeros(n)
+    r = b_own.copy()
+    u_ext = torch.zeros(comm.plan["n_ext_free"], dtype=torch.float64)
+    ctl = dict(gamma=1.0, alpha=0.0, beta=0.0, alpha_pend=0.0, iters=-1, rr=0.0, bb=0.0)
+    for launch in range(iters + 1):
+        alpha, beta, a_pend = ctl["alpha"], ctl["beta"], ctl["alpha_pend"]
+        skip_x = defer_x and a_pend == 0.0
+        s_new = w + beta * s
+        r_new = (r - alpha * s_new) * mask
+        u_new = dinv * r_new
+        p_new = dinv * r + beta * p
+        if not skip_x:
+            x = (x + a_pend * p) + alpha * p_new
+        p, s, r = p_new, s_new, r_new
+        u_ext.numpy()[lo:hi] = u_new
+        comm.halo(u_ext)                                   # the kernel: LL words into the neighbours' halo buffers
+        w = A_own @ u_ext.numpy()
+        tot = torch.tensor([r @ u_new, w @ u_new, r @ r], dtype=torch.float64)
+        comm.allreduce(tot)                                # the kernel: one exchange through the peer boards
+        g_new, delta, rr = tot.numpy()
+        if ctl["iters"] < 0:                               # start pass
+            ctl.update(gamma=g_new, alpha=g_new / delta, beta=0.0, alpha_pend=0.0, iters=0, rr=rr, bb=rr)
+        else:
+            beta_new = g_new / ctl["gamma"]
+            ctl.update(gamma=g_new, beta=beta_new, alpha=g_new / (delta - beta_new * g_new / alpha),
+                       alpha_pend=alpha if skip_x else 0.0, iters=ctl["iters"] + 1, rr=rr)
+    if ctl["alpha_pend"] != 0.0:
+        x = x + ctl["alpha_pend"] * p
+    return x, ctl
+
+
+def _worker(rank, world, port, N, M, iters, out_dir, rollers=False, et="quad", fused=False):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import torch
@@ -138,8 +176,13 @@ def _worker(rank, world, port, N, M, iters, out_dir, rollers=False, et="quad"):
               out3=torch.zeros(3, dtype=f64), parity=0, iters=0)
     ops = NumpyOps(A_own)
     comm = Comm(part, plan, dist)
-    pcg_start(ops, comm, st, torch.from_numpy(b_own.copy()))
-    pcg_iterations(ops, comm, st, iters)
+    if fused:
+        xf, ctl = _fused_strip_iterations(A_own, lo, hi, b_own, dinv, comm, dist, torch, iters)
+        st["x"] = torch.from_numpy(xf)
+        st["out2"].numpy()[1] = ctl["rr"]
+    else:
+        pcg_start(ops, comm, st, torch.from_numpy(b_own.copy()))
+        pcg_iterations(ops, comm, st, iters)
     np.savez(os.path.join(out_dir, f"rank{rank}.npz"), x=st["x"].numpy(), rr=st["out2"].numpy()[1], free=mask[part.own_lo:part.own_hi],
              rows=A_own.toarray() if A_own.shape[0] * A_own.shape[1] < 4e6 else np.zeros(1), lo=lo, hi=hi)
     dist.barrier()
@@ -200,3 +243,39 @@ def test_masked_strip_pcg_over_gloo_matches_reduced_system(tmp_path, psfem, worl
     assert x.shape[0] == K.shape[0] and free.sum() == x_ref.shape[0]
     assert np.all(x[~free] == 0.0)
     assert np.abs(x[free] - x_ref).max() <= 1e-7 * np.abs(x_ref).max()
+
+
+@pytest.mark.parametrize("world,rollers", [(2, False), (3, False), (2, True), (3, True)])
+def test_fused_strip_recurrence_over_gloo(tmp_path, psfem, world, rollers):
+    """The one-kernel-per-iteration strip solver (Chronopoulos-Gear recurrence, ONE halo exchange of u and ONE all-reduce of
+    three scalars per launch, start pass, x written every other iteration) restated in NumPy over gloo: after k launches
+    the strips hold the iterate of the classic single-process PCG, up to the rounding of the different recurrence --
+    clamped edge (reduced strips) and rollers (masked rows)."""
+    import torch.multiprocessing as mp
+    import psfem_oracle as O
+    N, M = 12, 5
+    for iters in (40, 41):                                  # an even and an odd launch count: with and without a pending x half
+        out = tmp_path / f"k{iters}"
+        out.mkdir()
+        port = 33500 + os.getpid() % 2000 + 4 * world + (2 if rollers else 0) + (iters & 1)
+        mp.spawn(_worker, args=(world, port, N, M, iters, str(out), rollers, "quad", True), nprocs=world, join=True)
+        nodes, conn = O.mesh(0.001 * N, 0.001 * M, N, M, element_type="quad")
+        K = O.global_stiffness_matrix(nodes, conn, 210e9, 0.3, 0.1, "quad")
+        if rollers:
+            bc = [(0, [0, 0])] + O.boundary("bottom", [None, 0], N, M)[1:]
+            F = O.edge_forces(np.zeros(K.shape[0]), [2e5, -1e6], "top", 0.001 * N, N, M)
+        else:
+            bc = O.boundary("left", [0, 0], N, M)
+            F = O.edge_forces(np.zeros(K.shape[0]), [0, -1e6], "right", 0.001 * M, N, M)
+        K_red, F_red, _ = O.apply_boundary_conditions(K, F, bc)
+        x_ref, it, rel = O.jacobi_pcg(K_red, F_red, rtol=0.0, maxit=iters)
+        xs = [np.load(out / f"rank{r}.npz") for r in range(world)]
+        x = np.concatenate([d["x"] for d in xs])
+        if rollers:
+            free = np.concatenate([d["free"] for d in xs])
+            assert np.all(x[~free] == 0.0)
+            x = x[free]
+        assert x.shape == x_ref.shape
+        assert np.abs(x - x_ref).max() <= 1e-6 * np.abs(x_ref).max()
+        rr = float(xs[0]["rr"])
+        assert abs(np.sqrt(rr) - rel * np.linalg.norm(F_red)) <= 1e-3 * np.sqrt(rr)     # the recurrence residual r.r is the global one (unconverged iterates amplify the rounding of the other recurrence: 3e-5 measured)
