@@ -126,17 +126,6 @@ int psfem_assemble(const double *d_nodes, const int32_t *d_conn, int64_t nel, in
                    const int32_t *d_perm, double *d_K_vals, double *d_M_vals,
                    void *d_ws, size_t ws_bytes, int64_t *h_bad_element, void *stream);
 
-/* Gather formulation of the same numeric phase for the Gauss-integrated kinds (Q4, T6, Q9), any connectivity: one thread
- * per NODE ROW walks its incident elements in ascending id (contribution list of the diagonal pair of the plan), computes
- * the row node's blocks of each element matrix in registers and adds them into the two CSR rows it owns.  Same summation
- * order, same bits as psfem_assemble; HBM traffic = coordinates + CSR values (no element blocks: 3.6x less for Q9).  The path
- * of the quadratic elements (mesh_type='fine').  d_col_idx: the CSR column indices of psfem_pattern_fill.  d_ws >= 16 B. */
-int psfem_assemble_gather(const double *d_nodes, const int32_t *d_conn, int64_t nel, int etype, int64_t n_nodes,
-                          double E, double nu, double rho, double t, int what,
-                          const int32_t *d_node_ptr, const int32_t *d_col_idx, const int32_t *d_pair_ptr,
-                          const int32_t *d_perm, double *d_K_vals, double *d_M_vals, void *d_ws, size_t ws_bytes,
-                          int64_t *h_bad_element, void *stream);
-
 /* ---- tile-fused numeric assembly for T3 / Q4 (the fast path of psfem_assemble) ------------------
  * A CTA owns a tile of tile_nodes_R (even, 32..256) node rows that are neighbours in space (Morton order
  * of the coordinates, so any mesh tiles well).  Every element touching the tile is computed once, in

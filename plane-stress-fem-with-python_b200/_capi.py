@@ -77,8 +77,6 @@ SIGNATURES = {
     "psfem_assemble_workspace": [_i64, _i32, _i32, _psz],
     "psfem_assemble": [_ptr, _ptr, _i64, _i32, _i64, _dbl, _dbl, _dbl, _dbl, _i32, _i64, _ptr, _ptr, _ptr, _ptr,
                        _ptr, _ptr, _ptr, _sz, _pi64, _ptr],
-    "psfem_assemble_gather": [_ptr, _ptr, _i64, _i32, _i64, _dbl, _dbl, _dbl, _dbl, _i32, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _sz,
-                              _pi64, _ptr],
     "psfem_tileplan_workspace": [_i64, _i32, _i64, _i32, _psz],
     "psfem_tileplan_build": [_ptr, _ptr, _i64, _i32, _i64, _i32, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _pi64,
                              _ptr, _sz, _ptr],

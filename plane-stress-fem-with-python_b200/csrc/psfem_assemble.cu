@@ -135,15 +135,27 @@ __global__ void t3_kernel(const double2 *__restrict__ nodes, const int32_t *__re
     }
 }
 
-// ---- Gauss-integrated elements (Q4, T6, Q9) ---------------------------------------------------
+// ---- Gauss-integrated elements (Q4, T6, Q9): one thread per (element, row node i) ------------
 // Per Gauss point: J (Polygones.py:675-682), detJ guard (:685-687), dN/dx, dN/dy (:697-698),
 // Ke += w B^T D B |detJ| t (:595), Me += w rho t N^T N |detJ| (:1291).
-// gauss_row: the 2x2 blocks of ROW NODE i of one element matrix (acc[j] = {K(2i,2j), K(2i,2j+1), K(2i+1,2j), K(2i+1,2j+1)},
-// macc[j] = M(2i,2j)); shared by the element-block kernel and the gather assembly so that both produce the same bits.
 template <int ETYPE, int NPE, bool DO_K, bool DO_M>
-__device__ __forceinline__ bool gauss_row(const double (&x)[NPE], const double (&y)[NPE], const int i, const Material &mat,
-                                          double4 (&acc)[NPE], double (&macc)[NPE]) {
+__global__ void __launch_bounds__(128)
+gauss_kernel(const double2 *__restrict__ nodes, const int32_t *__restrict__ conn, int64_t nel, Material mat,
+             double4 *__restrict__ kblk, double *__restrict__ mblk, unsigned long long *__restrict__ bad) {
+    int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (tid >= nel * NPE) return;
+    const int64_t e = tid / NPE;
+    const int i = (int)(tid - e * NPE);
     const ShapeTab &tab = c_tab[ETYPE];
+    double x[NPE], y[NPE];
+#pragma unroll
+    for (int j = 0; j < NPE; ++j) {
+        double2 p = nodes[conn[e * NPE + j]];
+        x[j] = p.x;
+        y[j] = p.y;
+    }
+    double4 acc[NPE];
+    double macc[NPE];
 #pragma unroll
     for (int j = 0; j < NPE; ++j) { acc[j] = make_double4(0, 0, 0, 0); macc[j] = 0; }
     const int ngp = (ETYPE == PSFEM_T6) ? 3 : 9;
@@ -158,7 +170,10 @@ __device__ __forceinline__ bool gauss_row(const double (&x)[NPE], const double (
         }
         const double detJ = j00 * j11 - j01 * j10;
         const double ad = fabs(detJ);
-        if (ad < 1e-10) return false;   // Polygones.py:686-687
+        if (ad < 1e-10) {  // Polygones.py:686-687
+            atomicMin(bad, (unsigned long long)e);
+            return;
+        }
         if (DO_K) {
             const double inv = 1.0 / detJ;
             const double i00 = j11 * inv, i01 = -j01 * inv, i10 = -j10 * inv, i11 = j00 * inv;
@@ -184,38 +199,10 @@ __device__ __forceinline__ bool gauss_row(const double (&x)[NPE], const double (
             }
         }
         if (DO_M) {
-            double ni = 0;
-#pragma unroll
-            for (int j = 0; j < NPE; ++j) if (j == i) ni = tab.N[g][j];
-            const double cm = tab.w[g] * mat.rho * mat.t * ad * ni;
+            const double cm = tab.w[g] * mat.rho * mat.t * ad * tab.N[g][i];
 #pragma unroll
             for (int j = 0; j < NPE; ++j) macc[j] += cm * tab.N[g][j];
         }
-    }
-    return true;
-}
-
-// element blocks to HBM: one thread per (element, row node i)
-template <int ETYPE, int NPE, bool DO_K, bool DO_M>
-__global__ void __launch_bounds__(128)
-gauss_kernel(const double2 *__restrict__ nodes, const int32_t *__restrict__ conn, int64_t nel, Material mat,
-             double4 *__restrict__ kblk, double *__restrict__ mblk, unsigned long long *__restrict__ bad) {
-    int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (tid >= nel * NPE) return;
-    const int64_t e = tid / NPE;
-    const int i = (int)(tid - e * NPE);
-    double x[NPE], y[NPE];
-#pragma unroll
-    for (int j = 0; j < NPE; ++j) {
-        double2 p = nodes[conn[e * NPE + j]];
-        x[j] = p.x;
-        y[j] = p.y;
-    }
-    double4 acc[NPE];
-    double macc[NPE];
-    if (!gauss_row<ETYPE, NPE, DO_K, DO_M>(x, y, i, mat, acc, macc)) {
-        atomicMin(bad, (unsigned long long)e);
-        return;
     }
     const int64_t base = tid * NPE;
     if (DO_K) {
@@ -225,68 +212,6 @@ gauss_kernel(const double2 *__restrict__ nodes, const int32_t *__restrict__ conn
     if (DO_M) {
 #pragma unroll
         for (int j = 0; j < NPE; ++j) mblk[base + j] = macc[j];
-    }
-}
-
-// ---- GATHER ASSEMBLY: one thread per node row, no element blocks through HBM ---------------------------------------
-// Thread a walks the elements incident to node a in ascending id (the contribution list of the diagonal pair (a, a) of the
-// sorted plan), computes row node i of each element matrix in registers (gauss_row) and adds its blocks into the CSR rows
-// 2a, 2a+1, which it owns: same summation order as the reference's loop (Polygones.py:717-726) and as the segmented
-// reduction of the two-kernel path, hence the same bits -- but HBM sees coordinates in and CSR values out, nothing else
-// (the two-kernel path moves ~3.6x that for Q9).  Any connectivity; used for the quadratic element kinds.
-template <int ETYPE, int NPE, bool DO_K, bool DO_M>
-__global__ void __launch_bounds__(128)
-gather_assemble_kernel(const double2 *__restrict__ nodes, const int32_t *__restrict__ conn, int64_t n_nodes, Material mat,
-                       const int32_t *__restrict__ node_ptr, const int32_t *__restrict__ col_idx,
-                       const int32_t *__restrict__ pair_ptr, const int32_t *__restrict__ perm,
-                       double *__restrict__ K_vals, double *__restrict__ M_vals, unsigned long long *__restrict__ bad) {
-    const int64_t a = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (a >= n_nodes) return;
-    const int32_t p0 = node_ptr[a], deg = node_ptr[a + 1] - p0;
-    if (deg <= 0) return;
-    const int32_t *nb = col_idx + 4ll * p0;          // row 2a: columns 2b, 2b+1 of the neighbour nodes b, ascending
-    auto find = [&](int32_t b) -> int {              // position of neighbour b in the row (it is there by construction)
-        int lo = 0, hi = deg;
-        while (lo < hi) { const int mid = (lo + hi) >> 1; if (nb[2 * mid] < 2 * b) lo = mid + 1; else hi = mid; }
-        return lo;
-    };
-    double *k0 = DO_K ? K_vals + 4ll * p0 : nullptr, *k1 = DO_K ? k0 + 2 * deg : nullptr;
-    double *m0 = DO_M ? M_vals + 4ll * p0 : nullptr, *m1 = DO_M ? m0 + 2 * deg : nullptr;
-    for (int k = 0; k < deg; ++k) {                  // start from zero like the segmented reduction (0 + v = v exactly)
-        if (DO_K) { reinterpret_cast<double2 *>(k0)[k] = make_double2(0.0, 0.0); reinterpret_cast<double2 *>(k1)[k] = make_double2(0.0, 0.0); }
-        if (DO_M) { reinterpret_cast<double2 *>(m0)[k] = make_double2(0.0, 0.0); reinterpret_cast<double2 *>(m1)[k] = make_double2(0.0, 0.0); }
-    }
-    const int kd = find((int32_t)a);
-    const int32_t c0 = pair_ptr[p0 + kd], c1 = pair_ptr[p0 + kd + 1];
-    for (int32_t c = c0; c < c1; ++c) {
-        const int32_t code = perm[c];
-        const int32_t e = code / (NPE * NPE), ij = code - e * (NPE * NPE), i = ij / NPE, jj = ij - i * NPE;
-        if (i != jj) continue;                       // (a degenerate element lists a node twice: one visit per local index)
-        double x[NPE], y[NPE];
-        int32_t cn[NPE];
-#pragma unroll
-        for (int j = 0; j < NPE; ++j) {
-            cn[j] = conn[(int64_t)e * NPE + j];
-            const double2 p = nodes[cn[j]];
-            x[j] = p.x; y[j] = p.y;
-        }
-        double4 acc[NPE];
-        double macc[NPE];
-        if (!gauss_row<ETYPE, NPE, DO_K, DO_M>(x, y, i, mat, acc, macc)) { atomicMin(bad, (unsigned long long)e); continue; }
-#pragma unroll
-        for (int j = 0; j < NPE; ++j) {
-            const int k = find(cn[j]);
-            if (DO_K) {
-                double2 u = reinterpret_cast<double2 *>(k0)[k], v = reinterpret_cast<double2 *>(k1)[k];
-                u.x += acc[j].x; u.y += acc[j].y; v.x += acc[j].z; v.y += acc[j].w;
-                reinterpret_cast<double2 *>(k0)[k] = u; reinterpret_cast<double2 *>(k1)[k] = v;
-            }
-            if (DO_M) {
-                double2 u = reinterpret_cast<double2 *>(m0)[k], v = reinterpret_cast<double2 *>(m1)[k];
-                u.x += macc[j]; v.y += macc[j];
-                reinterpret_cast<double2 *>(m0)[k] = u; reinterpret_cast<double2 *>(m1)[k] = v;
-            }
-        }
     }
 }
 
@@ -522,41 +447,4 @@ extern "C" int psfem_b_matrix_at_point(const double *d_nodes, const int32_t *d_c
         return PSFEM_EJACOBIAN;
     }
     return PSFEM_OK;
-}
-
-// Gather assembly (quadratic elements / any connectivity): same result, bit for bit, as psfem_assemble, without the element
-// blocks in HBM.  Needs the CSR column indices next to the plan.  d_ws: >= 16 bytes.
-extern "C" int psfem_assemble_gather(const double *d_nodes, const int32_t *d_conn, int64_t nel, int etype, int64_t n_nodes,
-                                     double E, double nu, double rho, double t, int what,
-                                     const int32_t *d_node_ptr, const int32_t *d_col_idx, const int32_t *d_pair_ptr,
-                                     const int32_t *d_perm, double *d_K_vals, double *d_M_vals, void *d_ws, size_t ws_bytes,
-                                     int64_t *h_bad_element, void *stream_) {
-    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    PSFEM_REQUIRE(etype == PSFEM_Q4 || etype == PSFEM_T6 || etype == PSFEM_Q9, "assemble_gather: Gauss-integrated element kinds only (Q4, T6, Q9)");
-    PSFEM_REQUIRE(what >= 1 && what <= 3, "assemble_gather: what must be 1 (K), 2 (M) or 3 (both)");
-    PSFEM_REQUIRE(!(what & 1) || d_K_vals, "assemble_gather: K requested but d_K_vals is null");
-    PSFEM_REQUIRE(!(what & 2) || d_M_vals, "assemble_gather: M requested but d_M_vals is null");
-    PSFEM_REQUIRE(d_nodes && d_conn && d_node_ptr && d_col_idx && d_pair_ptr && d_perm && d_ws && ws_bytes >= 16, "assemble_gather: null argument");
-    if (h_bad_element) *h_bad_element = -1;
-    if (nel == 0 || n_nodes == 0) return PSFEM_OK;
-    int rc = upload_tabs(stream);
-    if (rc) return rc;
-    unsigned long long *bad = static_cast<unsigned long long *>(d_ws);
-    PSFEM_CUDA_CHECK(cudaMemsetAsync(bad, 0xff, sizeof(unsigned long long), stream));
-    const Material mat = make_material(E, nu, rho, t, etype);
-    const double2 *nodes = reinterpret_cast<const double2 *>(d_nodes);
-    const int T = 128;
-    const unsigned grid = (unsigned)ceil_div(n_nodes, T);
-#define PSFEM_GATHER(ET, NPE_)                                                                                                    \
-    do {                                                                                                                          \
-        if (what == 3) gather_assemble_kernel<ET, NPE_, true, true><<<grid, T, 0, stream>>>(nodes, d_conn, n_nodes, mat, d_node_ptr, d_col_idx, d_pair_ptr, d_perm, d_K_vals, d_M_vals, bad); \
-        else if (what == 1) gather_assemble_kernel<ET, NPE_, true, false><<<grid, T, 0, stream>>>(nodes, d_conn, n_nodes, mat, d_node_ptr, d_col_idx, d_pair_ptr, d_perm, d_K_vals, d_M_vals, bad); \
-        else gather_assemble_kernel<ET, NPE_, false, true><<<grid, T, 0, stream>>>(nodes, d_conn, n_nodes, mat, d_node_ptr, d_col_idx, d_pair_ptr, d_perm, d_K_vals, d_M_vals, bad); \
-    } while (0)
-    if (etype == PSFEM_Q4) PSFEM_GATHER(PSFEM_Q4, 4);
-    else if (etype == PSFEM_T6) PSFEM_GATHER(PSFEM_T6, 6);
-    else PSFEM_GATHER(PSFEM_Q9, 9);
-#undef PSFEM_GATHER
-    PSFEM_LAUNCH_CHECK();
-    return finish_bad(bad, h_bad_element, stream);
 }

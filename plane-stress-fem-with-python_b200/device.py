@@ -436,13 +436,6 @@ class Assembler:
                 return K_vals, M_vals
         if self.perm is None:
             self._sort_pattern(keep_pattern=False)
-        if self.etype in (_capi.T6, _capi.Q9) and not os.environ.get("PSFEM_NO_GATHER"):
-            # quadratic elements: gather assembly, one thread per node row, no element blocks through HBM (same bits)
-            rc = lib.psfem_assemble_gather(ptr(nodes_dev), ptr(self.conn), self.nel, self.etype, self.n_nodes, float(E), float(nu),
-                                           float(rho), float(t), what, ptr(self.node_ptr), ptr(self.col_idx), ptr(self.pair_ptr),
-                                           ptr(self.perm), ptr(K_vals), ptr(M_vals), ptr(self._small_ws), 256, C.byref(bad), stream_ptr())
-            check(rc, bad.value)
-            return K_vals, M_vals
         ws, nbytes = self._ws(what)
         rc = lib.psfem_assemble(ptr(nodes_dev), ptr(self.conn), self.nel, self.etype, self.n_nodes, float(E), float(nu),
                                 float(rho), float(t), what, self.n_pairs, ptr(self.node_ptr), ptr(self.pair_row),
