@@ -71,7 +71,7 @@ __device__ __forceinline__ double2 cg_ll_load(const unsigned long long *src, uns
 // four adjacent 28-row strips of one column segment.  Per lattice column the producer issues 24 bulk copies (cp.async.bulk, completion
 // on an mbarrier) of the CTA's 116-row window: the 17 off-diagonal components of column c, the two diagonal components of
 // column c+1, and r, w, s, p of column c+1 -- into a 3-stage ring, two columns ahead of the consumers.  Nothing is
-// prefetched in registers (98 registers instead of 182), the loads in flight no longer depend on occupancy.
+// prefetched in registers (94 registers instead of 182), the loads in flight no longer depend on occupancy.
 // Consumer step for stage {M(c), D(c+1), V(c+1)}:  u(c+1) from V and 1/D  ->  r, s, p, x of column c+1 written;  row sums of
 // column c from M(c), D(c) (carried in registers), u(c), u(c+1)  ->  w of column c written;  chain heads for column c+1.
 // ---------------------------------------------------------------------------------------------
