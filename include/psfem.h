@@ -252,7 +252,10 @@ int psfem_spmv_nb_compress(int64_t n, const int32_t *d_node_ptr, const int32_t *
  * and the solves of Statictest.py:69, main.py:286,314 through PCG).
  *   psfem_spmv_sl_candidates: proposals for the lattice column height m of a node-block operand (h_m[8], *h_count of them;
  *                             0 when the operand cannot be a lattice); synchronises
- *   psfem_spmv_sl_size:       bytes of the storage for (row nodes, row_node_offset, m); allocate 256 bytes more
+ *   psfem_spmv_sl_size:       bytes of the storage for (row nodes, row_node_offset, m); allocate 256 bytes more -- and, for
+ *                             the TMA-staged kernels (psfem_cg_sl_*, the SpMV itself), keep 256 readable bytes IN FRONT of
+ *                             d_sl_vals and 2 KB behind the storage: their 116-row window copies start two rows before a
+ *                             strip group and run past the last one (the Python side allocates that slack)
  *   psfem_spmv_sl_build:      checks that A is a 3x3-lattice matrix with column height m whose 2x2 blocks (a,b) and (b,a)
  *                             are transposes (tol = 0: bit for bit, which makes the SpMV bit-identical to the CSR kernels;
  *                             tol > 0: within tol * the node's diagonal) and writes the storage; *h_ok = 1 on success.

@@ -364,3 +364,134 @@ __global__ void cg_sl_dinv_kernel(const double *__restrict__ sv, const SlGeom g,
         reinterpret_cast<double2 *>(dinv)[a] = make_double2(1.0 / pd[0], 1.0 / pd[2 * mp]);
     }
 }
+
+// ---------------------------------------------------------------------------------------------
+// The plain SpMV (+ dot) on symmetric-lattice storage with the same TMA + mbarrier staging: y = alpha A x + gamma z.
+// Same arithmetic, same order, same bits as spmv_sl_kernel (and hence as the CSR kernels); the matrix goes through a 4-stage
+// shared ring fed by the producer warp instead of a register prefetch (154 registers, 12 warps per SM, 6.2 TB/s there).
+// x is the caller's vector (possibly extended by halo columns): plain loads, one column ahead.  Single-GPU operands only:
+// the strip solver's classic kernels keep spmv_sl_kernel, which carries the peer waits.
+// ---------------------------------------------------------------------------------------------
+#ifndef PSFEM_SPMV_TMA_STAGES
+#define PSFEM_SPMV_TMA_STAGES 4
+#endif
+constexpr int SPT_STAGES = PSFEM_SPMV_TMA_STAGES;
+struct SpStage { double M[SL_NC][CGT_RW]; };
+
+template <bool DOT>
+__global__ void __launch_bounds__(CGT_THREADS, 2)
+spmv_sl_tma_kernel(const double *__restrict__ sv, const SlGeom g, const double *__restrict__ x, double alpha, double gamma,
+                   const double *__restrict__ z, double *__restrict__ y, double *__restrict__ dot_out, double *__restrict__ partials,
+                   unsigned int *counter, const int *__restrict__ done, const int n_groups) {
+    extern __shared__ __align__(128) unsigned char cg_smem[];
+    __shared__ double red[CGT_THREADS / 32];
+    __shared__ uint64_t full_bar[SPT_STAGES], empty_bar[SPT_STAGES];
+    SpStage *stages = reinterpret_cast<SpStage *>(cg_smem);
+    pdl_enter();
+    if (done && *done) return;
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
+    const int gidx = blockIdx.x % n_groups, seg = blockIdx.x / n_groups;
+    const int owned_cols = g.S - g.pre;
+    const int sa = g.pre + (int)((long long)seg * owned_cols / g.G);
+    const int sb = g.pre + (int)((long long)(seg + 1) * owned_cols / g.G);
+    const int q0 = sa > 0 ? 0 : 1;                     // step 0 = the column before the segment (chain heads only)
+    const int nsteps = (sb - sa) + 1;
+    const size_t mp = (size_t)g.mpad, cstride = (size_t)SL_NC * mp;
+    const long long row0 = (long long)SL_ROWS * CGT_CONSUMERS * gidx - 2;
+    if (threadIdx.x == 0) {
+        for (int q = 0; q < SPT_STAGES; ++q) { mbar_init(&full_bar[q], 1); mbar_init(&empty_bar[q], CGT_CONSUMERS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    double dot[1] = {0.0};
+    if (wq == CGT_CONSUMERS) {
+        for (int q = q0; q < nsteps; ++q) {
+            const int it = q - q0, st = it % SPT_STAGES;
+            if (it >= SPT_STAGES) mbar_wait(&empty_bar[st], ((it / SPT_STAGES) - 1) & 1);
+            const int cM = sa - 1 + q;
+            const uint32_t bM = (uint32_t)(CGT_RW * sizeof(double));
+            if (lane == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_expect_tx(&full_bar[st], (uint32_t)SL_NC * bM);
+            }
+            __syncwarp();
+            if (lane < SL_NC) bulk_g2s(&stages[st].M[lane][0], sv + (size_t)cM * cstride + (size_t)lane * mp + row0, bM, &full_bar[st]);
+        }
+    } else {
+        const int sidx = gidx * CGT_CONSUMERS + wq;
+        const int j = sidx * SL_ROWS - 2 + lane;
+        const int wrow = wq * SL_ROWS + lane;
+        const bool active = sidx < g.n_strips;
+        const bool valid = active && j >= 0 && j < g.m && lane >= 1 && lane <= SL_ROWS + 2;
+        const bool owned = valid && lane >= 2 && lane <= SL_ROWS + 1;
+        const bool lo = valid && lane <= SL_ROWS + 1;
+        const bool hi = valid && lane >= 2;
+        const double2 *__restrict__ x2 = reinterpret_cast<const double2 *>(x);
+        auto xload = [&](int s) -> double2 {
+            const int xc = s + g.xcol0;
+            if (valid && xc >= 0 && xc < g.xcols) return __ldcg(x2 + (size_t)xc * g.m + j);
+            return make_double2(0.0, 0.0);
+        };
+        double p0 = 0.0, p1 = 0.0;
+        double2 xc = xload(sa - 1 + q0), xn = xload(sa + q0);
+        for (int q = q0; q < nsteps; ++q) {
+            const int it = q - q0, st = it % SPT_STAGES;
+            const int cM = sa - 1 + q;
+            const double2 xnn = xload(cM + 2);
+            mbar_wait(&full_bar[st], (it / SPT_STAGES) & 1);
+            const SpStage &S = stages[st];
+            auto F = [&](int k, bool on) -> double { return on ? S.M[k][wrow] : 0.0; };
+            if (q >= 1) {
+                const double f3 = F(3, lo), f4 = F(4, lo), f5 = F(5, lo), f6 = F(6, lo);
+                double s0 = p0, s1 = p1;
+                s0 += alpha * f3 * xc.x; s0 += alpha * f5 * xc.y;
+                s1 += alpha * f4 * xc.x; s1 += alpha * f6 * xc.y;
+                s0 = __shfl_up_sync(FULL, s0, 1); s1 = __shfl_up_sync(FULL, s1, 1);
+                double2 xr, xnl, xnr;
+                xr.x = __shfl_down_sync(FULL, xc.x, 1); xr.y = __shfl_down_sync(FULL, xc.y, 1);
+                xnl.x = __shfl_up_sync(FULL, xn.x, 1); xnl.y = __shfl_up_sync(FULL, xn.y, 1);
+                xnr.x = __shfl_down_sync(FULL, xn.x, 1); xnr.y = __shfl_down_sync(FULL, xn.y, 1);
+                const double f0 = F(0, owned), f1 = F(1, owned), f2 = F(2, owned);
+                s0 += alpha * f0 * xc.x; s0 += alpha * f1 * xc.y;
+                s1 += alpha * f1 * xc.x; s1 += alpha * f2 * xc.y;
+                s0 += alpha * f3 * xr.x; s0 += alpha * f4 * xr.y;
+                s1 += alpha * f5 * xr.x; s1 += alpha * f6 * xr.y;
+                s0 += alpha * F(7, hi) * xnl.x; s0 += alpha * F(8, hi) * xnl.y;
+                s1 += alpha * F(9, hi) * xnl.x; s1 += alpha * F(10, hi) * xnl.y;
+                s0 += alpha * F(11, owned) * xn.x; s0 += alpha * F(12, owned) * xn.y;
+                s1 += alpha * F(13, owned) * xn.x; s1 += alpha * F(14, owned) * xn.y;
+                s0 += alpha * F(15, lo) * xnr.x; s0 += alpha * F(16, lo) * xnr.y;
+                s1 += alpha * F(17, lo) * xnr.x; s1 += alpha * F(18, lo) * xnr.y;
+                if (owned) {
+                    const size_t a = (size_t)(cM - g.pre) * g.m + j;
+                    if (z) {
+                        const double2 zz = reinterpret_cast<const double2 *>(z)[a];
+                        s0 += gamma * zz.x; s1 += gamma * zz.y;
+                    }
+                    reinterpret_cast<double2 *>(y)[a] = make_double2(s0, s1);
+                    if (DOT) { dot[0] += xc.x * s0; dot[0] += xc.y * s1; }
+                }
+            }
+            if (q + 1 < nsteps) {   // chain heads of column cM + 1
+                double c0 = 0.0, c1 = 0.0;
+                c0 += alpha * F(15, lo) * xc.x; c0 += alpha * F(17, lo) * xc.y;
+                c1 += alpha * F(16, lo) * xc.x; c1 += alpha * F(18, lo) * xc.y;
+                c0 = __shfl_up_sync(FULL, c0, 1); c1 = __shfl_up_sync(FULL, c1, 1);
+                c0 += alpha * F(11, owned) * xc.x; c0 += alpha * F(13, owned) * xc.y;
+                c1 += alpha * F(12, owned) * xc.x; c1 += alpha * F(14, owned) * xc.y;
+                c0 = __shfl_up_sync(FULL, c0, 1); c1 = __shfl_up_sync(FULL, c1, 1);
+                c0 += alpha * F(7, hi) * xc.x; c0 += alpha * F(9, hi) * xc.y;
+                c1 += alpha * F(8, hi) * xc.x; c1 += alpha * F(10, hi) * xc.y;
+                p0 = __shfl_down_sync(FULL, c0, 2); p1 = __shfl_down_sync(FULL, c1, 2);
+            }
+            xc = xn; xn = xnn;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[st]);
+        }
+    }
+    if (DOT) {
+        double total[1];
+        if (grid_sum<CGT_THREADS, 1>(dot, partials, counter, red, total)) *dot_out = total[0];
+    }
+}

@@ -686,6 +686,7 @@ spmv_nb_kernel(const int32_t *__restrict__ node_ptr, const void *__restrict__ pc
 }
 
 #include "psfem_spmv_sl.cuh"
+#include "psfem_cg_sl.cuh"
 
 // geometry of the symmetric-lattice operand attached to A (psfem_spmv_sl_build)
 bool sl_geometry(const psfem_csr *A, SlGeom *g, int sms, int ctas_per_sm = PSFEM_SL_CTAS) {
@@ -735,6 +736,27 @@ int launch_spmv(const psfem_csr *A, const double *v2, const double *x1, const do
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         SlGeom g;
+        static const bool no_tma = getenv("PSFEM_SPMV_NO_TMA") != nullptr;   // A/B switch: the register-prefetch kernel
+        // TMA-staged kernel (single-GPU operands whose storage carries the window slack: see psfem_spmv_sl_size)
+        if (!no_tma && !peer && sl_geometry(A, &g, sms, 2) && g.S - g.pre >= 8) {
+            const int n_groups = (int)ceil_div(g.n_strips, CGT_CONSUMERS);
+            int64_t G = (int64_t)sms * 2 / n_groups;
+            const int64_t owned_cols = g.S - g.pre;
+            if (G > owned_cols / 4) G = owned_cols / 4;
+            if (G < 1) G = 1;
+            g.G = (int)G;
+            const unsigned grid = (unsigned)(n_groups * g.G);
+            const size_t smem_t = sizeof(SpStage) * SPT_STAGES + 128;
+            if (dot) {
+                PSFEM_CUDA_CHECK(cudaFuncSetAttribute(spmv_sl_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
+                PSFEM_CUDA_CHECK(launch_pdl(spmv_sl_tma_kernel<true>, grid, CGT_THREADS, smem_t, stream, A->sl_vals, g, x1, alpha, gamma, z, y, dot_out, partials, counter, done, n_groups));
+            } else {
+                PSFEM_CUDA_CHECK(cudaFuncSetAttribute(spmv_sl_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
+                PSFEM_CUDA_CHECK(launch_pdl(spmv_sl_tma_kernel<false>, grid, CGT_THREADS, smem_t, stream, A->sl_vals, g, x1, alpha, gamma, z, y, dot_out, partials, counter, done, n_groups));
+            }
+            PSFEM_LAUNCH_CHECK();
+            return PSFEM_OK;
+        }
         if (sl_geometry(A, &g, sms)) {
             const unsigned grid = (unsigned)ceil_div((int64_t)g.n_strips * g.G, SL_WARPS);
             if (dot)
@@ -1197,8 +1219,6 @@ HaloPush make_halo(const psfem_dist_ctx *c) {
     h.left_n = c->send_left_n; h.right_n = c->send_right_n; h.n = c->n_own;
     return h;
 }
-
-#include "psfem_cg_sl.cuh"
 
 struct CgWs {
     double *r[2], *s[2], *w[2], *p, *dinv, *partials, *scal;
