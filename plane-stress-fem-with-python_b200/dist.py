@@ -673,8 +673,8 @@ class StripProblem:
     @staticmethod
     def dominant_kernel(sym_lat, node_block, idx_bytes):
         if sym_lat:
-            return ("spmv_sl_kernel<true> (PCG SpMV + dot on symmetric-lattice storage: marching warps, 152 B of matrix per node, "
-                    "bit-identical to the CSR kernels)")
+            return ("spmv_sl_tma_kernel<true> (SpMV + dot on symmetric-lattice storage: marching warps, matrix staged by TMA bulk copies, "
+                    "152 B of matrix per node, bit-identical to the CSR kernels)")
         if node_block:
             return f"spmv_nb_kernel<true> (PCG SpMV + dot on the 2x2 node-block structure, TMA-staged, {8 + idx_bytes / 4:g} B/non-zero)"
         return "spmv2_kernel<true> (PCG SpMV + dot, CSR, TMA-staged, 12 B/non-zero)"
