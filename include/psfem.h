@@ -341,7 +341,15 @@ int psfem_csr_symmetry(const psfem_csr *A, double rtol, double atol, int64_t *h_
  *   psfem_cg_sl_state      h_info = {iterations, relative residual, ||b||, done, status}; synchronises
  *   psfem_cg_sl_finish     x is written every other iteration only (x += alpha_{i-1} p_{i-1} + alpha_i p_i): this adds the
  *                          pending half, if any; call it before reading d_x after psfem_cg_sl_iterations
- *   psfem_cg_sl_solve      start + batches of check_every iterations until ||r|| <= rtol ||b|| (decided on the device) */
+ *   psfem_cg_sl_solve      start + batches of check_every iterations until ||r|| <= rtol ||b|| (decided on the device);
+ *                          h_info = {iterations, relative residual of the recurrence, ||b||}
+ *   psfem_cg_sl_solve_checked  the same, then the TRUE residual b - A x (scipy.sparse.linalg.cg, the solver of
+ *                          Statictest.py:69, stops on its recurrence as well; over 10^4..10^5 iterations the recurred residual
+ *                          drifts below the true one): the solve is started again from x and continued until the true
+ *                          residual passes the test, stops improving by a factor 2 per cycle, or `polish` cycles are spent.
+ *                          polish = 0: evaluate only; polish < 0: none.  h_info = {iterations of all cycles, recurrence relres
+ *                          at the first convergence, ||b||, true relres at the last evaluation (-1: none), cycles continued,
+ *                          iterations spent in them} */
 int psfem_cg_sl_usable(const psfem_csr *A, int *h_usable);
 int psfem_cg_sl_workspace(int64_t n, size_t *bytes);
 int psfem_cg_sl_start(const psfem_csr *A, const double *d_b, double *d_x, const int32_t *d_new_id, double rtol,
@@ -351,7 +359,10 @@ int psfem_cg_sl_iterations(const psfem_csr *A, double *d_x, int masked, int64_t 
 int psfem_cg_sl_state(void *d_ws, int64_t n, double *h_info /* [5] */, void *stream);
 int psfem_cg_sl_finish(double *d_x, int64_t n, void *d_ws, void *stream);
 int psfem_cg_sl_solve(const psfem_csr *A, const double *d_b, double *d_x, const int32_t *d_new_id, double rtol, int64_t maxit,
-                      int64_t check_every, double *h_info, void *d_ws, size_t ws_bytes, void *stream);
+                      int64_t check_every, double *h_info /* [3] */, void *d_ws, size_t ws_bytes, void *stream);
+int psfem_cg_sl_solve_checked(const psfem_csr *A, const double *d_b, double *d_x, const int32_t *d_new_id, double rtol,
+                              int64_t maxit, int64_t check_every, int64_t polish, double *h_info /* [6] */, void *d_ws,
+                              size_t ws_bytes, void *stream);
 
 /* The kernels of one PCG iteration, exposed so the strip-partitioned multi-GPU driver can put its
  * halo exchange and all-reduces between them (scalars stay on the device):
@@ -429,7 +440,10 @@ int psfem_dist_pcg_residual(const psfem_dist_ctx *ctx, uint64_t seq, double *h_o
  *   psfem_dist_cg_start       x = 0, r = b and the start pass (launch 0, sequence number seq >= 1); masked strips pass the free
  *                             map of their owned rows (d_new_id[i] < 0: constrained DOF kept in the matrix)
  *   psfem_dist_cg_iterations  k launches; launches_done counts launches since the start (>= 1), seq_first = seq + launches_done
- *   psfem_dist_cg_state       {iterations, relative residual, ||b||, done, status}, global; reports a peer time-out */
+ *   psfem_dist_cg_state       {iterations, relative residual, ||b||, done, status}, global; reports a peer time-out
+ *   psfem_dist_cg_apply       y = A x over the strips (owned rows in, owned rows out; one launch of the same kernel in apply
+ *                             mode, sequence number seq): the TRUE residual b - A x of a finished strip solve.  Overwrites
+ *                             the recurrence vectors (continue with psfem_dist_cg_start on the residual), keeps the state */
 typedef struct psfem_dist_cg_ctx {
     int32_t rank, world, has_left, has_right;
     void *board[PSFEM_MAX_RANKS];          /* psfem_peer_board_bytes boards, board[rank] is this rank's own                */
@@ -446,6 +460,8 @@ int psfem_dist_cg_start(const psfem_csr *A, const psfem_dist_cg_ctx *ctx, const 
 int psfem_dist_cg_iterations(const psfem_csr *A, const psfem_dist_cg_ctx *ctx, int64_t k, int64_t launches_done,
                              uint64_t seq_first, void *d_ws, size_t ws_bytes, void *stream);
 int psfem_dist_cg_state(const psfem_dist_cg_ctx *ctx, int64_t n, void *d_ws, double *h_info /* [5] */, void *stream);
+int psfem_dist_cg_apply(const psfem_csr *A, const psfem_dist_cg_ctx *ctx, const double *d_x, double *d_y, uint64_t seq,
+                        void *d_ws, size_t ws_bytes, void *stream);
 
 /* ---- BLAS-1 helpers for the drivers (Lanczos, K_eff = K + c M, energies) ------------------ */
 int psfem_axpby(int64_t n, double a, const double *d_x, double b, const double *d_y /* may be NULL */,

@@ -125,6 +125,7 @@ SIGNATURES = {
     "psfem_cg_sl_state": [_ptr, _i64, _pdbl, _ptr],
     "psfem_cg_sl_finish": [_ptr, _i64, _ptr, _ptr],
     "psfem_cg_sl_solve": [_pcsr, _ptr, _ptr, _ptr, _dbl, _i64, _i64, _pdbl, _ptr, _sz, _ptr],
+    "psfem_cg_sl_solve_checked": [_pcsr, _ptr, _ptr, _ptr, _dbl, _i64, _i64, _i64, _pdbl, _ptr, _sz, _ptr],
     "psfem_pcg_init": [_i64, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr],
     "psfem_pcg_spmv_dot": [_pcsr, _ptr, _i64, _ptr, _ptr, _ptr, _ptr, _ptr],
     "psfem_pcg_update": [_i64, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr],
@@ -143,6 +144,7 @@ SIGNATURES = {
     "psfem_dist_cg_start": [_pcsr, _pcgctx, _ptr, _ptr, _dbl, _u64, _ptr, _sz, _ptr],
     "psfem_dist_cg_iterations": [_pcsr, _pcgctx, _i64, _i64, _u64, _ptr, _sz, _ptr],
     "psfem_dist_cg_state": [_pcgctx, _i64, _ptr, _pdbl, _ptr],
+    "psfem_dist_cg_apply": [_pcsr, _pcgctx, _ptr, _ptr, _u64, _ptr, _sz, _ptr],
     "psfem_axpby": [_i64, _dbl, _ptr, _dbl, _ptr, _ptr, _ptr],
     "psfem_dot_workspace": [_i64, _psz],
     "psfem_dot": [_i64, _ptr, _ptr, _pdbl, _ptr, _sz, _ptr],

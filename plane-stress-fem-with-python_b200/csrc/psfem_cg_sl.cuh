@@ -26,8 +26,10 @@
 struct CgCtl {
     double gamma, alpha, beta, rr, bb, tol2, delta;
     double alpha_pend;        // x lags by alpha_pend * p (the x update of every other iteration is folded into the next one)
-    long long iters;
+    long long iters;          // -1: the next launch is a start pass, -2: an apply pass (w_out = A r_in, nothing else)
     int done, status;         // status 2: breakdown (delta - beta gamma / alpha <= 0)
+    long long saved_iters;    // apply pass: iters / done of the finished solve, put back by its last block
+    int saved_done, pad_;
 };
 
 struct CgVec {
@@ -99,6 +101,8 @@ cg_sl_tma_kernel(const double *__restrict__ sv, const SlGeom g, const CgVec v, C
     CgStage *stages = reinterpret_cast<CgStage *>(cg_smem);
     pdl_enter();
     if (ctl->done) return;
+    const long long mode = ctl->iters;
+    const bool apply = mode == -2;                  // y = A x for the true residual of a finished strip solve: u := r_in
     const double alpha = ctl->alpha, beta = ctl->beta, a_pend = ctl->alpha_pend;
     const bool skip_x = defer_x && a_pend == 0.0;   // this iteration leaves x alone; the next one adds both steps
     constexpr unsigned FULL = 0xffffffffu;
@@ -177,7 +181,7 @@ cg_sl_tma_kernel(const double *__restrict__ sv, const SlGeom g, const CgVec v, C
                 sn.x = w_.x + beta * s_.x; sn.y = w_.y + beta * s_.y;
                 rn.x = r_.x - alpha * sn.x; rn.y = r_.y - alpha * sn.y;
                 if (DINV_VEC) { rn.x *= (di.x == 0.0 ? 0.0 : 1.0); rn.y *= (di.y == 0.0 ? 0.0 : 1.0); }
-                cg_ll_store(v.ll_to_right + 4 * (size_t)j, make_double2(di.x * rn.x, di.y * rn.y), ps.seq);
+                cg_ll_store(v.ll_to_right + 4 * (size_t)j, apply ? r_ : make_double2(di.x * rn.x, di.y * rn.y), ps.seq);
             }
         }
         double2 u_prev = make_double2(0.0, 0.0);      // u of column cM
@@ -208,7 +212,8 @@ cg_sl_tma_kernel(const double *__restrict__ sv, const SlGeom g, const CgVec v, C
                     rn.x = r_.x - alpha * sn.x; rn.y = r_.y - alpha * sn.y;
                     if (DINV_VEC) { rn.x *= (di.x == 0.0 ? 0.0 : 1.0); rn.y *= (di.y == 0.0 ? 0.0 : 1.0); }
                     un.x = di.x * rn.x; un.y = di.y * rn.y;
-                    if (mineV && owned) {
+                    if (apply) un = r_;
+                    if (!apply && mineV && owned) {
                         const size_t a = (size_t)(cV - own0) * g.m + j;
                         const double2 p_ = S.P[wrow];
                         double2 pn;
@@ -223,8 +228,8 @@ cg_sl_tma_kernel(const double *__restrict__ sv, const SlGeom g, const CgVec v, C
                         reinterpret_cast<double2 *>(v.s_out)[a] = sn;
                         dots[0] += rn.x * un.x; dots[0] += rn.y * un.y;
                         dots[2] += rn.x * rn.x; dots[2] += rn.y * rn.y;
-                        if (DIST && cV == own0 && ps.has_left) cg_ll_store(v.ll_to_left + 4 * (size_t)j, un, ps.seq);
                     }
+                    if (DIST && mineV && owned && cV == own0 && ps.has_left) cg_ll_store(v.ll_to_left + 4 * (size_t)j, un, ps.seq);
                 }
             } else if (DIST && valid) {
                 if (cV == own0 - 1 && left_halo) un = cg_ll_load(v.ll_from_left + 4 * (size_t)j, ps.seq, err);
@@ -290,7 +295,10 @@ cg_sl_tma_kernel(const double *__restrict__ sv, const SlGeom g, const CgVec v, C
             total[0] = gsum[0]; total[1] = gsum[1]; total[2] = gsum[2];
         }
         const double gamma_new = total[0], delta = total[1];
-        if (ctl->iters < 0) {
+        if (apply) {
+            // APPLY PASS (psfem_dist_cg_apply): w_out = A r_in is in place; the control block of the finished solve comes back
+            ctl->iters = ctl->saved_iters; ctl->done = ctl->saved_done;
+        } else if (mode < 0) {
             // START PASS (psfem_dist_cg_start): launched with r = b, w = s = p = x = 0, alpha = beta = 0, the kernel has
             // just produced u_0 = D^-1 b (left in p), w_0 = A u_0 (halo exchange included), gamma_0, delta_0 and b.b
             ctl->gamma = gamma_new; ctl->delta = delta; ctl->rr = total[2]; ctl->bb = total[2];
@@ -317,6 +325,15 @@ cg_sl_tma_kernel(const double *__restrict__ sv, const SlGeom g, const CgVec v, C
         }
         __threadfence();
     }
+}
+
+// control block of an apply pass: the kernel must run although the solve is done, and must leave the solve's state readable
+__global__ void cg_apply_ctl_kernel(CgCtl *ctl) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    ctl->saved_iters = ctl->iters; ctl->saved_done = ctl->done;
+    ctl->alpha = 0.0; ctl->beta = 0.0; ctl->alpha_pend = 0.0;
+    ctl->iters = -2;
+    ctl->done = 0;
 }
 
 // the pending half of the deferred x update: x += alpha_pend * p (then alpha_pend = 0); run before x is read

@@ -671,12 +671,21 @@ class FusedCG:
         call("psfem_cg_sl_state", ptr(self.ws), self.n, h, stream_ptr())
         return dict(iterations=int(h[0]), relres=float(h[1]), bnorm=float(h[2]), done=bool(h[3]), status=int(h[4]))
 
-    def solve(self, b, x, rtol, maxit, check_every):
+    def solve(self, b, x, rtol, maxit, check_every, polish=None):
+        """Solve, then evaluate the TRUE residual b - A x and continue from x while it is above the tolerance and still
+        improving (psfem_cg_sl_solve_checked; at most `polish` cycles, default PSFEM_PCG_POLISH or 3; negative: no check).
+        info["relres"] is the recurrence residual at convergence (what scipy's cg tests as well), info["relres_true"] the
+        last evaluated ||b - A x|| / ||b||."""
+        if polish is None:
+            polish = int(os.environ.get("PSFEM_PCG_POLISH", "3"))
         s = self.A.struct()
-        info = (C.c_double * 4)()
-        rc = lib.psfem_cg_sl_solve(C.byref(s), ptr(b), ptr(x), ptr(self.new_id), float(rtol), int(maxit), int(check_every), info,
-                                   ptr(self.ws), self.ws_bytes, stream_ptr())
-        return rc, dict(iterations=int(info[0]), relres=float(info[1]), bnorm=float(info[2]), converged=(rc == _capi.OK), pcg="fused")
+        info = (C.c_double * 8)()
+        rc = lib.psfem_cg_sl_solve_checked(C.byref(s), ptr(b), ptr(x), ptr(self.new_id), float(rtol), int(maxit), int(check_every),
+                                           int(polish), info, ptr(self.ws), self.ws_bytes, stream_ptr())
+        out = dict(iterations=int(info[0]), relres=float(info[1]), bnorm=float(info[2]), converged=(rc == _capi.OK), pcg="fused")
+        if info[3] >= 0.0:
+            out.update(relres_true=float(info[3]), polish_cycles=int(info[4]), polish_iterations=int(info[5]))
+        return rc, out
 
 
 def pcg_jacobi(A: DeviceCSR, b, x0=None, rtol=1e-8, maxit=None, check_every=50, raise_on_fail=True):
