@@ -50,7 +50,7 @@ __device__ __forceinline__ void cg_ll_store(unsigned long long *dst, double2 v, 
     st_relaxed_sys(dst + 2, tag | (b & 0xffffffffull));
     st_relaxed_sys(dst + 3, tag | (b >> 32));
 }
-__device__ __forceinline__ double2 cg_ll_load(const unsigned long long *src, unsigned long long seq, int *err) {
+__device__ __forceinline__ double2 cg_ll_load(const unsigned long long *src, unsigned long long seq, int *err, int site = 1) {
     const unsigned long long tag = seq & 0xffffffffull;
     unsigned long long q[4];
     long long spins = 0;
@@ -58,7 +58,7 @@ __device__ __forceinline__ double2 cg_ll_load(const unsigned long long *src, uns
 #pragma unroll
         for (int k = 0; k < 4; ++k) q[k] = ld_relaxed_sys_u64(src + k);
         if ((q[0] >> 32) == tag && (q[1] >> 32) == tag && (q[2] >> 32) == tag && (q[3] >> 32) == tag) break;
-        if (++spins > PEER_SPIN_LIMIT) { *err = 1; break; }
+        if (++spins > PEER_SPIN_LIMIT) { *err = site | (int)((seq & 0xfffffull) << 8); break; }   // which wait gave up, at which sequence number
     }
     return make_double2(__longlong_as_double((long long)((q[0] & 0xffffffffull) | (q[1] << 32))),
                         __longlong_as_double((long long)((q[2] & 0xffffffffull) | (q[3] << 32))));
@@ -233,7 +233,7 @@ cg_sl_tma_kernel(const double *__restrict__ sv, const SlGeom g, const CgVec v, C
                 }
             } else if (DIST && valid) {
                 if (cV == own0 - 1 && left_halo) un = cg_ll_load(v.ll_from_left + 4 * (size_t)j, ps.seq, err);
-                else if (cV == own1 && right_halo) un = cg_ll_load(v.ll_from_right + 4 * (size_t)j, ps.seq, err);
+                else if (cV == own1 && right_halo) un = cg_ll_load(v.ll_from_right + 4 * (size_t)j, ps.seq, err, 2);
             }
             // ---- column cM: row sums (q >= 2) and chain heads for the next column (q >= 1) ----
             if (q >= 1 && cM >= 0 && cM < g.S) {

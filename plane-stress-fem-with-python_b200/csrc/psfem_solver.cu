@@ -240,7 +240,7 @@ template <int NV> __device__ __forceinline__ void peer_wait_sum(const PeerSync &
                 a = ld_relaxed_sys_u64(&me->ll[stage][w][2 * q]);
                 b = ld_relaxed_sys_u64(&me->ll[stage][w][2 * q + 1]);
                 if ((a >> 32) == tag && (b >> 32) == tag) break;
-                if (++spins > PEER_SPIN_LIMIT) { *ps.err = 1; break; }
+                if (++spins > PEER_SPIN_LIMIT) { *ps.err = 3 | (w << 4) | (int)((seq & 0xfffffull) << 8); break; }
             }
             s[q] += __longlong_as_double((long long)((a & 0xffffffffull) | (b << 32)));
         }
@@ -2131,6 +2131,12 @@ extern "C" int psfem_dist_cg_state(const psfem_dist_cg_ctx *c, int64_t n, void *
     int err = 0;
     PSFEM_CUDA_CHECK(cudaMemcpyAsync(&err, c->counter + 3, sizeof(int), cudaMemcpyDeviceToHost, stream));
     PSFEM_CUDA_CHECK(cudaStreamSynchronize(stream));
-    if (err) { set_error("dist_cg: a wait on a peer rank timed out"); return PSFEM_ECUDA; }
+    if (err) {
+        static const char *site[4] = {"a wait", "the wait for the left neighbour's halo column", "the wait for the right neighbour's halo column",
+                                      "the wait for the scalars"};
+        set_error("dist_cg: %s%s timed out (code 0x%x: source rank %d, sequence number %d mod 2^20)", site[err & 3],
+                  (err & 3) == 3 ? " of a rank" : "", err, (err >> 4) & 15, (err >> 8) & 0xfffff);
+        return PSFEM_ECUDA;
+    }
     return PSFEM_OK;
 }
