@@ -688,6 +688,31 @@ class FusedCG:
         return rc, out
 
 
+def continue_from_true_residual(run, residual, rtol, out, polish=None):
+    """The classic (three-kernel) PCG paths after convergence, like psfem_cg_sl_solve_checked for the fused one: evaluate
+    ||b - A x|| (residual() -> relative norm), and while it is above rtol and improves by a factor 2 per cycle, run the
+    solver again FROM x (run() -> (rc, iterations); the C entry points take x0 = d_x).  At most `polish` cycles
+    (PSFEM_PCG_POLISH, default 3; negative: no evaluation).  Adds relres_true / polish_cycles / polish_iterations to `out`."""
+    if polish is None:
+        polish = int(os.environ.get("PSFEM_PCG_POLISH", "3"))
+    if polish < 0 or not out.get("converged", False):
+        return out
+    cycles, extra, prev = 0, 0, None
+    while True:
+        true = residual()
+        if true <= rtol or cycles >= polish or (cycles > 0 and not true < 0.5 * prev):
+            break
+        prev = true
+        cycles += 1
+        rc, its = run()
+        extra += its
+        if rc != _capi.OK:
+            break
+    out["iterations"] += extra
+    out.update(relres_true=true, polish_cycles=cycles, polish_iterations=extra)
+    return out
+
+
 def pcg_jacobi(A: DeviceCSR, b, x0=None, rtol=1e-8, maxit=None, check_every=50, raise_on_fail=True):
     """Jacobi-PCG on the device.  Returns (x, info) with info = dict(iterations, relres, bnorm)."""
     torch = _capi.torch_cuda()
@@ -715,6 +740,15 @@ def pcg_jacobi(A: DeviceCSR, b, x0=None, rtol=1e-8, maxit=None, check_every=50, 
     if rc == _capi.ENOCONV and not raise_on_fail:
         return x, out
     check(rc)
+    if n > SL_MIN_ROWS and out["bnorm"] > 0:      # the multi-kernel path (the single-CTA kernel of small systems runs too few iterations to drift)
+
+        def again():
+            h = (C.c_double * 4)()
+            rc2 = lib.psfem_pcg_jacobi(C.byref(s), ptr(b), ptr(x), float(rtol), int(maxit), int(check_every), h, ptr(ws), sz.value,
+                                       stream_ptr())
+            return rc2, int(h[0])
+        continue_from_true_residual(again, lambda: float(torch.linalg.vector_norm(A.matvec(x, alpha=-1.0, gamma=1.0, z=b)).item())
+                                    / out["bnorm"], rtol, out)
     return x, out
 
 

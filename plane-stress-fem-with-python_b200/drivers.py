@@ -14,7 +14,7 @@ import numpy as np
 
 from . import _capi
 from ._capi import call, check, lib, ptr, stream_ptr, workspace
-from .device import (SL_MIN_ROWS, Blas, DeviceCSR, FreeMap, FusedCG, constrained_dofs_of, direct_limits, direct_solve, half_bandwidth,
+from .device import (SL_MIN_ROWS, Blas, DeviceCSR, FreeMap, FusedCG, constrained_dofs_of, continue_from_true_residual, direct_limits, direct_solve, half_bandwidth,
                      pcg_jacobi, residual_dd, to_host)
 from .Polygones import device_copy
 
@@ -68,6 +68,21 @@ def _pcg_masked(Kd: DeviceCSR, fm: FreeMap, F_dev, rtol, maxit, check_every, rai
     if rc == _capi.ENOCONV and not raise_on_fail:
         return x, out
     check(rc)
+    if out["bnorm"] > 0:
+        cd_idx = fm.constrained_dev.long() if fm.constrained_dev is not None else None
+
+        def again():
+            h = (C.c_double * 4)()
+            rc2 = lib.psfem_pcg_jacobi_masked(C.byref(s), ptr(F_dev), ptr(x), ptr(fm.new_id), float(rtol), int(maxit), int(check_every),
+                                              h, ptr(ws), sz.value, stream_ptr())
+            return rc2, int(h[0])
+
+        def true_residual():
+            r = Kd.matvec(x, alpha=-1.0, gamma=1.0, z=F_dev)
+            if cd_idx is not None:
+                r.index_fill_(0, cd_idx, 0.0)          # rows of constrained DOFs are not part of the system
+            return float(torch.linalg.vector_norm(r).item()) / out["bnorm"]
+        continue_from_true_residual(again, true_residual, rtol, out)
     return x, out
 
 
