@@ -85,42 +85,60 @@ template <int ETYPE> struct Stencil {
     }
 };
 
+// One thread per node; the column indices of a warp's 32 nodes are one contiguous piece of col_idx (up to 32 x 144 B), built in
+// shared memory in the global layout and written out with coalesced 16-byte stores (per-thread 8-byte stores at a stride of
+// 144 B ran at 0.95 TB/s: 2.67 ms for the 2.5 GB of the 4096 x 4096 plate).
 template <int ETYPE>
-__global__ void lattice_pattern_kernel(int n, int m, int32_t *__restrict__ row_ptr, int32_t *__restrict__ col_idx,
-                                       int32_t *__restrict__ node_ptr) {
+__global__ void __launch_bounds__(128) lattice_pattern_kernel(int n, int m, int32_t *__restrict__ row_ptr, int32_t *__restrict__ col_idx,
+                                                              int32_t *__restrict__ node_ptr) {
+    __shared__ __align__(16) int32_t stage[4][32 * 36];     // at most 9 neighbours x 4 indices per node
     const int64_t a = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t n_nodes = (int64_t)n * m;
-    if (a > n_nodes) return;
+    const int lane = threadIdx.x & 31;
+    int32_t *buf = stage[threadIdx.x >> 5];
     using S = Stencil<ETYPE>;
     if (a == n_nodes) {   // closing entries
         const long long tot = S::pairs_before(n - 1, m, n, m);
         node_ptr[a] = (int32_t)tot;
         row_ptr[2 * a] = (int32_t)(4 * tot);
-        return;
     }
-    const int i = (int)(a / m), j = (int)(a % m);
-    const long long p0 = S::pairs_before(i, j, n, m);
-    int deg = 0;
+    const bool node = a < n_nodes;
+    long long p0 = 0;
+    int deg = 0, i = 0, j = 0;
+    if (node) {
+        i = (int)(a / m); j = (int)(a % m);
+        p0 = S::pairs_before(i, j, n, m);
 #pragma unroll
-    for (int di = -1; di <= 1; ++di)
-        if (i + di >= 0 && i + di < n) deg += S::count(di, j, m);
-    node_ptr[a] = (int32_t)p0;
-    row_ptr[2 * a] = (int32_t)(4 * p0);
-    row_ptr[2 * a + 1] = (int32_t)(4 * p0 + 2 * deg);
-    int2 *r0 = reinterpret_cast<int2 *>(col_idx + 4 * p0);   // 4*p0 and 2*deg are even: 8-byte aligned
-    int2 *r1 = r0 + deg;
-    int q = 0;
+        for (int di = -1; di <= 1; ++di)
+            if (i + di >= 0 && i + di < n) deg += S::count(di, j, m);
+        node_ptr[a] = (int32_t)p0;
+        *reinterpret_cast<int2 *>(row_ptr + 2 * a) = make_int2((int32_t)(4 * p0), (int32_t)(4 * p0 + 2 * deg));
+    }
+    if (!__shfl_sync(FULL, node ? 1 : 0, 0)) return;        // the whole warp is past the last node
+    const long long base = __shfl_sync(FULL, p0, 0);        // consecutive nodes own consecutive pieces of col_idx
+    if (node) {
+        int2 *r0 = reinterpret_cast<int2 *>(buf + 4 * (int)(p0 - base));
+        int2 *r1 = r0 + deg;
+        int q = 0;
 #pragma unroll
-    for (int di = -1; di <= 1; ++di)
+        for (int di = -1; di <= 1; ++di)
 #pragma unroll
-        for (int dj = -1; dj <= 1; ++dj) {
-            if (!S::has(di, dj) || i + di < 0 || i + di >= n || j + dj < 0 || j + dj >= m) continue;
-            const int b = (int)(a + (int64_t)di * m + dj);
-            const int2 c = make_int2(2 * b, 2 * b + 1);
-            r0[q] = c;
-            r1[q] = c;
-            ++q;
-        }
+            for (int dj = -1; dj <= 1; ++dj) {
+                if (!S::has(di, dj) || i + di < 0 || i + di >= n || j + dj < 0 || j + dj >= m) continue;
+                const int b = (int)(a + (int64_t)di * m + dj);
+                const int2 c = make_int2(2 * b, 2 * b + 1);
+                r0[q] = c;
+                r1[q] = c;
+                ++q;
+            }
+    }
+    int pairs = deg;                                         // 4 indices = one int4 per pair
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) pairs += __shfl_xor_sync(FULL, pairs, o);
+    __syncwarp();
+    int4 *dst = reinterpret_cast<int4 *>(col_idx + 4 * base);
+    const int4 *src = reinterpret_cast<const int4 *>(buf);
+    for (int q = lane; q < pairs; q += 32) dst[q] = src[q];
 }
 
 // ---- 2x2 blocks: {K(2a,2b), K(2a,2b+1), K(2a+1,2b), K(2a+1,2b+1)}; the mass block is m*I2 -> one scalar ----

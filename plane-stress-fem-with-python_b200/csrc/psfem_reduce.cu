@@ -46,21 +46,51 @@ __global__ void reduce_count_kernel(int64_t n, const int32_t *__restrict__ row_p
     cnt[nr] = c;
 }
 
-__global__ void reduce_fill_kernel(int64_t n, const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col_idx,
-                                   const int32_t *__restrict__ new_id, const int32_t *__restrict__ row_ptr_red,
-                                   int32_t *__restrict__ col_idx_red, int32_t *__restrict__ keep) {
-    int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (r >= n) return;
-    int32_t nr = new_id[r];
-    if (nr < 0) return;
-    int32_t o = row_ptr_red[nr];
-    for (int32_t k = row_ptr[r]; k < row_ptr[r + 1]; ++k) {
-        int32_t nc = new_id[col_idx[k]];
-        if (nc >= 0) {
-            col_idx_red[o] = nc;
-            keep[o] = k;
-            ++o;
+// One thread per row.  The free rows of a block are consecutive rows of the reduced matrix, so the block's output is one
+// contiguous piece of col_idx_red / keep: it is compacted in shared memory and leaves with coalesced stores (the per-thread
+// 4-byte stores at a stride of one row ran at 1 TB/s: 7 ms at 33.6 M rows).  Blocks whose rows do not fit the staging buffer
+// (very long rows) write directly.
+constexpr int RF_T = 256, RF_CAP = RF_T * 40;
+constexpr size_t RF_SMEM = (size_t)RF_CAP * (sizeof(int32_t) + sizeof(uint16_t));
+__global__ void __launch_bounds__(RF_T)
+reduce_fill_kernel(int64_t n, const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col_idx,
+                   const int32_t *__restrict__ new_id, const int32_t *__restrict__ row_ptr_red,
+                   int32_t *__restrict__ col_idx_red, int32_t *__restrict__ keep) {
+    extern __shared__ __align__(16) unsigned char rf_smem[];
+    int32_t *s_col = reinterpret_cast<int32_t *>(rf_smem);
+    uint16_t *s_k = reinterpret_cast<uint16_t *>(s_col + RF_CAP);
+    __shared__ int s_lo, s_hi;
+    const int64_t r0 = blockIdx.x * (int64_t)RF_T, r = r0 + threadIdx.x;
+    if (threadIdx.x == 0) { s_lo = INT32_MAX; s_hi = -1; }
+    __syncthreads();
+    const int32_t nr = r < n ? new_id[r] : -1;
+    int32_t o = 0;
+    if (nr >= 0) {
+        o = row_ptr_red[nr];
+        atomicMin(&s_lo, o);
+        atomicMax(&s_hi, row_ptr_red[nr + 1]);
+    }
+    __syncthreads();
+    if (s_hi < 0) return;                                  // no free row in this block
+    const int base = s_lo, cnt = s_hi - s_lo;
+    const int64_t r_end = r0 + RF_T < n ? r0 + RF_T : n;
+    const int32_t k_base = row_ptr[r0];
+    const bool staged = cnt <= RF_CAP && row_ptr[r_end] - k_base <= 65535;   // the same decision in every thread
+    if (nr >= 0) {
+        for (int32_t k = row_ptr[r]; k < row_ptr[r + 1]; ++k) {
+            const int32_t nc = new_id[col_idx[k]];
+            if (nc >= 0) {
+                if (staged) { s_col[o - base] = nc; s_k[o - base] = (uint16_t)(k - k_base); }
+                else { col_idx_red[o] = nc; keep[o] = k; }
+                ++o;
+            }
         }
+    }
+    if (!staged) return;
+    __syncthreads();
+    for (int q = threadIdx.x; q < cnt; q += RF_T) {
+        col_idx_red[base + q] = s_col[q];
+        keep[base + q] = k_base + (int32_t)s_k[q];
     }
 }
 
@@ -168,8 +198,8 @@ extern "C" int psfem_reduce_count(int64_t n, const int32_t *d_row_ptr, const int
 extern "C" int psfem_reduce_fill(int64_t n, const int32_t *d_row_ptr, const int32_t *d_col_idx, const int32_t *d_new_id,
                                  const int32_t *d_row_ptr_red, int32_t *d_col_idx_red, int32_t *d_keep, void *stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    const int T = 256;
-    reduce_fill_kernel<<<(unsigned)ceil_div(n, T), T, 0, stream>>>(n, d_row_ptr, d_col_idx, d_new_id, d_row_ptr_red, d_col_idx_red, d_keep);
+    PSFEM_CUDA_CHECK(cudaFuncSetAttribute(reduce_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RF_SMEM));
+    reduce_fill_kernel<<<(unsigned)ceil_div(n, RF_T), RF_T, RF_SMEM, stream>>>(n, d_row_ptr, d_col_idx, d_new_id, d_row_ptr_red, d_col_idx_red, d_keep);
     PSFEM_LAUNCH_CHECK();
     return PSFEM_OK;
 }
