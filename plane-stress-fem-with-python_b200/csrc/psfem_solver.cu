@@ -1983,9 +1983,15 @@ extern "C" int psfem_cg_sl_solve_checked(const psfem_csr *A, const double *d_b, 
         if (first_relres < 0.0) first_relres = st[1];
         h_info[0] = total; h_info[1] = first_relres; h_info[2] = st[2];
         h_info[3] = true_relres; h_info[4] = (double)cycles; h_info[5] = polish_iters;
-        if (st[4] != 0.0) { set_error("cg_sl: breakdown (matrix not positive definite?) after %.0f iterations, relres %.3e", total, st[1]); return PSFEM_ENOCONV; }
-        if (!(st[1] <= rtol) && st[2] > 0) { set_error("pcg: not converged (relres %.3e after %.0f iterations)", st[1], total); return PSFEM_ENOCONV; }
+        const bool failed = st[4] != 0.0 || (!(st[1] <= rtol) && st[2] > 0);
+        if (failed && cycles == 0) {
+            if (st[4] != 0.0) set_error("cg_sl: breakdown (matrix not positive definite?) after %.0f iterations, relres %.3e", total, st[1]);
+            else set_error("pcg: not converged (relres %.3e after %.0f iterations)", st[1], total);
+            return PSFEM_ENOCONV;
+        }
         if (polish < 0) return PSFEM_OK;
+        if (failed) polish = 0;     // a continuation cycle ran out of iterations (or broke down at the rounding level): the solve
+                                    // had converged before it; evaluate the residual of what is returned and stop
         // r = b - A x from the SpMV; the start leaves the solve ready to continue from x
         rc = psfem_cg_sl_start(A, d_b, d_x, d_new_id, rtol, d_ws, ws_bytes, stream_);
         if (rc) return rc;
