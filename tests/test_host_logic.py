@@ -197,3 +197,43 @@ def test_device_backed_csr_never_goes_stale(psfem):
     assert not A._psfem_valid()
     A = fresh()
     assert A.copy()._psfem_dev is None and A.copy().data.flags.writeable and A._psfem_valid()
+
+
+def test_continuation_from_true_residual_control_flow(psfem, monkeypatch):
+    """device.continue_from_true_residual (the host loop around the classic PCG entry points): stops when the evaluated
+    residual passes, when a cycle does not halve it (rounding floor), after `polish` cycles, and never runs for an
+    unconverged solve or with a negative `polish`; iterations of the cycles are added and reported."""
+    from psfem_b200.device import continue_from_true_residual
+
+    def scenario(residuals, polish, converged=True, rc_seq=None):
+        res, runs = list(residuals), []
+
+        def run():
+            runs.append(1)
+            return (rc_seq.pop(0) if rc_seq else 0), 7
+
+        out = dict(iterations=100, relres=9e-9, converged=converged)
+        continue_from_true_residual(run, lambda: res.pop(0), 1e-8, out, polish=polish)
+        return out, len(runs)
+
+    out, runs = scenario([5e-9], 3)                              # already below rtol: evaluated, nothing run
+    assert runs == 0 and out["relres_true"] == 5e-9 and out["polish_cycles"] == 0 and out["iterations"] == 100
+    out, runs = scenario([4e-7, 2e-8, 6e-9], 3)                  # two cycles bring it below rtol
+    assert runs == 2 and out["relres_true"] == 6e-9 and out["polish_cycles"] == 2 and out["iterations"] == 114 and out["polish_iterations"] == 14
+    out, runs = scenario([4e-7, 2e-8, 1.5e-8, 1.4e-8], 5)        # floor: the second cycle does not halve the residual
+    assert runs == 2 and out["relres_true"] == 1.5e-8 and out["polish_cycles"] == 2
+    out, runs = scenario([4e-7, 1e-7, 4e-8, 1.5e-8, 1e-9], 3)    # cycle limit
+    assert runs == 3 and out["relres_true"] == 1.5e-8 and out["polish_cycles"] == 3
+    out, runs = scenario([4e-7], 0)                              # evaluate only
+    assert runs == 0 and out["relres_true"] == 4e-7
+    out, runs = scenario([4e-7], -1)                             # switched off
+    assert runs == 0 and "relres_true" not in out
+    out, runs = scenario([4e-7], 3, converged=False)             # an unconverged solve is left alone
+    assert runs == 0 and "relres_true" not in out
+    out, runs = scenario([4e-7, 3e-7], 3, rc_seq=[psfem._capi.ENOCONV])   # a cycle that fails ends the loop; the solve stays converged
+    assert runs == 1 and out["converged"] and out["polish_cycles"] == 1
+    monkeypatch.setenv("PSFEM_PCG_POLISH", "1")                  # the default comes from the environment
+    res = [4e-7, 1e-7, 1e-9]
+    out = dict(iterations=10, relres=9e-9, converged=True)
+    continue_from_true_residual(lambda: (0, 1), lambda: res.pop(0), 1e-8, out)
+    assert out["polish_cycles"] == 1 and out["relres_true"] == 1e-7
