@@ -918,7 +918,7 @@ class StripProblem:
             self.st["p_ext"] = None
             self.fabric.close()
             self.fabric = None
-        for k in ("asm", "K_vals", "K_ext_red", "K_red", "fm", "st", "ops", "A", "b_own", "nodes", "conn", "ctx", "_cd_owned", "fused", "cg_ws", "cg_ctx"):
+        for k in ("asm", "K_vals", "K_ext_red", "K_red", "fm", "st", "ops", "A", "b_own", "nodes", "conn", "ctx", "_cd_owned", "fused", "cg_ws", "cg_ctx", "_x_acc", "_b_cycle"):
             if hasattr(self, k):
                 delattr(self, k)
 
