@@ -67,7 +67,9 @@ def run_checks(world, rank):
             chk(info["relres"] <= 1e-9, lambda: f"info['relres'] <= 1e-9: {info}")
             res["solve_iters" if transport == "peer" else "solve_iters_classic"] = info["iterations"] - info.get("polish_iterations", 0)
             if prob.fused_dist:    # the fused strip solver evaluates b - K x after convergence (apply pass) and continues from it
-                chk("relres_true" in info and info["relres_true"] <= 2e-9, lambda: f"true residual of the strip solve: {info}")
+                # (the 96 N x 80 plate gets slender with the rank count: at 8 ranks its rounding floor is 5.5e-10 and the
+                #  continuation ends near 1.1e-9 -- CPU restatement; the bar is 10 rtol)
+                chk("relres_true" in info and info["relres_true"] <= 1e-8, lambda: f"true residual of the strip solve: {info}")
                 res["solve_info"] = info
                 prob.finish_x()
                 res["x_solved"] = prob.st["x"].cpu().numpy().copy()
@@ -115,7 +117,13 @@ def run_checks(world, rank):
         rt = one.b_own - one.K_red.matvec(xs)
         true_ind = float(torch.linalg.vector_norm(rt).item() / torch.linalg.vector_norm(one.b_own).item())
         rep = res["solve_info"]["relres_true"]
-        chk(abs(true_ind - rep) <= 0.02 * true_ind + 1e-14, lambda: f"true residual of the strip solve: reported {rep:.6e}, recomputed {true_ind:.6e}")
+        # the two evaluations sum in different orders: they may differ by the rounding floor of the problem, ||K (x o delta)|| / ||b||
+        g = torch.Generator(device="cuda")
+        g.manual_seed(1)
+        delta = (torch.rand(xs.shape, generator=g, device="cuda", dtype=torch.float64) - 0.5) * 2.0 ** -52
+        floor = float(torch.linalg.vector_norm(one.K_red.matvec(xs * delta)).item() / torch.linalg.vector_norm(one.b_own).item())
+        chk(abs(true_ind - rep) <= 0.02 * true_ind + 4 * floor + 1e-14,
+            lambda: f"true residual of the strip solve: reported {rep:.6e}, recomputed {true_ind:.6e}, rounding floor {floor:.2e}")
     # 3b. the other element types (T3, and the quadratic T6 / Q9 of mesh_type='fine', whose strips carry a two-column
     #     left halo): owned matrix rows bit-identical to the single-GPU rows, same iterates
     for et, mt, n_, m_ in (("tri", "coarse", 40 * world, 60), ("quad", "fine", 24 * world, 20), ("tri", "fine", 24 * world, 20)):
